@@ -1,0 +1,236 @@
+"""CPU oracle for the ScaLAPACK dense-LU path (TEST INFRASTRUCTURE ONLY).
+
+ctypes front end of ``oracle/oracle.c`` -- a serial restatement of the
+reference's PDGETRF/PDGETRS/PZGETRF algorithm, its test-matrix generators
+(TESTING/traditional/LIN/pdmatgen.f) and its residual checks
+(pdlafchk.f, pdlaschk.f).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this
+package; the product (``scalapack_b200``) must never do so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c with gcc (no GPU, no reference sources needed)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def _find_openblas() -> str | None:
+    try:
+        import scipy  # noqa: F401
+        base = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+        hits = sorted(glob.glob(os.path.join(base, "libscipy_openblas*.so")))
+        return hits[0] if hits else None
+    except Exception:
+        return None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_wtime.restype = C.c_double
+        L.orc_dlange_inf.restype = C.c_double
+        for f in ("orc_fresid", "orc_sresid", "orc_zfresid", "orc_zsresid"):
+            getattr(L, f).restype = C.c_double
+        p = _find_openblas()
+        if p is not None:
+            L.orc_init_blas(p.encode())
+        _LIB = L
+    return _LIB
+
+
+def have_blas() -> bool:
+    return bool(lib().orc_have_blas())
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
+
+
+def get_threads() -> int:
+    return int(lib().orc_get_threads())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- index algebra
+def numroc(n, nb, iproc, isrc, nprocs):
+    return lib().orc_numroc(n, nb, iproc, isrc, nprocs)
+
+
+def indxg2p(ig, nb, iproc, isrc, nprocs):
+    return lib().orc_indxg2p(ig, nb, iproc, isrc, nprocs)
+
+
+def indxg2l(ig, nb, iproc, isrc, nprocs):
+    return lib().orc_indxg2l(ig, nb, iproc, isrc, nprocs)
+
+
+def indxl2g(il, nb, iproc, isrc, nprocs):
+    return lib().orc_indxl2g(il, nb, iproc, isrc, nprocs)
+
+
+def infog2l(gr, gc, desc, nprow, npcol, myrow, mycol):
+    d = (C.c_int * 9)(*desc)
+    lr, lc, rs, cs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib().orc_infog2l(gr, gc, d, nprow, npcol, myrow, mycol, C.byref(lr), C.byref(lc), C.byref(rs), C.byref(cs))
+    return lr.value, lc.value, rs.value, cs.value
+
+
+def descinit(m, n, mb, nb, irsrc, icsrc, ictxt, lld, nprow, npcol, myrow):
+    d = (C.c_int * 9)()
+    info = lib().orc_descinit(d, m, n, mb, nb, irsrc, icsrc, ictxt, lld, nprow, npcol, myrow)
+    return list(d), info
+
+
+def chk1mat(ma, mapos0, na, napos0, ia, ja, desc, descpos0, nprow, npcol, myrow, mycol, info=0):
+    d = (C.c_int * 9)(*desc)
+    inf = C.c_int(info)
+    lib().orc_chk1mat(ma, mapos0, na, napos0, ia, ja, d, descpos0, nprow, npcol, myrow, mycol, C.byref(inf))
+    return inf.value
+
+
+# ---------------------------------------------------------------- generators
+def pdmatgen(m, n, iseed=100):
+    """Global M x N PDMATGEN matrix (Fortran order)."""
+    a = np.empty((m, n), dtype=np.float64, order="F")
+    lib().orc_pdmatgen_global(m, n, iseed, _p(a), C.c_int64(max(m, 1)))
+    return a
+
+
+def pdmatgen_local(m, n, mb, nb, myrow, mycol, nprow, npcol, iseed=100, iarow=0, iacol=0):
+    mp = numroc(m, mb, myrow, iarow, nprow)
+    nq = numroc(n, nb, mycol, iacol, npcol)
+    a = np.zeros((max(mp, 1), max(nq, 1)), dtype=np.float64, order="F")
+    lib().orc_pdmatgen_local(m, n, mb, nb, _p(a), max(mp, 1), iarow, iacol, iseed, myrow, mycol, nprow, npcol)
+    return a[:mp, :nq]
+
+
+def pzmatgen(m, n, iseed=100):
+    a = np.empty((m, n), dtype=np.complex128, order="F")
+    lib().orc_pzmatgen_global(m, n, iseed, _p(a), C.c_int64(max(m, 1)))
+    return a
+
+
+def matgen64_tile(m, seed, i0, mr, j0, nc, complex_=False):
+    """Tile of the 64-bit HPL-style generator (not in the reference)."""
+    a = np.empty((mr, nc), dtype=np.complex128 if complex_ else np.float64, order="F")
+    f = lib().orc_zmatgen64_tile if complex_ else lib().orc_matgen64_tile
+    f(C.c_int64(m), C.c_uint64(seed), C.c_int64(i0), C.c_int64(mr), C.c_int64(j0), C.c_int64(nc), _p(a),
+      C.c_int64(max(mr, 1)))
+    return a
+
+
+# ---------------------------------------------------------------- distribution
+def scatter(ag, mb, nb, nprow, npcol, myrow, mycol, rsrc=0, csrc=0, lld=None):
+    m, n = ag.shape
+    ag = np.asfortranarray(ag)
+    mp = numroc(m, mb, myrow, rsrc, nprow)
+    nq = numroc(n, nb, mycol, csrc, npcol)
+    lld = max(1, mp) if lld is None else lld
+    al = np.zeros((lld, max(nq, 1)), dtype=ag.dtype, order="F")
+    lib().orc_scatter(m, n, mb, nb, rsrc, csrc, nprow, npcol, myrow, mycol, _p(ag), C.c_int64(max(m, 1)), _p(al),
+                      C.c_int64(lld), ag.dtype.itemsize)
+    return al
+
+
+def gather_into(ag, al, mb, nb, nprow, npcol, myrow, mycol, rsrc=0, csrc=0):
+    m, n = ag.shape
+    assert ag.flags.f_contiguous and al.flags.f_contiguous
+    lib().orc_gather(m, n, mb, nb, rsrc, csrc, nprow, npcol, myrow, mycol, _p(ag), C.c_int64(max(m, 1)), _p(al),
+                     C.c_int64(al.shape[0]), ag.dtype.itemsize)
+
+
+def ipiv_local(m, mn, mb, nprow, myrow, ipiv_g, nloc, rsrc=0, fill=-1):
+    out = np.empty(nloc, dtype=np.int32)
+    g = np.ascontiguousarray(ipiv_g, dtype=np.int32)
+    lib().orc_ipiv_local(m, mn, mb, rsrc, nprow, myrow, _p(g), _p(out), nloc, fill)
+    return out
+
+
+# ---------------------------------------------------------------- LU / solve / residuals
+def getrf(a, nb, phase_times=False):
+    """In-place restated PDGETRF on the global matrix.  Returns (ipiv[1-based], info)."""
+    assert a.flags.f_contiguous
+    m, n = a.shape
+    ipiv = np.zeros(max(min(m, n), 1), dtype=np.int32)
+    if a.dtype == np.complex128:
+        info = lib().orc_zgetrf(m, n, _p(a), C.c_int64(max(m, 1)), nb, _p(ipiv))
+        return ipiv[:min(m, n)], info
+    assert a.dtype == np.float64
+    pt = np.zeros(4)
+    info = lib().orc_dgetrf(m, n, _p(a), C.c_int64(max(m, 1)), nb, _p(ipiv), _p(pt))
+    if phase_times:
+        return ipiv[:min(m, n)], info, pt
+    return ipiv[:min(m, n)], info
+
+
+def getrf_steps(a, nb, nsteps):
+    """First `nsteps` block steps only (bounded CPU-baseline sample). Returns (info, flops)."""
+    m, n = a.shape
+    ipiv = np.zeros(max(min(m, n), 1), dtype=np.int32)
+    fl = C.c_double(0)
+    info = lib().orc_dgetrf_steps(m, n, _p(a), C.c_int64(max(m, 1)), nb, _p(ipiv), nsteps, C.byref(fl))
+    return info, fl.value
+
+
+def getrs(lu, ipiv, b, trans="N"):
+    assert lu.flags.f_contiguous and b.flags.f_contiguous
+    n = lu.shape[0]
+    nrhs = b.shape[1]
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    if lu.dtype == np.complex128:
+        lib().orc_zgetrs(C.c_char(trans.encode()), n, nrhs, _p(lu), C.c_int64(max(n, 1)), _p(ip), _p(b),
+                         C.c_int64(b.shape[0]))
+    else:
+        lib().orc_dgetrs(C.c_char(trans.encode()), n, nrhs, _p(lu), C.c_int64(max(n, 1)), _p(ip), _p(b),
+                         C.c_int64(b.shape[0]))
+    return b
+
+
+def fresid(lu, ipiv, a0):
+    m, n = lu.shape
+    lu = np.asfortranarray(lu)
+    a0 = np.asfortranarray(a0)
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    f = lib().orc_zfresid if lu.dtype == np.complex128 else lib().orc_fresid
+    return f(m, n, _p(lu), C.c_int64(max(m, 1)), _p(ip), _p(a0), C.c_int64(max(m, 1)))
+
+
+def sresid(a0, x, b0):
+    n = a0.shape[0]
+    a0 = np.asfortranarray(a0)
+    x = np.asfortranarray(x)
+    b0 = np.asfortranarray(b0)
+    f = lib().orc_zsresid if a0.dtype == np.complex128 else lib().orc_sresid
+    return f(n, x.shape[1], _p(a0), C.c_int64(max(n, 1)), _p(x), C.c_int64(x.shape[0]), _p(b0),
+             C.c_int64(b0.shape[0]))
+
+
+def lu_tolerance_ok(lu_test, lu_ref, a0):
+    """LU-factor tolerance of SURVEY.md 8a(vi): with identical IPIV,
+    max|LU_test - LU_ref| / (||A||_inf * N * eps) < 1."""
+    n = max(a0.shape)
+    anorm = np.abs(a0).sum(axis=1).max()
+    err = np.abs(lu_test - lu_ref).max() / (anorm * n * 2.0 ** -53)
+    return err, err < 1.0
