@@ -1,0 +1,139 @@
+/*
+ * scalapack_b200.h -- C-ABI of the B200-native distributed dense LU path.
+ *
+ * Every entry point below is a drop-in for the reference ScaLAPACK symbol of
+ * the same name (Fortran-77 calling convention: lower case + trailing
+ * underscore, all arguments by reference, INTEGER = 32-bit int, CHARACTER as
+ * char* whose first letter is significant; hidden string lengths are ignored
+ * exactly as the reference's C code ignores them).  Reference file:line of the
+ * interface each symbol replaces is cited next to it (paths relative to the
+ * reference source root).
+ *
+ * One process drives one GPU (device = $LOCAL_RANK, else rank % device count).
+ * Process bootstrap replaces MPI_Init: rank/size come from RANK/WORLD_SIZE
+ * (torchrun), OMPI_COMM_WORLD_*, or PMI_*; rendezvous is TCP on
+ * MASTER_ADDR : MASTER_PORT + SLB200_PORT_OFFSET (default 23).
+ *
+ * Matrix arguments (A, B) may be HOST pointers (staged through device memory,
+ * the drop-in case for an unmodified Fortran caller) or DEVICE pointers
+ * (factored in place in HBM).  IPIV / descriptors / scalars are host memory.
+ */
+#ifndef SCALAPACK_B200_H
+#define SCALAPACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } slb200_z;   /* COMPLEX*16 */
+
+/* ---- BLACS setup API (BLACS/SRC/*.c) ------------------------------------ */
+void blacs_pinfo_(int *mypnum, int *nprocs);                                  /* BLACS/SRC/blacs_pinfo_.c:3-28 */
+void blacs_get_(const int *ictxt, const int *what, int *val);                 /* BLACS/SRC/blacs_get_.c */
+void blacs_set_(const int *ictxt, const int *what, const int *val);           /* BLACS/SRC/blacs_set_.c (accepted, ignored) */
+void blacs_gridinit_(int *ictxt, const char *order, const int *nprow, const int *npcol);   /* BLACS/SRC/blacs_init_.c:3-40 */
+void blacs_gridmap_(int *ictxt, const int *usermap, const int *ldumap, const int *nprow, const int *npcol); /* blacs_map_.c:84-141 */
+void blacs_gridinfo_(const int *ictxt, int *nprow, int *npcol, int *myrow, int *mycol);    /* BLACS/SRC/blacs_info_.c */
+void blacs_gridexit_(const int *ictxt);                                       /* BLACS/SRC/blacs_grid_.c */
+void blacs_exit_(const int *notdone);                                         /* BLACS/SRC/blacs_exit_.c */
+void blacs_abort_(const int *ictxt, const int *errnum);                       /* BLACS/SRC/blacs_abort_.c */
+void blacs_barrier_(const int *ictxt, const char *scope);                     /* BLACS/SRC/blacs_barr_.c:16-26 */
+int  blacs_pnum_(const int *ictxt, const int *prow, const int *pcol);         /* BLACS/SRC/blacs_pnum_.c */
+void blacs_pcoord_(const int *ictxt, const int *pnum, int *prow, int *pcol);  /* BLACS/SRC/blacs_pcoord_.c */
+/* C twins (BLACS/SRC/*.c compile both bindings from one file, dgebs2d_.c:3-8) */
+void Cblacs_pinfo(int *mypnum, int *nprocs);
+void Cblacs_get(int ictxt, int what, int *val);
+void Cblacs_gridinit(int *ictxt, const char *order, int nprow, int npcol);
+void Cblacs_gridinfo(int ictxt, int *nprow, int *npcol, int *myrow, int *mycol);
+void Cblacs_gridexit(int ictxt);
+void Cblacs_exit(int notdone);
+void Cblacs_barrier(int ictxt, const char *scope);
+int  Cblacs_pnum(int ictxt, int prow, int pcol);
+void Cblacs_pcoord(int ictxt, int pnum, int *prow, int *pcol);
+/* the two integer combines the LU path itself calls directly */
+void igamn2d_(const int *ictxt, const char *scope, const char *top, const int *m, const int *n, int *a,
+              const int *lda, int *ra, int *ca, const int *rcflag, const int *rdest, const int *cdest); /* BLACS/SRC/igamn2d_.c */
+void igamx2d_(const int *ictxt, const char *scope, const char *top, const int *m, const int *n, int *a,
+              const int *lda, int *ra, int *ca, const int *rcflag, const int *rdest, const int *cdest); /* BLACS/SRC/igamx2d_.c */
+
+/* ---- TOOLS (TOOLS/*.f, SL_init.f) ---------------------------------------- */
+void sl_init_(int *ictxt, const int *nprow, const int *npcol);                /* TOOLS/SL_init.f */
+void descinit_(int *desc, const int *m, const int *n, const int *mb, const int *nb, const int *irsrc,
+               const int *icsrc, const int *ictxt, const int *lld, int *info);                  /* TOOLS/descinit.f:1-2 */
+void descset_(int *desc, const int *m, const int *n, const int *mb, const int *nb, const int *irsrc,
+              const int *icsrc, const int *ictxt, const int *lld);                               /* TOOLS/descset.f */
+int  numroc_(const int *n, const int *nb, const int *iproc, const int *isrcproc, const int *nprocs);   /* TOOLS/numroc.f */
+int  indxg2p_(const int *indxglob, const int *nb, const int *iproc, const int *isrcproc, const int *nprocs); /* TOOLS/indxg2p.f */
+int  indxg2l_(const int *indxglob, const int *nb, const int *iproc, const int *isrcproc, const int *nprocs); /* TOOLS/indxg2l.f */
+int  indxl2g_(const int *indxloc, const int *nb, const int *iproc, const int *isrcproc, const int *nprocs);  /* TOOLS/indxl2g.f */
+void infog2l_(const int *grindx, const int *gcindx, const int *desc, const int *nprow, const int *npcol,
+              const int *myrow, const int *mycol, int *lrindx, int *lcindx, int *rsrc, int *csrc);  /* TOOLS/infog2l.f */
+int  iceil_(const int *inum, const int *idenom);                              /* TOOLS/iceil.f */
+int  ilcm_(const int *m, const int *n);                                       /* TOOLS/ilcm.f */
+void chk1mat_(const int *ma, const int *mapos0, const int *na, const int *napos0, const int *ia, const int *ja,
+              const int *desca, const int *descapos0, int *info);             /* TOOLS/chk1mat.f:1 */
+void pchk1mat_(const int *ma, const int *mapos0, const int *na, const int *napos0, const int *ia, const int *ja,
+               const int *desca, const int *descapos0, const int *nextra, const int *ex, const int *expos,
+               int *info);                                                     /* TOOLS/pchkxmat.f:1 */
+void pchk2mat_(const int *ma, const int *mapos0, const int *na, const int *napos0, const int *ia, const int *ja,
+               const int *desca, const int *descapos0, const int *mb, const int *mbpos0, const int *nb,
+               const int *nbpos0, const int *ib, const int *jb, const int *descb, const int *descbpos0,
+               const int *nextra, const int *ex, const int *expos, int *info); /* TOOLS/pchkxmat.f:173 */
+void pxerbla_(const int *ictxt, const char *srname, const int *info);         /* PBLAS/SRC/PTZBLAS/pxerbla.f:53-58 */
+void pb_topget_(const int *ictxt, const char *op, const char *scope, char *top);   /* PBLAS/SRC/PTOOLS/PB_Ctop.c:76-141 */
+void pb_topset_(const int *ictxt, const char *op, const char *scope, const char *top);
+
+/* ---- the hot path: distributed LU factor / solve ------------------------- */
+void pdgetrf_(const int *m, const int *n, double *a, const int *ia, const int *ja, const int *desca,
+              int *ipiv, int *info);                                          /* SRC/pdgetrf.f:1 */
+void pdgetrs_(const char *trans, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja,
+              const int *desca, const int *ipiv, double *b, const int *ib, const int *jb, const int *descb,
+              int *info);                                                     /* SRC/pdgetrs.f:1-2 */
+void pdgesv_(const int *n, const int *nrhs, double *a, const int *ia, const int *ja, const int *desca,
+             int *ipiv, double *b, const int *ib, const int *jb, const int *descb, int *info);   /* SRC/pdgesv.f:1-2 */
+void pzgetrf_(const int *m, const int *n, slb200_z *a, const int *ia, const int *ja, const int *desca,
+              int *ipiv, int *info);                                          /* SRC/pzgetrf.f:1 */
+void pzgetrs_(const char *trans, const int *n, const int *nrhs, const slb200_z *a, const int *ia, const int *ja,
+              const int *desca, const int *ipiv, slb200_z *b, const int *ib, const int *jb, const int *descb,
+              int *info);                                                     /* SRC/pzgetrs.f:1-2 */
+void pzgesv_(const int *n, const int *nrhs, slb200_z *a, const int *ia, const int *ja, const int *desca,
+             int *ipiv, slb200_z *b, const int *ib, const int *jb, const int *descb, int *info); /* SRC/pzgesv.f:1-2 */
+
+/* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
+/* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
+ * a may be host or device. */
+void slb200_pdmatgen(const int *ictxt, const int *m, const int *n, const int *mb, const int *nb, double *a,
+                     const int *lda, const int *iarow, const int *iacol, const int *iseed);
+/* 64-bit LCG test matrix for N beyond PDMATGEN's 2^31 period (not in the reference). */
+void slb200_matgen64(const int *ictxt, const int64_t *m, const int64_t *n, const int *mb, const int *nb, double *a,
+                     const int64_t *lda, const int *iarow, const int *iacol, const uint64_t *seed);
+void slb200_zmatgen64(const int *ictxt, const int64_t *m, const int64_t *n, const int *mb, const int *nb, slb200_z *a,
+                      const int64_t *lda, const int *iarow, const int *iacol, const uint64_t *seed);
+/* Solve residual of pdlaschk.f:187,296 with A and B regenerated on the device from the 64-bit
+ * generator (gen=64) or PDMATGEN (gen=31).  x: local block-cyclic solution (host or device). */
+double slb200_pdlaschk(const int *ictxt, const int *n, const int *nrhs, const double *x, const int *descx,
+                       const int *desca, const uint64_t *aseed, const uint64_t *bseed, const int *gen);
+
+/* ---- runtime controls / introspection (not in the reference) ------------- */
+int  slb200_device(void);                  /* CUDA device this process drives, -1 if none */
+int  slb200_has_cuda(void);                /* 1 when a usable sm_100 device is present     */
+const char *slb200_version(void);
+void slb200_set_option(const char *key, int64_t value);   /* "lookahead", "verbose", "panel_width", ... */
+int64_t slb200_get_counter(const char *key);             /* "kernel_launches", "h2d_bytes", "d2h_bytes", ... */
+void slb200_reset_counters(void);
+/* Device-time (ms) of the last pdgetrf_/pdgetrs_ call on this rank, measured with CUDA events
+ * on the library's own streams (host staging excluded). */
+double slb200_last_factor_ms(void);
+double slb200_last_solve_ms(void);
+/* per-kernel event timing of the dominant kernel (trailing update) in the last pdgetrf_ */
+double slb200_last_update_ms(void);
+double slb200_last_update_flops(void);
+int64_t slb200_last_update_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCALAPACK_B200_H */

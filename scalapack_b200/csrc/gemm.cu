@@ -1,0 +1,356 @@
+// gemm.cu -- trailing-matrix update  C[MxN] -= A[MxK] * B[KxN]  in FP64 on the tensor cores.
+//
+// Replaces the one local dgemm_ per LU step of the reference (PBLAS/SRC/PTOOLS/PB_CpgemmAB.c:345 reached
+// from SRC/pdgetrf.f:288) -- >= 99 % of the factorisation's flops.
+//
+// sm_100a has no FP64 kind of tcgen05.mma (kinds: f16, tf32, f8f6f4, i8, mxf8f6f4, mxf4, mxf4nvf4), so
+// the FP64 tensor path is the warp-level DMMA  mma.sync.aligned.m16n8k4.row.col.f64  with register
+// accumulators.  Tiling: CTA 128(m) x 128(n) x 16(k), 8 warps as 2(m) x 4(n), warp tile 64 x 32.
+// The MMA is issued "transposed" (MMA-M runs along the problem's n, MMA-N along m) so that each thread's
+// accumulator pair (c0,c1) is two consecutive rows of one column of column-major C: the epilogue is
+// 16-byte read-modify-writes, 64 B contiguous per column per warp request.
+// Operands are staged by a 4-stage cp.async (LDGSTS) ring into padded shared memory:
+//   As[k][m] stride 132 doubles, Bs[n][k] stride 20 doubles -> every fragment LDS.64 is bank-conflict free.
+// Tile order: groups of 16 m-tiles swept along n so a group's A rows stay L2-resident while B streams.
+#include "kernels.cuh"
+#include "common.h"
+
+namespace slb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
+constexpr int SA = BM + 4;            // As row stride (doubles)
+constexpr int SB = BK + 4;            // Bs row stride (doubles)
+constexpr int AS_STAGE = BK * SA;     // doubles per stage
+constexpr int BS_STAGE = BN * SB;
+constexpr int GROUP_M = 16;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(16x8) += A(16x4) * B(4x8), FP64 tensor core
+__device__ __forceinline__ void dmma_16x8x4(double (&d)[4], double a0, double a1, double b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+                 : "d"(a0), "d"(a1), "d"(b0));
+}
+
+// Stage loader.  VEC=2: 16-byte chunks (needs 16 B aligned base pointers and even lda/ldb); VEC=1: 8-byte.
+template <int VEC>
+__device__ __forceinline__ void load_stage(double *As, double *Bs, const double *__restrict__ A, int64_t lda,
+                                           const double *__restrict__ B, int64_t ldb, int64_t m0, int64_t n0, int k0,
+                                           int64_t M, int64_t N, int K, int tid)
+{
+    if (VEC == 2) {
+#pragma unroll
+        for (int i = 0; i < (BK * BM / 2) / NTHREADS; ++i) {       // A: 16 k-rows x 64 chunks
+            int c = tid + i * NTHREADS;
+            int k = c >> 6, mc = (c & 63) * 2;
+            int64_t m = m0 + mc;
+            int kk = k0 + k;
+            int bytes = 0;
+            if (kk < K && m < M) bytes = (M - m >= 2) ? 16 : 8;
+            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
+            cp_async16(As + k * SA + mc, src, bytes);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK / 2) / NTHREADS; ++i) {       // B: 128 n-cols x 8 chunks
+            int c = tid + i * NTHREADS;
+            int n = c >> 3, kc = (c & 7) * 2;
+            int64_t nn = n0 + n;
+            int kk = k0 + kc;
+            int bytes = 0;
+            if (nn < N && kk < K) bytes = (K - kk >= 2) ? 16 : 8;
+            const double *src = bytes ? (B + kk + nn * ldb) : B;
+            cp_async16(Bs + n * SB + kc, src, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (BK * BM) / NTHREADS; ++i) {
+            int c = tid + i * NTHREADS;
+            int k = c >> 7, mc = c & 127;
+            int64_t m = m0 + mc;
+            int kk = k0 + k;
+            int bytes = (kk < K && m < M) ? 8 : 0;
+            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
+            cp_async8(As + k * SA + mc, src, bytes);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / NTHREADS; ++i) {
+            int c = tid + i * NTHREADS;
+            int n = c >> 4, kc = c & 15;
+            int64_t nn = n0 + n;
+            int kk = k0 + kc;
+            int bytes = (nn < N && kk < K) ? 8 : 0;
+            const double *src = bytes ? (B + kk + nn * ldb) : B;
+            cp_async8(Bs + n * SB + kc, src, bytes);
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_minus_kernel(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+                   int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;                                 // [STAGES][BK][SA]
+    double *Bs = smem + STAGES * AS_STAGE;             // [STAGES][BN][SB]
+
+    // grouped tile order
+    int64_t t = blockIdx.x;
+    int group_sz = GROUP_M * tiles_n;
+    int grp = (int)(t / group_sz);
+    int first_m = grp * GROUP_M;
+    int gm = min(GROUP_M, tiles_m - first_m);
+    int r = (int)(t % group_sz);
+    int tm = first_m + r % gm;
+    int tn = r / gm;
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;           // 2 x 4 warps
+    const int wm0 = wm * 64, wn0 = wn * 32;
+
+    double acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+    const int KT = (K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage<VEC>(As + s * AS_STAGE, Bs + s * BS_STAGE, A, lda, B, ldb, m0, n0, s * BK, M, N, K, tid);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) {
+                int st = nk % STAGES;
+                load_stage<VEC>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, m0, n0, nk * BK, M, N, K, tid);
+            }
+            cp_async_commit();
+        }
+        const double *as = As + (kt % STAGES) * AS_STAGE;
+        const double *bs = Bs + (kt % STAGES) * BS_STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double fa[2][2], fb[8];
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {            // MMA-A operand = problem B: rows n, cols k
+                fa[nf][0] = bs[(wn0 + nf * 16 + g) * SB + k4 + tig];
+                fa[nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + k4 + tig];
+            }
+#pragma unroll
+            for (int mf = 0; mf < 8; ++mf)              // MMA-B operand = problem A: k rows, m cols
+                fb[mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int mf = 0; mf < 8; ++mf) dmma_16x8x4(acc[nf][mf], fa[nf][0], fa[nf][1], fb[mf]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C -= acc.  (c0,c1) = rows m, m+1 of column n; (c2,c3) = same rows of column n+8
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+            if (n >= N) continue;
+#pragma unroll
+            for (int mf = 0; mf < 8; ++mf) {
+                int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
+                if (m >= M) continue;
+                double *p = C + m + n * ldc;
+                double v0 = acc[nf][mf][2 * h], v1 = acc[nf][mf][2 * h + 1];
+                if (VEC == 2 && m + 1 < M) {
+                    double2 c = *reinterpret_cast<double2 *>(p);
+                    c.x -= v0; c.y -= v1;
+                    *reinterpret_cast<double2 *>(p) = c;
+                } else {
+                    p[0] -= v0;
+                    if (m + 1 < M) p[1] -= v1;
+                }
+            }
+        }
+    }
+}
+
+// ---- complex: C -= A*B with interleaved (re,im); four real DMMAs per complex MMA ---------------------
+// Tiling: CTA 64(m) x 64(n) x 16(k) complex, 8 warps as 2(m) x 4(n), warp tile 32 x 16.
+constexpr int ZBM = 64, ZBN = 64, ZBK = 16;
+constexpr int ZSA = ZBM + 2;            // complex elements; 16 B each -> stride 66*16 B
+constexpr int ZSB = ZBK + 4;            // 16-byte banks: (g*4 + tig) mod 8 distinct over a quarter warp
+constexpr int ZAS_STAGE = ZBK * ZSA, ZBS_STAGE = ZBN * ZSB;
+constexpr int ZSTAGES = 3;
+
+__device__ __forceinline__ void zload_stage(zcomplex *As, zcomplex *Bs, const zcomplex *__restrict__ A, int64_t lda,
+                                            const zcomplex *__restrict__ B, int64_t ldb, int64_t m0, int64_t n0, int k0,
+                                            int64_t M, int64_t N, int K, int tid)
+{
+#pragma unroll
+    for (int i = 0; i < (ZBK * ZBM) / NTHREADS; ++i) {
+        int c = tid + i * NTHREADS;
+        int k = c >> 6, mc = c & 63;
+        int64_t m = m0 + mc; int kk = k0 + k;
+        int bytes = (kk < K && m < M) ? 16 : 0;
+        const zcomplex *src = bytes ? (A + m + (int64_t)kk * lda) : A;
+        cp_async16(As + k * ZSA + mc, src, bytes);
+    }
+#pragma unroll
+    for (int i = 0; i < (ZBN * ZBK) / NTHREADS; ++i) {
+        int c = tid + i * NTHREADS;
+        int n = c >> 4, kc = c & 15;
+        int64_t nn = n0 + n; int kk = k0 + kc;
+        int bytes = (nn < N && kk < K) ? 16 : 0;
+        const zcomplex *src = bytes ? (B + kk + nn * ldb) : B;
+        cp_async16(Bs + n * ZSB + kc, src, bytes);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+zgemm_minus_kernel(int64_t M, int64_t N, int K, const zcomplex *__restrict__ A, int64_t lda, const zcomplex *__restrict__ B,
+                   int64_t ldb, zcomplex *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n)
+{
+    extern __shared__ __align__(16) double smem[];
+    zcomplex *As = reinterpret_cast<zcomplex *>(smem);
+    zcomplex *Bs = As + ZSTAGES * ZAS_STAGE;
+
+    int64_t t = blockIdx.x;
+    int group_sz = GROUP_M * tiles_n;
+    int grp = (int)(t / group_sz);
+    int first_m = grp * GROUP_M;
+    int gm = min(GROUP_M, tiles_m - first_m);
+    int r = (int)(t % group_sz);
+    int tm = first_m + r % gm, tn = r / gm;
+    const int64_t m0 = (int64_t)tm * ZBM, n0 = (int64_t)tn * ZBN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;
+
+    double accr[4][4], acci[4][4];       // one n-frag (16) x four m-frags (8)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { accr[j][v] = 0.0; acci[j][v] = 0.0; }
+
+    const int KT = (K + ZBK - 1) / ZBK;
+#pragma unroll
+    for (int s = 0; s < ZSTAGES - 1; ++s) {
+        if (s < KT) zload_stage(As + s * ZAS_STAGE, Bs + s * ZBS_STAGE, A, lda, B, ldb, m0, n0, s * ZBK, M, N, K, tid);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<ZSTAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + ZSTAGES - 1;
+            if (nk < KT) { int st = nk % ZSTAGES; zload_stage(As + st * ZAS_STAGE, Bs + st * ZBS_STAGE, A, lda, B, ldb, m0, n0, nk * ZBK, M, N, K, tid); }
+            cp_async_commit();
+        }
+        const zcomplex *as = As + (kt % ZSTAGES) * ZAS_STAGE;
+        const zcomplex *bs = Bs + (kt % ZSTAGES) * ZBS_STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < ZBK; k4 += 4) {
+            zcomplex b0 = bs[(wn0 + g) * ZSB + k4 + tig];          // MMA-A operand rows n
+            zcomplex b1 = bs[(wn0 + g + 8) * ZSB + k4 + tig];
+#pragma unroll
+            for (int mf = 0; mf < 4; ++mf) {
+                zcomplex a = as[(k4 + tig) * ZSA + wm0 + mf * 8 + g];
+                // (br + i bi)(ar + i ai): real += br*ar - bi*ai ; imag += br*ai + bi*ar
+                dmma_16x8x4(accr[mf], b0.x, b1.x, a.x);
+                dmma_16x8x4(accr[mf], -b0.y, -b1.y, a.y);
+                dmma_16x8x4(acci[mf], b0.x, b1.x, a.y);
+                dmma_16x8x4(acci[mf], b0.y, b1.y, a.x);
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int64_t n = n0 + wn0 + g + h * 8;
+        if (n >= N) continue;
+#pragma unroll
+        for (int mf = 0; mf < 4; ++mf) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int64_t m = m0 + wm0 + mf * 8 + 2 * tig + e;
+                if (m >= M) continue;
+                zcomplex *p = C + m + n * ldc;
+                zcomplex c = *p;
+                c.x -= accr[mf][2 * h + e]; c.y -= acci[mf][2 * h + e];
+                *p = c;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
+                        double *C, int64_t ldc, cudaStream_t s)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return;
+    static bool attr_done = false;
+    const size_t smem_bytes = (size_t)STAGES * (AS_STAGE + BS_STAGE) * sizeof(double);
+    if (!attr_done) {
+        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_done = true;
+    }
+    int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N + BN - 1) / BN);
+    int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    if (ntiles > 0x7fffffffLL) fatal("dgemm: too many tiles");
+    bool aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0 && (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0);
+    if (aligned)
+        dgemm_minus_kernel<2><<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+    else
+        dgemm_minus_kernel<1><<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+    SLB_CUDA(cudaGetLastError());
+    counter_add("kernel_launches", 1);
+    counter_add("gemm_launches", 1);
+}
+
+void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
+                        zcomplex *C, int64_t ldc, cudaStream_t s)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return;
+    static bool attr_done = false;
+    const size_t smem_bytes = (size_t)ZSTAGES * (ZAS_STAGE + ZBS_STAGE) * sizeof(zcomplex);
+    if (!attr_done) {
+        SLB_CUDA(cudaFuncSetAttribute(zgemm_minus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_done = true;
+    }
+    int tiles_m = (int)((M + ZBM - 1) / ZBM), tiles_n = (int)((N + ZBN - 1) / ZBN);
+    int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    if (ntiles > 0x7fffffffLL) fatal("zgemm: too many tiles");
+    zgemm_minus_kernel<<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+    SLB_CUDA(cudaGetLastError());
+    counter_add("kernel_launches", 1);
+    counter_add("gemm_launches", 1);
+}
+
+}  // namespace slb

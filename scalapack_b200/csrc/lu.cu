@@ -1,0 +1,245 @@
+// lu.cu -- blocked right-looking LU with partial pivoting on a P x Q block-cyclic grid, one GPU per process.
+// Device-side orchestration of what SRC/pdgetrf.f:219-302 does with PDGETF2 / PDLASWP / PDTRSM / PDGEMM and
+// the BLACS broadcasts of PBLAS/SRC/PTOOLS/PB_CInV.c:327-347,472-493 -- redesigned for NVLink-connected GPUs:
+//
+//  * panel (PDGETF2): the process column's panel is gathered onto the GPU that owns the diagonal block and
+//    factored there by ONE cooperative kernel (panel.cu); P <= 2..8 peers on NVSwitch make the gather (one
+//    message per peer) far cheaper than the reference's ~3 latency-bound messages per COLUMN.
+//  * pivots + L11 + L21 travel in ONE message per process ("Pbuf"): scatter down the column, broadcast
+//    along the row (the reference: IGEBS2D of pivots + Cdgebs2d of L strips + the L21 panel).
+//  * row interchanges (PDLASWP left and right) + U12 formation are fused: each GPU packs the rows it owns
+//    that end in the top block, the process column all-gathers them, and EVERY process row then holds the
+//    whole permuted block row; each solves U12 = L11^-1 (...) redundantly, so the reference's separate U12
+//    column broadcast disappears.
+//  * trailing update (PDGEMM): local DMMA kernel (gemm.cu) on Lloc (contiguous) x U (contiguous).
+// All message sizes are known on the host up front; pivots stay on the device (no host sync per step).
+#include "common.h"
+#include "kernels.cuh"
+#include "ncclw.h"
+#include "lu.h"
+
+namespace slb {
+
+template <typename T> struct Ops;
+template <> struct Ops<double> {
+    static void gemm(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s)
+    { launch_dgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static void trsm(int jb, int64_t n, const double *L, int64_t ldl, double *B, int64_t ldb, cudaStream_t s) { launch_dtrsm_llnu(jb, n, L, ldl, B, ldb, s); }
+    static void panel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s)
+    { launch_dpanel(m, jb, W, ldw, map, ipiv, info, off, work, s); }
+    static constexpr double flop_mul = 1.0;
+};
+template <> struct Ops<zcomplex> {
+    static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s)
+    { launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static void trsm(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t s) { launch_ztrsm_llnu(jb, n, L, ldl, B, ldb, s); }
+    static void panel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s)
+    { launch_zpanel(m, jb, W, ldw, map, ipiv, info, off, work, s); }
+    static constexpr double flop_mul = 4.0;
+};
+
+LuStats g_last_lu;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host)
+{
+    Runtime &r = rt();
+    cudaStream_t s = r.s_main;
+    const int P = g->nprow, Q = g->npcol, myrow = g->myrow, mycol = g->mycol;
+    const int mn = M < N ? M : N;
+    const int64_t mloc = numroc(M, nb, myrow, rsrc, P), nloc = numroc(N, nb, mycol, csrc, Q);
+    const bool multi = P * Q > 1;
+    if (multi && !g->nccl) g->nccl = nccl_create(g);
+    NcclComms *nc = g->nccl;
+
+    // ---- workspaces ----
+    int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
+    int *info_dev = (int *)workspace("lu_info", 64);
+    int *plan_mem = (int *)workspace("lu_plan", (size_t)3 * nb * sizeof(int));
+    SwapPlan plan{ plan_mem, plan_mem + nb, plan_mem + 2 * nb };
+    void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
+    T *Ubuf = (T *)workspace("lu_U", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
+    T *Obuf = (T *)workspace("lu_O", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
+    const size_t hdr_bytes = align_up((size_t)nb * nb * sizeof(T), 256) + align_up((size_t)nb * sizeof(int), 256);
+    const size_t ipiv_off = align_up((size_t)nb * nb * sizeof(T), 256);
+    unsigned char *Pbuf = nullptr, *Psend = nullptr;
+    T *Wbuf = nullptr, *Stage = nullptr, *Cmine = nullptr, *Call = nullptr;
+    if (multi) {
+        Pbuf = (unsigned char *)workspace("lu_Pbuf", hdr_bytes + (size_t)(mloc + nb) * nb * sizeof(T));
+        if (P > 1) {
+            Wbuf = (T *)workspace("lu_W", (size_t)(M + nb) * nb * sizeof(T));
+            Stage = (T *)workspace("lu_stage", (size_t)(M + nb) * nb * sizeof(T));
+            Psend = (unsigned char *)workspace("lu_Psend", (size_t)P * hdr_bytes + (size_t)(M + nb) * nb * sizeof(T));
+            Cmine = (T *)workspace("lu_Cmine", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
+            Call = (T *)workspace("lu_Call", (size_t)P * nb * (nloc > 0 ? nloc : 1) * sizeof(T));
+        }
+    }
+    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), s));
+
+    cudaEvent_t ev0, ev1; SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1));
+    const int nsteps = (mn + nb - 1) / nb;
+    std::vector<cudaEvent_t> gev((size_t)2 * nsteps, nullptr);
+    std::vector<double> gflops((size_t)nsteps, 0.0);
+    const bool time_updates = opt("time_updates", 1) != 0;
+    SLB_CUDA(cudaEventRecord(ev0, s));
+
+    RowDist rd{ nb, P, myrow, rsrc };
+    auto rows_before = [&](int prow, int gidx) { return (int64_t)numroc(gidx, nb, prow, rsrc, P); };
+    auto mloc_of = [&](int prow) { return (int64_t)numroc(M, nb, prow, rsrc, P); };
+
+    for (int k = 0; k < nsteps; ++k) {
+        const int j0 = k * nb;
+        const int jb = (mn - j0) < nb ? (mn - j0) : nb;
+        const int pr = (rsrc + k) % P, pc = (csrc + k) % Q;
+        const int64_t lr0 = rows_before(myrow, j0);
+        const int64_t mtr = mloc - lr0;
+        const int64_t lcl = numroc(j0, nb, mycol, csrc, Q);
+        const int64_t lcr = numroc(j0 + jb, nb, mycol, csrc, Q);
+        const int m = M - j0;
+        const T *L11 = nullptr, *Lop = nullptr; int64_t ldl = 0, ld11 = 0;
+
+        // =============== panel ===============
+        if (!multi) {
+            PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = (int)lr0; map.seg_prow[0] = 0;
+            map.nb = nb; map.nprow = 1; map.rsrc = 0;
+            T *Wp = A + lr0 + lcl * lld;
+            Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
+            L11 = Wp; ld11 = lld; Lop = Wp + jb; ldl = lld;
+        } else {
+            T *pL11 = (T *)Pbuf; int *pIpiv = (int *)(Pbuf + ipiv_off); T *pLloc = (T *)(Pbuf + hdr_bytes);
+            const size_t my_pbytes = hdr_bytes + (size_t)mtr * jb * sizeof(T);
+            if (mycol == pc) {
+                if (P == 1) {
+                    PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = (int)lr0; map.seg_prow[0] = myrow;
+                    map.nb = nb; map.nprow = 1; map.rsrc = rsrc;
+                    T *Wp = A + lr0 + lcl * lld;
+                    Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
+                    launch_copy2d<T>(jb, jb, Wp, lld, pL11, jb, s);
+                    SLB_CUDA(cudaMemcpyAsync(pIpiv, ipiv_dev + j0, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
+                    launch_copy2d<T>(mtr, jb, Wp, lld, pLloc, mtr, s);
+                } else {
+                    // ---- gather the column's panel on the diagonal owner ----
+                    PanelRowMap map{}; map.nseg = P; map.nb = nb; map.nprow = P; map.rsrc = rsrc;
+                    int64_t v = 0; std::vector<int64_t> segrows((size_t)P), segv0((size_t)P);
+                    for (int sg = 0; sg < P; ++sg) {
+                        int prow = (pr + sg) % P;
+                        int64_t lr = rows_before(prow, j0), rows = mloc_of(prow) - lr;
+                        map.seg_v0[sg] = (int)v; map.seg_lr0[sg] = (int)lr; map.seg_prow[sg] = prow;
+                        segv0[sg] = v; segrows[sg] = rows; v += rows;
+                    }
+                    map.seg_v0[P] = (int)v;
+                    const int64_t mtot = v;       // == m
+                    if (myrow != pr) {
+                        launch_copy2d<T>(mtr, jb, A + lr0 + lcl * lld, lld, Stage, mtr, s);
+                        if (mtr > 0) nccl_send(nc->col, Stage, (size_t)mtr * jb * sizeof(T), NT_U8, pr, s);
+                        // ---- receive my factored rows + L11 + pivots ----
+                        nccl_recv(nc->col, Pbuf, my_pbytes, NT_U8, pr, s);
+                        launch_copy2d<T>(mtr, jb, pLloc, mtr, A + lr0 + lcl * lld, lld, s);
+                    } else {
+                        launch_copy2d<T>(segrows[0], jb, A + lr0 + lcl * lld, lld, Wbuf, mtot, s);
+                        nccl_group_start();
+                        { int64_t off = 0;
+                          for (int sg = 1; sg < P; ++sg) {
+                              if (segrows[sg] > 0) nccl_recv(nc->col, Stage + off, (size_t)segrows[sg] * jb * sizeof(T), NT_U8, map.seg_prow[sg], s);
+                              off += segrows[sg] * jb;
+                          } }
+                        nccl_group_end();
+                        { int64_t off = 0;
+                          for (int sg = 1; sg < P; ++sg) {
+                              launch_copy2d<T>(segrows[sg], jb, Stage + off, segrows[sg], Wbuf + segv0[sg], mtot, s);
+                              off += segrows[sg] * jb;
+                          } }
+                        Ops<T>::panel((int)mtot, jb, Wbuf, mtot, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
+                        // own copy + own Pbuf
+                        launch_copy2d<T>(segrows[0], jb, Wbuf, mtot, A + lr0 + lcl * lld, lld, s);
+                        launch_copy2d<T>(jb, jb, Wbuf, mtot, pL11, jb, s);
+                        SLB_CUDA(cudaMemcpyAsync(pIpiv, ipiv_dev + j0, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
+                        launch_copy2d<T>(segrows[0], jb, Wbuf, mtot, pLloc, segrows[0], s);
+                        // peers' Pbufs
+                        size_t soff = 0; std::vector<size_t> soffs((size_t)P, 0);
+                        for (int sg = 1; sg < P; ++sg) {
+                            soffs[sg] = soff;
+                            unsigned char *pb = Psend + soff;
+                            SLB_CUDA(cudaMemcpyAsync(pb, Pbuf, hdr_bytes, cudaMemcpyDeviceToDevice, s));
+                            launch_copy2d<T>(segrows[sg], jb, Wbuf + segv0[sg], mtot, (T *)(pb + hdr_bytes), segrows[sg], s);
+                            soff += align_up(hdr_bytes + (size_t)segrows[sg] * jb * sizeof(T), 256);
+                        }
+                        nccl_group_start();
+                        for (int sg = 1; sg < P; ++sg)
+                            nccl_send(nc->col, Psend + soffs[sg], hdr_bytes + (size_t)segrows[sg] * jb * sizeof(T), NT_U8, map.seg_prow[sg], s);
+                        nccl_group_end();
+                    }
+                }
+            }
+            if (Q > 1) nccl_bcast(nc->row, Pbuf, my_pbytes, NT_U8, pc, s);
+            if (!(mycol == pc && myrow == pr))
+                SLB_CUDA(cudaMemcpyAsync(ipiv_dev + j0, pIpiv, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
+            L11 = pL11; ld11 = jb;
+            Lop = pLloc + (myrow == pr ? jb : 0); ldl = mtr > 0 ? mtr : 1;
+        }
+
+        // =============== row interchanges + U12 ===============
+        launch_swap_plan(j0, jb, ipiv_dev + j0, plan, s);
+        const int64_t nright = nloc - lcr;
+        T *Uall = Ubuf;                      // jb x nloc, column index = local column
+        if (P == 1) {
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, lcl, Uall, jb, Obuf, jb, s);
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, lcr, nloc, Uall + lcr * jb, jb, Obuf + lcr * jb, jb, s);
+        } else {
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, lcl, Cmine, jb, Obuf, jb, s);
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, lcr, nloc, Cmine + lcr * jb, jb, Obuf + lcr * jb, jb, s);
+            const size_t cnt = (size_t)jb * nloc * sizeof(T);
+            if (cnt > 0) {
+                nccl_allgather(nc->col, Cmine, Call, cnt, NT_U8, s);
+                nccl_bcast(nc->col, Obuf, cnt, NT_U8, pr, s);
+                launch_swap_select<T>(jb, plan, rd, Call, jb, (int64_t)jb * nloc, nloc, Uall, jb, s);
+            }
+        }
+        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, lcl, Obuf, jb, s);
+        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, lcr, nloc, Obuf + lcr * jb, jb, s);
+        if (myrow == pr) launch_copy2d<T>(jb, lcl, Uall, jb, A + lr0, lld, s);           // left columns: final rows
+        if (nright > 0) {
+            T *U = Uall + lcr * jb;
+            Ops<T>::trsm(jb, nright, L11, ld11, U, jb, s);
+            if (myrow == pr) launch_copy2d<T>(jb, nright, U, jb, A + lr0 + lcr * lld, lld, s);
+            // =============== trailing update ===============
+            const int64_t rbeg = lr0 + (myrow == pr ? jb : 0);
+            const int64_t mrows = mloc - rbeg;
+            if (mrows > 0) {
+                if (time_updates) { SLB_CUDA(cudaEventCreate(&gev[2 * k])); SLB_CUDA(cudaEventCreate(&gev[2 * k + 1])); SLB_CUDA(cudaEventRecord(gev[2 * k], s)); }
+                Ops<T>::gemm(mrows, nright, jb, Lop, ldl, U, jb, A + rbeg + lcr * lld, lld, s);
+                if (time_updates) SLB_CUDA(cudaEventRecord(gev[2 * k + 1], s));
+                gflops[k] = 2.0 * (double)mrows * (double)nright * jb * Ops<T>::flop_mul;
+            }
+        }
+    }
+    SLB_CUDA(cudaEventRecord(ev1, s));
+    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, s));
+    int info_local = 0;
+    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SLB_CUDA(cudaStreamSynchronize(s));
+    float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    g_last_lu.factor_ms = ms;
+    g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
+    for (int k = 0; k < nsteps; ++k) {
+        if (gev[2 * k]) {
+            float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[2 * k], gev[2 * k + 1]));
+            g_last_lu.update_ms += t; g_last_lu.update_flops += gflops[k]; g_last_lu.update_launches += 1;
+            cudaEventDestroy(gev[2 * k]); cudaEventDestroy(gev[2 * k + 1]);
+        }
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    // INFO: first zero pivot is known on the diagonal owners only -> min over the grid (SRC/pdgetrf.f:297-302)
+    int inf = info_local == 0 ? mn + 1 : info_local;
+    inf = grid_imin(g, 'A', inf);
+    *info_host = inf == mn + 1 ? 0 : inf;
+    return 0;
+}
+
+template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *);
+template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *);
+
+}  // namespace slb

@@ -1,0 +1,173 @@
+"""GPU parity tests of the drop-in entry points on a 1x1 grid, through the C-ABI, against the CPU oracle:
+IPIV bit-exact, LU factors within tolerance, the reference's FRESID / SRESID below its threshold 1.0
+(TESTING/traditional/LU.dat:17), guard zones intact (pdludriver.f:340-358,397-402)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import lu_err, first_mismatch, load_example_6x6, PADVAL
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run_getrf(S, O, ctx, a0, nb, pad=0, device=False):
+    """PDGETRF on a 1x1 grid with `pad` guard rows (LLD = M + pad) filled with PADVAL."""
+    m, n = a0.shape
+    lld = max(1, m) + pad
+    al = np.full((lld, max(n, 1)), PADVAL, dtype=a0.dtype, order="F")
+    al[:m, :n] = a0
+    desc, info = S.descinit(m, n, nb, nb, 0, 0, ctx, lld)
+    assert info == 0
+    ipiv = np.full(m + nb + 4, -77, np.int32)
+    f = S.pzgetrf if a0.dtype == np.complex128 else S.pdgetrf
+    if device:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(al.T)).cuda()       # (n, lld) row-major == (lld, n) column-major
+        info = f(m, n, t, 1, 1, desc, ipiv)
+        al = np.asfortranarray(t.cpu().numpy().T)
+    else:
+        info = f(m, n, al, 1, 1, desc, ipiv)
+    assert np.all(al[m:, :] == PADVAL), "guard zone below A overwritten"
+    assert np.all(ipiv[m + nb:] == -77), "IPIV written beyond LOCr(M_A)+MB_A"
+    return al[:m, :n], ipiv[:min(m, n)].copy(), info, desc
+
+
+def check_against_oracle(O, a0, lu, ipiv, info, nb, thresh=1.0):
+    ref = a0.copy(order="F")
+    ipr, infr = O.getrf(ref, nb)
+    assert info == infr
+    assert np.array_equal(ipiv, ipr), ("first IPIV mismatch at row", first_mismatch(ipiv, ipr))
+    assert lu_err(lu, ref, a0) < 1.0
+    fres = O.fresid(np.asfortranarray(lu), ipiv, a0)
+    assert fres < thresh and fres - fres == 0.0
+    return fres
+
+
+@pytest.mark.parametrize("mn", [(4, 4), (10, 12), (17, 13), (13, 13)])
+@pytest.mark.parametrize("nb", [2, 3, 4])
+def test_lu_dat_grid_1x1(S, O, ctx11, mn, nb):
+    """The reference's own test inputs (TESTING/traditional/LU.dat), grid 1x1."""
+    m, n = mn
+    a0 = O.pdmatgen(m, n, 100)
+    lu, ipiv, info, desc = run_getrf(S, O, ctx11, a0, nb, pad=3)
+    check_against_oracle(O, a0, lu, ipiv, info, nb)
+    if m == n:
+        for nrhs, nbrhs in [(1, 1), (3, 3), (9, 5)]:
+            b0 = O.pdmatgen(n, nrhs, 200)
+            descb, _ = S.descinit(n, nrhs, nb, nbrhs, 0, 0, ctx11, n)
+            x = b0.copy(order="F")
+            ipl = np.zeros(n + nb, np.int32); ipl[:n] = ipiv
+            assert S.pdgetrs("N", n, nrhs, np.asfortranarray(lu), 1, 1, desc[:8] + [n], ipl, x, 1, 1, descb) == 0
+            assert O.sresid(a0, x, b0) < 1.0
+
+
+def test_example_pdgesv_6x6(S, O, ctx11):
+    """EXAMPLE/pdscaex.f:155 on the shipped 6x6 system."""
+    A, B = load_example_6x6(os.path.join(G, "DSCAEXMAT.dat"), os.path.join(G, "DSCAEXRHS.dat"))
+    gold = np.load(os.path.join(G, "golden.npz"))
+    a = A.copy(order="F"); b = B.copy(order="F")
+    da, _ = S.descinit(6, 6, 2, 2, 0, 0, ctx11, 6); db, _ = S.descinit(6, 1, 2, 2, 0, 0, ctx11, 6)
+    ipiv = np.zeros(8, np.int32)
+    assert S.pdgesv(6, 1, a, 1, 1, da, ipiv, b, 1, 1, db) == 0
+    assert np.array_equal(ipiv[:6], gold["ex6_ipiv"])
+    assert np.allclose(b, gold["ex6_x"], rtol=1e-13)
+    assert O.sresid(A, b, B) < 10.0
+
+
+@pytest.mark.parametrize("n,nb,device", [(64, 8, False), (200, 64, False), (500, 32, True), (1000, 128, False), (2000, 64, True),
+                                         (2000, 64, False), (1536, 512, True), (4096, 512, True), (3000, 500, False)])
+def test_pdgetrf_square(S, O, ctx11, n, nb, device):
+    """includes BASELINE config 1's matrix (PDMATGEN N=2000 NB=64 seed 100) on a 1x1 grid."""
+    a0 = O.pdmatgen(n, n, 100)
+    lu, ipiv, info, desc = run_getrf(S, O, ctx11, a0, nb, pad=2 if not device else 0, device=device)
+    fres = check_against_oracle(O, a0, lu, ipiv, info, nb)
+    b0 = O.pdmatgen(n, 1, 200)
+    descb, _ = S.descinit(n, 1, nb, 1, 0, 0, ctx11, n)
+    x = b0.copy(order="F")
+    ipl = np.zeros(n + nb, np.int32); ipl[:n] = ipiv
+    assert S.pdgetrs("N", n, 1, np.asfortranarray(lu), 1, 1, desc[:8] + [n], ipl, x, 1, 1, descb) == 0
+    sres = O.sresid(a0, x, b0)
+    assert sres < 1.0
+    print(f"N={n} NB={nb} FRESID={fres:.4f} SRESID={sres:.5f} factor_ms={S.last_factor_ms():.2f}")
+
+
+@pytest.mark.parametrize("m,n,nb", [(300, 200, 64), (200, 300, 64), (1000, 64, 64), (64, 1000, 32), (777, 513, 100)])
+def test_pdgetrf_rectangular(S, O, ctx11, m, n, nb):
+    a0 = O.pdmatgen(m, n, 100)
+    lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, nb, pad=1)
+    check_against_oracle(O, a0, lu, ipiv, info, nb)
+
+
+def test_zero_pivot_info(S, O, ctx11):
+    a0 = O.pdmatgen(96, 96, 100); a0[:, 40] = 0.0
+    lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, 32)
+    ref = a0.copy(order="F"); ipr, infr = O.getrf(ref, 32)
+    assert info == infr == 41 and np.array_equal(ipiv, ipr)
+    # PDGESV must skip the solve when INFO > 0 (pdgesv.f:231)
+    a = a0.copy(order="F"); b0 = O.pdmatgen(96, 1, 200); b = b0.copy(order="F")
+    da, _ = S.descinit(96, 96, 32, 32, 0, 0, ctx11, 96); db, _ = S.descinit(96, 1, 32, 1, 0, 0, ctx11, 96)
+    assert S.pdgesv(96, 1, a, 1, 1, da, np.zeros(128, np.int32), b, 1, 1, db) == 41
+    assert np.array_equal(b, b0)
+
+
+@pytest.mark.parametrize("n,nb,nrhs", [(60, 8, 3), (500, 64, 1), (1024, 256, 2)])
+def test_pzgetrf_pzgetrs(S, O, ctx11, n, nb, nrhs):
+    a0 = O.pzmatgen(n, n, 100)
+    lu, ipiv, info, desc = run_getrf(S, O, ctx11, a0, nb, pad=1)
+    check_against_oracle(O, a0, lu, ipiv, info, nb)
+    b0 = O.pzmatgen(n, nrhs, 200)
+    descb, _ = S.descinit(n, nrhs, nb, 1, 0, 0, ctx11, n)
+    x = b0.copy(order="F")
+    ipl = np.zeros(n + nb, np.int32); ipl[:n] = ipiv
+    assert S.pzgetrs("N", n, nrhs, np.asfortranarray(lu), 1, 1, desc[:8] + [n], ipl, x, 1, 1, descb) == 0
+    assert O.sresid(a0, x, b0) < 1.0
+
+
+def test_pdgesv_matches_oracle_solution(S, O, ctx11):
+    n, nb, nrhs = 1500, 128, 4
+    a0 = O.pdmatgen(n, n, 100); b0 = O.pdmatgen(n, nrhs, 200)
+    a = a0.copy(order="F"); b = b0.copy(order="F")
+    da, _ = S.descinit(n, n, nb, nb, 0, 0, ctx11, n); db, _ = S.descinit(n, nrhs, nb, 2, 0, 0, ctx11, n)
+    ipiv = np.zeros(n + nb, np.int32)
+    assert S.pdgesv(n, nrhs, a, 1, 1, da, ipiv, b, 1, 1, db) == 0
+    ref = a0.copy(order="F"); ipr, _ = O.getrf(ref, nb)
+    xr = b0.copy(order="F"); O.getrs(ref, ipr, xr)
+    assert np.array_equal(ipiv[:n], ipr)
+    assert np.abs(b - xr).max() / np.abs(xr).max() < 1e-9
+    assert O.sresid(a0, b, b0) < 1.0
+
+
+def test_device_generators_match_oracle(S, O, ctx11):
+    """Device PDMATGEN / 64-bit generator == oracle (bit exact), and the device residual check == oracle's."""
+    n, nb = 300, 32
+    a = np.zeros((n, n), order="F")
+    S.pdmatgen(ctx11, n, n, nb, nb, a, n, iseed=100)
+    assert np.array_equal(a, O.pdmatgen(n, n, 100))
+    a64 = np.zeros((n, n), order="F")
+    S.matgen64(ctx11, n, n, nb, nb, a64, n, seed=42)
+    assert np.array_equal(a64, O.matgen64_tile(n, 42, 0, n, 0, n))
+    z64 = np.zeros((n, n), dtype=np.complex128, order="F")
+    S.zmatgen64(ctx11, n, n, nb, nb, z64, n, seed=42)
+    assert np.array_equal(z64, O.matgen64_tile(n, 42, 0, n, 0, n, complex_=True))
+    # solve + device residual (b = first column of the generator with seed 43)
+    b0 = O.matgen64_tile(n, 43, 0, n, 0, 1)
+    lu = a64.copy(order="F"); x = b0.copy(order="F")
+    da, _ = S.descinit(n, n, nb, nb, 0, 0, ctx11, n); db, _ = S.descinit(n, 1, nb, 1, 0, 0, ctx11, n)
+    assert S.pdgesv(n, 1, lu, 1, 1, da, np.zeros(n + nb, np.int32), x, 1, 1, db) == 0
+    r_dev = S.pdlaschk(ctx11, n, 1, x, db, da, 42, 43, gen=64)
+    r_orc = O.sresid(a64, x, b0)
+    assert r_dev < 1.0 and abs(r_dev - r_orc) <= 0.05 * r_orc + 1e-6, (r_dev, r_orc)
+
+
+def test_large_properties_n8192(S, O, ctx11):
+    """Size-independent properties at a size the oracle still finishes: N=8192 NB=512 (the bench block size)."""
+    n, nb = 8192, 512
+    a0 = O.matgen64_tile(n, 2024, 0, n, 0, n)
+    lu, ipiv, info, desc = run_getrf(S, O, ctx11, a0, nb, device=True)
+    ref = a0.copy(order="F"); ipr, infr = O.getrf(ref, nb)
+    assert info == infr == 0 and np.array_equal(ipiv, ipr), first_mismatch(ipiv, ipr)
+    assert lu_err(lu, ref, a0) < 1.0
+    assert np.all(ipiv >= np.arange(1, n + 1)) and np.all(ipiv <= n)
+    assert np.abs(np.tril(lu, -1)).max() <= 1.0 + 1e-12        # partial pivoting bound |l_ij| <= 1

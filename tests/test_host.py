@@ -1,0 +1,162 @@
+"""CPU tests of the product's host side: the C-ABI library loads, exports every declared symbol, its TOOLS
+restatement equals the oracle's, argument checks return the reference's INFO codes, and the multi-process
+control plane (BLACS grid setup, scoped barriers, PCHK1MAT consistency) works at world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(S):
+    hdr = open(os.path.join(ROOT, "include", "scalapack_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr))
+    names -= {"defined", "if", "sizeof"}
+    names = {n for n in names if n.endswith("_") or n.startswith("Cblacs") or n.startswith("slb200_")}
+    assert len(names) > 50
+    L = S.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_tools_match_oracle(S, O, ctx11):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n, nb, P = int(rng.integers(0, 200)), int(rng.integers(1, 17)), int(rng.integers(1, 6))
+        p, src = int(rng.integers(0, P)), int(rng.integers(0, P))
+        assert S.numroc(n, nb, p, src, P) == O.numroc(n, nb, p, src, P)
+        ig = int(rng.integers(1, 300))
+        assert S.indxg2p(ig, nb, 0, src, P) == O.indxg2p(ig, nb, 0, src, P)
+        assert S.indxg2l(ig, nb, 0, 0, P) == O.indxg2l(ig, nb, 0, 0, P)
+        assert S.indxl2g(ig, nb, p, src, P) == O.indxl2g(ig, nb, p, src, P)
+        Q, q = int(rng.integers(1, 5)), 0
+        desc = [1, 0, 500, 400, nb, nb, src, 0, 500]
+        gr, gc = int(rng.integers(1, 500)), int(rng.integers(1, 400))
+        assert S.infog2l(gr, gc, desc, P, Q, p, q) == O.infog2l(gr, gc, desc, P, Q, p, q)
+    assert S.iceil(7, 3) == 3 and S.ilcm(4, 6) == 12
+
+
+def test_descinit_and_chk1mat(S, O, ctx11):
+    d, info = S.descinit(10, 12, 4, 4, 0, 0, ctx11, 10)
+    assert info == 0 and d == [1, ctx11, 10, 12, 4, 4, 0, 0, 10]
+    do, io = O.descinit(10, 12, 4, 4, 0, 0, ctx11, 10, 1, 1, 0)
+    assert d == do and io == 0
+    # illegal LLD -> -9 and clamped (descinit.f:172-186)
+    d2, info2 = S.descinit(10, 12, 4, 4, 0, 0, ctx11, 3)
+    assert info2 == -9 and d2[8] == 10
+    assert S.descinit(-1, 12, 4, 4, 0, 0, ctx11, 10)[1] == -2
+    assert S.descinit(10, 12, 4, 4, 1, 0, ctx11, 10)[1] == -6
+    # CHK1MAT codes (chk1mat.f:92-171) against the oracle restatement
+    for (ma, na, ia, ja, desc) in [(10, 12, 1, 1, d), (11, 12, 1, 1, d), (10, 12, 0, 1, d), (10, 12, 1, 13, d),
+                                   (10, 12, 1, 1, [2] + d[1:]), (10, 12, 1, 1, d[:4] + [0] + d[5:]), (10, 12, 1, 1, d[:8] + [4])]:
+        assert S.chk1mat(ma, 1, na, 2, ia, ja, desc, 6) == O.chk1mat(ma, 1, na, 2, ia, ja, desc, 6, 1, 1, 0, 0)
+
+
+def test_pdgetrf_error_exits(S, ctx11, capfd):
+    """INFO codes and PXERBLA text of SRC/pdgetrf.f:169-197 (no GPU is touched on these paths)."""
+    d, _ = S.descinit(10, 12, 4, 4, 0, 0, ctx11, 10)
+    a = np.zeros((10, 12), order="F")
+    ipiv = np.zeros(16, np.int32)
+    assert S.pdgetrf(-1, 12, a, 1, 1, d, ipiv) == -1
+    assert S.pdgetrf(10, -3, a, 1, 1, d, ipiv) == -2
+    assert S.pdgetrf(8, 12, a, 2, 1, d, ipiv) == -4
+    assert S.pdgetrf(10, 8, a, 1, 3, d, ipiv) == -5
+    assert S.pdgetrf(10, 12, a, 1, 1, d[:5] + [3] + d[6:], ipiv) == -606
+    assert S.pdgetrf(10, 12, a, 1, 1, [1, 77] + d[2:], ipiv) == -602
+    assert S.pdgetrf(10, 12, a, 1, 1, d[:8] + [5], ipiv) == -609
+    err = capfd.readouterr().err
+    assert "On entry to PDGETRF parameter number 606 had an illegal value" in err
+    # quick returns (pdgetrf.f:201-206)
+    assert S.pdgetrf(0, 12, a, 1, 1, d, ipiv) == 0
+    d1, _ = S.descinit(1, 1, 4, 4, 0, 0, ctx11, 1)
+    ipiv[:] = 0
+    assert S.pdgetrf(1, 1, np.ones((1, 1), order="F"), 1, 1, d1, ipiv) == 0 and ipiv[0] == 1
+
+
+def test_pdgetrs_pdgesv_error_exits(S, ctx11):
+    da, _ = S.descinit(8, 8, 4, 4, 0, 0, ctx11, 8)
+    db, _ = S.descinit(8, 2, 4, 1, 0, 0, ctx11, 8)
+    a = np.zeros((8, 8), order="F"); b = np.zeros((8, 2), order="F"); ipiv = np.zeros(12, np.int32)
+    assert S.pdgetrs("X", 8, 2, a, 1, 1, da, ipiv, b, 1, 1, db) == -1
+    assert S.pdgetrs("N", -1, 2, a, 1, 1, da, ipiv, b, 1, 1, db) == -2
+    assert S.pdgetrs("N", 8, -1, a, 1, 1, da, ipiv, b, 1, 1, db) == -3
+    assert S.pdgetrs("N", 8, 2, a, 1, 1, da, ipiv, b, 1, 1, db[:4] + [2] + db[5:]) == -1206      # the reference reports NB_ here (pdgetrs.f:223-224)
+    assert S.pdgetrs("N", 8, 2, a, 1, 1, da[:5] + [2] + da[6:], ipiv, b, 1, 1, db) == -706
+    assert S.pdgesv(-1, 2, a, 1, 1, da, ipiv, b, 1, 1, db) == -1
+    assert S.pdgesv(8, -1, a, 1, 1, da, ipiv, b, 1, 1, db) == -2
+    assert S.pdgesv(8, 2, a, 1, 1, da, ipiv, b, 1, 1, db[:4] + [2] + db[5:]) == -1106
+    assert S.pdgetrs("N", 0, 2, a, 1, 1, da, ipiv, b, 1, 1, db) == 0          # quick return
+
+
+def test_no_cpu_fallback(S, ctx11):
+    """Without a GPU the compute entry point must die loudly, never compute on the host."""
+    if S.has_cuda():
+        pytest.skip("GPU present")
+    code = ("import numpy as np, scalapack_b200 as S; c=S.blacs_gridinit(0,'R',1,1); d,_=S.descinit(8,8,4,4,0,0,c,8);"
+            "a=np.eye(8,order='F'); S.pdgetrf(8,8,a,1,1,d,np.zeros(12,np.int32)); print('COMPUTED')")
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "COMPUTED" not in p.stdout
+    assert "no CPU fallback" in p.stderr
+
+
+WORKER = r"""
+import sys, json
+sys.path.insert(0, %r)
+import numpy as np, scalapack_b200 as S
+me, n = S.blacs_pinfo()
+out = {"me": me, "n": n}
+ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 2, 1)
+out["grid"] = S.blacs_gridinfo(ctx)
+ctx2 = S.blacs_gridinit(S.blacs_get(-1, 0), "Col-major", 1, 2)
+out["grid2"] = S.blacs_gridinfo(ctx2)
+out["pnum"] = [S.blacs_pnum(ctx, 0, 0), S.blacs_pnum(ctx, 1, 0), S.blacs_pnum(ctx, 2, 0)]
+out["pcoord"] = S.blacs_pcoord(ctx, 1)
+S.blacs_barrier(ctx, "All"); S.blacs_barrier(ctx, "Column"); S.blacs_barrier(ctx, "Row")
+d, info = S.descinit(10, 10, 2, 2, 0, 0, ctx, 6)
+out["numroc"] = S.numroc(10, 2, out["grid"][2], 0, 2)
+a = np.zeros((6, 10), order="F"); ipiv = np.zeros(10, np.int32)
+# PCHK1MAT: N differs between the two processes -> both must return -2 (pchkxmat.f:404-490)
+out["incons"] = S.pdgetrf(10, 10 if me == 0 else 9, a, 1, 1, d, ipiv)
+# one-process grid inside a two-process job: rank 1 is outside -> context -1, gridinfo all -1
+c1 = S.blacs_gridinit(S.blacs_get(-1, 0), "R", 1, 1)
+out["solo_ctx_valid"] = c1 >= 0
+out["solo_info"] = S.blacs_gridinfo(c1)
+import ctypes as C
+v = (C.c_int * 2)(me + 5, 10 - me)
+S.lib().igamn2d_(C.byref(C.c_int(ctx)), b"All", b" ", C.byref(C.c_int(2)), C.byref(C.c_int(1)), v, C.byref(C.c_int(2)),
+                 None, None, C.byref(C.c_int(-1)), C.byref(C.c_int(-1)), C.byref(C.c_int(-1)))
+out["igamn"] = list(v)
+S.blacs_gridexit(ctx); S.blacs_gridexit(ctx2); S.blacs_exit(0)
+print("RESULT" + json.dumps(out), flush=True)
+"""
+
+
+def test_two_process_control_plane(S):
+    """world_size-2 run on CPU (the reference's analogue: mpiexec -n 2, TESTING/traditional/CMakeLists.txt:22-34)."""
+    import json
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SLB200_PORT_OFFSET="0")
+        procs.append(subprocess.Popen([sys.executable, "-c", WORKER % ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    res = []
+    for p in procs:
+        o, e = p.communicate(timeout=120)
+        assert p.returncode == 0, e
+        res.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT")][0][6:]))
+    res.sort(key=lambda d: d["me"])
+    assert [r["n"] for r in res] == [2, 2]
+    assert res[0]["grid"] == [2, 1, 0, 0] and res[1]["grid"] == [2, 1, 1, 0]           # row-major map (blacs_init_.c)
+    assert res[0]["grid2"] == [1, 2, 0, 0] and res[1]["grid2"] == [1, 2, 0, 1]
+    assert res[0]["pnum"] == [0, 1, -1] and res[0]["pcoord"] == [1, 0]
+    assert [r["numroc"] for r in res] == [6, 4]
+    assert [r["incons"] for r in res] == [-2, -2]
+    assert res[0]["solo_ctx_valid"] and not res[1]["solo_ctx_valid"] and res[1]["solo_info"] == [-1, -1, -1, -1]
+    assert res[0]["igamn"] == [5, 9] and res[1]["igamn"] == [5, 9]
