@@ -198,6 +198,210 @@ dgemm_minus_kernel(int64_t M, int64_t N, int K, const double *__restrict__ A, in
     }
 }
 
+// ---- v2: persistent CTAs, 16 warps (4 per scheduler), continuous cp.async ring across tiles -------------
+// ncu on v1 (profiles/r01_gemm_v1.md): DMMA pipe 70 % busy; each tile lost ~30 us to an un-overlapped prologue
+// and a serialised load->store epilogue with 1 CTA / SM.  v2 keeps ONE CTA per SM resident for the whole launch:
+//   * 512 threads = 16 warps as 4(m) x 4(n), warp tile 32 x 32 (64 accumulator registers, <= 128 regs/thread);
+//   * the (tile, k-stage) sequence is one stream: loads run STAGES-1 stages ahead ACROSS tile boundaries, so
+//     the next tile's operands are already in shared memory when the epilogue of the current one starts;
+//   * the C tile is prefetched into L2 when the tile starts; the epilogue issues its 16 LDG.128 back to back,
+//     then subtracts and stores (one memory latency per tile instead of 32).
+constexpr int P_THREADS = 512;
+
+template <int VEC, int PBK>
+__device__ __forceinline__ void load_stage_p(double *As, double *Bs, const double *__restrict__ A, int64_t lda,
+                                             const double *__restrict__ B, int64_t ldb, int64_t m0, int64_t n0, int k0,
+                                             int64_t M, int64_t N, int K, int tid)
+{
+    if (VEC == 2) {
+#pragma unroll
+        for (int i = 0; i < (PBK * BM / 2) / P_THREADS; ++i) {
+            int c = tid + i * P_THREADS;
+            int k = c >> 6, mc = (c & 63) * 2;
+            int64_t m = m0 + mc; int kk = k0 + k;
+            int bytes = 0;
+            if (kk < K && m < M) bytes = (M - m >= 2) ? 16 : 8;
+            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
+            cp_async16(As + k * SA + mc, src, bytes);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * PBK / 2) / P_THREADS; ++i) {
+            int c = tid + i * P_THREADS;
+            int n = c / (PBK / 2), kc = (c % (PBK / 2)) * 2;
+            int64_t nn = n0 + n; int kk = k0 + kc;
+            int bytes = 0;
+            if (nn < N && kk < K) bytes = (K - kk >= 2) ? 16 : 8;
+            const double *src = bytes ? (B + kk + nn * ldb) : B;
+            cp_async16(Bs + n * (PBK + 4) + kc, src, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (PBK * BM) / P_THREADS; ++i) {
+            int c = tid + i * P_THREADS;
+            int k = c >> 7, mc = c & 127;
+            int64_t m = m0 + mc; int kk = k0 + k;
+            int bytes = (kk < K && m < M) ? 8 : 0;
+            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
+            cp_async8(As + k * SA + mc, src, bytes);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * PBK) / P_THREADS; ++i) {
+            int c = tid + i * P_THREADS;
+            int n = c / PBK, kc = c % PBK;
+            int64_t nn = n0 + n; int kk = k0 + kc;
+            int bytes = (nn < N && kk < K) ? 8 : 0;
+            const double *src = bytes ? (B + kk + nn * ldb) : B;
+            cp_async8(Bs + n * (PBK + 4) + kc, src, bytes);
+        }
+    }
+}
+
+__device__ __forceinline__ void tile_coords(int64_t t, int tiles_m, int tiles_n, int64_t &m0, int64_t &n0)
+{
+    int group_sz = GROUP_M * tiles_n;
+    int grp = (int)(t / group_sz);
+    int first_m = grp * GROUP_M;
+    int gm = min(GROUP_M, tiles_m - first_m);
+    int r = (int)(t % group_sz);
+    m0 = (int64_t)(first_m + r % gm) * BM;
+    n0 = (int64_t)(r / gm) * BN;
+}
+
+template <int VEC, int PBK, int PST, int LOAD_MID>
+__global__ void __launch_bounds__(P_THREADS, 1)
+dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+                       int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int SBP = PBK + 4, AST = PBK * SA, BST = BN * SBP;
+    double *As = smem;
+    double *Bs = smem + PST * AST;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;      // 4 x 4 warps, 32 x 32 each
+
+    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    const int KT = (K + PBK - 1) / PBK;
+    const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total = my_tiles * KT;
+
+    // loader cursor (tile, k-stage) runs STAGES-1 ahead of the consumer cursor
+    int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
+    if (my_tiles > 0) tile_coords(blockIdx.x, tiles_m, tiles_n, l_m0, l_n0);
+    auto issue_load = [&](int64_t li) {
+        if (li < total) {
+            int st = (int)(li % PST);
+            load_stage_p<VEC, PBK>(As + st * AST, Bs + st * BST, A, lda, B, ldb, l_m0, l_n0, l_kt * PBK, M, N, K, tid);
+            if (++l_kt == KT) {
+                l_kt = 0; ++l_lt;
+                if (l_lt < my_tiles) tile_coords(blockIdx.x + l_lt * gridDim.x, tiles_m, tiles_n, l_m0, l_n0);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < PST - 1; ++s) issue_load(s);
+
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+    int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
+    for (int64_t ci = 0; ci < total; ++ci) {
+        if (kt == 0) {
+            tile_coords(blockIdx.x + lt * gridDim.x, tiles_m, tiles_n, m0, n0);
+            // pull this thread's part of the C tile into L2 while the k-loop runs
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+                    int64_t m = m0 + wm0 + 2 * tig;
+                    if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
+                }
+        }
+        cp_async_wait<PST - 2>();
+        __syncthreads();
+        if (!LOAD_MID) issue_load(ci + PST - 1);
+        const double *as = As + (ci % PST) * AST;
+        const double *bs = Bs + (ci % PST) * BST;
+#pragma unroll
+        for (int k4 = 0; k4 < PBK; k4 += 4) {
+            if (LOAD_MID && k4 == 4) issue_load(ci + PST - 1);
+            double fa[2][2], fb[4];
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {
+                fa[nf][0] = bs[(wn0 + nf * 16 + g) * SBP + k4 + tig];
+                fa[nf][1] = bs[(wn0 + nf * 16 + g + 8) * SBP + k4 + tig];
+            }
+#pragma unroll
+            for (int mf = 0; mf < 4; ++mf) fb[mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) dmma_16x8x4(acc[nf][mf], fa[nf][0], fa[nf][1], fb[mf]);
+        }
+        if (++kt == KT) {
+            kt = 0; ++lt;
+            // ---- epilogue of this tile: all loads first, then subtract + store ----
+            if (VEC == 2) {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf) {          // two batches of 8 x 16 B keep the kernel at 128 registers
+                    double2 cv[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int mf = 0; mf < 4; ++mf) {
+                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
+                            if (n < N && m + 1 < M) cv[h][mf] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
+                            else if (n < N && m < M) cv[h][mf] = make_double2(C[m + n * ldc], 0.0);
+                            else cv[h][mf] = make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int mf = 0; mf < 4; ++mf) {
+                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
+                            double2 c = cv[h][mf];
+                            c.x -= acc[nf][mf][2 * h]; c.y -= acc[nf][mf][2 * h + 1];
+                            if (n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
+                            else if (n < N && m < M) C[m + n * ldc] = c.x;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+                        if (n >= N) continue;
+#pragma unroll
+                        for (int mf = 0; mf < 4; ++mf) {
+                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
+                            if (m < M) C[m + n * ldc] -= acc[nf][mf][2 * h];
+                            if (m + 1 < M) C[m + 1 + n * ldc] -= acc[nf][mf][2 * h + 1];
+                        }
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ---- complex: C -= A*B with interleaved (re,im); four real DMMAs per complex MMA ---------------------
 // Tiling: CTA 64(m) x 64(n) x 16(k) complex, 8 warps as 2(m) x 4(n), warp tile 32 x 16.
 constexpr int ZBM = 64, ZBN = 64, ZBK = 16;
@@ -325,6 +529,33 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
     int64_t ntiles = (int64_t)tiles_m * tiles_n;
     if (ntiles > 0x7fffffffLL) fatal("dgemm: too many tiles");
     bool aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0 && (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0);
+    static int variant = -1;
+    constexpr size_t smem16 = (size_t)4 * (16 * SA + BN * 20) * sizeof(double), smem32 = (size_t)3 * (32 * SA + BN * 36) * sizeof(double);
+    if (variant < 0) {
+        variant = (int)opt("gemm_variant", 3);
+#define SET_ATTR(K, bytes) SLB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+        SET_ATTR((dgemm_minus_persistent<2, 16, 4, 0>), smem16); SET_ATTR((dgemm_minus_persistent<1, 16, 4, 0>), smem16);
+        SET_ATTR((dgemm_minus_persistent<2, 16, 4, 1>), smem16); SET_ATTR((dgemm_minus_persistent<2, 32, 3, 0>), smem32);
+        SET_ATTR((dgemm_minus_persistent<2, 32, 3, 1>), smem32);
+#undef SET_ATTR
+    }
+    if (variant >= 2) {
+        unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
+        if (!aligned)
+            dgemm_minus_persistent<1, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        else if (variant == 2)
+            dgemm_minus_persistent<2, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        else if (variant == 3)
+            dgemm_minus_persistent<2, 16, 4, 1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        else if (variant == 4)
+            dgemm_minus_persistent<2, 32, 3, 0><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        else
+            dgemm_minus_persistent<2, 32, 3, 1><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        SLB_CUDA(cudaGetLastError());
+        counter_add("kernel_launches", 1);
+        counter_add("gemm_launches", 1);
+        return;
+    }
     if (aligned)
         dgemm_minus_kernel<2><<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
     else

@@ -120,22 +120,31 @@ void launch_gen(long long M, int mb, int nb, long long mloc, long long nloc, int
 // ---------------- micro-benchmarks ----------------
 __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out)
 {
-    double acc[8][4];
+    // 2 x 4 grid of independent DMMA.8x8x4 accumulators with operands in registers: the register tiling that
+    // scripts/dmma_probe2.cu measured at the pipe's limit (37.0 TFLOP/s = 64 FMA/clk/SM at 1.965 GHz)
+    double acc[2][4][2];
+    double a[2], b[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 2; ++i) a[i] = out[64 + threadIdx.x + i];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[i][v] = 0.0;
-    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = 0.5, b0 = 1.0 - threadIdx.x * 1e-9;
+    for (int j = 0; j < 4; ++j) b[j] = out[512 + threadIdx.x + j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
-                         : "+d"(acc[i][0]), "+d"(acc[i][1]), "+d"(acc[i][2]), "+d"(acc[i][3])
-                         : "d"(a0), "d"(a1), "d"(b0));
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
     }
     double s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
     if (s == 12345.678) out[0] = s;
 }
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *out)
@@ -217,17 +226,17 @@ static void run_dfma(void *p) { PeakArg *a = (PeakArg *)p; dfma_peak_kernel<<<a-
 double bench_dmma_peak_tflops(int iters)
 {
     Runtime &r = rt();
-    double *out = (double *)workspace("bench_out", 64);
-    PeakArg a{ iters, out, r.sm_count * 4 };
+    double *out = (double *)workspace("bench_out", 16384, true);
+    PeakArg a{ iters, out, r.sm_count * 2 };
     double ms = time_kernel_ms(run_dmma, &a, 5);
-    // per warp per iteration: 8 MMAs x (16*8*4) FMAs x 2 flops
-    double flops = (double)a.blocks * 8.0 * iters * 8.0 * 512.0 * 2.0;
+    // per warp per iteration: 8 DMMA.8x8x4 x (8*8*4) FMAs x 2 flops; 8 warps per CTA
+    double flops = (double)a.blocks * 8.0 * iters * 8.0 * 256.0 * 2.0;
     return flops / (ms * 1e-3) / 1e12;
 }
 double bench_dfma_peak_tflops(int iters)
 {
     Runtime &r = rt();
-    double *out = (double *)workspace("bench_out", 64);
+    double *out = (double *)workspace("bench_out", 16384, true);
     PeakArg a{ iters, out, r.sm_count * 8 };
     double ms = time_kernel_ms(run_dfma, &a, 5);
     double flops = (double)a.blocks * 256.0 * iters * 16.0 * 2.0;

@@ -86,6 +86,10 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     const bool time_updates = opt("time_updates", 1) != 0;
     SLB_CUDA(cudaEventRecord(ev0, s));
 
+    // optional per-phase profile (SLB200_PROFILE=1): events only, no extra synchronisation
+    const bool prof = opt("profile", 0) != 0;
+    std::vector<cudaEvent_t> pev;
+    auto mark = [&]() { if (prof) { cudaEvent_t e; SLB_CUDA(cudaEventCreate(&e)); SLB_CUDA(cudaEventRecord(e, s)); pev.push_back(e); } };
     RowDist rd{ nb, P, myrow, rsrc };
     auto rows_before = [&](int prow, int gidx) { return (int64_t)numroc(gidx, nb, prow, rsrc, P); };
     auto mloc_of = [&](int prow) { return (int64_t)numroc(M, nb, prow, rsrc, P); };
@@ -102,6 +106,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         const T *L11 = nullptr, *Lop = nullptr; int64_t ldl = 0, ld11 = 0;
 
         // =============== panel ===============
+        mark();
         if (!multi) {
             PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = (int)lr0; map.seg_prow[0] = 0;
             map.nb = nb; map.nprow = 1; map.rsrc = 0;
@@ -182,6 +187,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         }
 
         // =============== row interchanges + U12 ===============
+        mark();
         launch_swap_plan(j0, jb, ipiv_dev + j0, plan, s);
         const int64_t nright = nloc - lcr;
         T *Uall = Ubuf;                      // jb x nloc, column index = local column
@@ -201,11 +207,13 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, lcl, Obuf, jb, s);
         launch_swap_unpack_out<T>(jb, plan, rd, A, lld, lcr, nloc, Obuf + lcr * jb, jb, s);
         if (myrow == pr) launch_copy2d<T>(jb, lcl, Uall, jb, A + lr0, lld, s);           // left columns: final rows
+        mark();
         if (nright > 0) {
             T *U = Uall + lcr * jb;
             Ops<T>::trsm(jb, nright, L11, ld11, U, jb, s);
             if (myrow == pr) launch_copy2d<T>(jb, nright, U, jb, A + lr0 + lcr * lld, lld, s);
             // =============== trailing update ===============
+            mark();
             const int64_t rbeg = lr0 + (myrow == pr ? jb : 0);
             const int64_t mrows = mloc - rbeg;
             if (mrows > 0) {
@@ -214,7 +222,8 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                 if (time_updates) SLB_CUDA(cudaEventRecord(gev[2 * k + 1], s));
                 gflops[k] = 2.0 * (double)mrows * (double)nright * jb * Ops<T>::flop_mul;
             }
-        }
+        } else mark();
+        mark();
     }
     SLB_CUDA(cudaEventRecord(ev1, s));
     SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -230,6 +239,18 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             g_last_lu.update_ms += t; g_last_lu.update_flops += gflops[k]; g_last_lu.update_launches += 1;
             cudaEventDestroy(gev[2 * k]); cudaEventDestroy(gev[2 * k + 1]);
         }
+    }
+    if (prof) {   // 5 marks per step: [panel][swap][trsm][gemm]
+        double tp = 0, tsw = 0, ttr = 0, tg = 0;
+        for (size_t i = 0; i + 4 < pev.size() + 1 && i + 4 < pev.size(); i += 5) {
+            float a, b, c, d;
+            SLB_CUDA(cudaEventElapsedTime(&a, pev[i], pev[i + 1])); SLB_CUDA(cudaEventElapsedTime(&b, pev[i + 1], pev[i + 2]));
+            SLB_CUDA(cudaEventElapsedTime(&c, pev[i + 2], pev[i + 3])); SLB_CUDA(cudaEventElapsedTime(&d, pev[i + 3], pev[i + 4]));
+            tp += a; tsw += b; ttr += c; tg += d;
+        }
+        for (auto e : pev) cudaEventDestroy(e);
+        counter_add("prof_panel_us", (int64_t)(tp * 1e3)); counter_add("prof_swap_us", (int64_t)(tsw * 1e3));
+        counter_add("prof_trsm_us", (int64_t)(ttr * 1e3)); counter_add("prof_gemm_us", (int64_t)(tg * 1e3));
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     // INFO: first zero pivot is known on the diagonal owners only -> min over the grid (SRC/pdgetrf.f:297-302)

@@ -1,0 +1,99 @@
+"""One rank of a multi-GPU parity run (spawned by tests/test_gpu_multi.py or scripts/run_mp.py).
+Every rank rebuilds the global test matrix with the oracle, factors its block-cyclic piece through the
+C-ABI (PDGETRF / PDGETRS / PDGESV on a P x Q grid, one GPU per rank) and compares its local result with the
+oracle's serial factorisation scattered the same way.  Prints one RESULT json line."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import oracle as O  # noqa: E402
+import scalapack_b200 as S  # noqa: E402
+
+EPS = 2.0 ** -53
+
+
+def run_case(P, Q, m, n, nb, nrhs, cplx=False, device=False):
+    ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", P, Q)
+    _, _, r, c = S.blacs_gridinfo(ctx)
+    res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)}", "ok": True, "msgs": []}
+    if r < 0:
+        return res
+    gen = O.pzmatgen if cplx else O.pdmatgen
+    a0 = gen(m, n, 100)
+    ref = a0.copy(order="F")
+    ipr, infr = O.getrf(ref, nb)
+    mloc, nloc = S.numroc(m, nb, r, 0, P), S.numroc(n, nb, c, 0, Q)
+    lld = max(1, mloc) + 1                                     # one guard row
+    al = O.scatter(a0, nb, nb, P, Q, r, c, lld=lld)
+    al[mloc:, :] = -9923.0
+    desca, info = S.descinit(m, n, nb, nb, 0, 0, ctx, lld)
+    ipiv = np.full(mloc + nb, -77, np.int32)
+    f = S.pzgetrf if cplx else S.pdgetrf
+    if device:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(al.T)).cuda()
+        info = f(m, n, t, 1, 1, desca, ipiv)
+        al = np.asfortranarray(t.cpu().numpy().T)
+    else:
+        info = f(m, n, al, 1, 1, desca, ipiv)
+    refl = O.scatter(ref, nb, nb, P, Q, r, c, lld=lld)
+    mn = min(m, n)
+    ipl = O.ipiv_local(m, mn, nb, P, r, ipr, mloc + nb, fill=-77)
+    own = ipl != -77
+    if info != infr:
+        res["ok"] = False; res["msgs"].append(f"info {info} != {infr}")
+    if not np.array_equal(ipiv[own], ipl[own]):
+        bad = np.nonzero(ipiv[own] != ipl[own])[0]
+        res["ok"] = False; res["msgs"].append(f"ipiv mismatch at local idx {bad[:5].tolist()} got {ipiv[own][bad[:5]].tolist()} want {ipl[own][bad[:5]].tolist()}")
+    anorm = np.abs(a0).sum(axis=1).max()
+    err = float(np.abs(al[:mloc, :nloc] - refl[:mloc, :nloc]).max() / (anorm * max(m, n) * EPS)) if mloc and nloc else 0.0
+    res["lu_err"] = err
+    if not err < 1.0:
+        res["ok"] = False; res["msgs"].append(f"lu_err {err}")
+    if not np.all(al[mloc:, :].real == -9923.0):
+        res["ok"] = False; res["msgs"].append("guard row overwritten")
+    if m == n and nrhs > 0 and res["ok"]:
+        b0 = gen(n, nrhs, 200)
+        nbr = 2
+        nlocb = S.numroc(nrhs, nbr, c, 0, Q)
+        bl = O.scatter(b0, nb, nbr, P, Q, r, c, lld=max(1, mloc))
+        descb, _ = S.descinit(n, nrhs, nb, nbr, 0, 0, ctx, max(1, mloc))
+        g = S.pzgetrs if cplx else S.pdgetrs
+        inf2 = g("N", n, nrhs, al, 1, 1, desca, ipiv, bl, 1, 1, descb)
+        xr = b0.copy(order="F"); O.getrs(ref, ipr, xr)
+        xl = O.scatter(xr, nb, nbr, P, Q, r, c, lld=max(1, mloc))
+        if inf2 != 0:
+            res["ok"] = False; res["msgs"].append(f"getrs info {inf2}")
+        if mloc and nlocb:
+            e2 = float(np.abs(bl[:mloc, :nlocb] - xl[:mloc, :nlocb]).max() / max(1e-300, np.abs(xr).max()))
+            res["x_err"] = e2
+            if not e2 < 1e-8:
+                res["ok"] = False; res["msgs"].append(f"x_err {e2}")
+        # PDGESV in one call on fresh copies
+        al2 = O.scatter(a0, nb, nb, P, Q, r, c, lld=lld); bl2 = O.scatter(b0, nb, nbr, P, Q, r, c, lld=max(1, mloc))
+        ip2 = np.zeros(mloc + nb, np.int32)
+        h = S.pzgesv if cplx else S.pdgesv
+        inf3 = h(n, nrhs, al2, 1, 1, desca, ip2, bl2, 1, 1, descb)
+        if inf3 != 0 or (mloc and nlocb and not np.allclose(bl2[:mloc, :nlocb], bl[:mloc, :nlocb], rtol=0, atol=1e-300)):
+            res["ok"] = False; res["msgs"].append(f"pdgesv differs from pdgetrf+pdgetrs (info {inf3})")
+    S.blacs_gridexit(ctx)
+    return res
+
+
+def main():
+    me, np_ = S.blacs_pinfo()
+    cases = json.loads(sys.argv[1])
+    out = []
+    for cs in cases:
+        if cs["P"] * cs["Q"] > np_:
+            continue
+        out.append(run_case(cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False)))
+    S.blacs_exit(0)
+    print("RESULT" + json.dumps({"rank": me, "results": out}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
