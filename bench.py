@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override N (default: 65536*sqrt(gpus), BASELINE config 2 at 1 GPU)")
+    ap.add_argument("--size", dest="n", type=int, default=0, help="override N (default: 65536*sqrt(gpus), BASELINE config 2 at 1 GPU)")
     ap.add_argument("--nb", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -33,7 +33,20 @@ constexpr int PT = 256;        // threads per CTA
 constexpr int UCH = 64;        // columns of U staged per chunk in phase G
 constexpr int MAXG = 160;      // max CTAs (>= SM count)
 
-struct CandHdr { double absval; long long key; int vrow; int pad; };
+struct __align__(16) CandHdr { double absval; int vrow; unsigned tag; };
+
+// 16-byte mailbox header: written / read as one vector access so {value,row,tag} are observed together
+__device__ __forceinline__ void st_hdr(CandHdr *p, double a, int v, unsigned tag)
+{
+    unsigned lo = (unsigned)(__double_as_longlong(a) & 0xffffffffLL), hi = (unsigned)((unsigned long long)__double_as_longlong(a) >> 32);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(lo), "r"(hi), "r"((unsigned)v), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_hdr(const CandHdr *p, double &a, int &v, unsigned &tag)
+{
+    unsigned lo, hi, uv;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(lo), "=r"(hi), "=r"(uv), "=r"(tag) : "l"(p) : "memory");
+    a = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo)); v = (int)uv;
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned *count, volatile unsigned *gen, unsigned nblocks)
 {
@@ -86,7 +99,7 @@ __device__ __forceinline__ bool better(double aa, long long ka, double ab, long 
 template <typename T, int W>
 __global__ void __launch_bounds__(PT, 1)
 panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, int *__restrict__ ipiv_out,
-             int *__restrict__ info_out, int info_offset, unsigned char *__restrict__ work, int rpb)
+             int *__restrict__ info_out, int info_offset, unsigned char *__restrict__ work, int rpb, unsigned tagbase)
 {
     constexpr int LS = W + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -96,16 +109,16 @@ panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, i
     T *Us = jrow_s + W;                                // [W][UCH]
     T *Ls = Us + W * UCH;                              // [W][W]  Ls[k*W + i] = L11[i][k]
     double *red_abs = reinterpret_cast<double *>(Ls + W * W);    // [8]
-    long long *red_key = reinterpret_cast<long long *>(red_abs + 8);   // [8]
-    int *red_v = reinterpret_cast<int *>(red_key + 8);           // [8]
+    int *red_v = reinterpret_cast<int *>(red_abs + 16);          // [8]   (red_abs[8] = block best)
     int *plan = red_v + 8;                             // top_src[W], out_dst[W], out_src[W]
     int *misc = plan + 3 * W;                          // [0]=winner cta [1]=winner vrow [2]=best local v
 
     // global work area
     unsigned *bar_count = reinterpret_cast<unsigned *>(work);
     volatile unsigned *bar_gen = reinterpret_cast<volatile unsigned *>(work + 128);
-    CandHdr *cand = reinterpret_cast<CandHdr *>(work + 256);                    // [2][MAXG]
-    T *candrow = reinterpret_cast<T *>(work + 256 + 2 * MAXG * sizeof(CandHdr));   // [2][MAXG][W]
+    unsigned *jtag = reinterpret_cast<unsigned *>(work + 256);                  // [2] tags of the published row jj (128 B apart)
+    CandHdr *cand = reinterpret_cast<CandHdr *>(work + 512);                    // [2][MAXG]
+    T *candrow = reinterpret_cast<T *>(work + 512 + 2 * MAXG * sizeof(CandHdr));   // [2][MAXG][W]
     T *rowj = candrow + 2 * MAXG * W;                                            // [2][W]
     int *piv_v = reinterpret_cast<int *>(rowj + 2 * W);                          // [jb]
 
@@ -125,74 +138,68 @@ panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, i
         __syncthreads();
 
         // ---------------- phase F: factor the sub-panel column by column ----------------
+        // Per column: block arg-max -> publish {|v|, row, tag} + candidate row in the mailbox -> every CTA polls
+        // the G headers until all carry this column's tag (the data IS the barrier: no counter, no second
+        // round trip) -> redundant reduction -> fetch pivot row + old row jj -> swap / scale / rank-1 update,
+        // which also produces each thread's candidate for the next column.
+        double babs = -1.0; int bv = -1;
+        auto consider = [&](double a, int v) {
+            if (bv < 0 || a > babs || (a == babs && vm.key(v) < vm.key(bv))) { babs = a; bv = v; }
+        };
+        for (int i = tid; i < nrows; i += PT)
+            if (base + i >= s0) consider(t_abs1(S[i * LS]), base + i);
         for (int j = 0; j < w; ++j) {
             const int jj = s0 + j;
-            // local arg-max of column j over my rows v >= jj
-            double babs = -1.0; long long bkey = 0; int bv = -1;
-            for (int i = tid; i < nrows; i += PT) {
-                int v = base + i;
-                if (v < jj) continue;
-                double a = t_abs1(S[i * LS + j]);
-                if (bv < 0 || a > babs) { babs = a; bv = v; bkey = -1; }
-                else if (a == babs) {            // tie: resolve by the reference's order (rare path)
-                    if (bkey < 0) bkey = vm.key(bv);
-                    long long k2 = vm.key(v);
-                    if (k2 < bkey) { bv = v; bkey = k2; }
-                }
-            }
-            if (bv >= 0 && bkey < 0) bkey = vm.key(bv);
+            const unsigned want = tagbase + (unsigned)jj + 1u;
+            // ---- block reduction of the per-thread candidates ----
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 double oa = __shfl_xor_sync(0xffffffffu, babs, off);
-                long long ok = __shfl_xor_sync(0xffffffffu, bkey, off);
                 int ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                if (ov >= 0 && (bv < 0 || better(oa, ok, babs, bkey))) { babs = oa; bkey = ok; bv = ov; }
+                if (ov >= 0 && (bv < 0 || oa > babs || (oa == babs && vm.key(ov) < vm.key(bv)))) { babs = oa; bv = ov; }
             }
-            if (lane == 0) { red_abs[warp] = babs; red_key[warp] = bkey; red_v[warp] = bv; }
+            if (lane == 0) { red_abs[warp] = babs; red_v[warp] = bv; }
             __syncthreads();
             if (warp == 0) {
                 double a = lane < PT / 32 ? red_abs[lane] : -1.0;
-                long long k = lane < PT / 32 ? red_key[lane] : 0;
                 int v = lane < PT / 32 ? red_v[lane] : -1;
 #pragma unroll
                 for (int off = 4; off > 0; off >>= 1) {
                     double oa = __shfl_xor_sync(0xffffffffu, a, off);
-                    long long ok = __shfl_xor_sync(0xffffffffu, k, off);
                     int ov = __shfl_xor_sync(0xffffffffu, v, off);
-                    if (ov >= 0 && (v < 0 || better(oa, ok, a, k))) { a = oa; k = ok; v = ov; }
+                    if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; }
                 }
-                if (lane == 0) {
-                    misc[2] = v;
-                    CandHdr h; h.absval = v >= 0 ? a : -1.0; h.key = k; h.vrow = v; h.pad = 0;
-                    cand[parity * MAXG + b] = h;
-                }
+                if (lane == 0) { misc[2] = v; red_abs[8] = a; }
             }
             __syncthreads();
-            {
-                int v = misc[2];
-                if (v >= 0 && tid < w) candrow[((size_t)parity * MAXG + b) * W + tid] = S[(v - base) * LS + tid];
-                if (jj >= base && jj < base + nrows && tid < w) rowj[parity * W + tid] = S[(jj - base) * LS + tid];
+            // ---- publish ----
+            const int myv = misc[2];
+            const bool own_jj = jj >= base && jj < base + nrows;
+            if (myv >= 0 && tid < w) candrow[((size_t)parity * MAXG + b) * W + tid] = S[(myv - base) * LS + tid];
+            if (own_jj && tid < w) rowj[parity * W + tid] = S[(jj - base) * LS + tid];
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                st_hdr(&cand[parity * MAXG + b], myv >= 0 ? red_abs[8] : -1.0, myv, want);
+                if (own_jj) *reinterpret_cast<volatile unsigned *>(&jtag[parity * 32]) = want;
             }
-            grid_barrier(bar_count, bar_gen, G);
-
-            // every CTA reduces the G candidates (warp 0), then fetches the pivot row and old row jj
+            // ---- gather: poll all headers (warp 0), reduce ----
             if (warp == 0) {
-                double a = -1.0; long long k = 0; int v = -1, wb = -1;
+                double a = -1.0; int v = -1, wb = -1;
                 for (int q = lane; q < G; q += 32) {
-                    const CandHdr *hp = &cand[parity * MAXG + q];
-                    double qa = __ldcg(&hp->absval);
-                    long long qk = __ldcg(&hp->key);
-                    int qv = __ldcg(&hp->vrow);
-                    if (qv >= 0 && (v < 0 || better(qa, qk, a, k))) { a = qa; k = qk; v = qv; wb = q; }
+                    double qa; int qv; unsigned qt;
+                    do { ld_hdr(&cand[parity * MAXG + q], qa, qv, qt); } while (qt != want);
+                    if (qv >= 0 && (v < 0 || qa > a || (qa == a && vm.key(qv) < vm.key(v)))) { a = qa; v = qv; wb = q; }
                 }
+                if (lane == 0) { while (*reinterpret_cast<volatile unsigned *>(&jtag[parity * 32]) != want) { } }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
                     double oa = __shfl_xor_sync(0xffffffffu, a, off);
-                    long long ok = __shfl_xor_sync(0xffffffffu, k, off);
                     int ov = __shfl_xor_sync(0xffffffffu, v, off);
                     int ob = __shfl_xor_sync(0xffffffffu, wb, off);
-                    if (ov >= 0 && (v < 0 || better(oa, ok, a, k))) { a = oa; k = ok; v = ov; wb = ob; }
+                    if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; wb = ob; }
                 }
+                __threadfence();
                 if (lane == 0) { misc[0] = wb; misc[1] = v; }
             }
             __syncthreads();
@@ -211,12 +218,13 @@ panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, i
                 ipiv_out[jj] = vm.global_row(pv) + 1;
                 if (!nonzero && *info_out == 0) *info_out = info_offset + jj + 1;
             }
+            if (nonzero && pv != jj) {
+                if (pv >= base && pv < base + nrows && tid < w) S[(pv - base) * LS + tid] = jrow_s[tid];
+                if (own_jj && tid < w) S[(jj - base) * LS + tid] = prow_s[tid];
+                __syncthreads();
+            }
+            babs = -1.0; bv = -1;
             if (nonzero) {
-                if (pv != jj) {
-                    if (pv >= base && pv < base + nrows && tid < w) S[(pv - base) * LS + tid] = jrow_s[tid];
-                    if (jj >= base && jj < base + nrows && tid < w) S[(jj - base) * LS + tid] = prow_s[tid];
-                    __syncthreads();
-                }
                 const T rinv = t_recip(pivot);
                 for (int i = tid; i < nrows; i += PT) {
                     if (base + i <= jj) continue;
@@ -224,7 +232,11 @@ panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, i
                     T l = t_mul(row[j], rinv);
                     row[j] = l;
                     for (int c = j + 1; c < w; ++c) row[c] = t_fnma(l, prow_s[c], row[c]);
+                    if (j + 1 < w) consider(t_abs1(row[j + 1]), base + i);
                 }
+            } else if (j + 1 < w) {
+                for (int i = tid; i < nrows; i += PT)
+                    if (base + i > jj) consider(t_abs1(S[i * LS + j + 1]), base + i);
             }
             parity ^= 1;
             __syncthreads();
@@ -348,8 +360,8 @@ panel_kernel(int m, int jb, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, i
 template <typename T, int W>
 size_t panel_smem_bytes(int rpb)
 {
-    return ((size_t)rpb * (W + 1) + 2 * W + (size_t)W * UCH + (size_t)W * W) * sizeof(T) + 8 * sizeof(double) +
-           8 * sizeof(long long) + 8 * sizeof(int) + 3 * W * sizeof(int) + 8 * sizeof(int) + 64;
+    return ((size_t)rpb * (W + 1) + 2 * W + (size_t)W * UCH + (size_t)W * W) * sizeof(T) + 16 * sizeof(double) +
+           8 * sizeof(int) + 3 * W * sizeof(int) + 8 * sizeof(int) + 64;
 }
 
 template <typename T, int W>
@@ -359,7 +371,7 @@ bool try_launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map,
     Runtime &r = rt();
     int nsm = r.sm_count < MAXG ? r.sm_count : MAXG;
     int rpb = (m + nsm - 1) / nsm;
-    if (rpb < 64) rpb = 64;
+    if (rpb < 128) rpb = 128;
     rpb = (rpb + 7) & ~7;
     size_t smem = panel_smem_bytes<T, W>(rpb);
     if (smem > r.smem_optin) return false;
@@ -371,7 +383,12 @@ bool try_launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map,
     }
     unsigned char *wk = (unsigned char *)work;
     PanelRowMap mp = map;
-    void *args[] = { &m, &jb, &Wp, &ldw, &mp, &ipiv_out, &info_out, &info_offset, &wk, &rpb };
+    // mailbox tags = (launch epoch << 16) + column + 1: never equal to a stale tag of an earlier launch
+    static unsigned epoch = 0;
+    if ((++epoch & 0x7fffu) == 0) { SLB_CUDA(cudaMemsetAsync(wk + 256, 0, 256 + 2 * MAXG * sizeof(CandHdr), s)); ++epoch; }
+    if (jb >= 65535) fatal("panel wider than 65534 columns");
+    unsigned tagbase = (epoch & 0x7fffu) << 16;
+    void *args[] = { &m, &jb, &Wp, &ldw, &mp, &ipiv_out, &info_out, &info_offset, &wk, &rpb, &tagbase };
     SLB_CUDA(cudaLaunchCooperativeKernel((void *)panel_kernel<T, W>, dim3(G), dim3(PT), args, smem, s));
     counter_add("kernel_launches", 1);
     counter_add("panel_launches", 1);
@@ -394,7 +411,7 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
 
 size_t panel_work_bytes(int jb)
 {
-    return 256 + 2 * MAXG * sizeof(CandHdr) + (size_t)(2 * MAXG * 32 + 2 * 32) * sizeof(zcomplex) + (size_t)(jb + 64) * sizeof(int) + 256;
+    return 512 + 2 * MAXG * sizeof(CandHdr) + (size_t)(2 * MAXG * 32 + 2 * 32) * sizeof(zcomplex) + (size_t)(jb + 64) * sizeof(int) + 256;
 }
 
 void launch_dpanel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,

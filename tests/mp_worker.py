@@ -15,8 +15,7 @@ import scalapack_b200 as S  # noqa: E402
 EPS = 2.0 ** -53
 
 
-def run_case(P, Q, m, n, nb, nrhs, cplx=False, device=False):
-    ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", P, Q)
+def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False):
     _, _, r, c = S.blacs_gridinfo(ctx)
     res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)}", "ok": True, "msgs": []}
     if r < 0:
@@ -79,7 +78,6 @@ def run_case(P, Q, m, n, nb, nrhs, cplx=False, device=False):
         inf3 = h(n, nrhs, al2, 1, 1, desca, ip2, bl2, 1, 1, descb)
         if inf3 != 0 or (mloc and nlocb and not np.allclose(bl2[:mloc, :nlocb], bl[:mloc, :nlocb], rtol=0, atol=1e-300)):
             res["ok"] = False; res["msgs"].append(f"pdgesv differs from pdgetrf+pdgetrs (info {inf3})")
-    S.blacs_gridexit(ctx)
     return res
 
 
@@ -87,10 +85,14 @@ def main():
     me, np_ = S.blacs_pinfo()
     cases = json.loads(sys.argv[1])
     out = []
+    grids = {}                      # one BLACS grid (and one set of NCCL communicators) per (P, Q)
     for cs in cases:
         if cs["P"] * cs["Q"] > np_:
             continue
-        out.append(run_case(cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False)))
+        key = (cs["P"], cs["Q"])
+        if key not in grids:
+            grids[key] = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", cs["P"], cs["Q"])
+        out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False)))
     S.blacs_exit(0)
     print("RESULT" + json.dumps({"rank": me, "results": out}), flush=True)
 
