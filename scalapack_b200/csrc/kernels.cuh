@@ -25,11 +25,8 @@ void launch_ztrsm_llnu(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcompl
 // column has been gathered onto one GPU); virtual row v of segment s is local row seg_lr0[s] + (v -
 // seg_v0[s]) of process row seg_prow[s]; global row = block-cyclic map with nb, nprow, rsrc.
 struct PanelRowMap {
-    int nseg;
-    int seg_v0[9];        // virtual start of segment s; seg_v0[nseg] = m
-    int seg_lr0[8];       // first local row (0-based) of the segment on its owner
-    int seg_prow[8];      // owning process row
-    int nb, nprow, rsrc;
+    int g0;               // global row (0-based) of panel row 0; panel rows are consecutive global rows
+    int nb, nprow, rsrc;  // block-cyclic row distribution: only used to order ties like the reference's combine
 };
 // W: m x jb panel (ld = ldw) in virtual row order.  ipiv_out[j] (j < jb) = 1-based GLOBAL row index chosen
 // for panel column j (reference IPIV semantics, SRC/pdgetrf.f:118-121).  *info_out receives the first zero
@@ -50,7 +47,7 @@ void launch_swap_plan(int j0, int jb, const int *ipiv_blk, SwapPlan plan, cudaSt
 
 // Row ownership of the local array: global row g lives on process row (rsrc + g/nb) % nprow at local row
 // nb*(g/(nb*nprow)) + g%nb.
-struct RowDist { int nb, nprow, myrow, rsrc; };
+struct RowDist { int nb, nprow, myrow, rsrc; int shift; };   // local row = block-cyclic local row - shift
 
 // pack: for local columns [c0, c1): Ubuf[t + (c-c0)*ldu] = A[lrow(top_src[t]) + c*lda] when I own top_src[t]
 // (else left untouched), and, on the process row owning the top block, Obuf[t + (c-c0)*ldo] =
@@ -66,6 +63,11 @@ void launch_swap_unpack_out(int jb, SwapPlan plan, RowDist rd, T *A, int64_t lda
 template <typename T>
 void launch_swap_select(int jb, SwapPlan plan, RowDist rd, const T *Call, int64_t ldc, int64_t stride_p, int64_t ncols,
                         T *U, int64_t ldu, cudaStream_t s);
+// block-cyclic <-> global row order for a gathered panel: local rows [l0, l0+rows) of process row prow_rel
+// (relative to rsrc) <-> rows (global - gshift) of G.  to_global=1: G <- L, else L <- G.
+template <typename T>
+void launch_rows_bc(int64_t rows, int cols, T *L, int64_t ldl, int64_t l0, T *G, int64_t ldg, int64_t gshift, int nb, int nprow,
+                    int prow_rel, int to_global, cudaStream_t s);
 // copy a jb x ncols block: dst[i + c*ldd] = src[i + c*lds]
 template <typename T>
 void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst, int64_t ldd, cudaStream_t s);

@@ -90,7 +90,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     const bool prof = opt("profile", 0) != 0;
     std::vector<cudaEvent_t> pev;
     auto mark = [&]() { if (prof) { cudaEvent_t e; SLB_CUDA(cudaEventCreate(&e)); SLB_CUDA(cudaEventRecord(e, s)); pev.push_back(e); } };
-    RowDist rd{ nb, P, myrow, rsrc };
+    RowDist rd{ nb, P, myrow, rsrc, 0 };
     auto rows_before = [&](int prow, int gidx) { return (int64_t)numroc(gidx, nb, prow, rsrc, P); };
     auto mloc_of = [&](int prow) { return (int64_t)numroc(M, nb, prow, rsrc, P); };
 
@@ -108,8 +108,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         // =============== panel ===============
         mark();
         if (!multi) {
-            PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = (int)lr0; map.seg_prow[0] = 0;
-            map.nb = nb; map.nprow = 1; map.rsrc = 0;
+            PanelRowMap map{ j0, nb, 1, 0 };
             T *Wp = A + lr0 + lcl * lld;
             Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
             L11 = Wp; ld11 = lld; Lop = Wp + jb; ldl = lld;
@@ -118,25 +117,19 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             const size_t my_pbytes = hdr_bytes + (size_t)mtr * jb * sizeof(T);
             if (mycol == pc) {
                 if (P == 1) {
-                    PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = (int)lr0; map.seg_prow[0] = myrow;
-                    map.nb = nb; map.nprow = 1; map.rsrc = rsrc;
+                    PanelRowMap map{ j0, nb, 1, rsrc };
                     T *Wp = A + lr0 + lcl * lld;
                     Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
                     launch_copy2d<T>(jb, jb, Wp, lld, pL11, jb, s);
                     SLB_CUDA(cudaMemcpyAsync(pIpiv, ipiv_dev + j0, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
                     launch_copy2d<T>(mtr, jb, Wp, lld, pLloc, mtr, s);
                 } else {
-                    // ---- gather the column's panel on the diagonal owner ----
-                    PanelRowMap map{}; map.nseg = P; map.nb = nb; map.nprow = P; map.rsrc = rsrc;
-                    int64_t v = 0; std::vector<int64_t> segrows((size_t)P), segv0((size_t)P);
-                    for (int sg = 0; sg < P; ++sg) {
-                        int prow = (pr + sg) % P;
-                        int64_t lr = rows_before(prow, j0), rows = mloc_of(prow) - lr;
-                        map.seg_v0[sg] = (int)v; map.seg_lr0[sg] = (int)lr; map.seg_prow[sg] = prow;
-                        segv0[sg] = v; segrows[sg] = rows; v += rows;
-                    }
-                    map.seg_v0[P] = (int)v;
-                    const int64_t mtot = v;       // == m
+                    // ---- gather the column's panel on the diagonal owner, rows in GLOBAL order (row v <-> global j0+v) ----
+                    PanelRowMap map{ j0, nb, P, rsrc };
+                    const int64_t mtot = m;
+                    std::vector<int64_t> prows((size_t)P), plr0((size_t)P);
+                    for (int prow = 0; prow < P; ++prow) { plr0[prow] = rows_before(prow, j0); prows[prow] = mloc_of(prow) - plr0[prow]; }
+                    auto rel = [&](int prow) { return (prow - rsrc + P) % P; };
                     if (myrow != pr) {
                         launch_copy2d<T>(mtr, jb, A + lr0 + lcl * lld, lld, Stage, mtr, s);
                         if (mtr > 0) nccl_send(nc->col, Stage, (size_t)mtr * jb * sizeof(T), NT_U8, pr, s);
@@ -144,37 +137,42 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                         nccl_recv(nc->col, Pbuf, my_pbytes, NT_U8, pr, s);
                         launch_copy2d<T>(mtr, jb, pLloc, mtr, A + lr0 + lcl * lld, lld, s);
                     } else {
-                        launch_copy2d<T>(segrows[0], jb, A + lr0 + lcl * lld, lld, Wbuf, mtot, s);
+                        launch_rows_bc<T>(mtr, jb, A + lr0 + lcl * lld, lld, lr0, Wbuf, mtot, j0, nb, P, rel(myrow), 1, s);
                         nccl_group_start();
                         { int64_t off = 0;
-                          for (int sg = 1; sg < P; ++sg) {
-                              if (segrows[sg] > 0) nccl_recv(nc->col, Stage + off, (size_t)segrows[sg] * jb * sizeof(T), NT_U8, map.seg_prow[sg], s);
-                              off += segrows[sg] * jb;
+                          for (int prow = 0; prow < P; ++prow) {
+                              if (prow == pr) continue;
+                              if (prows[prow] > 0) nccl_recv(nc->col, Stage + off, (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
+                              off += prows[prow] * jb;
                           } }
                         nccl_group_end();
                         { int64_t off = 0;
-                          for (int sg = 1; sg < P; ++sg) {
-                              launch_copy2d<T>(segrows[sg], jb, Stage + off, segrows[sg], Wbuf + segv0[sg], mtot, s);
-                              off += segrows[sg] * jb;
+                          for (int prow = 0; prow < P; ++prow) {
+                              if (prow == pr) continue;
+                              launch_rows_bc<T>(prows[prow], jb, Stage + off, prows[prow], plr0[prow], Wbuf, mtot, j0, nb, P, rel(prow), 1, s);
+                              off += prows[prow] * jb;
                           } }
                         Ops<T>::panel((int)mtot, jb, Wbuf, mtot, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
                         // own copy + own Pbuf
-                        launch_copy2d<T>(segrows[0], jb, Wbuf, mtot, A + lr0 + lcl * lld, lld, s);
+                        launch_rows_bc<T>(mtr, jb, A + lr0 + lcl * lld, lld, lr0, Wbuf, mtot, j0, nb, P, rel(myrow), 0, s);
                         launch_copy2d<T>(jb, jb, Wbuf, mtot, pL11, jb, s);
                         SLB_CUDA(cudaMemcpyAsync(pIpiv, ipiv_dev + j0, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
-                        launch_copy2d<T>(segrows[0], jb, Wbuf, mtot, pLloc, segrows[0], s);
+                        launch_rows_bc<T>(mtr, jb, pLloc, mtr, lr0, Wbuf, mtot, j0, nb, P, rel(myrow), 0, s);
                         // peers' Pbufs
                         size_t soff = 0; std::vector<size_t> soffs((size_t)P, 0);
-                        for (int sg = 1; sg < P; ++sg) {
-                            soffs[sg] = soff;
+                        for (int prow = 0; prow < P; ++prow) {
+                            if (prow == pr) continue;
+                            soffs[prow] = soff;
                             unsigned char *pb = Psend + soff;
                             SLB_CUDA(cudaMemcpyAsync(pb, Pbuf, hdr_bytes, cudaMemcpyDeviceToDevice, s));
-                            launch_copy2d<T>(segrows[sg], jb, Wbuf + segv0[sg], mtot, (T *)(pb + hdr_bytes), segrows[sg], s);
-                            soff += align_up(hdr_bytes + (size_t)segrows[sg] * jb * sizeof(T), 256);
+                            launch_rows_bc<T>(prows[prow], jb, (T *)(pb + hdr_bytes), prows[prow], plr0[prow], Wbuf, mtot, j0, nb, P, rel(prow), 0, s);
+                            soff += align_up(hdr_bytes + (size_t)prows[prow] * jb * sizeof(T), 256);
                         }
                         nccl_group_start();
-                        for (int sg = 1; sg < P; ++sg)
-                            nccl_send(nc->col, Psend + soffs[sg], hdr_bytes + (size_t)segrows[sg] * jb * sizeof(T), NT_U8, map.seg_prow[sg], s);
+                        for (int prow = 0; prow < P; ++prow) {
+                            if (prow == pr) continue;
+                            nccl_send(nc->col, Psend + soffs[prow], hdr_bytes + (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
+                        }
                         nccl_group_end();
                     }
                 }

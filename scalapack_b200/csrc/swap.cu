@@ -54,7 +54,8 @@ __global__ void swap_plan_kernel(int j0, int jb, const int *__restrict__ ipiv_bl
 }
 
 __device__ __forceinline__ int row_owner(const RowDist &rd, int g) { return (rd.rsrc + g / rd.nb) % rd.nprow; }
-__device__ __forceinline__ int64_t row_local(const RowDist &rd, int g) { return (int64_t)rd.nb * (g / (rd.nb * rd.nprow)) + g % rd.nb; }
+__device__ __forceinline__ int64_t row_local(const RowDist &rd, int g)
+{ return (int64_t)rd.nb * (g / ((int64_t)rd.nb * rd.nprow)) + g % rd.nb - rd.shift; }
 
 constexpr int SWAP_COLS = 8;      // columns per block
 
@@ -135,7 +136,33 @@ copy2d_kernel(int64_t rows, int64_t cols, const T *__restrict__ src, int64_t lds
             dst[i + c * ldd] = src[i + c * lds];
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+rows_bc_kernel(int64_t rows, int cols, T *__restrict__ L, int64_t ldl, int64_t l0, T *__restrict__ G, int64_t ldg, int64_t gshift,
+               int nb, int nprow, int prow_rel, int to_global)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int64_t l = l0 + i;
+    int64_t g = ((l / nb) * nprow + prow_rel) * nb + l % nb - gshift;
+    for (int c = blockIdx.y; c < cols; c += gridDim.y) {
+        if (to_global) G[g + (int64_t)c * ldg] = L[i + (int64_t)c * ldl];
+        else L[i + (int64_t)c * ldl] = G[g + (int64_t)c * ldg];
+    }
+}
+
 }  // namespace
+
+template <typename T>
+void launch_rows_bc(int64_t rows, int cols, T *L, int64_t ldl, int64_t l0, T *G, int64_t ldg, int64_t gshift, int nb, int nprow,
+                    int prow_rel, int to_global, cudaStream_t s)
+{
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)((rows + 255) / 256), (unsigned)(cols < 64 ? cols : 64));
+    rows_bc_kernel<T><<<grid, 256, 0, s>>>(rows, cols, L, ldl, l0, G, ldg, gshift, nb, nprow, prow_rel, to_global);
+    SLB_CUDA(cudaGetLastError());
+    counter_add("kernel_launches", 1);
+}
 
 void launch_swap_plan(int j0, int jb, const int *ipiv_blk, SwapPlan plan, cudaStream_t s)
 {
@@ -194,7 +221,8 @@ void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst
                                             cudaStream_t);                                                            \
     template void launch_swap_select<T>(int, SwapPlan, RowDist, const T *, int64_t, int64_t, int64_t, T *, int64_t,    \
                                         cudaStream_t);                                                                \
-    template void launch_copy2d<T>(int64_t, int64_t, const T *, int64_t, T *, int64_t, cudaStream_t);
+    template void launch_copy2d<T>(int64_t, int64_t, const T *, int64_t, T *, int64_t, cudaStream_t);                  \
+    template void launch_rows_bc<T>(int64_t, int, T *, int64_t, int64_t, T *, int64_t, int64_t, int, int, int, int, cudaStream_t);
 INST(double)
 INST(zcomplex)
 template void launch_copy2d<int>(int64_t, int64_t, const int *, int64_t, int *, int64_t, cudaStream_t);

@@ -71,8 +71,7 @@ double slb200_test_panel(int m, int jb, void *W, int64_t ldw, int *ipiv, int *in
     int *dpiv = (int *)workspace("t_piv", (size_t)(jb + 1) * sizeof(int));
     void *work = workspace("lu_panelwork", panel_work_bytes(jb > 512 ? jb : 512), true);
     SLB_CUDA(cudaMemsetAsync(dpiv, 0, (size_t)(jb + 1) * sizeof(int), r.s_main));
-    PanelRowMap map{}; map.nseg = 1; map.seg_v0[0] = 0; map.seg_v0[1] = m; map.seg_lr0[0] = 0; map.seg_prow[0] = 0;
-    map.nb = m > 0 ? m : 1; map.nprow = 1; map.rsrc = 0;
+    PanelRowMap map{}; map.g0 = 0; map.nb = m > 0 ? m : 1; map.nprow = 1; map.rsrc = 0;
     cudaEvent_t e0, e1; SLB_CUDA(cudaEventCreate(&e0)); SLB_CUDA(cudaEventCreate(&e1));
     SLB_CUDA(cudaEventRecord(e0, r.s_main));
     if (is_complex) launch_zpanel(m, jb, (zcomplex *)w.d, ldw, map, dpiv, dpiv + jb, 0, work, r.s_main);
@@ -89,6 +88,13 @@ double slb200_test_panel(int m, int jb, void *W, int64_t ldw, int *ipiv, int *in
     return ms;
 }
 
+// copies the panel kernel's debug timestamps (SLB200_PANEL_DEBUG=1): out[2][4096][8] u64
+void slb200_test_panel_dbg(unsigned long long *out)
+{
+    void *d = workspace("panel_dbg", 2 * 4096 * 8 * 8, true);
+    SLB_CUDA(cudaMemcpy(out, d, 2 * 4096 * 8 * 8, cudaMemcpyDeviceToHost));
+}
+
 // Row interchanges of one block on an m x n real matrix (single process row): rows j0+t <-> ipiv[t]-1.
 void slb200_test_laswp(int m, int64_t n, double *A, int64_t lda, int j0, int jb, const int *ipiv_blk)
 {
@@ -99,7 +105,7 @@ void slb200_test_laswp(int m, int64_t n, double *A, int64_t lda, int j0, int jb,
     int *pm = (int *)workspace("lu_plan", (size_t)3 * jb * sizeof(int));
     SwapPlan plan{ pm, pm + jb, pm + 2 * jb };
     double *U = (double *)workspace("lu_U", (size_t)jb * n * 8), *O = (double *)workspace("lu_O", (size_t)jb * n * 8);
-    RowDist rd{ m > 0 ? m : 1, 1, 0, 0 };
+    RowDist rd{ m > 0 ? m : 1, 1, 0, 0, 0 };
     launch_swap_plan(j0, jb, dp, plan, s);
     launch_swap_pack<double>(jb, j0, plan, rd, (double *)a.d, lda, 0, n, U, jb, O, jb, s);
     launch_swap_unpack_out<double>(jb, plan, rd, (double *)a.d, lda, 0, n, O, jb, s);
