@@ -210,7 +210,7 @@ def run_ours(args):
     dmma_peak = S.lib().slb200_bench_dmma_tflops(20000)
     dfma_peak = S.lib().slb200_bench_dfma_tflops(20000)
     achieved = u_fl / (u_ms * 1e-3) / 1e12 if u_ms > 0 else None
-    roof = {"bound": "tensor", "kernel": "dgemm_minus_kernel (FP64 DMMA trailing update)", "achieved": achieved, "peak": dmma_peak,
+    roof = {"bound": "tensor", "kernel": "dgemm_minus_persistent (FP64 DMMA trailing update, gemm.cu)", "achieved": achieved, "peak": dmma_peak,
             "unit": "TFLOP/s", "frac": (achieved / dmma_peak) if achieved else None, "traffic": None,
             "peak_source": "FP64 DMMA peak measured live by slb200_bench_dmma_tflops (MEASURED_PEAKS.json has no FP64 entry)",
             "fp64_fma_peak_tflops": dfma_peak, "share_of_step": u_ms / sum(times) if times else None,

@@ -270,7 +270,7 @@ __device__ __forceinline__ void tile_coords(int64_t t, int tiles_m, int tiles_n,
 template <int VEC, int PBK, int PST, int LOAD_MID>
 __global__ void __launch_bounds__(P_THREADS, 1)
 dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-                       int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n)
+                       int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int SBP = PBK + 4, AST = PBK * SA, BST = BN * SBP;
@@ -282,19 +282,23 @@ dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A
 
     const int64_t ntiles = (int64_t)tiles_m * tiles_n;
     const int KT = (K + PBK - 1) / PBK;
-    const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // persistent (chunk == 0): tiles b, b+grid, ...;  chunked: tiles [b*chunk, (b+1)*chunk) then the CTA retires so a
+    // higher-priority stream (the look-ahead panel) can take the SM
+    const int64_t t_first = chunk > 0 ? (int64_t)blockIdx.x * chunk : blockIdx.x;
+    const int64_t t_stride = chunk > 0 ? 1 : gridDim.x;
+    const int64_t my_tiles = chunk > 0 ? max((int64_t)0, min((int64_t)chunk, ntiles - t_first)) : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t total = my_tiles * KT;
 
     // loader cursor (tile, k-stage) runs STAGES-1 ahead of the consumer cursor
     int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
-    if (my_tiles > 0) tile_coords(blockIdx.x, tiles_m, tiles_n, l_m0, l_n0);
+    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
     auto issue_load = [&](int64_t li) {
         if (li < total) {
             int st = (int)(li % PST);
             load_stage_p<VEC, PBK>(As + st * AST, Bs + st * BST, A, lda, B, ldb, l_m0, l_n0, l_kt * PBK, M, N, K, tid);
             if (++l_kt == KT) {
                 l_kt = 0; ++l_lt;
-                if (l_lt < my_tiles) tile_coords(blockIdx.x + l_lt * gridDim.x, tiles_m, tiles_n, l_m0, l_n0);
+                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
             }
         }
         cp_async_commit();
@@ -313,7 +317,7 @@ dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A
     int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
     for (int64_t ci = 0; ci < total; ++ci) {
         if (kt == 0) {
-            tile_coords(blockIdx.x + lt * gridDim.x, tiles_m, tiles_n, m0, n0);
+            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
             // pull this thread's part of the C tile into L2 while the k-loop runs
 #pragma unroll
             for (int nf = 0; nf < 2; ++nf)
@@ -515,7 +519,7 @@ zgemm_minus_kernel(int64_t M, int64_t N, int K, const zcomplex *__restrict__ A, 
 }  // namespace
 
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
-                        double *C, int64_t ldc, cudaStream_t s)
+                        double *C, int64_t ldc, cudaStream_t s, int chunk)
 {
     if (M <= 0 || N <= 0 || K <= 0) return;
     static bool attr_done = false;
@@ -541,16 +545,17 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
     }
     if (variant >= 2) {
         unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
+        if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
         if (!aligned)
-            dgemm_minus_persistent<1, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+            dgemm_minus_persistent<1, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else if (variant == 2)
-            dgemm_minus_persistent<2, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+            dgemm_minus_persistent<2, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else if (variant == 3)
-            dgemm_minus_persistent<2, 16, 4, 1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+            dgemm_minus_persistent<2, 16, 4, 1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else if (variant == 4)
-            dgemm_minus_persistent<2, 32, 3, 0><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+            dgemm_minus_persistent<2, 32, 3, 0><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else
-            dgemm_minus_persistent<2, 32, 3, 1><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+            dgemm_minus_persistent<2, 32, 3, 1><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         SLB_CUDA(cudaGetLastError());
         counter_add("kernel_launches", 1);
         counter_add("gemm_launches", 1);

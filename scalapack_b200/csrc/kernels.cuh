@@ -10,8 +10,9 @@ typedef double2 zcomplex;   // COMPLEX*16 as (re, im)
 
 // ---- trailing update (replaces PDGEMM 'N','N', alpha=-1, beta=1; PBLAS/SRC/PTOOLS/PB_CpgemmAB.c:345) ----
 // C[M x N] -= A[M x K] * B[K x N].  FP64 tensor cores (DMMA mma.sync m16n8k4), cp.async 4-stage pipeline.
+// chunk > 0: each CTA processes `chunk` tiles and retires (lets a higher-priority stream interleave); 0: persistent.
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
-                        double *C, int64_t ldc, cudaStream_t s);
+                        double *C, int64_t ldc, cudaStream_t s, int chunk = 0);
 void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
                         zcomplex *C, int64_t ldc, cudaStream_t s);
 
@@ -32,10 +33,12 @@ struct PanelRowMap {
 // for panel column j (reference IPIV semantics, SRC/pdgetrf.f:118-121).  *info_out receives the first zero
 // pivot column (1-based, relative to the panel) if it was 0 on entry.  work: >= panel_work_bytes().
 size_t panel_work_bytes(int jb);
+// gmax > 0 caps the number of CTAs (SMs) the leaf kernels use and launches them non-cooperatively: look-ahead mode,
+// the panel shares the GPU with the trailing update of the previous step.
 void launch_dpanel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
-                   int info_offset, void *work, cudaStream_t s);
+                   int info_offset, void *work, cudaStream_t s, int gmax = 0);
 void launch_zpanel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
-                   int info_offset, void *work, cudaStream_t s);
+                   int info_offset, void *work, cudaStream_t s, int gmax = 0);
 
 // ---- row interchanges (replaces PDLASWP / PDSWAP; SRC/pdlaswp.f:163-182, PBLAS/SRC/pdswap_.c:448-534) ----
 // Plan of one block of jb sequential interchanges rows (j0+t) <-> ipiv[t]-1, t = 0..jb-1 (global, 0-based j0):

@@ -22,19 +22,19 @@ namespace slb {
 
 template <typename T> struct Ops;
 template <> struct Ops<double> {
-    static void gemm(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s)
-    { launch_dgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static void gemm(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s, int chunk = 0)
+    { launch_dgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s, chunk); }
     static void trsm(int jb, int64_t n, const double *L, int64_t ldl, double *B, int64_t ldb, cudaStream_t s) { launch_dtrsm_llnu(jb, n, L, ldl, B, ldb, s); }
-    static void panel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s)
-    { launch_dpanel(m, jb, W, ldw, map, ipiv, info, off, work, s); }
+    static void panel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax = 0)
+    { launch_dpanel(m, jb, W, ldw, map, ipiv, info, off, work, s, gmax); }
     static constexpr double flop_mul = 1.0;
 };
 template <> struct Ops<zcomplex> {
-    static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s)
-    { launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s, int chunk = 0)
+    { (void)chunk; launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
     static void trsm(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t s) { launch_ztrsm_llnu(jb, n, L, ldl, B, ldb, s); }
-    static void panel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s)
-    { launch_zpanel(m, jb, W, ldw, map, ipiv, info, off, work, s); }
+    static void panel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax = 0)
+    { launch_zpanel(m, jb, W, ldw, map, ipiv, info, off, work, s, gmax); }
     static constexpr double flop_mul = 4.0;
 };
 
@@ -42,9 +42,116 @@ LuStats g_last_lu;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- 1 x 1 grid with look-ahead: panel k+1 (high-priority stream, few SMs) under the trailing update of step k ----
+// The reference's loop is strictly serial (SRC/pdgetrf.f:254-295).  Here step k first updates only the next panel's
+// columns, hands them to the panel stream, and updates the rest of the trailing matrix with a CHUNKED DMMA kernel
+// whose CTAs retire every few tiles so the panel's kernels (<= gmax CTAs, launched non-cooperatively) find SMs.
+template <typename T>
+static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host)
+{
+    Runtime &r = rt();
+    cudaStream_t sm = r.s_main, sp = r.s_panel;
+    const int mn = M < N ? M : N;
+    const int nsteps = (mn + nb - 1) / nb;
+    int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
+    int *info_dev = (int *)workspace("lu_info", 64);
+    int *plan_mem = (int *)workspace("lu_plan", (size_t)3 * nb * sizeof(int));
+    SwapPlan plan{ plan_mem, plan_mem + nb, plan_mem + 2 * nb };
+    void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
+    T *Ubuf = (T *)workspace("lu_U", (size_t)nb * N * sizeof(T));
+    T *Obuf = (T *)workspace("lu_O", (size_t)nb * N * sizeof(T));
+    const int gmax_opt = (int)opt("panel_gmax", 48), chunk_opt = (int)opt("gemm_chunk", 8);
+    const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
+
+    cudaEvent_t ev0, ev1, evs;
+    SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1)); SLB_CUDA(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> evp((size_t)nsteps + 1), evn((size_t)nsteps + 1), gev((size_t)4 * nsteps, nullptr);
+    for (auto &e : evp) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : evn) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<double> gflops((size_t)nsteps, 0.0);
+
+    SLB_CUDA(cudaEventRecord(ev0, sm));
+    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), sm));
+    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), sm));
+    SLB_CUDA(cudaEventRecord(evs, sm));
+    SLB_CUDA(cudaStreamWaitEvent(sp, evs, 0));
+    RowDist rd{ nb, 1, 0, 0, 0 };
+    auto run_panel = [&](int k, int gmax) {
+        const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
+        PanelRowMap map{ j0, nb, 1, 0 };
+        Ops<T>::panel(M - j0, jb, A + j0 + (int64_t)j0 * lld, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, sp, gmax);
+        SLB_CUDA(cudaEventRecord(evp[k], sp));
+    };
+    run_panel(0, 0);
+    for (int k = 0; k < nsteps; ++k) {
+        const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
+        T *Wp = A + j0 + (int64_t)j0 * lld;
+        SLB_CUDA(cudaStreamWaitEvent(sm, evp[k], 0));
+        launch_swap_plan(j0, jb, ipiv_dev + j0, plan, sm);
+        const int64_t cr = j0 + jb, nright = N - cr;
+        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sm);
+        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, cr, N, Ubuf + cr * jb, jb, Obuf + cr * jb, jb, sm);
+        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sm);
+        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, cr, N, Obuf + cr * jb, jb, sm);
+        launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sm);
+        if (nright <= 0) continue;
+        T *U = Ubuf + cr * jb;
+        Ops<T>::trsm(jb, nright, Wp, lld, U, jb, sm);
+        launch_copy2d<T>(jb, nright, U, jb, A + j0 + cr * lld, lld, sm);
+        const int64_t mrows = M - cr;
+        if (mrows <= 0) continue;
+        const T *Lop = Wp + jb;
+        T *C = A + cr + cr * lld;
+        const bool have_next = k + 1 < nsteps;
+        auto timed_gemm = [&](int slot, int64_t nn, const T *Bp, T *Cp, int chunk) {
+            SLB_CUDA(cudaEventCreate(&gev[4 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[4 * k + slot + 1]));
+            SLB_CUDA(cudaEventRecord(gev[4 * k + slot], sm));
+            Ops<T>::gemm(mrows, nn, jb, Lop, lld, Bp, jb, Cp, lld, sm, chunk);
+            SLB_CUDA(cudaEventRecord(gev[4 * k + slot + 1], sm));
+            gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
+        };
+        if (!have_next) { timed_gemm(0, nright, U, C, 0); continue; }
+        const int jbn = (mn - (int)cr) < nb ? (mn - (int)cr) : nb;
+        const int64_t rest = nright - jbn;
+        const double rest_ms = 2.0 * (double)mrows * (double)rest * jb * Ops<T>::flop_mul / 28e12 * 1e3;
+        const bool overlap = rest > 0 && rest_ms >= overlap_min_ms;
+        timed_gemm(0, jbn, U, C, 0);                                      // next panel's columns first
+        SLB_CUDA(cudaEventRecord(evn[k], sm));
+        SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
+        run_panel(k + 1, overlap ? gmax_opt : 0);
+        if (rest > 0) timed_gemm(2, rest, U + (int64_t)jbn * jb, C + (int64_t)jbn * lld, overlap ? chunk_opt : 0);
+    }
+    SLB_CUDA(cudaStreamWaitEvent(sm, evp[nsteps - 1], 0));
+    SLB_CUDA(cudaEventRecord(ev1, sm));
+    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sm));
+    int info_local = 0;
+    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sm));
+    SLB_CUDA(cudaStreamSynchronize(sm));
+    SLB_CUDA(cudaStreamSynchronize(sp));
+    float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    g_last_lu.factor_ms = ms;
+    g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
+    for (int k = 0; k < nsteps; ++k) {
+        for (int slot = 0; slot < 4; slot += 2)
+            if (gev[4 * k + slot]) {
+                float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[4 * k + slot], gev[4 * k + slot + 1]));
+                g_last_lu.update_ms += t; g_last_lu.update_launches += 1;
+                cudaEventDestroy(gev[4 * k + slot]); cudaEventDestroy(gev[4 * k + slot + 1]);
+            }
+        g_last_lu.update_flops += gflops[k];
+    }
+    for (auto &e : evp) cudaEventDestroy(e);
+    for (auto &e : evn) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs);
+    *info_host = info_local;
+    return 0;
+}
+
 template <typename T>
 int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host)
 {
+    if (g->nprow * g->npcol == 1 && opt("lookahead", 1) != 0 && opt("profile", 0) == 0)
+        return getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host);
     Runtime &r = rt();
     cudaStream_t s = r.s_main;
     const int P = g->nprow, Q = g->npcol, myrow = g->myrow, mycol = g->mycol;

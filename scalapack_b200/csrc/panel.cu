@@ -227,10 +227,11 @@ size_t leaf_smem_bytes(int rpb)
 
 // rows per CTA for an m-row leaf of width W; 0 if it does not fit
 template <typename T, int W>
-int leaf_rpb(int m)
+int leaf_rpb(int m, int gmax)
 {
     Runtime &r = rt();
     int nsm = r.sm_count < MAXG ? r.sm_count : MAXG;
+    if (gmax > 0 && gmax < nsm) nsm = gmax;
     int rpb = (m + nsm - 1) / nsm;
     if (rpb < 128) rpb = 128;
     rpb = (rpb + 7) & ~7;
@@ -239,10 +240,10 @@ int leaf_rpb(int m)
 
 template <typename T, int W>
 void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out, int info_offset,
-                 void *work, cudaStream_t s)
+                 void *work, cudaStream_t s, int gmax)
 {
     Runtime &r = rt();
-    int rpb = leaf_rpb<T, W>(m);
+    int rpb = leaf_rpb<T, W>(m, gmax);
     if (rpb == 0) fatal("panel leaf of %d rows does not fit in shared memory", m);
     int G = (m + rpb - 1) / rpb;
     static bool attr_done = false;
@@ -261,7 +262,11 @@ void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *
     // CTA per SM; launched as a cooperative grid so the runtime checks exactly that.
     PanelRowMap mp = map;
     void *args[] = { &m, &w, &Wp, &ldw, &mp, &ipiv_out, &info_out, &info_offset, &wk, &rpb, &tagbase, &dbg };
-    SLB_CUDA(cudaLaunchCooperativeKernel((void *)panel_leaf_kernel<T, W>, dim3(G), dim3(PT), args, smem, s));
+    if (gmax > 0) {     // look-ahead: plain launch; the CTAs become resident as the update's chunked CTAs retire
+        panel_leaf_kernel<T, W><<<G, PT, smem, s>>>(m, w, Wp, ldw, mp, ipiv_out, info_out, info_offset, wk, rpb, tagbase, dbg);
+        SLB_CUDA(cudaGetLastError());
+    } else
+        SLB_CUDA(cudaLaunchCooperativeKernel((void *)panel_leaf_kernel<T, W>, dim3(G), dim3(PT), args, smem, s));
     counter_add("kernel_launches", 1);
     counter_add("panel_launches", 1);
 }
@@ -271,22 +276,22 @@ template <> struct LeafCfg<double> { static constexpr int W0 = 32; };
 template <> struct LeafCfg<zcomplex> { static constexpr int W0 = 16; };
 
 template <typename T>
-int pick_leaf_width(int m)
+int pick_leaf_width(int m, int gmax)
 {
     int forced = (int)opt("panel_width", 0);
     if (forced == 8 || forced == 16 || (forced == 32 && LeafCfg<T>::W0 == 32)) return forced;
-    if constexpr (LeafCfg<T>::W0 == 32) { if (leaf_rpb<T, 32>(m)) return 32; }
-    if (leaf_rpb<T, 16>(m)) return 16;
-    if (leaf_rpb<T, 8>(m)) return 8;
+    if constexpr (LeafCfg<T>::W0 == 32) { if (leaf_rpb<T, 32>(m, gmax)) return 32; }
+    if (leaf_rpb<T, 16>(m, gmax)) return 16;
+    if (leaf_rpb<T, 8>(m, gmax)) return 8;
     fatal("panel of %d rows does not fit the shared-memory slabs", m);
 }
 
 template <typename T>
-void leaf_dispatch(int W, int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s)
+void leaf_dispatch(int W, int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax)
 {
-    if (W == 32) { if constexpr (LeafCfg<T>::W0 == 32) launch_leaf<T, 32>(m, w, Wp, ldw, map, ipiv, info, off, work, s); }
-    else if (W == 16) launch_leaf<T, 16>(m, w, Wp, ldw, map, ipiv, info, off, work, s);
-    else launch_leaf<T, 8>(m, w, Wp, ldw, map, ipiv, info, off, work, s);
+    if (W == 32) { if constexpr (LeafCfg<T>::W0 == 32) launch_leaf<T, 32>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax); }
+    else if (W == 16) launch_leaf<T, 16>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax);
+    else launch_leaf<T, 8>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax);
 }
 
 inline void gemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s)
@@ -299,7 +304,7 @@ inline void trsm_llnu(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomple
 template <typename T>
 struct PanelCtx {
     int m, W; T *Wp; int64_t ldw; PanelRowMap map; int *ipiv; int *info; int info_offset; void *work;
-    SwapPlan plan; T *U; T *O; cudaStream_t s;
+    SwapPlan plan; T *U; T *O; cudaStream_t s; int gmax;
 };
 
 // interchanges of panel columns [p0,p1) (pivots ipiv[p0..p1)) applied to panel columns [c0,c1); the permuted top
@@ -323,7 +328,7 @@ void panel_rec(PanelCtx<T> &c, int c0, int c1)
     const int n = c1 - c0;
     if (n <= c.W) {
         PanelRowMap mp = c.map; mp.g0 += c0;
-        leaf_dispatch<T>(c.W, c.m - c0, n, c.Wp + c0 + (int64_t)c0 * c.ldw, c.ldw, mp, c.ipiv + c0, c.info, c.info_offset + c0, c.work, c.s);
+        leaf_dispatch<T>(c.W, c.m - c0, n, c.Wp + c0 + (int64_t)c0 * c.ldw, c.ldw, mp, c.ipiv + c0, c.info, c.info_offset + c0, c.work, c.s, c.gmax);
         return;
     }
     const int half = ((n / 2 + c.W - 1) / c.W) * c.W;
@@ -340,11 +345,12 @@ void panel_rec(PanelCtx<T> &c, int c0, int c1)
 
 template <typename T>
 void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
-                  int info_offset, void *work, cudaStream_t s)
+                  int info_offset, void *work, cudaStream_t s, int gmax)
 {
     if (m <= 0 || jb <= 0) return;
     PanelCtx<T> c;
-    c.m = m; c.W = pick_leaf_width<T>(m); c.Wp = Wp; c.ldw = ldw; c.map = map; c.ipiv = ipiv_out; c.info = info_out;
+    c.gmax = gmax;
+    c.m = m; c.W = pick_leaf_width<T>(m, gmax); c.Wp = Wp; c.ldw = ldw; c.map = map; c.ipiv = ipiv_out; c.info = info_out;
     c.info_offset = info_offset; c.work = work; c.s = s;
     int *pm = (int *)workspace("panel_plan", (size_t)3 * jb * sizeof(int));
     c.plan = SwapPlan{ pm, pm + jb, pm + 2 * jb };
@@ -362,10 +368,10 @@ size_t panel_work_bytes(int jb)
 }
 
 void launch_dpanel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
-                   int info_offset, void *work, cudaStream_t s)
-{ launch_panel<double>(m, jb, W, ldw, map, ipiv_out, info_out, info_offset, work, s); }
+                   int info_offset, void *work, cudaStream_t s, int gmax)
+{ launch_panel<double>(m, jb, W, ldw, map, ipiv_out, info_out, info_offset, work, s, gmax); }
 void launch_zpanel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
-                   int info_offset, void *work, cudaStream_t s)
-{ launch_panel<zcomplex>(m, jb, W, ldw, map, ipiv_out, info_out, info_offset, work, s); }
+                   int info_offset, void *work, cudaStream_t s, int gmax)
+{ launch_panel<zcomplex>(m, jb, W, ldw, map, ipiv_out, info_out, info_offset, work, s, gmax); }
 
 }  // namespace slb
