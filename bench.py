@@ -135,6 +135,8 @@ def workload_n(args):
 
 
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"                     # keep NCCL's version banner off stdout (one JSON line only)
     import numpy as np
     import torch
     import scalapack_b200 as S

@@ -406,6 +406,283 @@ dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A
     cp_async_wait<0>();
 }
 
+// ---- v6: persistent / chunked like v2-v5 but 8 warps with 64 x 32 warp tiles (0.375 LDS per DMMA instead of 0.5),
+// explicit register double-buffering of the fragments inside a stage, loads issued after the first k4 step --------
+template <int VEC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_minus_p8(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+               int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;
+    double *Bs = smem + STAGES * AS_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;      // 2 x 4 warps, 64 x 32 each
+
+    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    const int KT = (K + BK - 1) / BK;
+    const int64_t t_first = chunk > 0 ? (int64_t)blockIdx.x * chunk : blockIdx.x;
+    const int64_t t_stride = chunk > 0 ? 1 : gridDim.x;
+    const int64_t my_tiles = chunk > 0 ? max((int64_t)0, min((int64_t)chunk, ntiles - t_first)) : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total = my_tiles * KT;
+
+    int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
+    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
+    auto issue_load = [&](int64_t li) {
+        if (li < total) {
+            int st = (int)(li % STAGES);
+            load_stage<VEC>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, l_m0, l_n0, l_kt * BK, M, N, K, tid);
+            if (++l_kt == KT) {
+                l_kt = 0; ++l_lt;
+                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue_load(s);
+
+    double acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+    int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
+    for (int64_t ci = 0; ci < total; ++ci) {
+        if (kt == 0) {
+            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int mq = 0; mq < 4; ++mq) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+                        int64_t m = m0 + wm0 + mq * 16 + 2 * tig;
+                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
+                    }
+        }
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const double *as = As + (ci % STAGES) * AS_STAGE;
+        const double *bs = Bs + (ci % STAGES) * BS_STAGE;
+        double fa[2][2][2], fb[2][8];
+        auto load_frags = [&](int buf, int k4) {
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {
+                fa[buf][nf][0] = bs[(wn0 + nf * 16 + g) * SB + k4 + tig];
+                fa[buf][nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + k4 + tig];
+            }
+#pragma unroll
+            for (int mf = 0; mf < 8; ++mf) fb[buf][mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
+        };
+        load_frags(0, 0);
+#pragma unroll
+        for (int s4 = 0; s4 < BK / 4; ++s4) {
+            if (s4 == 1) issue_load(ci + STAGES - 1);
+            if (s4 + 1 < BK / 4) load_frags((s4 + 1) & 1, (s4 + 1) * 4);
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int mf = 0; mf < 8; ++mf) dmma_16x8x4(acc[nf][mf], fa[s4 & 1][nf][0], fa[s4 & 1][nf][1], fb[s4 & 1][mf]);
+        }
+        if (++kt == KT) {
+            kt = 0; ++lt;
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh) {                 // batches of 8 x 16 B
+                    double2 cv[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
+                            if (VEC == 2 && n < N && m + 1 < M) cv[h][q] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
+                            else if (n < N && m < M) cv[h][q] = make_double2(C[m + n * ldc], (m + 1 < M) ? C[m + 1 + n * ldc] : 0.0);
+                            else cv[h][q] = make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
+                            double2 c = cv[h][q];
+                            c.x -= acc[nf][mh * 4 + q][2 * h]; c.y -= acc[nf][mh * 4 + q][2 * h + 1];
+                            if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
+                            else if (n < N && m < M) { C[m + n * ldc] = c.x; if (m + 1 < M) C[m + 1 + n * ldc] = c.y; }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- v7: v6 with the per-stage block barrier moved to the MIDDLE of the stage: at the stage boundary the fragments
+// of the next stage are already being prefetched (its data became visible at the mid-stage barrier), so the DMMA
+// pipe never drains waiting for LDS after a barrier --------
+template <int VEC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_minus_p8b(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+               int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;
+    double *Bs = smem + STAGES * AS_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;      // 2 x 4 warps, 64 x 32 each
+
+    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    const int KT = (K + BK - 1) / BK;
+    const int64_t t_first = chunk > 0 ? (int64_t)blockIdx.x * chunk : blockIdx.x;
+    const int64_t t_stride = chunk > 0 ? 1 : gridDim.x;
+    const int64_t my_tiles = chunk > 0 ? max((int64_t)0, min((int64_t)chunk, ntiles - t_first)) : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total = my_tiles * KT;
+
+    int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
+    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
+    auto issue_load = [&](int64_t li) {
+        if (li < total) {
+            int st = (int)(li % STAGES);
+            load_stage<VEC>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, l_m0, l_n0, l_kt * BK, M, N, K, tid);
+            if (++l_kt == KT) {
+                l_kt = 0; ++l_lt;
+                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue_load(s);
+
+    double acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+    double fa[2][2][2], fb[2][8];
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (total > 0) {
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf) {
+            fa[0][nf][0] = Bs[(wn0 + nf * 16 + g) * SB + tig];
+            fa[0][nf][1] = Bs[(wn0 + nf * 16 + g + 8) * SB + tig];
+        }
+#pragma unroll
+        for (int mf = 0; mf < 8; ++mf) fb[0][mf] = As[tig * SA + wm0 + mf * 8 + g];
+    }
+    int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
+    for (int64_t ci = 0; ci < total; ++ci) {
+        if (kt == 0) {
+            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int mq = 0; mq < 4; ++mq) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+                        int64_t m = m0 + wm0 + mq * 16 + 2 * tig;
+                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
+                    }
+        }
+        const double *as = As + (ci % STAGES) * AS_STAGE;
+        const double *bs = Bs + (ci % STAGES) * BS_STAGE;
+        const double *asn = As + ((ci + 1) % STAGES) * AS_STAGE;
+        const double *bsn = Bs + ((ci + 1) % STAGES) * BS_STAGE;
+#pragma unroll
+        for (int s4 = 0; s4 < BK / 4; ++s4) {
+            if (s4 == 1) {
+                cp_async_wait<STAGES - 3>();       // stage ci+1 has landed (this thread's copies) ...
+                __syncthreads();                   // ... for every thread; and everyone is done with stage ci-1
+                issue_load(ci + STAGES - 1);       // refill the buffer of stage ci-1
+            }
+            const int cur = s4 & 1, nxt = cur ^ 1;
+            if (s4 + 1 < BK / 4) {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf) {
+                    fa[nxt][nf][0] = bs[(wn0 + nf * 16 + g) * SB + (s4 + 1) * 4 + tig];
+                    fa[nxt][nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + (s4 + 1) * 4 + tig];
+                }
+#pragma unroll
+                for (int mf = 0; mf < 8; ++mf) fb[nxt][mf] = as[((s4 + 1) * 4 + tig) * SA + wm0 + mf * 8 + g];
+            } else if (ci + 1 < total) {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf) {
+                    fa[nxt][nf][0] = bsn[(wn0 + nf * 16 + g) * SB + tig];
+                    fa[nxt][nf][1] = bsn[(wn0 + nf * 16 + g + 8) * SB + tig];
+                }
+#pragma unroll
+                for (int mf = 0; mf < 8; ++mf) fb[nxt][mf] = asn[tig * SA + wm0 + mf * 8 + g];
+            }
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int mf = 0; mf < 8; ++mf) dmma_16x8x4(acc[nf][mf], fa[cur][nf][0], fa[cur][nf][1], fb[cur][mf]);
+        }
+        if (++kt == KT) {
+            kt = 0; ++lt;
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh) {                 // batches of 8 x 16 B
+                    double2 cv[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
+                            if (VEC == 2 && n < N && m + 1 < M) cv[h][q] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
+                            else if (n < N && m < M) cv[h][q] = make_double2(C[m + n * ldc], (m + 1 < M) ? C[m + 1 + n * ldc] : 0.0);
+                            else cv[h][q] = make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
+                            double2 c = cv[h][q];
+                            c.x -= acc[nf][mh * 4 + q][2 * h]; c.y -= acc[nf][mh * 4 + q][2 * h + 1];
+                            if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
+                            else if (n < N && m < M) { C[m + n * ldc] = c.x; if (m + 1 < M) C[m + 1 + n * ldc] = c.y; }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ---- complex: C -= A*B with interleaved (re,im); four real DMMAs per complex MMA ---------------------
 // Tiling: CTA 64(m) x 64(n) x 16(k) complex, 8 warps as 2(m) x 4(n), warp tile 32 x 16.
 constexpr int ZBM = 64, ZBN = 64, ZBK = 16;
@@ -536,17 +813,27 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
     static int variant = -1;
     constexpr size_t smem16 = (size_t)4 * (16 * SA + BN * 20) * sizeof(double), smem32 = (size_t)3 * (32 * SA + BN * 36) * sizeof(double);
     if (variant < 0) {
-        variant = (int)opt("gemm_variant", 3);
+        variant = (int)opt("gemm_variant", 7);
 #define SET_ATTR(K, bytes) SLB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
         SET_ATTR((dgemm_minus_persistent<2, 16, 4, 0>), smem16); SET_ATTR((dgemm_minus_persistent<1, 16, 4, 0>), smem16);
         SET_ATTR((dgemm_minus_persistent<2, 16, 4, 1>), smem16); SET_ATTR((dgemm_minus_persistent<2, 32, 3, 0>), smem32);
         SET_ATTR((dgemm_minus_persistent<2, 32, 3, 1>), smem32);
+        SET_ATTR((dgemm_minus_p8<2>), smem16); SET_ATTR((dgemm_minus_p8<1>), smem16);
+        SET_ATTR((dgemm_minus_p8b<2>), smem16); SET_ATTR((dgemm_minus_p8b<1>), smem16);
 #undef SET_ATTR
     }
     if (variant >= 2) {
         unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
         if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
-        if (!aligned)
+        if (variant == 7 && aligned)
+            dgemm_minus_p8b<2><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (variant == 7)
+            dgemm_minus_p8b<1><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (variant == 6 && aligned)
+            dgemm_minus_p8<2><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (variant == 6)
+            dgemm_minus_p8<1><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (!aligned)
             dgemm_minus_persistent<1, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else if (variant == 2)
             dgemm_minus_persistent<2, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);

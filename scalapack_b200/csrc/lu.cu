@@ -50,13 +50,13 @@ template <typename T>
 static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host)
 {
     Runtime &r = rt();
-    cudaStream_t sm = r.s_main, sp = r.s_panel;
+    cudaStream_t sm = r.s_main, sp = r.s_panel, sc = r.s_copy;
     const int mn = M < N ? M : N;
     const int nsteps = (mn + nb - 1) / nb;
     int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
     int *info_dev = (int *)workspace("lu_info", 64);
-    int *plan_mem = (int *)workspace("lu_plan", (size_t)3 * nb * sizeof(int));
-    SwapPlan plan{ plan_mem, plan_mem + nb, plan_mem + 2 * nb };
+    int *plan_mem = (int *)workspace("lu_plan", (size_t)6 * nb * sizeof(int));
+    SwapPlan plans[2] = { { plan_mem, plan_mem + nb, plan_mem + 2 * nb }, { plan_mem + 3 * nb, plan_mem + 4 * nb, plan_mem + 5 * nb } };
     void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
     T *Ubuf = (T *)workspace("lu_U", (size_t)nb * N * sizeof(T));
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * N * sizeof(T));
@@ -65,9 +65,11 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
 
     cudaEvent_t ev0, ev1, evs;
     SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1)); SLB_CUDA(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
-    std::vector<cudaEvent_t> evp((size_t)nsteps + 1), evn((size_t)nsteps + 1), gev((size_t)4 * nsteps, nullptr);
+    std::vector<cudaEvent_t> evp((size_t)nsteps + 1), evn((size_t)nsteps + 1), evq((size_t)nsteps + 1), evl((size_t)nsteps + 1), gev((size_t)4 * nsteps, nullptr);
     for (auto &e : evp) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : evn) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : evq) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : evl) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<double> gflops((size_t)nsteps, 0.0);
 
     SLB_CUDA(cudaEventRecord(ev0, sm));
@@ -87,13 +89,20 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
         const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
         T *Wp = A + j0 + (int64_t)j0 * lld;
         SLB_CUDA(cudaStreamWaitEvent(sm, evp[k], 0));
+        if (k >= 2) SLB_CUDA(cudaStreamWaitEvent(sm, evl[k - 2], 0));          // plan buffer k&1 is free again
+        SwapPlan plan = plans[k & 1];
         launch_swap_plan(j0, jb, ipiv_dev + j0, plan, sm);
         const int64_t cr = j0 + jb, nright = N - cr;
-        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sm);
+        // interchanges on the already-factored columns [0, j0): nothing on the critical path reads them again, so
+        // they run on the copy stream (ordered among themselves), off the critical path
+        SLB_CUDA(cudaEventRecord(evq[k], sm));
+        SLB_CUDA(cudaStreamWaitEvent(sc, evq[k], 0));
+        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
+        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
+        launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
+        SLB_CUDA(cudaEventRecord(evl[k], sc));
         launch_swap_pack<T>(jb, j0, plan, rd, A, lld, cr, N, Ubuf + cr * jb, jb, Obuf + cr * jb, jb, sm);
-        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sm);
         launch_swap_unpack_out<T>(jb, plan, rd, A, lld, cr, N, Obuf + cr * jb, jb, sm);
-        launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sm);
         if (nright <= 0) continue;
         T *U = Ubuf + cr * jb;
         Ops<T>::trsm(jb, nright, Wp, lld, U, jb, sm);
@@ -122,6 +131,7 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
         if (rest > 0) timed_gemm(2, rest, U + (int64_t)jbn * jb, C + (int64_t)jbn * lld, overlap ? chunk_opt : 0);
     }
     SLB_CUDA(cudaStreamWaitEvent(sm, evp[nsteps - 1], 0));
+    SLB_CUDA(cudaStreamWaitEvent(sm, evl[nsteps - 1], 0));
     SLB_CUDA(cudaEventRecord(ev1, sm));
     SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sm));
     int info_local = 0;
@@ -142,6 +152,8 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     }
     for (auto &e : evp) cudaEventDestroy(e);
     for (auto &e : evn) cudaEventDestroy(e);
+    for (auto &e : evq) cudaEventDestroy(e);
+    for (auto &e : evl) cudaEventDestroy(e);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs);
     *info_host = info_local;
     return 0;
@@ -150,31 +162,39 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
 template <typename T>
 int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host)
 {
-    if (g->nprow * g->npcol == 1 && opt("lookahead", 1) != 0 && opt("profile", 0) == 0)
+    const bool prof = opt("profile", 0) != 0;
+    if (g->nprow * g->npcol == 1 && opt("lookahead", 1) != 0 && !prof)
         return getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host);
     Runtime &r = rt();
-    cudaStream_t s = r.s_main;
     const int P = g->nprow, Q = g->npcol, myrow = g->myrow, mycol = g->mycol;
     const int mn = M < N ? M : N;
     const int64_t mloc = numroc(M, nb, myrow, rsrc, P), nloc = numroc(N, nb, mycol, csrc, Q);
     const bool multi = P * Q > 1;
     if (multi && !g->nccl) g->nccl = nccl_create(g);
     NcclComms *nc = g->nccl;
+    // look-ahead on P x Q grids: the panel phase of step k+1 (gather, factor, scatter, row broadcast) runs on the
+    // high-priority panel stream with its own column communicator while the update stream finishes step k
+    const bool la = multi && opt("lookahead", 1) != 0 && opt("lookahead_multi", 1) != 0 && !prof;
+    cudaStream_t sm = r.s_main, sp = la ? r.s_panel : r.s_main;
+    const int gmax_opt = (int)opt("panel_gmax", 48), chunk_opt = (int)opt("gemm_chunk", 8);
+    const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
 
     // ---- workspaces ----
     int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
     int *info_dev = (int *)workspace("lu_info", 64);
-    int *plan_mem = (int *)workspace("lu_plan", (size_t)3 * nb * sizeof(int));
+    int *plan_mem = (int *)workspace("lu_plan", (size_t)6 * nb * sizeof(int));
     SwapPlan plan{ plan_mem, plan_mem + nb, plan_mem + 2 * nb };
     void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
     T *Ubuf = (T *)workspace("lu_U", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
     const size_t hdr_bytes = align_up((size_t)nb * nb * sizeof(T), 256) + align_up((size_t)nb * sizeof(int), 256);
     const size_t ipiv_off = align_up((size_t)nb * nb * sizeof(T), 256);
-    unsigned char *Pbuf = nullptr, *Psend = nullptr;
+    const size_t pbuf_bytes = align_up(hdr_bytes + (size_t)(mloc + nb) * nb * sizeof(T), 256);
+    unsigned char *Pb[2] = { nullptr, nullptr }, *Psend = nullptr;
     T *Wbuf = nullptr, *Stage = nullptr, *Cmine = nullptr, *Call = nullptr;
     if (multi) {
-        Pbuf = (unsigned char *)workspace("lu_Pbuf", hdr_bytes + (size_t)(mloc + nb) * nb * sizeof(T));
+        Pb[0] = (unsigned char *)workspace("lu_Pbuf", 2 * pbuf_bytes);
+        Pb[1] = la ? Pb[0] + pbuf_bytes : Pb[0];
         if (P > 1) {
             Wbuf = (T *)workspace("lu_W", (size_t)(M + nb) * nb * sizeof(T));
             Stage = (T *)workspace("lu_stage", (size_t)(M + nb) * nb * sizeof(T));
@@ -183,50 +203,50 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             Call = (T *)workspace("lu_Call", (size_t)P * nb * (nloc > 0 ? nloc : 1) * sizeof(T));
         }
     }
-    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
-    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), s));
+    ncclComm_t_ colp = multi ? (la ? nc->colp : nc->col) : nullptr;     // column communicator of the panel phase
 
-    cudaEvent_t ev0, ev1; SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1));
+    cudaEvent_t ev0, ev1, evs;
+    SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1)); SLB_CUDA(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
     const int nsteps = (mn + nb - 1) / nb;
-    std::vector<cudaEvent_t> gev((size_t)2 * nsteps, nullptr);
+    std::vector<cudaEvent_t> gev((size_t)4 * nsteps, nullptr), evp((size_t)nsteps + 1), evn((size_t)nsteps + 1);
+    for (auto &e : evp) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : evn) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<double> gflops((size_t)nsteps, 0.0);
-    const bool time_updates = opt("time_updates", 1) != 0;
-    SLB_CUDA(cudaEventRecord(ev0, s));
+    SLB_CUDA(cudaEventRecord(ev0, sm));
+    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), sm));
+    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), sm));
+    SLB_CUDA(cudaEventRecord(evs, sm));
+    if (sp != sm) SLB_CUDA(cudaStreamWaitEvent(sp, evs, 0));
 
-    // optional per-phase profile (SLB200_PROFILE=1): events only, no extra synchronisation
-    const bool prof = opt("profile", 0) != 0;
+    // optional per-phase profile (SLB200_PROFILE=1, serial schedule only): events, no extra synchronisation
     std::vector<cudaEvent_t> pev;
-    auto mark = [&]() { if (prof) { cudaEvent_t e; SLB_CUDA(cudaEventCreate(&e)); SLB_CUDA(cudaEventRecord(e, s)); pev.push_back(e); } };
+    auto mark = [&]() { if (prof) { cudaEvent_t e; SLB_CUDA(cudaEventCreate(&e)); SLB_CUDA(cudaEventRecord(e, sm)); pev.push_back(e); } };
     RowDist rd{ nb, P, myrow, rsrc, 0 };
     auto rows_before = [&](int prow, int gidx) { return (int64_t)numroc(gidx, nb, prow, rsrc, P); };
     auto mloc_of = [&](int prow) { return (int64_t)numroc(M, nb, prow, rsrc, P); };
 
-    for (int k = 0; k < nsteps; ++k) {
+    // =============== panel phase of step k (stream sp) ===============
+    auto panel_phase = [&](int k, int gmax) {
+        cudaStream_t s = sp;
         const int j0 = k * nb;
         const int jb = (mn - j0) < nb ? (mn - j0) : nb;
         const int pr = (rsrc + k) % P, pc = (csrc + k) % Q;
         const int64_t lr0 = rows_before(myrow, j0);
         const int64_t mtr = mloc - lr0;
         const int64_t lcl = numroc(j0, nb, mycol, csrc, Q);
-        const int64_t lcr = numroc(j0 + jb, nb, mycol, csrc, Q);
         const int m = M - j0;
-        const T *L11 = nullptr, *Lop = nullptr; int64_t ldl = 0, ld11 = 0;
-
-        // =============== panel ===============
-        mark();
         if (!multi) {
             PanelRowMap map{ j0, nb, 1, 0 };
-            T *Wp = A + lr0 + lcl * lld;
-            Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
-            L11 = Wp; ld11 = lld; Lop = Wp + jb; ldl = lld;
+            Ops<T>::panel(m, jb, A + lr0 + lcl * lld, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s, gmax);
         } else {
+            unsigned char *Pbuf = Pb[k & 1];
             T *pL11 = (T *)Pbuf; int *pIpiv = (int *)(Pbuf + ipiv_off); T *pLloc = (T *)(Pbuf + hdr_bytes);
             const size_t my_pbytes = hdr_bytes + (size_t)mtr * jb * sizeof(T);
             if (mycol == pc) {
                 if (P == 1) {
                     PanelRowMap map{ j0, nb, 1, rsrc };
                     T *Wp = A + lr0 + lcl * lld;
-                    Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
+                    Ops<T>::panel(m, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, s, gmax);
                     launch_copy2d<T>(jb, jb, Wp, lld, pL11, jb, s);
                     SLB_CUDA(cudaMemcpyAsync(pIpiv, ipiv_dev + j0, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
                     launch_copy2d<T>(mtr, jb, Wp, lld, pLloc, mtr, s);
@@ -239,9 +259,9 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                     auto rel = [&](int prow) { return (prow - rsrc + P) % P; };
                     if (myrow != pr) {
                         launch_copy2d<T>(mtr, jb, A + lr0 + lcl * lld, lld, Stage, mtr, s);
-                        if (mtr > 0) nccl_send(nc->col, Stage, (size_t)mtr * jb * sizeof(T), NT_U8, pr, s);
+                        if (mtr > 0) nccl_send(colp, Stage, (size_t)mtr * jb * sizeof(T), NT_U8, pr, s);
                         // ---- receive my factored rows + L11 + pivots ----
-                        nccl_recv(nc->col, Pbuf, my_pbytes, NT_U8, pr, s);
+                        nccl_recv(colp, Pbuf, my_pbytes, NT_U8, pr, s);
                         launch_copy2d<T>(mtr, jb, pLloc, mtr, A + lr0 + lcl * lld, lld, s);
                     } else {
                         launch_rows_bc<T>(mtr, jb, A + lr0 + lcl * lld, lld, lr0, Wbuf, mtot, j0, nb, P, rel(myrow), 1, s);
@@ -249,7 +269,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                         { int64_t off = 0;
                           for (int prow = 0; prow < P; ++prow) {
                               if (prow == pr) continue;
-                              if (prows[prow] > 0) nccl_recv(nc->col, Stage + off, (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
+                              if (prows[prow] > 0) nccl_recv(colp, Stage + off, (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
                               off += prows[prow] * jb;
                           } }
                         nccl_group_end();
@@ -259,7 +279,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                               launch_rows_bc<T>(prows[prow], jb, Stage + off, prows[prow], plr0[prow], Wbuf, mtot, j0, nb, P, rel(prow), 1, s);
                               off += prows[prow] * jb;
                           } }
-                        Ops<T>::panel((int)mtot, jb, Wbuf, mtot, map, ipiv_dev + j0, info_dev, j0, panel_work, s);
+                        Ops<T>::panel((int)mtot, jb, Wbuf, mtot, map, ipiv_dev + j0, info_dev, j0, panel_work, s, gmax);
                         // own copy + own Pbuf
                         launch_rows_bc<T>(mtr, jb, A + lr0 + lcl * lld, lld, lr0, Wbuf, mtot, j0, nb, P, rel(myrow), 0, s);
                         launch_copy2d<T>(jb, jb, Wbuf, mtot, pL11, jb, s);
@@ -278,7 +298,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                         nccl_group_start();
                         for (int prow = 0; prow < P; ++prow) {
                             if (prow == pr) continue;
-                            nccl_send(nc->col, Psend + soffs[prow], hdr_bytes + (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
+                            nccl_send(colp, Psend + soffs[prow], hdr_bytes + (size_t)prows[prow] * jb * sizeof(T), NT_U8, prow, s);
                         }
                         nccl_group_end();
                     }
@@ -287,9 +307,28 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             if (Q > 1) nccl_bcast(nc->row, Pbuf, my_pbytes, NT_U8, pc, s);
             if (!(mycol == pc && myrow == pr))
                 SLB_CUDA(cudaMemcpyAsync(ipiv_dev + j0, pIpiv, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
-            L11 = pL11; ld11 = jb;
-            Lop = pLloc + (myrow == pr ? jb : 0); ldl = mtr > 0 ? mtr : 1;
         }
+        SLB_CUDA(cudaEventRecord(evp[k], s));
+    };
+
+    panel_phase(0, 0);
+    for (int k = 0; k < nsteps; ++k) {
+        cudaStream_t s = sm;
+        const int j0 = k * nb;
+        const int jb = (mn - j0) < nb ? (mn - j0) : nb;
+        const int pr = (rsrc + k) % P;
+        const int64_t lr0 = rows_before(myrow, j0);
+        const int64_t mtr = mloc - lr0;
+        const int64_t lcl = numroc(j0, nb, mycol, csrc, Q);
+        const int64_t lcr = numroc(j0 + jb, nb, mycol, csrc, Q);
+        const T *L11, *Lop; int64_t ldl, ld11;
+        if (!multi) { T *Wp = A + lr0 + lcl * lld; L11 = Wp; ld11 = lld; Lop = Wp + jb; ldl = lld; }
+        else {
+            unsigned char *Pbuf = Pb[k & 1];
+            L11 = (T *)Pbuf; ld11 = jb;
+            Lop = (T *)(Pbuf + hdr_bytes) + (myrow == pr ? jb : 0); ldl = mtr > 0 ? mtr : 1;
+        }
+        if (sp != sm) SLB_CUDA(cudaStreamWaitEvent(sm, evp[k], 0));
 
         // =============== row interchanges + U12 ===============
         mark();
@@ -313,51 +352,81 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         launch_swap_unpack_out<T>(jb, plan, rd, A, lld, lcr, nloc, Obuf + lcr * jb, jb, s);
         if (myrow == pr) launch_copy2d<T>(jb, lcl, Uall, jb, A + lr0, lld, s);           // left columns: final rows
         mark();
+        const bool have_next = k + 1 < nsteps;
+        T *U = Uall + lcr * jb;
+        const int64_t rbeg = lr0 + (myrow == pr ? jb : 0);
+        const int64_t mrows = mloc - rbeg;
         if (nright > 0) {
-            T *U = Uall + lcr * jb;
             Ops<T>::trsm(jb, nright, L11, ld11, U, jb, s);
             if (myrow == pr) launch_copy2d<T>(jb, nright, U, jb, A + lr0 + lcr * lld, lld, s);
-            // =============== trailing update ===============
-            mark();
-            const int64_t rbeg = lr0 + (myrow == pr ? jb : 0);
-            const int64_t mrows = mloc - rbeg;
-            if (mrows > 0) {
-                if (time_updates) { SLB_CUDA(cudaEventCreate(&gev[2 * k])); SLB_CUDA(cudaEventCreate(&gev[2 * k + 1])); SLB_CUDA(cudaEventRecord(gev[2 * k], s)); }
-                Ops<T>::gemm(mrows, nright, jb, Lop, ldl, U, jb, A + rbeg + lcr * lld, lld, s);
-                if (time_updates) SLB_CUDA(cudaEventRecord(gev[2 * k + 1], s));
-                gflops[k] = 2.0 * (double)mrows * (double)nright * jb * Ops<T>::flop_mul;
-            }
-        } else mark();
+        }
+        // =============== trailing update (+ hand-over of the next panel's columns) ===============
         mark();
+        auto timed_gemm = [&](int slot, int64_t c_off, int64_t nn, int chunk) {
+            if (mrows <= 0 || nn <= 0) return;
+            SLB_CUDA(cudaEventCreate(&gev[4 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[4 * k + slot + 1]));
+            SLB_CUDA(cudaEventRecord(gev[4 * k + slot], s));
+            Ops<T>::gemm(mrows, nn, jb, Lop, ldl, U + c_off * jb, jb, A + rbeg + (lcr + c_off) * lld, lld, s, chunk);
+            SLB_CUDA(cudaEventRecord(gev[4 * k + slot + 1], s));
+            gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
+        };
+        if (!have_next) { timed_gemm(0, 0, nright, 0); mark(); mark(); continue; }
+        const int pcn = (csrc + k + 1) % Q;
+        const int jbn = (mn - (j0 + jb)) < nb ? (mn - (j0 + jb)) : nb;
+        if (la) {
+            const int64_t nfirst = (mycol == pcn) ? (jbn < nright ? jbn : nright) : 0;
+            const int64_t rest = nright - nfirst;
+            const double rest_ms = 2.0 * (double)(mrows > 0 ? mrows : 0) * (double)rest * jb * Ops<T>::flop_mul / 28e12 * 1e3;
+            // the overlap decision must be the same on every rank of the grid: use the global trailing size
+            const double glob_ms = 2.0 * (double)(M - j0 - jb) / P * (double)(N - j0 - jb) / Q * jb * Ops<T>::flop_mul / 28e12 * 1e3;
+            const bool overlap = glob_ms >= overlap_min_ms;
+            (void)rest_ms;
+            timed_gemm(0, 0, nfirst, 0);                                  // next panel's columns first
+            SLB_CUDA(cudaEventRecord(evn[k], sm));
+            SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
+            panel_phase(k + 1, overlap ? gmax_opt : 0);
+            timed_gemm(2, nfirst, rest, overlap ? chunk_opt : 0);
+        } else {
+            timed_gemm(0, 0, nright, 0);
+            mark();
+            panel_phase(k + 1, 0);
+            mark();
+        }
     }
-    SLB_CUDA(cudaEventRecord(ev1, s));
-    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (sp != sm) SLB_CUDA(cudaStreamWaitEvent(sm, evp[nsteps - 1], 0));
+    SLB_CUDA(cudaEventRecord(ev1, sm));
+    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sm));
     int info_local = 0;
-    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-    SLB_CUDA(cudaStreamSynchronize(s));
+    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sm));
+    SLB_CUDA(cudaStreamSynchronize(sm));
+    if (sp != sm) SLB_CUDA(cudaStreamSynchronize(sp));
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g_last_lu.factor_ms = ms;
     g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
     for (int k = 0; k < nsteps; ++k) {
-        if (gev[2 * k]) {
-            float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[2 * k], gev[2 * k + 1]));
-            g_last_lu.update_ms += t; g_last_lu.update_flops += gflops[k]; g_last_lu.update_launches += 1;
-            cudaEventDestroy(gev[2 * k]); cudaEventDestroy(gev[2 * k + 1]);
-        }
+        for (int slot = 0; slot < 4; slot += 2)
+            if (gev[4 * k + slot]) {
+                float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[4 * k + slot], gev[4 * k + slot + 1]));
+                g_last_lu.update_ms += t; g_last_lu.update_launches += 1;
+                cudaEventDestroy(gev[4 * k + slot]); cudaEventDestroy(gev[4 * k + slot + 1]);
+            }
+        g_last_lu.update_flops += gflops[k];
     }
-    if (prof) {   // 5 marks per step: [panel][swap][trsm][gemm]
+    if (prof) {   // 5 marks per step: [swap][trsm][gemm][next panel]
         double tp = 0, tsw = 0, ttr = 0, tg = 0;
-        for (size_t i = 0; i + 4 < pev.size() + 1 && i + 4 < pev.size(); i += 5) {
+        for (size_t i = 0; i + 4 < pev.size(); i += 5) {
             float a, b, c, d;
             SLB_CUDA(cudaEventElapsedTime(&a, pev[i], pev[i + 1])); SLB_CUDA(cudaEventElapsedTime(&b, pev[i + 1], pev[i + 2]));
             SLB_CUDA(cudaEventElapsedTime(&c, pev[i + 2], pev[i + 3])); SLB_CUDA(cudaEventElapsedTime(&d, pev[i + 3], pev[i + 4]));
-            tp += a; tsw += b; ttr += c; tg += d;
+            tsw += a; ttr += b; tg += c; tp += d;
         }
         for (auto e : pev) cudaEventDestroy(e);
         counter_add("prof_panel_us", (int64_t)(tp * 1e3)); counter_add("prof_swap_us", (int64_t)(tsw * 1e3));
         counter_add("prof_trsm_us", (int64_t)(ttr * 1e3)); counter_add("prof_gemm_us", (int64_t)(tg * 1e3));
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    for (auto &e : evp) cudaEventDestroy(e);
+    for (auto &e : evn) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs);
     // INFO: first zero pivot is known on the diagonal owners only -> min over the grid (SRC/pdgetrf.f:297-302)
     int inf = info_local == 0 ? mn + 1 : info_local;
     inf = grid_imin(g, 'A', inf);

@@ -84,6 +84,7 @@ NcclComms *nccl_create(Grid *g)
     // same colours / keys as blacs_map_.c:114,118
     NCHECK(N.CommSplit(c->all, g->myrow, g->mycol, &c->row, nullptr));
     NCHECK(N.CommSplit(c->all, g->mycol, g->myrow, &c->col, nullptr));
+    NCHECK(N.CommSplit(c->all, g->mycol, g->myrow, &c->colp, nullptr));
     vlog(1, "NCCL %s communicators up: grid %dx%d me=(%d,%d)", N.version, g->nprow, g->npcol, g->myrow, g->mycol);
     return c;
 }
@@ -93,6 +94,7 @@ void nccl_destroy(NcclComms *c)
     if (!c) return;
     if (c->row) N.CommDestroy(c->row);
     if (c->col) N.CommDestroy(c->col);
+    if (c->colp) N.CommDestroy(c->colp);
     if (c->all) N.CommDestroy(c->all);
     delete c;
 }

@@ -12,6 +12,7 @@ typedef struct ncclComm *ncclComm_t_;
 
 struct NcclComms {
     ncclComm_t_ all = nullptr, row = nullptr, col = nullptr;
+    ncclComm_t_ colp = nullptr;     // second column communicator: panel phase on the look-ahead stream
 };
 
 enum NcclType { NT_U8 = 1, NT_I32 = 2, NT_F64 = 8 };   // values of ncclDataType_t

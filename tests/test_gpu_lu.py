@@ -171,3 +171,40 @@ def test_large_properties_n8192(S, O, ctx11):
     assert lu_err(lu, ref, a0) < 1.0
     assert np.all(ipiv >= np.arange(1, n + 1)) and np.all(ipiv <= n)
     assert np.abs(np.tril(lu, -1)).max() <= 1.0 + 1e-12        # partial pivoting bound |l_ij| <= 1
+
+
+def test_lookahead_is_bit_identical(S, O, ctx11):
+    """Look-ahead only reorders independent work (next panel's columns first, left swaps on a side stream): the
+    factors and pivots must be bit-identical to the serial schedule."""
+    n, nb = 3072, 256
+    a0 = O.matgen64_tile(n, 99, 0, n, 0, n)
+    outs = []
+    for la in (0, 1):
+        S.set_option("lookahead", la)
+        lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, nb, pad=0, device=True)
+        outs.append((np.array(lu), ipiv, info))
+    S.set_option("lookahead", 1)
+    assert outs[0][2] == outs[1][2] == 0
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
+    check_against_oracle(O, a0, outs[1][0], outs[1][1], 0, nb)
+
+
+@pytest.mark.parametrize("variant", [1, 3, 6, 7])
+def test_update_kernel_variants_agree(S, variant):
+    """Every DMMA update-kernel variant kept in gemm.cu computes the same C - A*B (same k order per element)."""
+    import ctypes as C
+    import subprocess, sys, os
+    code = (
+        "import numpy as np, ctypes as C, scalapack_b200 as S\n"
+        "rng=np.random.default_rng(5); M,N,K=777,1030,200\n"
+        "A=np.asfortranarray(rng.uniform(-1,1,(M,K))); B=np.asfortranarray(rng.uniform(-1,1,(K,N))); Cm=np.asfortranarray(rng.uniform(-1,1,(M,N)))\n"
+        "ref=Cm-A@B; out=Cm.copy(order='F'); I=C.c_int64\n"
+        "S.lib().slb200_test_gemm(I(M),I(N),K,S.api._ptr(A),I(M),S.api._ptr(B),I(K),S.api._ptr(out),I(M),0,1)\n"
+        "print('ERR', float(np.abs(out-ref).max()))\n")
+    env = dict(os.environ, SLB200_GEMM_VARIANT=str(variant))
+    p = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    err = float([l for l in p.stdout.splitlines() if l.startswith("ERR")][0].split()[1])
+    assert err < 1e-12, err
