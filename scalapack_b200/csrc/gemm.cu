@@ -267,6 +267,17 @@ __device__ __forceinline__ void tile_coords(int64_t t, int tiles_m, int tiles_n,
     n0 = (int64_t)(r / gm) * BN;
 }
 
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int &m0, int &n0)
+{
+    int group_sz = GROUP_M * tiles_n;
+    int grp = t / group_sz;
+    int first_m = grp * GROUP_M;
+    int gm = min(GROUP_M, tiles_m - first_m);
+    int r = t - grp * group_sz;
+    m0 = (first_m + r % gm) * BM;
+    n0 = (r / gm) * BN;
+}
+
 template <int VEC, int PBK, int PST, int LOAD_MID>
 __global__ void __launch_bounds__(P_THREADS, 1)
 dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
@@ -683,6 +694,151 @@ dgemm_minus_p8b(int64_t M, int64_t N, int K, const double *__restrict__ A, int64
     cp_async_wait<0>();
 }
 
+// ---- v8: v7's schedule (mid-stage barrier, fragments double-buffered across stage and tile boundaries) with 16 warps
+// of 32 x 32 (4 per scheduler, <= 128 registers).  ncu on v7 (profiles/r01_gemm_v7_ncu.md): each of the 2 warps per
+// scheduler sits ~40 % of the time in the fixed issue stall that follows every DMMA, so ~0.4^2 = 16 % of the cycles no
+// warp can feed the pipe (measured: 83 % busy).  With 4 warps per scheduler that probability is ~3 %. --------
+template <int VEC>
+__global__ void __launch_bounds__(P_THREADS, 1)
+dgemm_minus_p16(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+                int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;
+    double *Bs = smem + STAGES * AS_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;      // 4 x 4 warps, 32 x 32 each
+
+    const int ntiles = tiles_m * tiles_n;                       // host guarantees < 2^31 (and total stages < 2^31)
+    const int KT = (K + BK - 1) / BK;
+    const int t_first = chunk > 0 ? (int)blockIdx.x * chunk : (int)blockIdx.x;
+    const int t_stride = chunk > 0 ? 1 : (int)gridDim.x;
+    const int my_tiles = chunk > 0 ? max(0, min(chunk, ntiles - t_first)) : (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * KT;
+
+    int l_lt = 0; int l_kt = 0; int l_m0 = 0, l_n0 = 0;
+    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
+    auto issue_load = [&](int li) {
+        if (li < total) {
+            int st = li % STAGES;
+            load_stage_p<VEC, BK>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, l_m0, l_n0, l_kt * BK, M, N, K, tid);
+            if (++l_kt == KT) {
+                l_kt = 0; ++l_lt;
+                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue_load(s);
+
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+    double fa[2][2][2], fb[2][4];
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (total > 0) {
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf) {
+            fa[0][nf][0] = Bs[(wn0 + nf * 16 + g) * SB + tig];
+            fa[0][nf][1] = Bs[(wn0 + nf * 16 + g + 8) * SB + tig];
+        }
+#pragma unroll
+        for (int mf = 0; mf < 4; ++mf) fb[0][mf] = As[tig * SA + wm0 + mf * 8 + g];
+    }
+    int kt = 0; int lt = 0; int m0 = 0, n0 = 0;
+    for (int ci = 0; ci < total; ++ci) {
+        if (kt == 0) {
+            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int mq = 0; mq < 2; ++mq) {
+                        int n = n0 + wn0 + nf * 16 + g + h * 8;
+                        int m = m0 + wm0 + mq * 16 + 2 * tig;
+                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + (int64_t)n * ldc));
+                    }
+        }
+        const double *as = As + (ci % STAGES) * AS_STAGE;
+        const double *bs = Bs + (ci % STAGES) * BS_STAGE;
+        const double *asn = As + ((ci + 1) % STAGES) * AS_STAGE;
+        const double *bsn = Bs + ((ci + 1) % STAGES) * BS_STAGE;
+#pragma unroll
+        for (int s4 = 0; s4 < BK / 4; ++s4) {
+            if (s4 == 1) {
+                cp_async_wait<STAGES - 3>();
+                __syncthreads();
+                issue_load(ci + STAGES - 1);
+            }
+            const int cur = s4 & 1, nxt = cur ^ 1;
+            if (s4 + 1 < BK / 4) {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf) {
+                    fa[nxt][nf][0] = bs[(wn0 + nf * 16 + g) * SB + (s4 + 1) * 4 + tig];
+                    fa[nxt][nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + (s4 + 1) * 4 + tig];
+                }
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) fb[nxt][mf] = as[((s4 + 1) * 4 + tig) * SA + wm0 + mf * 8 + g];
+            } else if (ci + 1 < total) {
+#pragma unroll
+                for (int nf = 0; nf < 2; ++nf) {
+                    fa[nxt][nf][0] = bsn[(wn0 + nf * 16 + g) * SB + tig];
+                    fa[nxt][nf][1] = bsn[(wn0 + nf * 16 + g + 8) * SB + tig];
+                }
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) fb[nxt][mf] = asn[tig * SA + wm0 + mf * 8 + g];
+            }
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) dmma_16x8x4(acc[nf][mf], fa[cur][nf][0], fa[cur][nf][1], fb[cur][mf]);
+        }
+        if (++kt == KT) {
+            kt = 0; ++lt;
+#pragma unroll
+            for (int nf = 0; nf < 2; ++nf) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                     // batches of 4 x 16 B keep the kernel within 128 registers
+                    const int n = n0 + wn0 + nf * 16 + g + h * 8;
+                    double *cp = C + (int64_t)n * ldc;
+                    double2 cv[4];
+#pragma unroll
+                    for (int mf = 0; mf < 4; ++mf) {
+                        int m = m0 + wm0 + mf * 8 + 2 * tig;
+                        if (VEC == 2 && n < N && m + 1 < M) cv[mf] = *reinterpret_cast<const double2 *>(cp + m);
+                        else if (n < N && m < M) cv[mf] = make_double2(cp[m], (m + 1 < M) ? cp[m + 1] : 0.0);
+                        else cv[mf] = make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int mf = 0; mf < 4; ++mf) {
+                        int m = m0 + wm0 + mf * 8 + 2 * tig;
+                        double2 c = cv[mf];
+                        c.x -= acc[nf][mf][2 * h]; c.y -= acc[nf][mf][2 * h + 1];
+                        if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(cp + m) = c;
+                        else if (n < N && m < M) { cp[m] = c.x; if (m + 1 < M) cp[m + 1] = c.y; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ---- complex: C -= A*B with interleaved (re,im); four real DMMAs per complex MMA ---------------------
 // Tiling: CTA 64(m) x 64(n) x 16(k) complex, 8 warps as 2(m) x 4(n), warp tile 32 x 16.
 constexpr int ZBM = 64, ZBN = 64, ZBK = 16;
@@ -820,12 +976,17 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
         SET_ATTR((dgemm_minus_persistent<2, 32, 3, 1>), smem32);
         SET_ATTR((dgemm_minus_p8<2>), smem16); SET_ATTR((dgemm_minus_p8<1>), smem16);
         SET_ATTR((dgemm_minus_p8b<2>), smem16); SET_ATTR((dgemm_minus_p8b<1>), smem16);
+        SET_ATTR((dgemm_minus_p16<2>), smem16); SET_ATTR((dgemm_minus_p16<1>), smem16);
 #undef SET_ATTR
     }
     if (variant >= 2) {
         unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
         if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
-        if (variant == 7 && aligned)
+        if (variant == 8 && aligned)
+            dgemm_minus_p16<2><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (variant == 8)
+            dgemm_minus_p16<1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
+        else if (variant == 7 && aligned)
             dgemm_minus_p8b<2><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
         else if (variant == 7)
             dgemm_minus_p8b<1><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);

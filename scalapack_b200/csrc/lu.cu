@@ -60,7 +60,7 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
     T *Ubuf = (T *)workspace("lu_U", (size_t)nb * N * sizeof(T));
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * N * sizeof(T));
-    const int gmax_opt = (int)opt("panel_gmax", 48), chunk_opt = (int)opt("gemm_chunk", 8);
+    const int gmax_opt = (int)opt("panel_gmax", 32), chunk_opt = (int)opt("gemm_chunk", 4);
     const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
 
     cudaEvent_t ev0, ev1, evs;
@@ -176,7 +176,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     // high-priority panel stream with its own column communicator while the update stream finishes step k
     const bool la = multi && opt("lookahead", 1) != 0 && opt("lookahead_multi", 1) != 0 && !prof;
     cudaStream_t sm = r.s_main, sp = la ? r.s_panel : r.s_main;
-    const int gmax_opt = (int)opt("panel_gmax", 48), chunk_opt = (int)opt("gemm_chunk", 8);
+    const int gmax_opt = (int)opt("panel_gmax", 32), chunk_opt = (int)opt("gemm_chunk", 4);
     const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
 
     // ---- workspaces ----

@@ -349,6 +349,8 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
 {
     if (m <= 0 || jb <= 0) return;
     PanelCtx<T> c;
+    // look-ahead mode caps the CTAs; if the slabs of so few CTAs cannot hold m rows, allow more (0 = whole GPU)
+    while (gmax > 0 && leaf_rpb<T, 8>(m, gmax) == 0) gmax = (2 * gmax >= rt().sm_count) ? 0 : 2 * gmax;
     c.gmax = gmax;
     c.m = m; c.W = pick_leaf_width<T>(m, gmax); c.Wp = Wp; c.ldw = ldw; c.map = map; c.ipiv = ipiv_out; c.info = info_out;
     c.info_offset = info_offset; c.work = work; c.s = s;

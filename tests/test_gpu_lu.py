@@ -190,7 +190,7 @@ def test_lookahead_is_bit_identical(S, O, ctx11):
     check_against_oracle(O, a0, outs[1][0], outs[1][1], 0, nb)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 6, 7])
+@pytest.mark.parametrize("variant", [1, 3, 6, 7, 8])
 def test_update_kernel_variants_agree(S, variant):
     """Every DMMA update-kernel variant kept in gemm.cu computes the same C - A*B (same k order per element)."""
     import ctypes as C
