@@ -951,10 +951,21 @@ zgemm_minus_kernel(int64_t M, int64_t N, int K, const zcomplex *__restrict__ A, 
 
 }  // namespace
 
+bool dgemm_takes_packed(int64_t M, int K, int flags)
+{
+    static int64_t variant = -1, min_m = 0;
+    if (variant < 0) { variant = opt("gemm_variant", 9); min_m = opt("gemm_packed_min", 3072); }
+    return variant == 9 && (flags & GEMM_MAIN) && M >= min_m && K >= 16;
+}
+
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
-                        double *C, int64_t ldc, cudaStream_t s, int chunk)
+                        double *C, int64_t ldc, cudaStream_t s, int chunk, int flags)
 {
     if (M <= 0 || N <= 0 || K <= 0) return;
+    if (dgemm_takes_packed(M, K, flags)) {
+        launch_dgemm_minus_packed(M, N, K, A, lda, B, ldb, C, ldc, s, chunk, (flags & GEMM_REUSE_A) != 0);
+        return;
+    }
     static bool attr_done = false;
     const size_t smem_bytes = (size_t)STAGES * (AS_STAGE + BS_STAGE) * sizeof(double);
     if (!attr_done) {
@@ -969,7 +980,8 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
     static int variant = -1;
     constexpr size_t smem16 = (size_t)4 * (16 * SA + BN * 20) * sizeof(double), smem32 = (size_t)3 * (32 * SA + BN * 36) * sizeof(double);
     if (variant < 0) {
-        variant = (int)opt("gemm_variant", 7);
+        variant = (int)opt("gemm_variant", 9);
+        if (variant == 9) variant = 7;                     // 9 = packed kernel for the big updates, v7 for everything else
 #define SET_ATTR(K, bytes) SLB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
         SET_ATTR((dgemm_minus_persistent<2, 16, 4, 0>), smem16); SET_ATTR((dgemm_minus_persistent<1, 16, 4, 0>), smem16);
         SET_ATTR((dgemm_minus_persistent<2, 16, 4, 1>), smem16); SET_ATTR((dgemm_minus_persistent<2, 32, 3, 0>), smem32);

@@ -11,8 +11,14 @@ typedef double2 zcomplex;   // COMPLEX*16 as (re, im)
 // ---- trailing update (replaces PDGEMM 'N','N', alpha=-1, beta=1; PBLAS/SRC/PTOOLS/PB_CpgemmAB.c:345) ----
 // C[M x N] -= A[M x K] * B[K x N].  FP64 tensor cores (DMMA mma.sync m16n8k4), cp.async 4-stage pipeline.
 // chunk > 0: each CTA processes `chunk` tiles and retires (lets a higher-priority stream interleave); 0: persistent.
+// flags: GEMM_MAIN = the big trailing update on the main stream: may take the packed-operand kernel (gemm_packed.cu,
+// one pack workspace, so one stream only); GEMM_REUSE_A = the previous GEMM_MAIN call packed this very A (same step).
+enum { GEMM_MAIN = 1, GEMM_REUSE_A = 2 };
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
-                        double *C, int64_t ldc, cudaStream_t s, int chunk = 0);
+                        double *C, int64_t ldc, cudaStream_t s, int chunk = 0, int flags = 0);
+bool dgemm_takes_packed(int64_t M, int K, int flags);   // the decision launch_dgemm_minus makes (depends on M, K only)
+void launch_dgemm_minus_packed(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
+                               double *C, int64_t ldc, cudaStream_t s, int chunk, bool reuse_a);
 void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
                         zcomplex *C, int64_t ldc, cudaStream_t s);
 

@@ -22,16 +22,18 @@ namespace slb {
 
 template <typename T> struct Ops;
 template <> struct Ops<double> {
-    static void gemm(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s, int chunk = 0)
-    { launch_dgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s, chunk); }
+    static void gemm(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s, int chunk = 0, int flags = 0)
+    { launch_dgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s, chunk, flags); }
+    static bool packs(int64_t M, int K) { return dgemm_takes_packed(M, K, GEMM_MAIN); }
     static void trsm(int jb, int64_t n, const double *L, int64_t ldl, double *B, int64_t ldb, cudaStream_t s) { launch_dtrsm_llnu(jb, n, L, ldl, B, ldb, s); }
     static void panel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax = 0)
     { launch_dpanel(m, jb, W, ldw, map, ipiv, info, off, work, s, gmax); }
     static constexpr double flop_mul = 1.0;
 };
 template <> struct Ops<zcomplex> {
-    static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s, int chunk = 0)
-    { (void)chunk; launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s, int chunk = 0, int flags = 0)
+    { (void)chunk; (void)flags; launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
+    static bool packs(int64_t, int) { return false; }
     static void trsm(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t s) { launch_ztrsm_llnu(jb, n, L, ldl, B, ldb, s); }
     static void panel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax = 0)
     { launch_zpanel(m, jb, W, ldw, map, ipiv, info, off, work, s, gmax); }
@@ -112,10 +114,12 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
         const T *Lop = Wp + jb;
         T *C = A + cr + cr * lld;
         const bool have_next = k + 1 < nsteps;
+        bool a_packed = false;                                           // L21 of this step already in packed form
         auto timed_gemm = [&](int slot, int64_t nn, const T *Bp, T *Cp, int chunk) {
             SLB_CUDA(cudaEventCreate(&gev[4 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[4 * k + slot + 1]));
             SLB_CUDA(cudaEventRecord(gev[4 * k + slot], sm));
-            Ops<T>::gemm(mrows, nn, jb, Lop, lld, Bp, jb, Cp, lld, sm, chunk);
+            Ops<T>::gemm(mrows, nn, jb, Lop, lld, Bp, jb, Cp, lld, sm, chunk, GEMM_MAIN | (a_packed ? GEMM_REUSE_A : 0));
+            a_packed = Ops<T>::packs(mrows, jb);
             SLB_CUDA(cudaEventRecord(gev[4 * k + slot + 1], sm));
             gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
         };
@@ -362,11 +366,13 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         }
         // =============== trailing update (+ hand-over of the next panel's columns) ===============
         mark();
+        bool a_packed = false;
         auto timed_gemm = [&](int slot, int64_t c_off, int64_t nn, int chunk) {
             if (mrows <= 0 || nn <= 0) return;
             SLB_CUDA(cudaEventCreate(&gev[4 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[4 * k + slot + 1]));
             SLB_CUDA(cudaEventRecord(gev[4 * k + slot], s));
-            Ops<T>::gemm(mrows, nn, jb, Lop, ldl, U + c_off * jb, jb, A + rbeg + (lcr + c_off) * lld, lld, s, chunk);
+            Ops<T>::gemm(mrows, nn, jb, Lop, ldl, U + c_off * jb, jb, A + rbeg + (lcr + c_off) * lld, lld, s, chunk, GEMM_MAIN | (a_packed ? GEMM_REUSE_A : 0));
+            a_packed = Ops<T>::packs(mrows, jb);
             SLB_CUDA(cudaEventRecord(gev[4 * k + slot + 1], s));
             gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
         };

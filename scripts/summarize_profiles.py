@@ -73,6 +73,14 @@ if __name__ == "__main__":
     ncu_raw("prof_gemm_v2.ncu-rep", "r01: trailing-update kernel v2 (dgemm_minus_persistent, 16 warps, persistent)", "r01_gemm_v2_ncu.md",
             "M=N=16384, K=512. DMMA pipe 72.7 % busy; 11 % of samples at the per-stage block barrier -> load issue moved mid-stage (variant 3: 29.7 TFLOP/s).")
     ncu_raw("prof_gemm_v3.ncu-rep", "r01: trailing-update kernel v3", "r01_gemm_v3_ncu.md")
+    ncu_raw("prof_gemm_v7.ncu-rep", "r01: trailing-update kernel v7 (dgemm_minus_p8b, 8 warps of 64x32, mid-stage barrier)", "r01_gemm_v7_ncu.md",
+            "M=N=32768, K=512 (one launch, 35.6 ms under ncu = 30.9 TFLOP/s). DMMA pipe 83.2 % busy. DRAM traffic 11.14 GB read + 8.54 GB written = 19.7 GB "
+            "for 17.45 GB of algorithmic bytes (16*M*N for C + 8*(M+N)*K for the operands): 1.13x, the A/B re-reads are served by L2.\n\n"
+            "PC-sampling split of the 2.52 M warp samples (ncu --page source): main loop 84.2 % (stall_wait 36 %, math_pipe_throttle 32 %, selected 8 %), "
+            "the 227 address/LDGSTS instructions each warp executes per k-stage 10.0 %, the per-tile epilogue + C prefetch 5.2 % (long_scoreboard), "
+            "block barrier 0.7 %. -> generation 9 (gemm_packed.cu) removes the per-thread load code (bulk copies of pre-packed blocks issued by one thread), "
+            "the block barrier (mbarriers) and de-phases the two warps of a scheduler so epilogues overlap the other warp's main loop.")
+    launches("launches_n16384.csv", "r01_launches_n16384_v7.md", "r01: launch list of `bench.py --size 16384 --steps 1 --warmup 0` with update kernel v7 and look-ahead")
     launches("launches_n8192.csv", "r01_launches_n8192.md", "r01: launch list of `bench.py --n 8192 --steps 1` (1 GPU)",
              "dmma/dfma_peak_kernel are the roofline micro-benchmarks bench.py runs after the timed region.")
     launches("launches_full.csv", "r01_launches_n65536.md", "r01: launch list of the default bench (N=65536)")

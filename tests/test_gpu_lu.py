@@ -190,21 +190,42 @@ def test_lookahead_is_bit_identical(S, O, ctx11):
     check_against_oracle(O, a0, outs[1][0], outs[1][1], 0, nb)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 6, 7, 8])
-def test_update_kernel_variants_agree(S, variant):
-    """Every DMMA update-kernel variant kept in gemm.cu computes the same C - A*B (same k order per element)."""
-    import ctypes as C
+def _gemm_in_subprocess(env_extra, M, N, K, tmp_path, tag):
+    """C - A*B through slb200_test_gemm in a fresh process (kernel variant options are read once per process)."""
     import subprocess, sys, os
+    out = str(tmp_path / f"gemm_{tag}.npy")
     code = (
         "import numpy as np, ctypes as C, scalapack_b200 as S\n"
-        "rng=np.random.default_rng(5); M,N,K=777,1030,200\n"
+        f"rng=np.random.default_rng(5); M,N,K={M},{N},{K}\n"
         "A=np.asfortranarray(rng.uniform(-1,1,(M,K))); B=np.asfortranarray(rng.uniform(-1,1,(K,N))); Cm=np.asfortranarray(rng.uniform(-1,1,(M,N)))\n"
         "ref=Cm-A@B; out=Cm.copy(order='F'); I=C.c_int64\n"
         "S.lib().slb200_test_gemm(I(M),I(N),K,S.api._ptr(A),I(M),S.api._ptr(B),I(K),S.api._ptr(out),I(M),0,1)\n"
+        f"np.save(r'{out}', out)\n"
         "print('ERR', float(np.abs(out-ref).max()))\n")
-    env = dict(os.environ, SLB200_GEMM_VARIANT=str(variant))
+    env = dict(os.environ, **{k: str(v) for k, v in env_extra.items()})
     p = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env,
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     err = float([l for l in p.stdout.splitlines() if l.startswith("ERR")][0].split()[1])
+    return np.load(out), err
+
+
+@pytest.mark.parametrize("variant", [1, 3, 6, 7, 8])
+def test_update_kernel_variants_agree(S, variant, tmp_path):
+    """Every DMMA update-kernel variant kept in gemm.cu computes the same C - A*B (same k order per element)."""
+    _, err = _gemm_in_subprocess({"SLB200_GEMM_VARIANT": variant}, 777, 1030, 200, tmp_path, f"v{variant}")
     assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("opts", [{}, {"SLB200_GEMM_LAG": 0}, {"SLB200_GEMM_EPI": 1}, {"SLB200_GEMM_TEST_CHUNK": 3}])
+@pytest.mark.parametrize("shape", [(777, 1030, 200), (2048, 2304, 512), (130, 5000, 37)])
+def test_packed_update_kernel_is_bit_identical_to_v7(S, opts, shape, tmp_path):
+    """gemm_packed.cu (fragment-ordered operands, bulk-copy ring, mbarriers) vs the cp.async kernel: same bits, on ragged
+    shapes (zero-padded blocks), with the late-start lag off, with the red.add epilogue and with chunked CTAs."""
+    M, N, K = shape
+    ref, err7 = _gemm_in_subprocess({"SLB200_GEMM_VARIANT": 7}, M, N, K, tmp_path, "v7")
+    env = {"SLB200_GEMM_VARIANT": 9, "SLB200_GEMM_PACKED_MIN": 1}
+    env.update(opts)
+    out, err9 = _gemm_in_subprocess(env, M, N, K, tmp_path, "v9")
+    assert err7 < 1e-11 and err9 < 1e-11, (err7, err9)
+    assert np.array_equal(out, ref)
