@@ -44,15 +44,24 @@ LuStats g_last_lu;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// ---- 1 x 1 grid with look-ahead: panel k+1 (high-priority stream, few SMs) under the trailing update of step k ----
-// The reference's loop is strictly serial (SRC/pdgetrf.f:254-295).  Here step k first updates only the next panel's
-// columns, hands them to the panel stream, and updates the rest of the trailing matrix with a CHUNKED DMMA kernel
-// whose CTAs retire every few tiles so the panel's kernels (<= gmax CTAs, launched non-cooperatively) find SMs.
+// ---- 1 x 1 grid: look-ahead + two-half software pipeline --------------------------------------------------------
+// The reference's loop is strictly serial (SRC/pdgetrf.f:254-295).  Here four streams run one step's phases against
+// the previous step's trailing update:
+//   sp (highest priority)  panel k+1 (+ its interchange plan) as soon as the update of step k has done the next
+//                          panel's columns;
+//   sq (high)              "prep" = row interchanges (PDLASWP, right part) + U12 solve (PDTRSM) of step k, in two column
+//                          halves: near = [cr, b), far = [b, N);
+//   sg (low)               the DMMA update (PDGEMM) of step k: next panel's columns, rest of near, far -- with CHUNKED CTAs
+//                          that retire every few tiles so the kernels of sp / sq find SMs;
+//   sc (high)              interchanges of the already factored columns [0, j0) (nothing reads them again).
+// prep_k(near) runs under update_{k-1}(far), prep_k(far) under update_k(near): the HBM-latency-bound interchanges and the
+// launch-latency-bound U12 solve leave the critical path, which becomes  update_k(near) + update_k(far)  per step.
+// The boundary b only moves when near has shrunk below a quarter of the trailing columns (then one step waits for both halves).
 template <typename T>
 static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host)
 {
     Runtime &r = rt();
-    cudaStream_t sm = r.s_main, sp = r.s_panel, sc = r.s_copy;
+    cudaStream_t sg = r.s_main, sp = r.s_panel, sc = r.s_copy, sq = r.s_prep;
     const int mn = M < N ? M : N;
     const int nsteps = (mn + nb - 1) / nb;
     int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
@@ -64,100 +73,176 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * N * sizeof(T));
     const int gmax_opt = (int)opt("panel_gmax", 32), chunk_opt = (int)opt("gemm_chunk", 4);
     const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
+    const bool pipe = opt("la_pipeline", 1) != 0;
+    const int64_t split_min = opt("la_split_min", 6144);      // fewer trailing columns: the step is not split
+    const bool trace = opt("la_trace", 0) != 0;               // per-step timeline on stderr
 
+    auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
     cudaEvent_t ev0, ev1, evs;
     SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1)); SLB_CUDA(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
-    std::vector<cudaEvent_t> evp((size_t)nsteps + 1), evn((size_t)nsteps + 1), evq((size_t)nsteps + 1), evl((size_t)nsteps + 1), gev((size_t)4 * nsteps, nullptr);
-    for (auto &e : evp) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : evn) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : evq) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : evl) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> evp, evn, evl, pdp, pdn, pdf, gdn, gdf;
+    mkev(evp, (size_t)nsteps + 1); mkev(evn, (size_t)nsteps + 1); mkev(evl, (size_t)nsteps + 1);
+    mkev(pdp, (size_t)nsteps); mkev(pdn, (size_t)nsteps); mkev(pdf, (size_t)nsteps); mkev(gdn, (size_t)nsteps); mkev(gdf, (size_t)nsteps);
+    std::vector<cudaEvent_t> gev((size_t)6 * nsteps, nullptr), eva((size_t)nsteps, nullptr);
     std::vector<double> gflops((size_t)nsteps, 0.0);
 
-    SLB_CUDA(cudaEventRecord(ev0, sm));
-    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), sm));
-    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), sm));
-    SLB_CUDA(cudaEventRecord(evs, sm));
-    SLB_CUDA(cudaStreamWaitEvent(sp, evs, 0));
+    SLB_CUDA(cudaEventRecord(ev0, sg));
+    SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), sg));
+    SLB_CUDA(cudaMemsetAsync(ipiv_dev, 0, (size_t)(mn + nb) * sizeof(int), sg));
+    SLB_CUDA(cudaEventRecord(evs, sg));
+    SLB_CUDA(cudaStreamWaitEvent(sp, evs, 0)); SLB_CUDA(cudaStreamWaitEvent(sq, evs, 0)); SLB_CUDA(cudaStreamWaitEvent(sc, evs, 0));
     RowDist rd{ nb, 1, 0, 0, 0 };
+    // panel k and its interchange plan; plan buffer k&1 was last read by step k-2 (prep on sq: ordered before this
+    // through pdf/pdn -> sg -> evn[k-1] -> sp; left interchanges on sc: evl[k-2])
     auto run_panel = [&](int k, int gmax) {
         const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
         PanelRowMap map{ j0, nb, 1, 0 };
         Ops<T>::panel(M - j0, jb, A + j0 + (int64_t)j0 * lld, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, sp, gmax);
+        if (k >= 2) SLB_CUDA(cudaStreamWaitEvent(sp, evl[k - 2], 0));
+        launch_swap_plan(j0, jb, ipiv_dev + j0, plans[k & 1], sp);
         SLB_CUDA(cudaEventRecord(evp[k], sp));
     };
     run_panel(0, 0);
+    int64_t b = -1;                 // absolute column of the near | far boundary of the previous step (-1: none yet)
+    bool far_prev = false;          // the previous step had a far half
+    cudaEvent_t last_gemm = nullptr;   // completion of the previous step's update (all of it)
     for (int k = 0; k < nsteps; ++k) {
         const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
         T *Wp = A + j0 + (int64_t)j0 * lld;
-        SLB_CUDA(cudaStreamWaitEvent(sm, evp[k], 0));
-        if (k >= 2) SLB_CUDA(cudaStreamWaitEvent(sm, evl[k - 2], 0));          // plan buffer k&1 is free again
         SwapPlan plan = plans[k & 1];
-        launch_swap_plan(j0, jb, ipiv_dev + j0, plan, sm);
         const int64_t cr = j0 + jb, nright = N - cr;
-        // interchanges on the already-factored columns [0, j0): nothing on the critical path reads them again, so
-        // they run on the copy stream (ordered among themselves), off the critical path
-        SLB_CUDA(cudaEventRecord(evq[k], sm));
-        SLB_CUDA(cudaStreamWaitEvent(sc, evq[k], 0));
-        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
-        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
-        launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
-        SLB_CUDA(cudaEventRecord(evl[k], sc));
-        launch_swap_pack<T>(jb, j0, plan, rd, A, lld, cr, N, Ubuf + cr * jb, jb, Obuf + cr * jb, jb, sm);
-        launch_swap_unpack_out<T>(jb, plan, rd, A, lld, cr, N, Obuf + cr * jb, jb, sm);
-        if (nright <= 0) continue;
-        T *U = Ubuf + cr * jb;
-        Ops<T>::trsm(jb, nright, Wp, lld, U, jb, sm);
-        launch_copy2d<T>(jb, nright, U, jb, A + j0 + cr * lld, lld, sm);
         const int64_t mrows = M - cr;
-        if (mrows <= 0) continue;
+        const bool have_next = k + 1 < nsteps && mrows > 0 && nright > 0;
+        const int jbn = have_next ? ((mn - (int)cr) < nb ? (mn - (int)cr) : nb) : 0;
+        // ---- sc: interchanges on the already factored columns [0, j0).  Columns [j0 - nb, j0) are the L21 operand of
+        // the previous step's update: wait for all of it; and stay out of the way of this step's g0 (evn[k]).
+        auto left_swaps = [&]() {
+            SLB_CUDA(cudaStreamWaitEvent(sc, evp[k], 0));
+            if (last_gemm) SLB_CUDA(cudaStreamWaitEvent(sc, last_gemm, 0));
+            if (have_next) SLB_CUDA(cudaStreamWaitEvent(sc, evn[k], 0));
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
+            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
+            launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
+            SLB_CUDA(cudaEventRecord(evl[k], sc));
+        };
+        if (nright <= 0) { left_swaps(); continue; }
+        // ---- near | far boundary ----
+        int64_t bk = N;
+        bool resplit = false;
+        if (pipe && have_next && nright >= split_min) {
+            if (b < 0 || b - cr < nright / 4 || b >= N) { bk = cr + ((nright / 2 + nb - 1) / nb) * nb; resplit = true; }
+            else bk = b;
+            if (bk >= N) bk = N;
+        }
+        if (bk > b || b < 0) resplit = true;          // near grows into the previous far half (or there was no split)
+        auto prep = [&](int64_t c_lo, int64_t c_hi) {
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, Obuf + c_lo * jb, jb, sq);
+            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c_lo, c_hi, Obuf + c_lo * jb, jb, sq);
+            Ops<T>::trsm(jb, c_hi - c_lo, Wp, lld, Ubuf + c_lo * jb, jb, sq);
+            launch_copy2d<T>(jb, c_hi - c_lo, Ubuf + c_lo * jb, jb, A + j0 + c_lo * lld, lld, sq);
+        };
         const T *Lop = Wp + jb;
-        T *C = A + cr + cr * lld;
-        const bool have_next = k + 1 < nsteps;
         bool a_packed = false;                                           // L21 of this step already in packed form
-        auto timed_gemm = [&](int slot, int64_t nn, const T *Bp, T *Cp, int chunk) {
-            SLB_CUDA(cudaEventCreate(&gev[4 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[4 * k + slot + 1]));
-            SLB_CUDA(cudaEventRecord(gev[4 * k + slot], sm));
-            Ops<T>::gemm(mrows, nn, jb, Lop, lld, Bp, jb, Cp, lld, sm, chunk, GEMM_MAIN | (a_packed ? GEMM_REUSE_A : 0));
+        auto timed_gemm = [&](int slot, int64_t c_lo, int64_t c_hi, bool may_chunk) {
+            const int64_t nn = c_hi - c_lo;
+            if (mrows <= 0 || nn <= 0) return;
+            const double est_ms = 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul / 30e12 * 1e3;
+            const int chunk = (may_chunk && est_ms >= overlap_min_ms * 0.5) ? chunk_opt : 0;
+            SLB_CUDA(cudaEventCreate(&gev[6 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[6 * k + slot + 1]));
+            SLB_CUDA(cudaEventRecord(gev[6 * k + slot], sg));
+            Ops<T>::gemm(mrows, nn, jb, Lop, lld, Ubuf + c_lo * jb, jb, A + cr + c_lo * lld, lld, sg, chunk, GEMM_MAIN | (a_packed ? GEMM_REUSE_A : 0));
             a_packed = Ops<T>::packs(mrows, jb);
-            SLB_CUDA(cudaEventRecord(gev[4 * k + slot + 1], sm));
+            SLB_CUDA(cudaEventRecord(gev[6 * k + slot + 1], sg));
             gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
         };
-        if (!have_next) { timed_gemm(0, nright, U, C, 0); continue; }
-        const int jbn = (mn - (int)cr) < nb ? (mn - (int)cr) : nb;
-        const int64_t rest = nright - jbn;
-        const double rest_ms = 2.0 * (double)mrows * (double)rest * jb * Ops<T>::flop_mul / 28e12 * 1e3;
-        const bool overlap = rest > 0 && rest_ms >= overlap_min_ms;
-        timed_gemm(0, jbn, U, C, 0);                                      // next panel's columns first
-        SLB_CUDA(cudaEventRecord(evn[k], sm));
-        SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
-        run_panel(k + 1, overlap ? gmax_opt : 0);
-        if (rest > 0) timed_gemm(2, rest, U + (int64_t)jbn * jb, C + (int64_t)jbn * lld, overlap ? chunk_opt : 0);
+        // ---- (a) sq: prep of the near half, the next panel's columns first (shortest path to panel k+1) ----
+        SLB_CUDA(cudaStreamWaitEvent(sq, evp[k], 0));
+        if (k > 0) SLB_CUDA(cudaStreamWaitEvent(sq, gdn[k - 1], 0));
+        if (k > 0 && far_prev && resplit) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+        if (jbn > 0 && cr + jbn < bk) {
+            prep(cr, cr + jbn);
+            SLB_CUDA(cudaEventRecord(pdp[k], sq));
+            prep(cr + jbn, bk);
+        } else {
+            prep(cr, bk);
+            SLB_CUDA(cudaEventRecord(pdp[k], sq));
+        }
+        SLB_CUDA(cudaEventRecord(pdn[k], sq));
+        // ---- (b) sg: next panel's columns, then hand them to the panel stream ----
+        SLB_CUDA(cudaStreamWaitEvent(sg, pdp[k], 0));
+        if (trace) { SLB_CUDA(cudaEventCreate(&eva[k])); SLB_CUDA(cudaEventRecord(eva[k], sg)); }
+        if (have_next) {
+            const double rest_ms = 2.0 * (double)mrows * (double)(nright - jbn) * jb * Ops<T>::flop_mul / 30e12 * 1e3;
+            const bool overlap = nright - jbn > 0 && rest_ms >= overlap_min_ms;
+            timed_gemm(0, cr, cr + jbn, false);
+            SLB_CUDA(cudaEventRecord(evn[k], sg));
+            SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
+            run_panel(k + 1, overlap ? gmax_opt : 0);
+        }
+        // ---- (c) sc: left interchanges; (d) sq: prep of the far half -- both only after g0 (they would take its SMs) ----
+        left_swaps();
+        if (bk < N) {
+            if (k > 0 && far_prev) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+            if (have_next) SLB_CUDA(cudaStreamWaitEvent(sq, evn[k], 0));
+            prep(bk, N);
+            SLB_CUDA(cudaEventRecord(pdf[k], sq));
+        }
+        // ---- (e) sg: rest of near, far ----
+        SLB_CUDA(cudaStreamWaitEvent(sg, pdn[k], 0));
+        timed_gemm(2, cr + jbn, bk, have_next);
+        SLB_CUDA(cudaEventRecord(gdn[k], sg));
+        last_gemm = gdn[k];
+        if (bk < N) {
+            SLB_CUDA(cudaStreamWaitEvent(sg, pdf[k], 0));
+            timed_gemm(4, bk, N, true);
+            SLB_CUDA(cudaEventRecord(gdf[k], sg));
+            last_gemm = gdf[k];
+        }
+        far_prev = bk < N;
+        b = bk;
     }
-    SLB_CUDA(cudaStreamWaitEvent(sm, evp[nsteps - 1], 0));
-    SLB_CUDA(cudaStreamWaitEvent(sm, evl[nsteps - 1], 0));
-    SLB_CUDA(cudaEventRecord(ev1, sm));
-    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sm));
+    SLB_CUDA(cudaStreamWaitEvent(sg, evp[nsteps - 1], 0));
+    SLB_CUDA(cudaStreamWaitEvent(sg, evl[nsteps - 1], 0));
+    SLB_CUDA(cudaEventRecord(evs, sq));
+    SLB_CUDA(cudaStreamWaitEvent(sg, evs, 0));
+    SLB_CUDA(cudaEventRecord(ev1, sg));
+    SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sg));
     int info_local = 0;
-    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sm));
-    SLB_CUDA(cudaStreamSynchronize(sm));
-    SLB_CUDA(cudaStreamSynchronize(sp));
+    SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sg));
+    SLB_CUDA(cudaStreamSynchronize(sg));
+    SLB_CUDA(cudaStreamSynchronize(sp)); SLB_CUDA(cudaStreamSynchronize(sq)); SLB_CUDA(cudaStreamSynchronize(sc));
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g_last_lu.factor_ms = ms;
     g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
+    if (trace) {
+        // step k: [gap = update stream idle: waits for panel k + prep of the near half] [g0 = next panel's columns] [gn = near] [gf = far]
+        double t_gap = 0, t_g0 = 0, t_gn = 0, t_gf = 0;
+        cudaEvent_t prev_end = ev0;
+        fprintf(stderr, "la_trace: k m gap_ms g0_ms gnear_ms gfar_ms\n");
+        for (int k = 0; k < nsteps; ++k) {
+            if (!eva[k]) continue;
+            float gap = 0, g[3] = { 0, 0, 0 };
+            SLB_CUDA(cudaEventElapsedTime(&gap, prev_end, eva[k]));
+            cudaEvent_t last = eva[k];
+            for (int q = 0; q < 3; ++q)
+                if (gev[6 * k + 2 * q]) { SLB_CUDA(cudaEventElapsedTime(&g[q], gev[6 * k + 2 * q], gev[6 * k + 2 * q + 1])); last = gev[6 * k + 2 * q + 1]; }
+            prev_end = last;
+            t_gap += gap; t_g0 += g[0]; t_gn += g[1]; t_gf += g[2];
+            if (k % 8 == 0 || k >= nsteps - 8) fprintf(stderr, "la_trace: %d %d %.3f %.3f %.3f %.3f\n", k, M - k * nb, gap, g[0], g[1], g[2]);
+        }
+        fprintf(stderr, "la_trace: total %.1f ms = gap %.1f + g0 %.1f + gnear %.1f + gfar %.1f (+ waits inside the update stream)\n", ms, t_gap, t_g0, t_gn, t_gf);
+        for (auto &e : eva) if (e) cudaEventDestroy(e);
+    }
     for (int k = 0; k < nsteps; ++k) {
-        for (int slot = 0; slot < 4; slot += 2)
-            if (gev[4 * k + slot]) {
-                float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[4 * k + slot], gev[4 * k + slot + 1]));
+        for (int slot = 0; slot < 6; slot += 2)
+            if (gev[6 * k + slot]) {
+                float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[6 * k + slot], gev[6 * k + slot + 1]));
                 g_last_lu.update_ms += t; g_last_lu.update_launches += 1;
-                cudaEventDestroy(gev[4 * k + slot]); cudaEventDestroy(gev[4 * k + slot + 1]);
+                cudaEventDestroy(gev[6 * k + slot]); cudaEventDestroy(gev[6 * k + slot + 1]);
             }
         g_last_lu.update_flops += gflops[k];
     }
-    for (auto &e : evp) cudaEventDestroy(e);
-    for (auto &e : evn) cudaEventDestroy(e);
-    for (auto &e : evq) cudaEventDestroy(e);
-    for (auto &e : evl) cudaEventDestroy(e);
+    for (auto *v : { &evp, &evn, &evl, &pdp, &pdn, &pdf, &gdn, &gdf }) for (auto &e : *v) cudaEventDestroy(e);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs);
     *info_host = info_local;
     return 0;

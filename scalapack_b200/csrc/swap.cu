@@ -65,9 +65,9 @@ swap_pack_kernel(int jb, int j0, const int *__restrict__ top_src, const int *__r
                  const int *__restrict__ out_src, RowDist rd, const T *__restrict__ A, int64_t lda, int64_t c0, int64_t c1,
                  T *__restrict__ Ubuf, int64_t ldu, T *__restrict__ Obuf, int64_t ldo)
 {
-    int64_t cb = c0 + (int64_t)blockIdx.x * SWAP_COLS;
-    int nc = (int)min((int64_t)SWAP_COLS, c1 - cb);
     bool own_top = row_owner(rd, j0) == rd.myrow;
+    for (int64_t cb = c0 + (int64_t)blockIdx.x * SWAP_COLS; cb < c1; cb += (int64_t)gridDim.x * SWAP_COLS) {
+    int nc = (int)min((int64_t)SWAP_COLS, c1 - cb);
     for (int t = threadIdx.x; t < jb; t += blockDim.x) {
         int src = top_src[t];
         if (row_owner(rd, src) == rd.myrow) {
@@ -90,6 +90,7 @@ swap_pack_kernel(int jb, int j0, const int *__restrict__ top_src, const int *__r
             }
         }
     }
+    }
 }
 
 template <typename T>
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256)
 swap_unpack_out_kernel(int jb, const int *__restrict__ out_dst, RowDist rd, T *__restrict__ A, int64_t lda, int64_t c0,
                        int64_t c1, const T *__restrict__ Obuf, int64_t ldo)
 {
-    int64_t cb = c0 + (int64_t)blockIdx.x * SWAP_COLS;
+    for (int64_t cb = c0 + (int64_t)blockIdx.x * SWAP_COLS; cb < c1; cb += (int64_t)gridDim.x * SWAP_COLS) {
     int nc = (int)min((int64_t)SWAP_COLS, c1 - cb);
     for (int t = threadIdx.x; t < jb; t += blockDim.x) {
         int d = out_dst[t];
@@ -108,6 +109,7 @@ swap_unpack_out_kernel(int jb, const int *__restrict__ out_dst, RowDist rd, T *_
         for (int c = 0; c < SWAP_COLS; ++c) if (c < nc) v[c] = Obuf[t + (cb - c0 + c) * ldo];
 #pragma unroll
         for (int c = 0; c < SWAP_COLS; ++c) if (c < nc) ap[(int64_t)c * lda] = v[c];
+    }
     }
 }
 
@@ -164,6 +166,15 @@ void launch_rows_bc(int64_t rows, int cols, T *L, int64_t ldl, int64_t l0, T *G,
     counter_add("kernel_launches", 1);
 }
 
+// The gather / scatter kernels are memory-latency bound: a few hundred CTAs keep the HBM queues full, and a capped
+// grid leaves the other SMs to the trailing update running underneath (lu.cu pipelines the two).  SLB200_SWAP_GRID=0: uncapped.
+static unsigned capped_grid(int64_t groups)
+{
+    static int64_t cap = -1;
+    if (cap < 0) cap = opt("swap_grid", 48);
+    return (unsigned)((cap > 0 && groups > cap) ? cap : groups);
+}
+
 void launch_swap_plan(int j0, int jb, const int *ipiv_blk, SwapPlan plan, cudaStream_t s)
 {
     if (jb <= 0) return;
@@ -178,7 +189,7 @@ void launch_swap_pack(int jb, int j0, SwapPlan plan, RowDist rd, const T *A, int
                       T *Ubuf, int64_t ldu, T *Obuf, int64_t ldo, cudaStream_t s)
 {
     if (c1 <= c0 || jb <= 0) return;
-    unsigned grid = (unsigned)((c1 - c0 + SWAP_COLS - 1) / SWAP_COLS);
+    unsigned grid = capped_grid((c1 - c0 + SWAP_COLS - 1) / SWAP_COLS);
     swap_pack_kernel<T><<<grid, 256, 0, s>>>(jb, j0, plan.top_src, plan.out_dst, plan.out_src, rd, A, lda, c0, c1, Ubuf, ldu, Obuf, ldo);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);
@@ -188,7 +199,7 @@ void launch_swap_unpack_out(int jb, SwapPlan plan, RowDist rd, T *A, int64_t lda
                             int64_t ldo, cudaStream_t s)
 {
     if (c1 <= c0 || jb <= 0) return;
-    unsigned grid = (unsigned)((c1 - c0 + SWAP_COLS - 1) / SWAP_COLS);
+    unsigned grid = capped_grid((c1 - c0 + SWAP_COLS - 1) / SWAP_COLS);
     swap_unpack_out_kernel<T><<<grid, 256, 0, s>>>(jb, plan.out_dst, rd, A, lda, c0, c1, Obuf, ldo);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);
@@ -207,8 +218,10 @@ template <typename T>
 void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst, int64_t ldd, cudaStream_t s)
 {
     if (rows <= 0 || cols <= 0) return;
+    // capped grid (both loops of the kernel are grid-stride): a copy needs few SMs to reach its bandwidth and must not
+    // flush the trailing update running underneath off the GPU
     unsigned gx = (unsigned)min((int64_t)64, (rows + 255) / 256);
-    unsigned gy = (unsigned)min((int64_t)32768, cols);
+    unsigned gy = (unsigned)min((int64_t)max(1, 1024 / (int)gx), cols);
     copy2d_kernel<T><<<dim3(gx, gy), 256, 0, s>>>(rows, cols, src, lds, dst, ldd);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);

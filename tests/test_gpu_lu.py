@@ -190,6 +190,30 @@ def test_lookahead_is_bit_identical(S, O, ctx11):
     check_against_oracle(O, a0, outs[1][0], outs[1][1], 0, nb)
 
 
+@pytest.mark.parametrize("n,nb,split_min", [(3072, 256, 512), (2560, 128, 256), (4096, 512, 1024)])
+def test_pipelined_schedule_is_bit_identical(S, O, ctx11, n, nb, split_min):
+    """The two-half pipeline (prep of one column half under the update of the other, moving boundary, re-splits) only
+    reorders independent work: same bits as the serial schedule, pivots equal to the oracle's."""
+    a0 = O.matgen64_tile(n, 1234 + n, 0, n, 0, n)
+    outs = []
+    for mode in ("serial", "pipe", "nopipe"):
+        S.set_option("lookahead", 0 if mode == "serial" else 1)
+        S.set_option("la_pipeline", 0 if mode == "nopipe" else 1)
+        S.set_option("la_split_min", split_min)
+        S.set_option("lookahead_min_us", 0)
+        try:
+            lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, nb, pad=0, device=True)
+        finally:
+            S.set_option("lookahead", 1); S.set_option("la_pipeline", 1); S.set_option("la_split_min", 6144)
+            S.set_option("lookahead_min_us", 4000)
+        outs.append((np.array(lu), ipiv, info))
+    for o in outs[1:]:
+        assert o[2] == outs[0][2] == 0
+        assert np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[0], outs[0][0])
+    check_against_oracle(O, a0, outs[1][0], outs[1][1], 0, nb)
+
+
 def _gemm_in_subprocess(env_extra, M, N, K, tmp_path, tag):
     """C - A*B through slb200_test_gemm in a fresh process (kernel variant options are read once per process)."""
     import subprocess, sys, os
