@@ -26,20 +26,22 @@ namespace {
 constexpr int PT = 256;        // threads per CTA
 constexpr int MAXG = 160;      // max CTAs (>= SM count)
 
-struct __align__(16) CandHdr { double absval; int vrow; unsigned tag; };
-
-// 16-byte mailbox header: written / read as one vector access so {value,row,tag} are observed together
-__device__ __forceinline__ void st_hdr(CandHdr *p, double a, int v, unsigned tag)
+// 16-byte self-validating mailbox packet {value, tag, aux}: written / read as ONE vector access, so a reader that sees
+// the tag it waits for also sees the value -- no fence and no second round trip ("the data is the flag").
+struct __align__(16) Pkt { double v; unsigned tag; unsigned aux; };
+__device__ __forceinline__ void st_pkt(Pkt *p, double a, unsigned tag, unsigned aux)
 {
     unsigned lo = (unsigned)(__double_as_longlong(a) & 0xffffffffLL), hi = (unsigned)((unsigned long long)__double_as_longlong(a) >> 32);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(lo), "r"(hi), "r"((unsigned)v), "r"(tag) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(lo), "r"(hi), "r"(tag), "r"(aux) : "memory");
 }
-__device__ __forceinline__ void ld_hdr(const CandHdr *p, double &a, int &v, unsigned &tag)
+__device__ __forceinline__ void ld_pkt(const Pkt *p, double &a, unsigned &tag, unsigned &aux)
 {
-    unsigned lo, hi, uv;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(lo), "=r"(hi), "=r"(uv), "=r"(tag) : "l"(p) : "memory");
-    a = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo)); v = (int)uv;
+    unsigned lo, hi;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(lo), "=r"(hi), "=r"(tag), "=r"(aux) : "l"(p) : "memory");
+    a = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
+
+constexpr int G1 = 32;         // up to G1 CTAs: one-phase exchange (every CTA reads every candidate row)
 
 struct VMap {
     PanelRowMap m;
@@ -53,6 +55,8 @@ struct VMap {
     }
 };
 
+// Mailbox layout in `work` (global): cand[2][MAXG][WN + 1] packets (packet 0 = {|v|, tag, vrow}, 1..WN = the candidate
+// row as doubles), rowj[2][WN] packets (the current row jj, published by its owner); WN = W doubles (2 W for complex).
 template <typename T, int W>
 __global__ void __launch_bounds__(PT, 1)
 panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map_, int *__restrict__ ipiv_out,
@@ -60,20 +64,22 @@ panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map
                   unsigned long long *__restrict__ dbg)
 {
     constexpr int LS = W + 1;
+    constexpr int NE = sizeof(T) / sizeof(double);
+    constexpr int WN = W * NE, WN1 = WN + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *S = reinterpret_cast<T *>(smem_raw);            // [rpb][LS]
-    T *prow_s = S + (size_t)rpb * LS;                  // [W] pivot row
-    T *jrow_s = prow_s + W;                            // [W] old row jj
-    double *red_abs = reinterpret_cast<double *>(jrow_s + W);    // [16]
-    int *red_v = reinterpret_cast<int *>(red_abs + 16);          // [16]
-    int *red_b = red_v + 16;                                     // [16]
-    int *misc = red_b + 16;                                      // [0]=winner cta [1]=winner vrow [2]=best local v
+    double *crow = reinterpret_cast<double *>(smem_raw);          // [G1][WN] candidate rows (one-phase) / [WN] winner row
+    double *jrow_d = crow + G1 * WN;                              // [WN] old row jj
+    double *cs_a = jrow_d + WN;                                   // [G1]
+    double *red_abs = cs_a + G1;                                  // [16]
+    int *cs_v = reinterpret_cast<int *>(red_abs + 16);            // [G1]
+    int *red_v = cs_v + G1;                                       // [16]
+    int *red_b = red_v + 16;                                      // [16]
+    int *misc = red_b + 16;                                       // [8]: [0]=winner cta [1]=winner vrow [2]=best local v
+    T *S = reinterpret_cast<T *>(misc + 8);                       // [rpb][LS]
+    const double *Sd = reinterpret_cast<const double *>(S);
 
-    // global mailbox
-    unsigned *jtag = reinterpret_cast<unsigned *>(work + 256);                  // [2] tags of the published row jj (128 B apart)
-    CandHdr *cand = reinterpret_cast<CandHdr *>(work + 512);                    // [2][MAXG]
-    T *candrow = reinterpret_cast<T *>(work + 512 + 2 * MAXG * sizeof(CandHdr));   // [2][MAXG][W]
-    T *rowj = candrow + 2 * MAXG * W;                                            // [2][W]
+    Pkt *candp = reinterpret_cast<Pkt *>(work + 512);             // [2][MAXG][WN1]
+    Pkt *rowjp = candp + (size_t)2 * MAXG * WN1;                  // [2][WN]
 
     VMap vm; vm.m = map_;
     auto stamp = [&](int jj, int k) {
@@ -91,6 +97,8 @@ panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map
     // ---------------- load my slab ----------------
     for (int c = 0; c < w; ++c)
         for (int i = tid; i < nrows; i += PT) S[i * LS + c] = ld_cg(Wp + (base + i) + (int64_t)c * ldw);
+    for (int i = tid; i < nrows; i += PT)
+        for (int c = w; c < W; ++c) S[i * LS + c] = t_zero(T());     // unused columns of a narrow leaf: defined values
     __syncthreads();
 
     double babs = -1.0; int bv = -1;
@@ -125,65 +133,96 @@ panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map
         }
         __syncthreads();
         stamp(jj, 1);
-        // ---- publish ----
+        // ---- publish: candidate row + header, and row jj from its owner -- plain packet stores, no fence ----
         const int myv = misc[2];
         const bool own_jj = jj >= base && jj < base + nrows;
-        if (myv >= 0 && tid < w) candrow[((size_t)parity * MAXG + b) * W + tid] = S[(myv - base) * LS + tid];
-        if (own_jj && tid < w) rowj[parity * W + tid] = S[(jj - base) * LS + tid];
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            st_hdr(&cand[parity * MAXG + b], myv >= 0 ? red_abs[8] : -1.0, myv, want);
-            if (own_jj) *reinterpret_cast<volatile unsigned *>(&jtag[parity * 32]) = want;
+        {
+            Pkt *mine = candp + ((size_t)parity * MAXG + b) * WN1;
+            if (tid < WN) st_pkt(mine + 1 + tid, myv >= 0 ? Sd[(size_t)(myv - base) * LS * NE + tid] : 0.0, want, 0u);
+            else if (tid == WN) st_pkt(mine, myv >= 0 ? red_abs[8] : -1.0, want, (unsigned)myv);
+            if (own_jj && tid >= 128 && tid < 128 + WN) st_pkt(rowjp + parity * WN + (tid - 128), Sd[(size_t)(jj - base) * LS * NE + (tid - 128)], want, 0u);
         }
         stamp(jj, 2);
-        // ---- gather: thread q polls header q (one L2 round trip for all G headers), then block reduce ----
-        {
-            double a = -1.0; int v = -1, wb = -1;
+        int wb, pv;
+        const double *prow_d;
+        if (G <= G1) {
+            // ---- one-phase gather: every packet of every candidate (+ row jj) in ONE L2 round trip ----
+            const int ncand = G * WN1, total = ncand + WN;
+            for (int p = tid; p < total; p += PT) {
+                const Pkt *src = p < ncand ? candp + ((size_t)parity * MAXG + p / WN1) * WN1 + p % WN1 : rowjp + parity * WN + (p - ncand);
+                double v; unsigned t, aux;
+                do { ld_pkt(src, v, t, aux); } while (t != want);
+                if (p < ncand) {
+                    const int q = p / WN1, e = p % WN1;
+                    if (e == 0) { cs_a[q] = v; cs_v[q] = (int)aux; } else crow[q * WN + e - 1] = v;
+                } else jrow_d[p - ncand] = v;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double a = -1.0; int v = -1, qb = -1;
+                if (lane < G) { a = cs_a[lane]; v = cs_v[lane]; qb = lane; if (v < 0) { a = -1.0; qb = -1; } }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    double oa = __shfl_xor_sync(0xffffffffu, a, off);
+                    int ov = __shfl_xor_sync(0xffffffffu, v, off);
+                    int ob = __shfl_xor_sync(0xffffffffu, qb, off);
+                    if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; qb = ob; }
+                }
+                if (lane == 0) { misc[0] = qb; misc[1] = v; }
+            }
+            __syncthreads();
+            wb = misc[0]; pv = misc[1];
+            prow_d = crow + (wb < 0 ? 0 : wb) * WN;
+        } else {
+            // ---- two-phase gather: thread q polls header q, block reduce, then the winner's row packets ----
+            double a = -1.0; int v = -1, qb = -1;
             if (tid < G) {
-                unsigned qt;
-                do { ld_hdr(&cand[parity * MAXG + tid], a, v, qt); } while (qt != want);
-                wb = tid;
-                if (v < 0) { a = -1.0; wb = -1; }
-            } else if (tid == PT - 1) {
-                while (*reinterpret_cast<volatile unsigned *>(&jtag[parity * 32]) != want) { }
+                unsigned qt, aux;
+                do { ld_pkt(candp + ((size_t)parity * MAXG + tid) * WN1, a, qt, aux); } while (qt != want);
+                v = (int)aux; qb = tid;
+                if (v < 0) { a = -1.0; qb = -1; }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 double oa = __shfl_xor_sync(0xffffffffu, a, off);
                 int ov = __shfl_xor_sync(0xffffffffu, v, off);
-                int ob = __shfl_xor_sync(0xffffffffu, wb, off);
-                if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; wb = ob; }
+                int ob = __shfl_xor_sync(0xffffffffu, qb, off);
+                if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; qb = ob; }
             }
-            if (lane == 0) { red_abs[warp] = a; red_v[warp] = v; red_b[warp] = wb; }
-            __threadfence();
+            if (lane == 0) { red_abs[warp] = a; red_v[warp] = v; red_b[warp] = qb; }
             __syncthreads();
             if (warp == 0) {
                 a = lane < PT / 32 ? red_abs[lane] : -1.0;
                 v = lane < PT / 32 ? red_v[lane] : -1;
-                wb = lane < PT / 32 ? red_b[lane] : -1;
+                qb = lane < PT / 32 ? red_b[lane] : -1;
 #pragma unroll
                 for (int off = 4; off > 0; off >>= 1) {
                     double oa = __shfl_xor_sync(0xffffffffu, a, off);
                     int ov = __shfl_xor_sync(0xffffffffu, v, off);
-                    int ob = __shfl_xor_sync(0xffffffffu, wb, off);
-                    if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; wb = ob; }
+                    int ob = __shfl_xor_sync(0xffffffffu, qb, off);
+                    if (ov >= 0 && (v < 0 || oa > a || (oa == a && vm.key(ov) < vm.key(v)))) { a = oa; v = ov; qb = ob; }
                 }
-                if (lane == 0) { misc[0] = wb; misc[1] = v; }
+                if (lane == 0) { misc[0] = qb; misc[1] = v; }
             }
             __syncthreads();
+            wb = misc[0]; pv = misc[1];
+            if (tid < WN) {
+                double x; unsigned t, aux;
+                do { ld_pkt(candp + ((size_t)parity * MAXG + (wb < 0 ? 0 : wb)) * WN1 + 1 + tid, x, t, aux); } while (t != want);
+                crow[tid] = x;
+            } else if (tid >= 128 && tid < 128 + WN) {
+                double x; unsigned t, aux;
+                do { ld_pkt(rowjp + parity * WN + (tid - 128), x, t, aux); } while (t != want);
+                jrow_d[tid - 128] = x;
+            }
+            __syncthreads();
+            prow_d = crow;
         }
-        stamp(jj, 3);
-        const int wb = misc[0];
-        int pv = misc[1];
-        if (tid < w) {
-            prow_s[tid] = ld_cg(candrow + ((size_t)parity * MAXG + wb) * W + tid);
-            jrow_s[tid] = ld_cg(rowj + parity * W + tid);
-        }
-        __syncthreads();
         stamp(jj, 4);
+        const T *prow_s = reinterpret_cast<const T *>(prow_d);
+        const T *jrow_s = reinterpret_cast<const T *>(jrow_d);
         const T pivot = prow_s[j];
-        const bool nonzero = !t_iszero(pivot);
+        const bool nonzero = wb >= 0 && !t_iszero(pivot);
         if (!nonzero) pv = jj;                       // AMAX == 0 => INDX = IX (pdamax_.c:486); no swap
         if (b == 0 && tid == 0) {
             ipiv_out[jj] = vm.global_row(pv) + 1;
@@ -222,7 +261,8 @@ panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map
 template <typename T, int W>
 size_t leaf_smem_bytes(int rpb)
 {
-    return ((size_t)rpb * (W + 1) + 2 * W) * sizeof(T) + 16 * sizeof(double) + 3 * 16 * sizeof(int) + 8 * sizeof(int) + 64;
+    constexpr int WN = W * (int)(sizeof(T) / sizeof(double));
+    return (size_t)(G1 * WN + WN + G1 + 16) * sizeof(double) + (size_t)(G1 + 16 + 16 + 8) * sizeof(int) + (size_t)rpb * (W + 1) * sizeof(T) + 32;
 }
 
 // rows per CTA for an m-row leaf of width W; 0 if it does not fit
@@ -240,7 +280,7 @@ int leaf_rpb(int m, int gmax)
 
 template <typename T, int W>
 void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out, int info_offset,
-                 void *work, cudaStream_t s, int gmax)
+                 void *work, cudaStream_t s, int gmax, bool coop)
 {
     Runtime &r = rt();
     int rpb = leaf_rpb<T, W>(m, gmax);
@@ -254,7 +294,7 @@ void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *
     unsigned char *wk = (unsigned char *)work;
     // mailbox tags = (launch epoch << 8) + column + 1: never equal to a stale tag of an earlier launch
     static unsigned epoch = 0;
-    if ((++epoch & 0x7fffffu) == 0) { SLB_CUDA(cudaMemsetAsync(wk + 256, 0, 256 + 2 * MAXG * sizeof(CandHdr), s)); ++epoch; }
+    if ((++epoch & 0x7fffffu) == 0) { SLB_CUDA(cudaMemsetAsync(wk, 0, panel_work_bytes(0), s)); ++epoch; }
     unsigned tagbase = (epoch & 0x7fffffu) << 8;
     unsigned long long *dbg = opt("panel_debug", 0) ? (unsigned long long *)workspace("panel_dbg", 2 * 4096 * 8 * 8, true) : nullptr;
     size_t smem = leaf_smem_bytes<T, W>(rpb);
@@ -262,7 +302,7 @@ void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *
     // CTA per SM; launched as a cooperative grid so the runtime checks exactly that.
     PanelRowMap mp = map;
     void *args[] = { &m, &w, &Wp, &ldw, &mp, &ipiv_out, &info_out, &info_offset, &wk, &rpb, &tagbase, &dbg };
-    if (gmax > 0) {     // look-ahead: plain launch; the CTAs become resident as the update's chunked CTAs retire
+    if (!coop) {        // look-ahead: plain launch; the CTAs become resident as the update's chunked CTAs retire
         panel_leaf_kernel<T, W><<<G, PT, smem, s>>>(m, w, Wp, ldw, mp, ipiv_out, info_out, info_offset, wk, rpb, tagbase, dbg);
         SLB_CUDA(cudaGetLastError());
     } else
@@ -287,11 +327,11 @@ int pick_leaf_width(int m, int gmax)
 }
 
 template <typename T>
-void leaf_dispatch(int W, int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax)
+void leaf_dispatch(int W, int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax, bool coop)
 {
-    if (W == 32) { if constexpr (LeafCfg<T>::W0 == 32) launch_leaf<T, 32>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax); }
-    else if (W == 16) launch_leaf<T, 16>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax);
-    else launch_leaf<T, 8>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax);
+    if (W == 32) { if constexpr (LeafCfg<T>::W0 == 32) launch_leaf<T, 32>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax, coop); }
+    else if (W == 16) launch_leaf<T, 16>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax, coop);
+    else launch_leaf<T, 8>(m, w, Wp, ldw, map, ipiv, info, off, work, s, gmax, coop);
 }
 
 inline void gemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, cudaStream_t s)
@@ -304,7 +344,7 @@ inline void trsm_llnu(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomple
 template <typename T>
 struct PanelCtx {
     int m, W; T *Wp; int64_t ldw; PanelRowMap map; int *ipiv; int *info; int info_offset; void *work;
-    SwapPlan plan; T *U; T *O; cudaStream_t s; int gmax;
+    SwapPlan plan; T *U; T *O; cudaStream_t s; int gmax; bool coop;
 };
 
 // interchanges of panel columns [p0,p1) (pivots ipiv[p0..p1)) applied to panel columns [c0,c1); the permuted top
@@ -328,7 +368,7 @@ void panel_rec(PanelCtx<T> &c, int c0, int c1)
     const int n = c1 - c0;
     if (n <= c.W) {
         PanelRowMap mp = c.map; mp.g0 += c0;
-        leaf_dispatch<T>(c.W, c.m - c0, n, c.Wp + c0 + (int64_t)c0 * c.ldw, c.ldw, mp, c.ipiv + c0, c.info, c.info_offset + c0, c.work, c.s, c.gmax);
+        leaf_dispatch<T>(c.W, c.m - c0, n, c.Wp + c0 + (int64_t)c0 * c.ldw, c.ldw, mp, c.ipiv + c0, c.info, c.info_offset + c0, c.work, c.s, c.gmax, c.coop);
         return;
     }
     const int half = ((n / 2 + c.W - 1) / c.W) * c.W;
@@ -350,7 +390,11 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
     if (m <= 0 || jb <= 0) return;
     PanelCtx<T> c;
     // look-ahead mode caps the CTAs; if the slabs of so few CTAs cannot hold m rows, allow more (0 = whole GPU)
+    c.coop = gmax == 0;                 // whole GPU to itself: cooperative launch (the runtime checks co-residency)
     while (gmax > 0 && leaf_rpb<T, 8>(m, gmax) == 0) gmax = (2 * gmax >= rt().sm_count) ? 0 : 2 * gmax;
+    // a panel that fits the slabs of G1 CTAs at the widest leaf uses no more: the one-phase exchange (one L2 round
+    // trip per column) needs G <= G1, and per-column latency, not bandwidth, bounds a panel of this size
+    if ((gmax == 0 || gmax > G1) && leaf_rpb<T, LeafCfg<T>::W0>(m, G1) != 0) gmax = G1;
     c.gmax = gmax;
     c.m = m; c.W = pick_leaf_width<T>(m, gmax); c.Wp = Wp; c.ldw = ldw; c.map = map; c.ipiv = ipiv_out; c.info = info_out;
     c.info_offset = info_offset; c.work = work; c.s = s;
@@ -365,8 +409,8 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
 
 size_t panel_work_bytes(int jb)
 {
-    (void)jb;
-    return 512 + 2 * MAXG * sizeof(CandHdr) + (size_t)(2 * MAXG * 32 + 2 * 32) * sizeof(zcomplex) + 256;
+    (void)jb;   // cand[2][MAXG][WN + 1] + rowj[2][WN] packets, WN <= 32 doubles (W = 32 real, W = 16 complex)
+    return 512 + (size_t)2 * MAXG * 33 * sizeof(Pkt) + (size_t)2 * 32 * sizeof(Pkt) + 256;
 }
 
 void launch_dpanel(int m, int jb, double *W, int64_t ldw, const PanelRowMap &map, int *ipiv_out, int *info_out,
