@@ -217,8 +217,14 @@ def run_ours(args):
     dmma_peak = S.lib().slb200_bench_dmma_tflops(20000)
     dfma_peak = S.lib().slb200_bench_dfma_tflops(20000)
     achieved = u_fl / (u_ms * 1e-3) / 1e12 if u_ms > 0 else None
-    roof = {"bound": "tensor", "kernel": "dgemm_minus_persistent (FP64 DMMA trailing update, gemm.cu)", "achieved": achieved, "peak": dmma_peak,
-            "unit": "TFLOP/s", "frac": (achieved / dmma_peak) if achieved else None, "traffic": None,
+    # DRAM traffic of the update kernel: one `ncu --set full` capture (profiles/r01_gemm_v9_ncu.md, M=N=32768, K=512) read
+    # 11.48 GB and wrote 8.54 GB for 17.45 GB of algorithmic bytes (16*m*n for C + the operands) = 1.147x; scaled here to
+    # the average launch of this run (algorithmic C bytes of a launch = its flops * 8 / NB).
+    traffic = (u_fl / u_n) * 8.0 / nb * 1.147 if u_n else None
+    roof = {"bound": "tensor", "kernel": "dgemm_minus_packed (FP64 DMMA trailing update, gemm_packed.cu; dgemm_minus_p8b for m < 3072)",
+            "achieved": achieved, "peak": dmma_peak,
+            "unit": "TFLOP/s", "frac": (achieved / dmma_peak) if achieved else None, "traffic": traffic,
+            "traffic_unit": "bytes per average launch = algorithmic C bytes x 1.147 (measured dram read+write / algorithmic bytes, ncu capture at M=N=32768)",
             "peak_source": "FP64 DMMA peak measured live by slb200_bench_dmma_tflops (MEASURED_PEAKS.json has no FP64 entry)",
             "fp64_fma_peak_tflops": dfma_peak, "share_of_step": u_ms / sum(times) if times else None,
             "launches": u_n, "avg_launch_ms": u_ms / u_n if u_n else None}

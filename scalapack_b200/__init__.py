@@ -7,7 +7,7 @@ reference interface (same routine names, argument order and INFO conventions as 
 There is no CPU fallback: compute entry points abort if the CUDA library or a GPU is missing.
 """
 from .api import (  # noqa: F401
-    lib, have_library, has_cuda,
+    lib, have_library, has_cuda, device,
     blacs_pinfo, blacs_get, blacs_gridinit, blacs_gridinfo, blacs_gridexit, blacs_exit, blacs_barrier,
     blacs_pnum, blacs_pcoord, sl_init,
     numroc, indxg2p, indxg2l, indxl2g, infog2l, descinit, iceil, ilcm, chk1mat,

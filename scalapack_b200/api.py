@@ -50,6 +50,12 @@ def has_cuda() -> bool:
     return bool(lib().slb200_has_cuda())
 
 
+def device() -> int:
+    """Index of the GPU this BLACS process drives (LOCAL_RANK modulo the device count); device-resident operands
+    must live there."""
+    return int(lib().slb200_device())
+
+
 def _i(v):
     return C.byref(C.c_int(int(v)))
 

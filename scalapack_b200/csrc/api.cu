@@ -15,6 +15,9 @@ static bool is_device_ptr(const void *p)
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, p);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type == cudaMemoryTypeDevice && at.device != rt().device)
+        fatal("a device-resident operand lives on GPU %d but this BLACS process drives GPU %d (LOCAL_RANK): allocate it on the "
+              "process's own GPU", at.device, rt().device);
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 

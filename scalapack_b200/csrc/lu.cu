@@ -272,7 +272,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
     int *info_dev = (int *)workspace("lu_info", 64);
     int *plan_mem = (int *)workspace("lu_plan", (size_t)6 * nb * sizeof(int));
-    SwapPlan plan{ plan_mem, plan_mem + nb, plan_mem + 2 * nb };
+    SwapPlan plans[2] = { { plan_mem, plan_mem + nb, plan_mem + 2 * nb }, { plan_mem + 3 * nb, plan_mem + 4 * nb, plan_mem + 5 * nb } };
     void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
     T *Ubuf = (T *)workspace("lu_U", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * (nloc > 0 ? nloc : 1) * sizeof(T));
@@ -397,10 +397,128 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             if (!(mycol == pc && myrow == pr))
                 SLB_CUDA(cudaMemcpyAsync(ipiv_dev + j0, pIpiv, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
         }
+        // the block's net row permutation, ready before the interchanges need it (plan buffer k&1: last read by step k-2)
+        launch_swap_plan(j0, jb, ipiv_dev + j0, plans[k & 1], s);
         SLB_CUDA(cudaEventRecord(evp[k], s));
     };
 
     panel_phase(0, 0);
+    const bool pipe = la && opt("la_pipeline", 1) != 0;
+    if (pipe) {
+        // ===== two-half software pipeline on P x Q grids (same idea as getrf_lookahead_1x1) =====
+        // sq carries the "prep" of a column range: pack -> column all-gather + broadcast (NCCL, nc->col) -> select ->
+        // unpack -> U12 solve; near half under the update of the previous step's far half, far half (+ the already
+        // factored left columns) under this step's near update.  sg carries the three update launches of a step.
+        cudaStream_t sg = sm, sq = r.s_prep;
+        const int64_t split_min = opt("la_split_min", 6144);
+        auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
+        std::vector<cudaEvent_t> pdp, pdn, pdf, gdn, gdf;
+        mkev(pdp, (size_t)nsteps); mkev(pdn, (size_t)nsteps); mkev(pdf, (size_t)nsteps); mkev(gdn, (size_t)nsteps); mkev(gdf, (size_t)nsteps);
+        gev.assign((size_t)6 * nsteps, nullptr);
+        SLB_CUDA(cudaStreamWaitEvent(sq, evs, 0));
+        int64_t bl = -1; bool far_prev = false;
+        for (int k = 0; k < nsteps; ++k) {
+            const int j0 = k * nb;
+            const int jb = (mn - j0) < nb ? (mn - j0) : nb;
+            const int pr = (rsrc + k) % P;
+            const int64_t lr0 = rows_before(myrow, j0);
+            const int64_t mtr = mloc - lr0;
+            const int64_t lcl = numroc(j0, nb, mycol, csrc, Q);
+            const int64_t lcr = numroc(j0 + jb, nb, mycol, csrc, Q);
+            unsigned char *Pbuf = Pb[k & 1];
+            const T *L11 = (T *)Pbuf; const int64_t ld11 = jb;
+            const T *Lop = (T *)(Pbuf + hdr_bytes) + (myrow == pr ? jb : 0); const int64_t ldl = mtr > 0 ? mtr : 1;
+            SwapPlan plan = plans[k & 1];
+            const int64_t nright = nloc - lcr;
+            const int64_t rbeg = lr0 + (myrow == pr ? jb : 0);
+            const int64_t mrows = mloc - rbeg;
+            const bool have_next = k + 1 < nsteps;
+            const int pcn = (csrc + k + 1) % Q;
+            const int jbn = have_next ? ((mn - (j0 + jb)) < nb ? (mn - (j0 + jb)) : nb) : 0;
+            const int64_t nfirst = (have_next && mycol == pcn) ? (jbn < nright ? jbn : nright) : 0;
+            const double glob_ms = 2.0 * (double)(M - j0 - jb) / P * (double)(N - j0 - jb) / Q * jb * Ops<T>::flop_mul / 30e12 * 1e3;
+            const bool overlap = have_next && glob_ms >= overlap_min_ms;
+            // one column range: [c0, c1) local columns
+            auto prep_range = [&](int64_t c0, int64_t c1, bool right) {
+                const int64_t ncols = c1 - c0;
+                if (ncols <= 0) return;
+                T *Ur = Ubuf + c0 * jb, *Or = Obuf + c0 * jb;
+                if (P == 1) launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c0, c1, Ur, jb, Or, jb, sq);
+                else {
+                    T *Cm = Cmine + c0 * jb, *Ca = Call + (int64_t)P * c0 * jb;
+                    launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c0, c1, Cm, jb, Or, jb, sq);
+                    const size_t cnt = (size_t)jb * ncols * sizeof(T);
+                    nccl_allgather(nc->col, Cm, Ca, cnt, NT_U8, sq);
+                    nccl_bcast(nc->col, Or, cnt, NT_U8, pr, sq);
+                    launch_swap_select<T>(jb, plan, rd, Ca, jb, (int64_t)jb * ncols, ncols, Ur, jb, sq);
+                }
+                launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c0, c1, Or, jb, sq);
+                if (right) Ops<T>::trsm(jb, ncols, L11, ld11, Ur, jb, sq);
+                if (myrow == pr) launch_copy2d<T>(jb, ncols, Ur, jb, A + lr0 + c0 * lld, lld, sq);
+            };
+            bool a_packed = false;
+            auto timed_gemm = [&](int slot, int64_t c0, int64_t c1, bool may_chunk) {
+                const int64_t nn = c1 - c0;
+                if (mrows <= 0 || nn <= 0) return;
+                SLB_CUDA(cudaEventCreate(&gev[6 * k + slot])); SLB_CUDA(cudaEventCreate(&gev[6 * k + slot + 1]));
+                SLB_CUDA(cudaEventRecord(gev[6 * k + slot], sg));
+                Ops<T>::gemm(mrows, nn, jb, Lop, ldl, Ubuf + c0 * jb, jb, A + rbeg + c0 * lld, lld, sg, (may_chunk && overlap) ? chunk_opt : 0,
+                             GEMM_MAIN | (a_packed ? GEMM_REUSE_A : 0));
+                a_packed = Ops<T>::packs(mrows, jb);
+                SLB_CUDA(cudaEventRecord(gev[6 * k + slot + 1], sg));
+                gflops[k] += 2.0 * (double)mrows * (double)nn * jb * Ops<T>::flop_mul;
+            };
+            // ---- near | far boundary (local columns); identical on all ranks of a process column ----
+            int64_t bk = nloc;
+            bool resplit = false;
+            if (have_next && nright >= split_min) {
+                if (bl < 0 || bl - lcr < nright / 4 || bl >= nloc) { bk = lcr + ((nright / 2 + nb - 1) / nb) * nb; resplit = true; }
+                else bk = bl;
+                if (bk >= nloc) bk = nloc;
+            }
+            if (bk > bl || bl < 0) resplit = true;
+            // ---- (a) sq: near half, the next panel's columns first ----
+            SLB_CUDA(cudaStreamWaitEvent(sq, evp[k], 0));
+            if (k > 0) SLB_CUDA(cudaStreamWaitEvent(sq, gdn[k - 1], 0));
+            if (k > 0 && far_prev && resplit) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+            if (nfirst > 0 && lcr + nfirst < bk) {
+                prep_range(lcr, lcr + nfirst, true);
+                SLB_CUDA(cudaEventRecord(pdp[k], sq));
+                prep_range(lcr + nfirst, bk, true);
+            } else {
+                prep_range(lcr, bk, true);
+                SLB_CUDA(cudaEventRecord(pdp[k], sq));
+            }
+            SLB_CUDA(cudaEventRecord(pdn[k], sq));
+            // ---- (b) sg: next panel's columns, hand-over to the panel stream ----
+            SLB_CUDA(cudaStreamWaitEvent(sg, pdp[k], 0));
+            if (have_next) {
+                timed_gemm(0, lcr, lcr + nfirst, false);
+                SLB_CUDA(cudaEventRecord(evn[k], sg));
+                SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
+                panel_phase(k + 1, overlap ? gmax_opt : 0);
+            }
+            // ---- (c) sq: far half, then the already factored left columns (nothing waits for those but the end) ----
+            if (k > 0 && far_prev) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+            if (have_next) SLB_CUDA(cudaStreamWaitEvent(sq, evn[k], 0));
+            prep_range(bk, nloc, true);
+            SLB_CUDA(cudaEventRecord(pdf[k], sq));
+            prep_range(0, lcl, false);
+            // ---- (d) sg: rest of near, far ----
+            SLB_CUDA(cudaStreamWaitEvent(sg, pdn[k], 0));
+            timed_gemm(2, lcr + nfirst, bk, true);
+            SLB_CUDA(cudaEventRecord(gdn[k], sg));
+            SLB_CUDA(cudaStreamWaitEvent(sg, pdf[k], 0));
+            timed_gemm(4, bk, nloc, true);
+            SLB_CUDA(cudaEventRecord(gdf[k], sg));
+            far_prev = true;               // gdf[k] is always recorded (an empty far half completes at once)
+            bl = bk;
+        }
+        SLB_CUDA(cudaStreamWaitEvent(sm, evp[nsteps - 1], 0));
+        SLB_CUDA(cudaEventRecord(evs, sq));
+        SLB_CUDA(cudaStreamWaitEvent(sm, evs, 0));
+        for (auto *v : { &pdp, &pdn, &pdf, &gdn, &gdf }) for (auto &e : *v) cudaEventDestroy(e);
+    } else
     for (int k = 0; k < nsteps; ++k) {
         cudaStream_t s = sm;
         const int j0 = k * nb;
@@ -421,7 +539,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
 
         // =============== row interchanges + U12 ===============
         mark();
-        launch_swap_plan(j0, jb, ipiv_dev + j0, plan, s);
+        SwapPlan plan = plans[k & 1];
         const int64_t nright = nloc - lcr;
         T *Uall = Ubuf;                      // jb x nloc, column index = local column
         if (P == 1) {
@@ -494,15 +612,13 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g_last_lu.factor_ms = ms;
     g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
-    for (int k = 0; k < nsteps; ++k) {
-        for (int slot = 0; slot < 4; slot += 2)
-            if (gev[4 * k + slot]) {
-                float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[4 * k + slot], gev[4 * k + slot + 1]));
-                g_last_lu.update_ms += t; g_last_lu.update_launches += 1;
-                cudaEventDestroy(gev[4 * k + slot]); cudaEventDestroy(gev[4 * k + slot + 1]);
-            }
-        g_last_lu.update_flops += gflops[k];
-    }
+    for (size_t i = 0; i + 1 < gev.size(); i += 2)
+        if (gev[i]) {
+            float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[i], gev[i + 1]));
+            g_last_lu.update_ms += t; g_last_lu.update_launches += 1;
+            cudaEventDestroy(gev[i]); cudaEventDestroy(gev[i + 1]);
+        }
+    for (int k = 0; k < nsteps; ++k) g_last_lu.update_flops += gflops[k];
     if (prof) {   // 5 marks per step: [swap][trsm][gemm][next panel]
         double tp = 0, tsw = 0, ttr = 0, tg = 0;
         for (size_t i = 0; i + 4 < pev.size(); i += 5) {

@@ -81,6 +81,11 @@ if __name__ == "__main__":
             "block barrier 0.7 %. -> generation 9 (gemm_packed.cu) removes the per-thread load code (bulk copies of pre-packed blocks issued by one thread), "
             "the block barrier (mbarriers) and de-phases the two warps of a scheduler so epilogues overlap the other warp's main loop.")
     launches("launches_n16384.csv", "r01_launches_n16384_v7.md", "r01: launch list of `bench.py --size 16384 --steps 1 --warmup 0` with update kernel v7 and look-ahead")
+    ncu_raw("prof_gemm_v9.ncu-rep", "r01: trailing-update kernel generation 9 (dgemm_minus_packed: packed operands, cp.async.bulk + mbarrier ring, setmaxnreg)", "r01_gemm_v9_ncu.md",
+            "M=N=32768, K=512 (one launch, 30.97 ms under ncu = 35.5 TFLOP/s for the kernel alone; 34.9 TFLOP/s with its two pack kernels). DMMA pipe 95.7 % busy "
+            "(v7: 83.2 %). DRAM traffic 11.48 GB read + 8.54 GB written = 20.02 GB per launch for 17.45 GB of algorithmic bytes (16*M*N for C + 8*(M+N)*K "
+            "for the operands): 1.147x.  PC sampling: main loop 80.6 % of the warp samples (stall_wait 37 %, math_pipe_throttle 31 % = the DMMA pipe itself), "
+            "epilogue 6.8 % (long_scoreboard on the C loads; overlapped by the other warp of the scheduler), producer warp 4.5 %.")
     launches("launches_n8192.csv", "r01_launches_n8192.md", "r01: launch list of `bench.py --n 8192 --steps 1` (1 GPU)",
              "dmma/dfma_peak_kernel are the roofline micro-benchmarks bench.py runs after the timed region.")
     launches("launches_full.csv", "r01_launches_n65536.md", "r01: launch list of the default bench (N=65536)")

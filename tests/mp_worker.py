@@ -15,9 +15,12 @@ import scalapack_b200 as S  # noqa: E402
 EPS = 2.0 ** -53
 
 
-def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False):
+def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False, split=0):
+    # split > 0: force the near | far column pipeline (and look-ahead overlap) at this small size
+    S.set_option("la_split_min", split if split else 6144)
+    S.set_option("lookahead_min_us", 0 if split else 4000)
     _, _, r, c = S.blacs_gridinfo(ctx)
-    res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)}", "ok": True, "msgs": []}
+    res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)} split={split}", "ok": True, "msgs": []}
     if r < 0:
         return res
     gen = O.pzmatgen if cplx else O.pdmatgen
@@ -33,11 +36,13 @@ def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False):
     f = S.pzgetrf if cplx else S.pdgetrf
     if device:
         import torch
+        torch.cuda.set_device(S.device())                       # the GPU this BLACS process drives (LOCAL_RANK), not cuda:0
         t = torch.from_numpy(np.ascontiguousarray(al.T)).cuda()
         info = f(m, n, t, 1, 1, desca, ipiv)
         al = np.asfortranarray(t.cpu().numpy().T)
     else:
         info = f(m, n, al, 1, 1, desca, ipiv)
+    print(f"[rank {r},{c}] factor done info={info}", file=sys.stderr, flush=True)
     refl = O.scatter(ref, nb, nb, P, Q, r, c, lld=lld)
     mn = min(m, n)
     ipl = O.ipiv_local(m, mn, nb, P, r, ipr, mloc + nb, fill=-77)
@@ -92,7 +97,8 @@ def main():
         key = (cs["P"], cs["Q"])
         if key not in grids:
             grids[key] = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", cs["P"], cs["Q"])
-        out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False)))
+        print(f"[rank {me}] case {cs}", file=sys.stderr, flush=True)
+        out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False), cs.get("split", 0)))
     S.blacs_exit(0)
     print("RESULT" + json.dumps({"rank": me, "results": out}), flush=True)
 

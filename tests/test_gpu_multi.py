@@ -29,10 +29,26 @@ def spawn(world, cases, timeout=600):
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py"), json.dumps(cases)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
-    for p in procs:
-        o, e = p.communicate(timeout=timeout)
-        assert p.returncode == 0, e[-3000:]
-        outs.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT")][0][6:]))
+    import time
+    deadline = time.time() + timeout
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=max(1.0, deadline - time.time()))
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT")][0][6:]))
+    except BaseException:
+        # a rank that died (or hangs) leaves its peers waiting in a collective: never leave them behind on the GPUs
+        tails = []
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+            try:
+                o, e = p.communicate(timeout=10)
+                tails.append((e or "")[-1500:])
+            except Exception:
+                pass
+        print("\n==== rank stderr tails ====\n" + "\n----\n".join(tails), file=sys.stderr)
+        raise
     bad = [(o["rank"], r["case"], r["msgs"]) for o in outs for r in o["results"] if not r["ok"]]
     assert not bad, bad
     return outs
@@ -47,7 +63,8 @@ def test_two_gpus(P, Q):
         pytest.skip("needs 2 GPUs")
     cases = [dict(c, P=P, Q=Q) for c in SMALL] + [dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2), dict(P=P, Q=Q, m=1000, n=1000, nb=64, nrhs=1, dev=True),
                                                    dict(P=P, Q=Q, m=300, n=200, nb=64, nrhs=0), dict(P=P, Q=Q, m=1536, n=1536, nb=512, nrhs=1),
-                                                   dict(P=P, Q=Q, m=120, n=120, nb=16, nrhs=2, z=True)]
+                                                   dict(P=P, Q=Q, m=120, n=120, nb=16, nrhs=2, z=True),
+                                                   dict(P=P, Q=Q, m=3072, n=3072, nb=128, nrhs=1, dev=True, split=256)]   # pipelined halves
     spawn(2, cases)
 
 
@@ -57,7 +74,8 @@ def test_four_gpus(P, Q):
         pytest.skip("needs 4 GPUs")
     cases = [dict(c, P=P, Q=Q) for c in SMALL] + [dict(P=P, Q=Q, m=2000, n=2000, nb=64, nrhs=1),           # BASELINE config 1
                                                    dict(P=P, Q=Q, m=777, n=513, nb=100, nrhs=0), dict(P=P, Q=Q, m=2048, n=2048, nb=512, nrhs=2, dev=True),
-                                                   dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2, z=True)]
+                                                   dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2, z=True),
+                                                   dict(P=P, Q=Q, m=4096, n=4096, nb=128, nrhs=1, dev=True, split=256)]  # pipelined halves
     spawn(4, cases)
 
 
