@@ -111,7 +111,7 @@ def run_reference(args):
         return
     res = []
     for _ in range(args.steps):
-        res.append(cpu_sample(args.nb, target_s=max(3.0, 12.0 / max(1, args.steps))))
+        res.append(cpu_sample(args.nb, target_s=float(os.environ.get("SLB200_BENCH_CPU_TARGET_S", max(3.0, 12.0 / max(1, args.steps))))))
     best = max(res, key=lambda r: r["value"])
     P, Q = GRIDS[args.gpus]
     n_full = workload_n(args)
@@ -233,6 +233,15 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         try:
+            # every rank of this node pins a host copy of its local array: refuse rather than drive the box out of memory
+            need = nloc * lld * 8 * world
+            try:
+                import psutil
+                avail = psutil.virtual_memory().available
+            except Exception:
+                avail = None
+            if avail is not None and need > 0.7 * avail:
+                raise MemoryError(f"pinned host copies of A need {need / 2**30:.0f} GiB, {avail / 2**30:.0f} GiB of host memory available")
             Ah = torch.empty(nloc * lld, dtype=torch.float64, pin_memory=True)
             e_times = []
             for _ in range(max(1, min(args.steps, args.e2e_steps))):

@@ -1,17 +1,21 @@
-// gemm.cu -- trailing-matrix update  C[MxN] -= A[MxK] * B[KxN]  in FP64 on the tensor cores.
+// gemm.cu -- C[MxN] -= A[MxK] * B[KxN] in FP64 on the tensor cores, cp.async flavour (operands read in place).
 //
-// Replaces the one local dgemm_ per LU step of the reference (PBLAS/SRC/PTOOLS/PB_CpgemmAB.c:345 reached
-// from SRC/pdgetrf.f:288) -- >= 99 % of the factorisation's flops.
+// The trailing update of the LU step (the reference's one local dgemm_ per step, PBLAS/SRC/PTOOLS/PB_CpgemmAB.c:345
+// reached from SRC/pdgetrf.f:288; >= 99 % of the flops) runs in gemm_packed.cu once its operands are worth packing
+// (M >= SLB200_GEMM_PACKED_MIN); this file is the kernel for everything smaller -- the DMMA updates inside the panel
+// recursion (panel.cu) and the U12 solve (trsm.cu), and short trailing updates -- plus the complex kernel.
 //
-// sm_100a has no FP64 kind of tcgen05.mma (kinds: f16, tf32, f8f6f4, i8, mxf8f6f4, mxf4, mxf4nvf4), so
-// the FP64 tensor path is the warp-level DMMA  mma.sync.aligned.m16n8k4.row.col.f64  with register
-// accumulators.  Tiling: CTA 128(m) x 128(n) x 16(k), 8 warps as 2(m) x 4(n), warp tile 64 x 32.
+// sm_100a has no FP64 kind of tcgen05.mma (kinds: f16, tf32, f8f6f4, i8, mxf8f6f4, mxf4, mxf4nvf4), so the FP64 tensor
+// path is the warp-level DMMA  mma.sync.aligned.m16n8k4.row.col.f64  with register accumulators
+// (profiles/r01_dmma_probe.md).  Tiling: CTA 128(m) x 128(n) x 16(k), 8 warps as 2(m) x 4(n), warp tile 64 x 32.
 // The MMA is issued "transposed" (MMA-M runs along the problem's n, MMA-N along m) so that each thread's
 // accumulator pair (c0,c1) is two consecutive rows of one column of column-major C: the epilogue is
 // 16-byte read-modify-writes, 64 B contiguous per column per warp request.
 // Operands are staged by a 4-stage cp.async (LDGSTS) ring into padded shared memory:
 //   As[k][m] stride 132 doubles, Bs[n][k] stride 20 doubles -> every fragment LDS.64 is bank-conflict free.
-// Tile order: groups of 16 m-tiles swept along n so a group's A rows stay L2-resident while B streams.
+// Persistent CTAs (one per SM) walk the tiles in groups of 16 m-tiles swept along n so a group's A rows stay
+// L2-resident while B streams; the ring runs across tile boundaries.  History of the variants that led here
+// (per-tile kernel 70 % DMMA-pipe busy -> persistent 16-warp 73 % -> this one 83 % -> packed 96 %): profiles/r01_gemm_v*_ncu.md.
 #include "kernels.cuh"
 #include "common.h"
 
@@ -100,162 +104,6 @@ __device__ __forceinline__ void load_stage(double *As, double *Bs, const double 
     }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(NTHREADS, 1)
-dgemm_minus_kernel(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-                   int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n)
-{
-    extern __shared__ __align__(16) double smem[];
-    double *As = smem;                                 // [STAGES][BK][SA]
-    double *Bs = smem + STAGES * AS_STAGE;             // [STAGES][BN][SB]
-
-    // grouped tile order
-    int64_t t = blockIdx.x;
-    int group_sz = GROUP_M * tiles_n;
-    int grp = (int)(t / group_sz);
-    int first_m = grp * GROUP_M;
-    int gm = min(GROUP_M, tiles_m - first_m);
-    int r = (int)(t % group_sz);
-    int tm = first_m + r % gm;
-    int tn = r / gm;
-    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;           // 2 x 4 warps
-    const int wm0 = wm * 64, wn0 = wn * 32;
-
-    double acc[2][8][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-
-    const int KT = (K + BK - 1) / BK;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_stage<VEC>(As + s * AS_STAGE, Bs + s * BS_STAGE, A, lda, B, ldb, m0, n0, s * BK, M, N, K, tid);
-        cp_async_commit();
-    }
-
-    for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int st = nk % STAGES;
-                load_stage<VEC>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, m0, n0, nk * BK, M, N, K, tid);
-            }
-            cp_async_commit();
-        }
-        const double *as = As + (kt % STAGES) * AS_STAGE;
-        const double *bs = Bs + (kt % STAGES) * BS_STAGE;
-#pragma unroll
-        for (int k4 = 0; k4 < BK; k4 += 4) {
-            double fa[2][2], fb[8];
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf) {            // MMA-A operand = problem B: rows n, cols k
-                fa[nf][0] = bs[(wn0 + nf * 16 + g) * SB + k4 + tig];
-                fa[nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + k4 + tig];
-            }
-#pragma unroll
-            for (int mf = 0; mf < 8; ++mf)              // MMA-B operand = problem A: k rows, m cols
-                fb[mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int mf = 0; mf < 8; ++mf) dmma_16x8x4(acc[nf][mf], fa[nf][0], fa[nf][1], fb[mf]);
-        }
-    }
-    cp_async_wait<0>();
-
-    // epilogue: C -= acc.  (c0,c1) = rows m, m+1 of column n; (c2,c3) = same rows of column n+8
-#pragma unroll
-    for (int nf = 0; nf < 2; ++nf) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-            if (n >= N) continue;
-#pragma unroll
-            for (int mf = 0; mf < 8; ++mf) {
-                int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
-                if (m >= M) continue;
-                double *p = C + m + n * ldc;
-                double v0 = acc[nf][mf][2 * h], v1 = acc[nf][mf][2 * h + 1];
-                if (VEC == 2 && m + 1 < M) {
-                    double2 c = *reinterpret_cast<double2 *>(p);
-                    c.x -= v0; c.y -= v1;
-                    *reinterpret_cast<double2 *>(p) = c;
-                } else {
-                    p[0] -= v0;
-                    if (m + 1 < M) p[1] -= v1;
-                }
-            }
-        }
-    }
-}
-
-// ---- v2: persistent CTAs, 16 warps (4 per scheduler), continuous cp.async ring across tiles -------------
-// ncu on v1 (profiles/r01_gemm_v1.md): DMMA pipe 70 % busy; each tile lost ~30 us to an un-overlapped prologue
-// and a serialised load->store epilogue with 1 CTA / SM.  v2 keeps ONE CTA per SM resident for the whole launch:
-//   * 512 threads = 16 warps as 4(m) x 4(n), warp tile 32 x 32 (64 accumulator registers, <= 128 regs/thread);
-//   * the (tile, k-stage) sequence is one stream: loads run STAGES-1 stages ahead ACROSS tile boundaries, so
-//     the next tile's operands are already in shared memory when the epilogue of the current one starts;
-//   * the C tile is prefetched into L2 when the tile starts; the epilogue issues its 16 LDG.128 back to back,
-//     then subtracts and stores (one memory latency per tile instead of 32).
-constexpr int P_THREADS = 512;
-
-template <int VEC, int PBK>
-__device__ __forceinline__ void load_stage_p(double *As, double *Bs, const double *__restrict__ A, int64_t lda,
-                                             const double *__restrict__ B, int64_t ldb, int64_t m0, int64_t n0, int k0,
-                                             int64_t M, int64_t N, int K, int tid)
-{
-    if (VEC == 2) {
-#pragma unroll
-        for (int i = 0; i < (PBK * BM / 2) / P_THREADS; ++i) {
-            int c = tid + i * P_THREADS;
-            int k = c >> 6, mc = (c & 63) * 2;
-            int64_t m = m0 + mc; int kk = k0 + k;
-            int bytes = 0;
-            if (kk < K && m < M) bytes = (M - m >= 2) ? 16 : 8;
-            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
-            cp_async16(As + k * SA + mc, src, bytes);
-        }
-#pragma unroll
-        for (int i = 0; i < (BN * PBK / 2) / P_THREADS; ++i) {
-            int c = tid + i * P_THREADS;
-            int n = c / (PBK / 2), kc = (c % (PBK / 2)) * 2;
-            int64_t nn = n0 + n; int kk = k0 + kc;
-            int bytes = 0;
-            if (nn < N && kk < K) bytes = (K - kk >= 2) ? 16 : 8;
-            const double *src = bytes ? (B + kk + nn * ldb) : B;
-            cp_async16(Bs + n * (PBK + 4) + kc, src, bytes);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < (PBK * BM) / P_THREADS; ++i) {
-            int c = tid + i * P_THREADS;
-            int k = c >> 7, mc = c & 127;
-            int64_t m = m0 + mc; int kk = k0 + k;
-            int bytes = (kk < K && m < M) ? 8 : 0;
-            const double *src = bytes ? (A + m + (int64_t)kk * lda) : A;
-            cp_async8(As + k * SA + mc, src, bytes);
-        }
-#pragma unroll
-        for (int i = 0; i < (BN * PBK) / P_THREADS; ++i) {
-            int c = tid + i * P_THREADS;
-            int n = c / PBK, kc = c % PBK;
-            int64_t nn = n0 + n; int kk = k0 + kc;
-            int bytes = (nn < N && kk < K) ? 8 : 0;
-            const double *src = bytes ? (B + kk + nn * ldb) : B;
-            cp_async8(Bs + n * (PBK + 4) + kc, src, bytes);
-        }
-    }
-}
-
 __device__ __forceinline__ void tile_coords(int64_t t, int tiles_m, int tiles_n, int64_t &m0, int64_t &n0)
 {
     int group_sz = GROUP_M * tiles_n;
@@ -267,286 +115,9 @@ __device__ __forceinline__ void tile_coords(int64_t t, int tiles_m, int tiles_n,
     n0 = (int64_t)(r / gm) * BN;
 }
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int &m0, int &n0)
-{
-    int group_sz = GROUP_M * tiles_n;
-    int grp = t / group_sz;
-    int first_m = grp * GROUP_M;
-    int gm = min(GROUP_M, tiles_m - first_m);
-    int r = t - grp * group_sz;
-    m0 = (first_m + r % gm) * BM;
-    n0 = (r / gm) * BN;
-}
-
-template <int VEC, int PBK, int PST, int LOAD_MID>
-__global__ void __launch_bounds__(P_THREADS, 1)
-dgemm_minus_persistent(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-                       int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
-{
-    extern __shared__ __align__(16) double smem[];
-    constexpr int SBP = PBK + 4, AST = PBK * SA, BST = BN * SBP;
-    double *As = smem;
-    double *Bs = smem + PST * AST;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;      // 4 x 4 warps, 32 x 32 each
-
-    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
-    const int KT = (K + PBK - 1) / PBK;
-    // persistent (chunk == 0): tiles b, b+grid, ...;  chunked: tiles [b*chunk, (b+1)*chunk) then the CTA retires so a
-    // higher-priority stream (the look-ahead panel) can take the SM
-    const int64_t t_first = chunk > 0 ? (int64_t)blockIdx.x * chunk : blockIdx.x;
-    const int64_t t_stride = chunk > 0 ? 1 : gridDim.x;
-    const int64_t my_tiles = chunk > 0 ? max((int64_t)0, min((int64_t)chunk, ntiles - t_first)) : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t total = my_tiles * KT;
-
-    // loader cursor (tile, k-stage) runs STAGES-1 ahead of the consumer cursor
-    int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
-    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
-    auto issue_load = [&](int64_t li) {
-        if (li < total) {
-            int st = (int)(li % PST);
-            load_stage_p<VEC, PBK>(As + st * AST, Bs + st * BST, A, lda, B, ldb, l_m0, l_n0, l_kt * PBK, M, N, K, tid);
-            if (++l_kt == KT) {
-                l_kt = 0; ++l_lt;
-                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
-            }
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int s = 0; s < PST - 1; ++s) issue_load(s);
-
-    double acc[2][4][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-
-    int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
-    for (int64_t ci = 0; ci < total; ++ci) {
-        if (kt == 0) {
-            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
-            // pull this thread's part of the C tile into L2 while the k-loop runs
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-                    int64_t m = m0 + wm0 + 2 * tig;
-                    if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
-                }
-        }
-        cp_async_wait<PST - 2>();
-        __syncthreads();
-        if (!LOAD_MID) issue_load(ci + PST - 1);
-        const double *as = As + (ci % PST) * AST;
-        const double *bs = Bs + (ci % PST) * BST;
-#pragma unroll
-        for (int k4 = 0; k4 < PBK; k4 += 4) {
-            if (LOAD_MID && k4 == 4) issue_load(ci + PST - 1);
-            double fa[2][2], fb[4];
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf) {
-                fa[nf][0] = bs[(wn0 + nf * 16 + g) * SBP + k4 + tig];
-                fa[nf][1] = bs[(wn0 + nf * 16 + g + 8) * SBP + k4 + tig];
-            }
-#pragma unroll
-            for (int mf = 0; mf < 4; ++mf) fb[mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int mf = 0; mf < 4; ++mf) dmma_16x8x4(acc[nf][mf], fa[nf][0], fa[nf][1], fb[mf]);
-        }
-        if (++kt == KT) {
-            kt = 0; ++lt;
-            // ---- epilogue of this tile: all loads first, then subtract + store ----
-            if (VEC == 2) {
-#pragma unroll
-                for (int nf = 0; nf < 2; ++nf) {          // two batches of 8 x 16 B keep the kernel at 128 registers
-                    double2 cv[2][4];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-#pragma unroll
-                        for (int mf = 0; mf < 4; ++mf) {
-                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
-                            if (n < N && m + 1 < M) cv[h][mf] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
-                            else if (n < N && m < M) cv[h][mf] = make_double2(C[m + n * ldc], 0.0);
-                            else cv[h][mf] = make_double2(0.0, 0.0);
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-#pragma unroll
-                        for (int mf = 0; mf < 4; ++mf) {
-                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
-                            double2 c = cv[h][mf];
-                            c.x -= acc[nf][mf][2 * h]; c.y -= acc[nf][mf][2 * h + 1];
-                            if (n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
-                            else if (n < N && m < M) C[m + n * ldc] = c.x;
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-                        if (n >= N) continue;
-#pragma unroll
-                        for (int mf = 0; mf < 4; ++mf) {
-                            int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
-                            if (m < M) C[m + n * ldc] -= acc[nf][mf][2 * h];
-                            if (m + 1 < M) C[m + 1 + n * ldc] -= acc[nf][mf][2 * h + 1];
-                        }
-                    }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ---- v6: persistent / chunked like v2-v5 but 8 warps with 64 x 32 warp tiles (0.375 LDS per DMMA instead of 0.5),
-// explicit register double-buffering of the fragments inside a stage, loads issued after the first k4 step --------
-template <int VEC>
-__global__ void __launch_bounds__(NTHREADS, 1)
-dgemm_minus_p8(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-               int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
-{
-    extern __shared__ __align__(16) double smem[];
-    double *As = smem;
-    double *Bs = smem + STAGES * AS_STAGE;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;      // 2 x 4 warps, 64 x 32 each
-
-    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
-    const int KT = (K + BK - 1) / BK;
-    const int64_t t_first = chunk > 0 ? (int64_t)blockIdx.x * chunk : blockIdx.x;
-    const int64_t t_stride = chunk > 0 ? 1 : gridDim.x;
-    const int64_t my_tiles = chunk > 0 ? max((int64_t)0, min((int64_t)chunk, ntiles - t_first)) : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t total = my_tiles * KT;
-
-    int64_t l_lt = 0; int l_kt = 0; int64_t l_m0 = 0, l_n0 = 0;
-    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
-    auto issue_load = [&](int64_t li) {
-        if (li < total) {
-            int st = (int)(li % STAGES);
-            load_stage<VEC>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, l_m0, l_n0, l_kt * BK, M, N, K, tid);
-            if (++l_kt == KT) {
-                l_kt = 0; ++l_lt;
-                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
-            }
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue_load(s);
-
-    double acc[2][8][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-
-    int kt = 0; int64_t lt = 0; int64_t m0 = 0, n0 = 0;
-    for (int64_t ci = 0; ci < total; ++ci) {
-        if (kt == 0) {
-            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int mq = 0; mq < 4; ++mq) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-                        int64_t m = m0 + wm0 + mq * 16 + 2 * tig;
-                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
-                    }
-        }
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const double *as = As + (ci % STAGES) * AS_STAGE;
-        const double *bs = Bs + (ci % STAGES) * BS_STAGE;
-        double fa[2][2][2], fb[2][8];
-        auto load_frags = [&](int buf, int k4) {
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf) {
-                fa[buf][nf][0] = bs[(wn0 + nf * 16 + g) * SB + k4 + tig];
-                fa[buf][nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + k4 + tig];
-            }
-#pragma unroll
-            for (int mf = 0; mf < 8; ++mf) fb[buf][mf] = as[(k4 + tig) * SA + wm0 + mf * 8 + g];
-        };
-        load_frags(0, 0);
-#pragma unroll
-        for (int s4 = 0; s4 < BK / 4; ++s4) {
-            if (s4 == 1) issue_load(ci + STAGES - 1);
-            if (s4 + 1 < BK / 4) load_frags((s4 + 1) & 1, (s4 + 1) * 4);
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int mf = 0; mf < 8; ++mf) dmma_16x8x4(acc[nf][mf], fa[s4 & 1][nf][0], fa[s4 & 1][nf][1], fb[s4 & 1][mf]);
-        }
-        if (++kt == KT) {
-            kt = 0; ++lt;
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf) {
-#pragma unroll
-                for (int mh = 0; mh < 2; ++mh) {                 // batches of 8 x 16 B
-                    double2 cv[2][4];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
-                            if (VEC == 2 && n < N && m + 1 < M) cv[h][q] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
-                            else if (n < N && m < M) cv[h][q] = make_double2(C[m + n * ldc], (m + 1 < M) ? C[m + 1 + n * ldc] : 0.0);
-                            else cv[h][q] = make_double2(0.0, 0.0);
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
-                            double2 c = cv[h][q];
-                            c.x -= acc[nf][mh * 4 + q][2 * h]; c.y -= acc[nf][mh * 4 + q][2 * h + 1];
-                            if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
-                            else if (n < N && m < M) { C[m + n * ldc] = c.x; if (m + 1 < M) C[m + 1 + n * ldc] = c.y; }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ---- v7: v6 with the per-stage block barrier moved to the MIDDLE of the stage: at the stage boundary the fragments
-// of the next stage are already being prefetched (its data became visible at the mid-stage barrier), so the DMMA
-// pipe never drains waiting for LDS after a barrier --------
+// The per-stage block barrier sits in the MIDDLE of the stage: at the stage boundary the fragments of the next stage
+// are already being prefetched (its data became visible at the mid-stage barrier), so the DMMA pipe never drains
+// waiting for LDS after a barrier.  chunk > 0: a CTA processes `chunk` consecutive tiles and retires.
 template <int VEC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dgemm_minus_p8b(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
@@ -694,151 +265,6 @@ dgemm_minus_p8b(int64_t M, int64_t N, int K, const double *__restrict__ A, int64
     cp_async_wait<0>();
 }
 
-// ---- v8: v7's schedule (mid-stage barrier, fragments double-buffered across stage and tile boundaries) with 16 warps
-// of 32 x 32 (4 per scheduler, <= 128 registers).  ncu on v7 (profiles/r01_gemm_v7_ncu.md): each of the 2 warps per
-// scheduler sits ~40 % of the time in the fixed issue stall that follows every DMMA, so ~0.4^2 = 16 % of the cycles no
-// warp can feed the pipe (measured: 83 % busy).  With 4 warps per scheduler that probability is ~3 %. --------
-template <int VEC>
-__global__ void __launch_bounds__(P_THREADS, 1)
-dgemm_minus_p16(int64_t M, int64_t N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-                int64_t ldb, double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int chunk)
-{
-    extern __shared__ __align__(16) double smem[];
-    double *As = smem;
-    double *Bs = smem + STAGES * AS_STAGE;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;      // 4 x 4 warps, 32 x 32 each
-
-    const int ntiles = tiles_m * tiles_n;                       // host guarantees < 2^31 (and total stages < 2^31)
-    const int KT = (K + BK - 1) / BK;
-    const int t_first = chunk > 0 ? (int)blockIdx.x * chunk : (int)blockIdx.x;
-    const int t_stride = chunk > 0 ? 1 : (int)gridDim.x;
-    const int my_tiles = chunk > 0 ? max(0, min(chunk, ntiles - t_first)) : (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * KT;
-
-    int l_lt = 0; int l_kt = 0; int l_m0 = 0, l_n0 = 0;
-    if (my_tiles > 0) tile_coords(t_first, tiles_m, tiles_n, l_m0, l_n0);
-    auto issue_load = [&](int li) {
-        if (li < total) {
-            int st = li % STAGES;
-            load_stage_p<VEC, BK>(As + st * AS_STAGE, Bs + st * BS_STAGE, A, lda, B, ldb, l_m0, l_n0, l_kt * BK, M, N, K, tid);
-            if (++l_kt == KT) {
-                l_kt = 0; ++l_lt;
-                if (l_lt < my_tiles) tile_coords(t_first + l_lt * t_stride, tiles_m, tiles_n, l_m0, l_n0);
-            }
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue_load(s);
-
-    double acc[2][4][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-
-    double fa[2][2][2], fb[2][4];
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (total > 0) {
-#pragma unroll
-        for (int nf = 0; nf < 2; ++nf) {
-            fa[0][nf][0] = Bs[(wn0 + nf * 16 + g) * SB + tig];
-            fa[0][nf][1] = Bs[(wn0 + nf * 16 + g + 8) * SB + tig];
-        }
-#pragma unroll
-        for (int mf = 0; mf < 4; ++mf) fb[0][mf] = As[tig * SA + wm0 + mf * 8 + g];
-    }
-    int kt = 0; int lt = 0; int m0 = 0, n0 = 0;
-    for (int ci = 0; ci < total; ++ci) {
-        if (kt == 0) {
-            tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, m0, n0);
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int mq = 0; mq < 2; ++mq) {
-                        int n = n0 + wn0 + nf * 16 + g + h * 8;
-                        int m = m0 + wm0 + mq * 16 + 2 * tig;
-                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + (int64_t)n * ldc));
-                    }
-        }
-        const double *as = As + (ci % STAGES) * AS_STAGE;
-        const double *bs = Bs + (ci % STAGES) * BS_STAGE;
-        const double *asn = As + ((ci + 1) % STAGES) * AS_STAGE;
-        const double *bsn = Bs + ((ci + 1) % STAGES) * BS_STAGE;
-#pragma unroll
-        for (int s4 = 0; s4 < BK / 4; ++s4) {
-            if (s4 == 1) {
-                cp_async_wait<STAGES - 3>();
-                __syncthreads();
-                issue_load(ci + STAGES - 1);
-            }
-            const int cur = s4 & 1, nxt = cur ^ 1;
-            if (s4 + 1 < BK / 4) {
-#pragma unroll
-                for (int nf = 0; nf < 2; ++nf) {
-                    fa[nxt][nf][0] = bs[(wn0 + nf * 16 + g) * SB + (s4 + 1) * 4 + tig];
-                    fa[nxt][nf][1] = bs[(wn0 + nf * 16 + g + 8) * SB + (s4 + 1) * 4 + tig];
-                }
-#pragma unroll
-                for (int mf = 0; mf < 4; ++mf) fb[nxt][mf] = as[((s4 + 1) * 4 + tig) * SA + wm0 + mf * 8 + g];
-            } else if (ci + 1 < total) {
-#pragma unroll
-                for (int nf = 0; nf < 2; ++nf) {
-                    fa[nxt][nf][0] = bsn[(wn0 + nf * 16 + g) * SB + tig];
-                    fa[nxt][nf][1] = bsn[(wn0 + nf * 16 + g + 8) * SB + tig];
-                }
-#pragma unroll
-                for (int mf = 0; mf < 4; ++mf) fb[nxt][mf] = asn[tig * SA + wm0 + mf * 8 + g];
-            }
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf)
-#pragma unroll
-                for (int mf = 0; mf < 4; ++mf) dmma_16x8x4(acc[nf][mf], fa[cur][nf][0], fa[cur][nf][1], fb[cur][mf]);
-        }
-        if (++kt == KT) {
-            kt = 0; ++lt;
-#pragma unroll
-            for (int nf = 0; nf < 2; ++nf) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {                     // batches of 4 x 16 B keep the kernel within 128 registers
-                    const int n = n0 + wn0 + nf * 16 + g + h * 8;
-                    double *cp = C + (int64_t)n * ldc;
-                    double2 cv[4];
-#pragma unroll
-                    for (int mf = 0; mf < 4; ++mf) {
-                        int m = m0 + wm0 + mf * 8 + 2 * tig;
-                        if (VEC == 2 && n < N && m + 1 < M) cv[mf] = *reinterpret_cast<const double2 *>(cp + m);
-                        else if (n < N && m < M) cv[mf] = make_double2(cp[m], (m + 1 < M) ? cp[m + 1] : 0.0);
-                        else cv[mf] = make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int mf = 0; mf < 4; ++mf) {
-                        int m = m0 + wm0 + mf * 8 + 2 * tig;
-                        double2 c = cv[mf];
-                        c.x -= acc[nf][mf][2 * h]; c.y -= acc[nf][mf][2 * h + 1];
-                        if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(cp + m) = c;
-                        else if (n < N && m < M) { cp[m] = c.x; if (m + 1 < M) cp[m + 1] = c.y; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-        }
-    }
-    cp_async_wait<0>();
-}
-
 // ---- complex: C -= A*B with interleaved (re,im); four real DMMAs per complex MMA ---------------------
 // Tiling: CTA 64(m) x 64(n) x 16(k) complex, 8 warps as 2(m) x 4(n), warp tile 32 x 16.
 constexpr int ZBM = 64, ZBN = 64, ZBK = 16;
@@ -953,9 +379,9 @@ zgemm_minus_kernel(int64_t M, int64_t N, int K, const zcomplex *__restrict__ A, 
 
 bool dgemm_takes_packed(int64_t M, int K, int flags)
 {
-    static int64_t variant = -1, min_m = 0;
-    if (variant < 0) { variant = opt("gemm_variant", 9); min_m = opt("gemm_packed_min", 3072); }
-    return variant == 9 && (flags & GEMM_MAIN) && M >= min_m && K >= 16;
+    static int64_t packed = -1, min_m = 0;
+    if (packed < 0) { packed = opt("gemm_variant", 9) == 9; min_m = opt("gemm_packed_min", 3072); }   // SLB200_GEMM_VARIANT=7: cp.async kernel only
+    return packed && (flags & GEMM_MAIN) && M >= min_m && K >= 16;
 }
 
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
@@ -966,65 +392,23 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
         launch_dgemm_minus_packed(M, N, K, A, lda, B, ldb, C, ldc, s, chunk, (flags & GEMM_REUSE_A) != 0);
         return;
     }
+    constexpr size_t smem_bytes = (size_t)STAGES * (AS_STAGE + BS_STAGE) * sizeof(double);
     static bool attr_done = false;
-    const size_t smem_bytes = (size_t)STAGES * (AS_STAGE + BS_STAGE) * sizeof(double);
     if (!attr_done) {
-        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_p8b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_p8b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_done = true;
     }
-    int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N + BN - 1) / BN);
-    int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    const int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N + BN - 1) / BN);
+    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
     if (ntiles > 0x7fffffffLL) fatal("dgemm: too many tiles");
-    bool aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0 && (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0);
-    static int variant = -1;
-    constexpr size_t smem16 = (size_t)4 * (16 * SA + BN * 20) * sizeof(double), smem32 = (size_t)3 * (32 * SA + BN * 36) * sizeof(double);
-    if (variant < 0) {
-        variant = (int)opt("gemm_variant", 9);
-        if (variant == 9) variant = 7;                     // 9 = packed kernel for the big updates, v7 for everything else
-#define SET_ATTR(K, bytes) SLB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-        SET_ATTR((dgemm_minus_persistent<2, 16, 4, 0>), smem16); SET_ATTR((dgemm_minus_persistent<1, 16, 4, 0>), smem16);
-        SET_ATTR((dgemm_minus_persistent<2, 16, 4, 1>), smem16); SET_ATTR((dgemm_minus_persistent<2, 32, 3, 0>), smem32);
-        SET_ATTR((dgemm_minus_persistent<2, 32, 3, 1>), smem32);
-        SET_ATTR((dgemm_minus_p8<2>), smem16); SET_ATTR((dgemm_minus_p8<1>), smem16);
-        SET_ATTR((dgemm_minus_p8b<2>), smem16); SET_ATTR((dgemm_minus_p8b<1>), smem16);
-        SET_ATTR((dgemm_minus_p16<2>), smem16); SET_ATTR((dgemm_minus_p16<1>), smem16);
-#undef SET_ATTR
-    }
-    if (variant >= 2) {
-        unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
-        if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
-        if (variant == 8 && aligned)
-            dgemm_minus_p16<2><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 8)
-            dgemm_minus_p16<1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 7 && aligned)
-            dgemm_minus_p8b<2><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 7)
-            dgemm_minus_p8b<1><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 6 && aligned)
-            dgemm_minus_p8<2><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 6)
-            dgemm_minus_p8<1><<<grid, NTHREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (!aligned)
-            dgemm_minus_persistent<1, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 2)
-            dgemm_minus_persistent<2, 16, 4, 0><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 3)
-            dgemm_minus_persistent<2, 16, 4, 1><<<grid, P_THREADS, smem16, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else if (variant == 4)
-            dgemm_minus_persistent<2, 32, 3, 0><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        else
-            dgemm_minus_persistent<2, 32, 3, 1><<<grid, P_THREADS, smem32, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
-        SLB_CUDA(cudaGetLastError());
-        counter_add("kernel_launches", 1);
-        counter_add("gemm_launches", 1);
-        return;
-    }
+    const bool aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0 && (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0);
+    unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
+    if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
     if (aligned)
-        dgemm_minus_kernel<2><<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        dgemm_minus_p8b<2><<<grid, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
     else
-        dgemm_minus_kernel<1><<<(unsigned)ntiles, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n);
+        dgemm_minus_p8b<1><<<grid, NTHREADS, smem_bytes, s>>>(M, N, K, A, lda, B, ldb, C, ldc, tiles_m, tiles_n, chunk);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);
     counter_add("gemm_launches", 1);

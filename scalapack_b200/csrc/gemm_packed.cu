@@ -10,9 +10,11 @@
 //     warps.  A k-stage is then TWO cp.async.bulk copies issued by one producer thread (no per-thread address
 //     math, no bounds checks: blocks are zero padded), every fragment load is a conflict-free LDS.128 at an
 //     immediate offset, and stages are handed over with full/empty mbarriers instead of __syncthreads().
-//   * Without block barriers the warps drift: the second warp of every scheduler starts `lag` cycles late, so
-//     its epilogue falls into the main loop of the first one (and vice versa) and the DMMA pipe keeps a warp
-//     to issue from during epilogues.  The 6-deep ring bounds the drift.
+//   * Without block barriers the warps drift apart, so one warp's epilogue falls into the main loop of the other
+//     warp of its scheduler and the DMMA pipe keeps a warp to issue from during epilogues; the 6-deep ring bounds the
+//     drift.  (SLB200_GEMM_LAG=cycles starts the second warp of each scheduler late to force the de-phasing; measured:
+//     no difference, the warps de-phase by themselves -- profiles/r01_gemm_ab_v7_v9.txt.  SLB200_GEMM_EPI=1 selects a
+//     red.global.add epilogue: also no difference.)
 // Per-element arithmetic (k order, one DMMA chain per element, C - acc) is identical to gemm.cu: results are
 // bit-identical to every other variant.
 #include "kernels.cuh"
@@ -312,7 +314,7 @@ void launch_dgemm_minus_packed(int64_t M, int64_t N, int K, const double *A, int
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
-        epi = (int)opt("gemm_epi", 0); lag = (int)opt("gemm_lag", 6000);
+        epi = (int)opt("gemm_epi", 0); lag = (int)opt("gemm_lag", 0);
         attr_done = true;
     }
     const int KT = (K + BK - 1) / BK;

@@ -234,16 +234,9 @@ def _gemm_in_subprocess(env_extra, M, N, K, tmp_path, tag):
     return np.load(out), err
 
 
-@pytest.mark.parametrize("variant", [1, 3, 6, 7, 8])
-def test_update_kernel_variants_agree(S, variant, tmp_path):
-    """Every DMMA update-kernel variant kept in gemm.cu computes the same C - A*B (same k order per element)."""
-    _, err = _gemm_in_subprocess({"SLB200_GEMM_VARIANT": variant}, 777, 1030, 200, tmp_path, f"v{variant}")
-    assert err < 1e-12, err
-
-
-@pytest.mark.parametrize("opts", [{}, {"SLB200_GEMM_LAG": 0}, {"SLB200_GEMM_EPI": 1}, {"SLB200_GEMM_TEST_CHUNK": 3}])
+@pytest.mark.parametrize("opts", [{}, {"SLB200_GEMM_LAG": 6000}, {"SLB200_GEMM_EPI": 1}, {"SLB200_GEMM_TEST_CHUNK": 3}])
 @pytest.mark.parametrize("shape", [(777, 1030, 200), (2048, 2304, 512), (130, 5000, 37)])
-def test_packed_update_kernel_is_bit_identical_to_v7(S, opts, shape, tmp_path):
+def test_packed_update_kernel_is_bit_identical_to_cp_async_kernel(S, opts, shape, tmp_path):
     """gemm_packed.cu (fragment-ordered operands, bulk-copy ring, mbarriers) vs the cp.async kernel: same bits, on ragged
     shapes (zero-padded blocks), with the late-start lag off, with the red.add epilogue and with chunked CTAs."""
     M, N, K = shape

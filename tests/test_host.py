@@ -160,3 +160,21 @@ def test_two_process_control_plane(S):
     assert [r["incons"] for r in res] == [-2, -2]
     assert res[0]["solo_ctx_valid"] and not res[1]["solo_ctx_valid"] and res[1]["solo_info"] == [-1, -1, -1, -1]
     assert res[0]["igamn"] == [5, 9] and res[1]["igamn"] == [5, 9]
+
+
+def test_bench_reference_arm_rank_contract():
+    """bench.py --impl reference: under torchrun only rank 0 works and prints the JSON line (with impl / cpu_baseline / e2e keys);
+    the other ranks exit 0 without output.  Runs on the host cores (no GPU)."""
+    import json
+    env1 = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        cwd=ROOT, env=env1, capture_output=True, text=True, timeout=120)
+    assert p1.returncode == 0 and p1.stdout.strip() == ""
+    env0 = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", SLB200_BENCH_CPU_TARGET_S="1")
+    p0 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        cwd=ROOT, env=env0, capture_output=True, text=True, timeout=300)
+    assert p0.returncode == 0, p0.stderr[-2000:]
+    line = json.loads([l for l in p0.stdout.splitlines() if l.startswith("{")][0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "TFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
