@@ -1,6 +1,6 @@
 #!/bin/bash
 # 4-GPU (2x2 grid): light parity (BASELINE config 1 + a pipelined split case), then the default-size bench line.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 120 python scripts/run_mp.py 4 '[{"P":2,"Q":2,"m":2000,"n":2000,"nb":64,"nrhs":1},{"P":2,"Q":2,"m":4096,"n":4096,"nb":128,"nrhs":1,"dev":true,"split":256}]' 80 2>&1 | tail -n 8 | cut -c1-300 | tee gpurun_out/mp4.log
 s=$(date +%s)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final 1-GPU pass: parity suite (minus the slow subprocess A/B cases), smoke, default bench line, reference arm.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 timeout 300 python -m pytest tests -m gpu -q -k "not variants and not packed" --timeout 240 --timeout-method=thread -p no:cacheprovider > gpurun_out/final_tests.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Call A: full GPU parity suite (1 GPU), smoke, the default bench line (e2e + cpu_baseline) and the reference arm.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 for f in tests/test_gpu_kernels.py tests/test_gpu_lu.py tests/test_gpu_multi.py; do

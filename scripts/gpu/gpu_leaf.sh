@@ -1,6 +1,6 @@
 #!/bin/bash
 # Call G: packet-mailbox leaf kernel: parity + panel timings + bench timeline.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_lu.py -m gpu -q -x -k "not variants and not packed" --timeout 300 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -n 8 | tee gpurun_out/leaf_parity.log
 timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/panel_times.txt

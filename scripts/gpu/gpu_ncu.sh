@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/launches_full.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu_bench_full.log 2>&1
 echo "launch list rc=$?"; tail -2 gpurun_out/ncu_bench_full.log | cut -c1-300

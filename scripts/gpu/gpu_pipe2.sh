@@ -1,6 +1,6 @@
 #!/bin/bash
 # Call F: pipeline v2 (g0 kept clear of prep/left swaps, capped grids): parity + trace + tuning.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_lu.py tests/test_gpu_kernels.py -m gpu -q -x -k "not variants and not packed" --timeout 300 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -n 8 | tee gpurun_out/pipe2_parity.log
 SLB200_LA_TRACE=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/trace_pipe2.json 2> gpurun_out/trace_pipe2.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Call C: look-ahead timeline with the packed kernel, chunk / gmax tuning, ncu capture of the packed kernel.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 run() {  # env assignments as args
   env "$@" timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu 2> gpurun_out/tune9.err | python -c "

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Call B: parity + A/B timing of the packed-operand update kernel (variant 9) against v7.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_lu.py -m gpu -q -x -k "packed" --timeout 120 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -n 15 | tee gpurun_out/v9_parity.log
 {
