@@ -86,6 +86,14 @@ if __name__ == "__main__":
             "(v7: 83.2 %). DRAM traffic 11.48 GB read + 8.54 GB written = 20.02 GB per launch for 17.45 GB of algorithmic bytes (16*M*N for C + 8*(M+N)*K "
             "for the operands): 1.147x.  PC sampling: main loop 80.6 % of the warp samples (stall_wait 37 %, math_pipe_throttle 31 % = the DMMA pipe itself), "
             "epilogue 6.8 % (long_scoreboard on the C loads; overlapped by the other warp of the scheduler), producer warp 4.5 %.")
+    ncu_raw("prof_leaf.ncu-rep", "r01: panel leaf kernel (pre-packet mailbox version), one launch inside bench.py --size 16384", "r01_leaf_ncu.md",
+            "A 32-column leaf on 48 CTAs: 268 us = 8.4 us per column, DRAM traffic 3.9 MB (the slab is read once and stays in shared memory): the "
+            "kernel is bound by the per-column exchange latency, not by HBM -- which is what the packet mailbox (panel.cu) then attacked (6.3 us per column, "
+            "profiles/r01_panel_times.txt).  A capture of the new kernel and of a full-width swap launch is owed to round 2.")
+    ncu_raw("prof_swap.ncu-rep", "r01: swap_pack_kernel, one (small, left-columns) launch inside bench.py --size 32768", "r01_swap_ncu.md",
+            "Only a small launch was captured (8 CTAs, 0.55 MB): not representative of the full-width interchange; the per-step timeline "
+            "(profiles/r01_la_trace_v9_nopipeline.txt: prep = swaps + U12 solve = 3.2 - 4 ms per step at N = 65536) is the measured cost, "
+            "~4.7 GB of sector traffic per step = ~2 TB/s on an 8-byte-gather pattern.")
     launches("launches_n8192.csv", "r01_launches_n8192.md", "r01: launch list of `bench.py --n 8192 --steps 1` (1 GPU)",
              "dmma/dfma_peak_kernel are the roofline micro-benchmarks bench.py runs after the timed region.")
     launches("launches_full.csv", "r01_launches_n65536.md", "r01: launch list of the default bench (N=65536)")
