@@ -246,3 +246,33 @@ def test_packed_update_kernel_is_bit_identical_to_cp_async_kernel(S, opts, shape
     out, err9 = _gemm_in_subprocess(env, M, N, K, tmp_path, "v9")
     assert err7 < 1e-11 and err9 < 1e-11, (err7, err9)
     assert np.array_equal(out, ref)
+
+
+def test_full_size_properties_n65536(S, ctx11):
+    """BASELINE config 2 at its full size (N=65536, NB=512, 32 GiB of A in HBM), where the oracle is out of reach:
+    size-independent properties only -- INFO = 0, every pivot within [i, N] (PDGETRF's IPIV contract, pdgetrf.f:118-121),
+    and the reference's solve residual ||Ax-b|| / (||A|| ||x|| N eps) (pdlaschk.f:187,296) of PDGETRS with the factors,
+    evaluated on the device against the regenerated matrix, below its threshold 1.0.  Mirrors what bench.py does."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n, nb = 65536, 512
+    if free < 48 * 2**30:
+        pytest.skip("needs 48 GiB of free HBM")
+    lld = n
+    desca, info = S.descinit(n, n, nb, nb, 0, 0, ctx11, lld)
+    assert info == 0
+    A = torch.empty(n * lld, dtype=torch.float64, device="cuda")
+    ipiv = np.zeros(n + nb, np.int32)
+    S.matgen64(ctx11, n, n, nb, nb, A, lld, 20261017)
+    torch.cuda.synchronize()
+    assert S.pdgetrf(n, n, A, 1, 1, desca, ipiv) == 0
+    rows = np.arange(1, n + 1)
+    assert np.all(ipiv[:n] >= rows) and np.all(ipiv[:n] <= n)
+    descb, _ = S.descinit(n, 1, nb, 1, 0, 0, ctx11, lld)
+    X = torch.zeros(lld, dtype=torch.float64, device="cuda")
+    S.matgen64(ctx11, n, 1, nb, 1, X, lld, 777)
+    assert S.pdgetrs("N", n, 1, A, 1, 1, desca, ipiv, X, 1, 1, descb) == 0
+    sresid = S.pdlaschk(ctx11, n, 1, X, descb, desca, 20261017, 777, gen=64)
+    assert 0.0 <= sresid < 1.0, sresid
+    del A, X
+    torch.cuda.empty_cache()
