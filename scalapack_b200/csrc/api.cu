@@ -109,8 +109,8 @@ static void getrf_entry(const char *name, const int *m, const int *n, T *a, cons
     }
     Staged<T> A("stage_A", a, (size_t)lld * (size_t)nloc);
     std::vector<int> ipg((size_t)mn);
-    getrf_device<T>(g, *m, *n, A.dev, lld, nb, rsrc, csrc, ipg.data(), info);
-    A.writeback();
+    getrf_device<T>(g, *m, *n, A.dev, lld, nb, rsrc, csrc, ipg.data(), info, A.staged ? A.host : nullptr);
+    if (!g_last_lu.host_written) A.writeback();
     fill_local_ipiv(ipg, mn, nb, rsrc, nprow, myrow, ipiv);
 }
 

@@ -78,6 +78,7 @@ struct Runtime {
     cudaStream_t s_main = nullptr;     // trailing update / swaps
     cudaStream_t s_panel = nullptr;    // look-ahead panel stream (high priority)
     cudaStream_t s_copy = nullptr;     // staging copies
+    cudaStream_t s_d2h = nullptr;      // write-back of finished block rows to a host-resident caller (experimental, e2e_overlap)
     cudaStream_t s_prep = nullptr;     // row interchanges + U12 solve of the next column half (above the update, below the panel)
 };
 Runtime &rt();                      // initialises CUDA lazily; fatal()s if no device (no CPU fallback)

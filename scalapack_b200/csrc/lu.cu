@@ -58,7 +58,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // launch-latency-bound U12 solve leave the critical path, which becomes  update_k(near) + update_k(far)  per step.
 // The boundary b only moves when near has shrunk below a quarter of the trailing columns (then one step waits for both halves).
 template <typename T>
-static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host)
+static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host, T *hA)
 {
     Runtime &r = rt();
     cudaStream_t sg = r.s_main, sp = r.s_panel, sc = r.s_copy, sq = r.s_prep;
@@ -76,6 +76,21 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     const bool pipe = opt("la_pipeline", 1) != 0;
     const int64_t split_min = opt("la_split_min", 6144);      // fewer trailing columns: the step is not split
     const bool trace = opt("la_trace", 0) != 0;               // per-step timeline on stderr
+    // experimental (default off until validated on hardware): block row k of the factors -- the L11/U11 block and U12, final once
+    // step k's prep is done -- goes back to a host-resident caller during the factorisation; only the L21 parts (final
+    // after the last left interchange) are left for the end.  Halves the serial D2H of the end-to-end path.
+    if (hA != nullptr && opt("e2e_overlap", 0) == 0) hA = nullptr;
+    if (hA != nullptr) {     // pageable memory would make every async copy block the enqueueing thread: pinned callers only
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, hA) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); hA = nullptr; }
+    }
+    cudaStream_t sd = r.s_d2h;
+    auto rows_to_host = [&](int64_t r0, int64_t nr, int64_t c0, int64_t c1) {
+        if (nr <= 0 || c1 <= c0) return;
+        SLB_CUDA(cudaMemcpy2DAsync(hA + r0 + c0 * lld, (size_t)lld * sizeof(T), A + r0 + c0 * lld, (size_t)lld * sizeof(T),
+                                   (size_t)nr * sizeof(T), (size_t)(c1 - c0), cudaMemcpyDeviceToHost, sd));
+        counter_add("d2h_bytes", (int64_t)((size_t)nr * (size_t)(c1 - c0) * sizeof(T)));
+    };
 
     auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
     cudaEvent_t ev0, ev1, evs;
@@ -125,7 +140,11 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
             SLB_CUDA(cudaEventRecord(evl[k], sc));
         };
-        if (nright <= 0) { left_swaps(); continue; }
+        if (nright <= 0) {
+            left_swaps();
+            if (hA) { SLB_CUDA(cudaStreamWaitEvent(sd, evp[k], 0)); rows_to_host(j0, jb, j0, N); }
+            continue;
+        }
         // ---- near | far boundary ----
         int64_t bk = N;
         bool resplit = false;
@@ -187,6 +206,11 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             prep(bk, N);
             SLB_CUDA(cudaEventRecord(pdf[k], sq));
         }
+        if (hA) {                                                      // block row k is final: panel block + U12
+            SLB_CUDA(cudaStreamWaitEvent(sd, pdn[k], 0));
+            rows_to_host(j0, jb, j0, bk);
+            if (bk < N) { SLB_CUDA(cudaStreamWaitEvent(sd, pdf[k], 0)); rows_to_host(j0, jb, bk, N); }
+        }
         // ---- (e) sg: rest of near, far ----
         SLB_CUDA(cudaStreamWaitEvent(sg, pdn[k], 0));
         timed_gemm(2, cr + jbn, bk, have_next);
@@ -209,6 +233,16 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     SLB_CUDA(cudaMemcpyAsync(ipiv_glob_host, ipiv_dev, (size_t)mn * sizeof(int), cudaMemcpyDeviceToHost, sg));
     int info_local = 0;
     SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sg));
+    g_last_lu.host_written = false;
+    if (hA) {                                                          // what is left: the L21 part of every block column
+        SLB_CUDA(cudaStreamWaitEvent(sd, ev1, 0));
+        for (int k = 0; k < nsteps; ++k) {
+            const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
+            rows_to_host(j0 + jb, M - (j0 + jb), j0, j0 + jb);
+        }
+        SLB_CUDA(cudaStreamSynchronize(sd));
+        g_last_lu.host_written = true;
+    }
     SLB_CUDA(cudaStreamSynchronize(sg));
     SLB_CUDA(cudaStreamSynchronize(sp)); SLB_CUDA(cudaStreamSynchronize(sq)); SLB_CUDA(cudaStreamSynchronize(sc));
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -249,11 +283,12 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
 }
 
 template <typename T>
-int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host)
+int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host, T *host_out)
 {
+    g_last_lu.host_written = false;
     const bool prof = opt("profile", 0) != 0;
     if (g->nprow * g->npcol == 1 && opt("lookahead", 1) != 0 && !prof)
-        return getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host);
+        return getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host, host_out);
     Runtime &r = rt();
     const int P = g->nprow, Q = g->npcol, myrow = g->myrow, mycol = g->mycol;
     const int mn = M < N ? M : N;
@@ -641,7 +676,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     return 0;
 }
 
-template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *);
-template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *);
+template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *, double *);
+template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *, zcomplex *);
 
 }  // namespace slb

@@ -41,6 +41,7 @@ Runtime &rt()
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_main, cudaStreamNonBlocking, lo));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_panel, cudaStreamNonBlocking, hi));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_copy, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
+    SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_d2h, cudaStreamNonBlocking, lo));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_prep, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
     g_rt.cuda_ok = true;
     return g_rt;

@@ -276,3 +276,29 @@ def test_full_size_properties_n65536(S, ctx11):
     assert 0.0 <= sresid < 1.0, sresid
     del A, X
     torch.cuda.empty_cache()
+
+
+@pytest.mark.skipif(not os.environ.get("SLB200_TEST_EXPERIMENTAL"), reason="experimental path (SLB200_E2E_OVERLAP), enabled once validated on hardware")
+@pytest.mark.parametrize("m,n,nb", [(3072, 3072, 256), (2000, 1500, 128), (1500, 2000, 128)])
+def test_e2e_overlap_writes_the_same_factors(S, O, ctx11, m, n, nb):
+    """Block rows written back to a pinned host array during the factorisation (e2e_overlap) must give exactly the
+    array the plain staged path gives, guard rows included."""
+    import torch
+    a0 = O.matgen64_tile(max(m, n), 4321, 0, m, 0, n)
+    lld = m + 3
+    outs = []
+    for ov in (0, 1):
+        S.set_option("e2e_overlap", ov)
+        S.set_option("la_split_min", 512); S.set_option("lookahead_min_us", 0)
+        try:
+            host = torch.full((n, lld), PADVAL, dtype=torch.float64).pin_memory()      # (lld, n) column-major
+            host[:, :m] = torch.from_numpy(np.ascontiguousarray(a0.T))
+            desc, info = S.descinit(m, n, nb, nb, 0, 0, ctx11, lld)
+            ipiv = np.zeros(m + nb, np.int32)
+            assert S.pdgetrf(m, n, host.numpy(), 1, 1, desc, ipiv) == 0
+        finally:
+            S.set_option("e2e_overlap", 0); S.set_option("la_split_min", 6144); S.set_option("lookahead_min_us", 4000)
+        outs.append((host.numpy().copy(), ipiv.copy()))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.all(outs[1][0][:, m:] == PADVAL)
