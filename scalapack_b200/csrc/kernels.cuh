@@ -68,6 +68,11 @@ void launch_swap_pack(int jb, int j0, SwapPlan plan, RowDist rd, const T *A, int
 template <typename T>
 void launch_swap_unpack_out(int jb, SwapPlan plan, RowDist rd, T *A, int64_t lda, int64_t c0, int64_t c1,
                             const T *Obuf, int64_t ldo, cudaStream_t s);
+// experimental one-pass variant of pack + unpack (+ top-row copy) for nprow == 1 (SLB200_SWAP_FUSED=1; swap.cu)
+bool swap_fused_enabled();
+template <typename T>
+void launch_swap_fused(int jb, int j0, SwapPlan plan, RowDist rd, T *A, int64_t lda, int64_t c0, int64_t c1, T *Ubuf, int64_t ldu,
+                       bool write_top, cudaStream_t s);
 // select: U[t + c*ldu] = Cbuf_{owner(top_src[t])}[t + c*ldc] where Cbuf_p = Call + p*stride_p (all-gathered packs)
 template <typename T>
 void launch_swap_select(int jb, SwapPlan plan, RowDist rd, const T *Call, int64_t ldc, int64_t stride_p, int64_t ncols,

@@ -76,6 +76,7 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     const bool pipe = opt("la_pipeline", 1) != 0;
     const int64_t split_min = opt("la_split_min", 6144);      // fewer trailing columns: the step is not split
     const bool trace = opt("la_trace", 0) != 0;               // per-step timeline on stderr
+    const bool fused = swap_fused_enabled();                  // experimental one-pass interchanges (swap.cu)
     // experimental (default off until validated on hardware): block row k of the factors -- the L11/U11 block and U12, final once
     // step k's prep is done -- goes back to a host-resident caller during the factorisation; only the L21 parts (final
     // after the last left interchange) are left for the end.  Halves the serial D2H of the end-to-end path.
@@ -135,9 +136,12 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             SLB_CUDA(cudaStreamWaitEvent(sc, evp[k], 0));
             if (last_gemm) SLB_CUDA(cudaStreamWaitEvent(sc, last_gemm, 0));
             if (have_next) SLB_CUDA(cudaStreamWaitEvent(sc, evn[k], 0));
-            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
-            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
-            launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
+            if (fused) launch_swap_fused<T>(jb, j0, plan, rd, A, lld, 0, j0, (T *)nullptr, 0, true, sc);
+            else {
+                launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
+                launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
+                launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
+            }
             SLB_CUDA(cudaEventRecord(evl[k], sc));
         };
         if (nright <= 0) {
@@ -155,8 +159,11 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
         }
         if (bk > b || b < 0) resplit = true;          // near grows into the previous far half (or there was no split)
         auto prep = [&](int64_t c_lo, int64_t c_hi) {
-            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, Obuf + c_lo * jb, jb, sq);
-            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c_lo, c_hi, Obuf + c_lo * jb, jb, sq);
+            if (fused) launch_swap_fused<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, false, sq);
+            else {
+                launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, Obuf + c_lo * jb, jb, sq);
+                launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c_lo, c_hi, Obuf + c_lo * jb, jb, sq);
+            }
             Ops<T>::trsm(jb, c_hi - c_lo, Wp, lld, Ubuf + c_lo * jb, jb, sq);
             launch_copy2d<T>(jb, c_hi - c_lo, Ubuf + c_lo * jb, jb, A + j0 + c_lo * lld, lld, sq);
         };

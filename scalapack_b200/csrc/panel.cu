@@ -357,6 +357,7 @@ void panel_swap(PanelCtx<T> &c, int p0, int p1, int c0, int c1)
     RowDist rd{ 1 << 30, 1, 0, 0, c.map.g0 };            // rows of Wp are global rows g0, g0+1, ...
     const int j0 = c.map.g0 + p0;
     launch_swap_plan(j0, jb, c.ipiv + p0, c.plan, c.s);
+    if (swap_fused_enabled()) { launch_swap_fused<T>(jb, j0, c.plan, rd, c.Wp, c.ldw, c0, c1, (T *)nullptr, 0, true, c.s); return; }
     launch_swap_pack<T>(jb, j0, c.plan, rd, c.Wp, c.ldw, c0, c1, c.U, jb, c.O, jb, c.s);
     launch_swap_unpack_out<T>(jb, c.plan, rd, c.Wp, c.ldw, c0, c1, c.O, jb, c.s);
     launch_copy2d<T>(jb, nc, c.U, jb, c.Wp + p0 + (int64_t)c0 * c.ldw, c.ldw, c.s);
