@@ -141,3 +141,89 @@ def test_index_tools(O):
                 il = O.indxg2l(ig, nb, 0, 0, P)
                 assert O.indxl2g(il, nb, p, src, P) == ig
                 assert 1 <= il <= O.numroc(n, nb, p, src, P)
+
+
+def _blocked_right_looking(a, nb):
+    """Plain blocked right-looking LU with partial pivoting (the order PDGETRF works in), numpy only."""
+    a = a.copy(order="F"); m, n = a.shape; mn = min(m, n)
+    piv = np.zeros(mn, np.int64)
+    for j0 in range(0, mn, nb):
+        jb = min(nb, mn - j0)
+        for j in range(j0, j0 + jb):                                   # unblocked panel
+            p = j + int(np.argmax(np.abs(a[j:, j])))
+            piv[j] = p
+            if p != j:
+                a[[j, p], j0:j0 + jb] = a[[p, j], j0:j0 + jb]
+            if a[j, j] != 0.0:
+                a[j + 1:, j] *= 1.0 / a[j, j]
+            a[j + 1:, j + 1:j0 + jb] -= np.outer(a[j + 1:, j], a[j, j + 1:j0 + jb])
+        for j in range(j0, j0 + jb):                                   # interchanges left and right of the panel
+            p = piv[j]
+            if p != j:
+                a[[j, p], :j0] = a[[p, j], :j0]
+                a[[j, p], j0 + jb:] = a[[p, j], j0 + jb:]
+        l11 = np.tril(a[j0:j0 + jb, j0:j0 + jb], -1) + np.eye(jb)
+        a[j0:j0 + jb, j0 + jb:] = np.linalg.solve(l11, a[j0:j0 + jb, j0 + jb:])
+        a[j0 + jb:, j0 + jb:] -= a[j0 + jb:, j0:j0 + jb] @ a[j0:j0 + jb, j0 + jb:]
+    return a, piv
+
+
+def _slab_left_looking(a, nb, ws):
+    """The schedule planned for overlapping the host->device upload (open item 2): columns arrive in slabs of
+    ws; a slab is first CAUGHT UP with every panel factored so far (interchanges, U12 solve, update -- in step order), then
+    its own panels are factored right-looking inside the slab.  The interchanges of the already factored columns are
+    DEFERRED: L stays in the row order of the step that produced it, and one permutation pass per block column at the
+    end brings it to LAPACK's layout."""
+    a = a.copy(order="F"); m, n = a.shape; mn = min(m, n)
+    piv = np.zeros(mn, np.int64)
+    steps = []                                                          # (j0, jb) of the panels factored so far
+
+    def apply_step(j0, jb, c0, c1):                                     # step (j0, jb) applied to columns [c0, c1)
+        for j in range(j0, j0 + jb):
+            p = piv[j]
+            if p != j:
+                a[[j, p], c0:c1] = a[[p, j], c0:c1]
+        l11 = np.tril(a[j0:j0 + jb, j0:j0 + jb], -1) + np.eye(jb)
+        a[j0:j0 + jb, c0:c1] = np.linalg.solve(l11, a[j0:j0 + jb, c0:c1])
+        a[j0 + jb:, c0:c1] -= a[j0 + jb:, j0:j0 + jb] @ a[j0:j0 + jb, c0:c1]
+
+    for s0 in range(0, n, ws):
+        s1 = min(n, s0 + ws)
+        for (j0, jb) in steps:                                          # catch-up, in step order
+            apply_step(j0, jb, s0, s1)
+        for j0 in range(s0, min(s1, mn), nb):                           # the slab's own panels
+            jb = min(nb, mn - j0)
+            for j in range(j0, j0 + jb):
+                p = j + int(np.argmax(np.abs(a[j:, j])))
+                piv[j] = p
+                if p != j:
+                    a[[j, p], j0:j0 + jb] = a[[p, j], j0:j0 + jb]
+                if a[j, j] != 0.0:
+                    a[j + 1:, j] *= 1.0 / a[j, j]
+                a[j + 1:, j + 1:j0 + jb] -= np.outer(a[j + 1:, j], a[j, j + 1:j0 + jb])
+            steps.append((j0, jb))
+            apply_step(j0, jb, j0 + jb, s1)                             # trailing columns of THIS slab only
+    for (j0, jb) in steps:                                              # deferred left interchanges, one pass per block column
+        for (k0, kb) in steps:
+            if k0 <= j0:
+                continue
+            for j in range(k0, k0 + kb):
+                p = piv[j]
+                if p != j:
+                    a[[j, p], j0:j0 + jb] = a[[p, j], j0:j0 + jb]
+    return a, piv
+
+
+@pytest.mark.parametrize("m,n,nb,ws", [(96, 96, 8, 32), (120, 90, 16, 48), (70, 110, 8, 24), (64, 64, 16, 16)])
+def test_slab_left_looking_schedule_is_the_same_factorisation(O, m, n, nb, ws):
+    """Schedule invariance behind the planned upload overlap: slab-wise left-looking with deferred left interchanges gives
+    the pivots of the right-looking order (and of the oracle) and the same factors up to round-off of the GEMM blocking."""
+    a0 = O.matgen64_tile(max(m, n), 77, 0, m, 0, n)
+    lu_r, piv_r = _blocked_right_looking(a0, nb)
+    lu_s, piv_s = _slab_left_looking(a0, nb, ws)
+    assert np.array_equal(piv_r, piv_s)
+    assert np.allclose(lu_r, lu_s, rtol=0, atol=1e-12)
+    ref = a0.copy(order="F")
+    ipr, info = O.getrf(ref, nb)
+    assert info == 0 and np.array_equal(ipr - 1, piv_r)
+    assert np.allclose(ref, lu_r, rtol=0, atol=1e-12)
