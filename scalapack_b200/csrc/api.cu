@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "lu.h"
 #include "ncclw.h"
+#include "stage.h"
 
 #include <cmath>
 
@@ -21,7 +22,7 @@ static bool is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// Stages a host-resident local array through HBM; a device-resident one is used in place.
+// A host-resident 1-D / small array staged through HBM in one piece (test-driver helpers); a device-resident one is used in place.
 template <typename T>
 struct Staged {
     T *dev = nullptr; T *host = nullptr; size_t bytes = 0; bool staged = false;
@@ -46,23 +47,61 @@ struct Staged {
 
 static void xerbla(int ictxt, const char *name, int info) { int p = -info; pxerbla_(&ictxt, name, &p); }
 
-// local IPIV(il) <- global pivot of each locally owned row < mn (SRC/pdgetrf.f:118-121)
-static void fill_local_ipiv(const std::vector<int> &ipg, int mn, int nb, int rsrc, int P, int myrow, int *ipiv)
+// Local window of a block-aligned sub-matrix sub(A) = A(IA:IA+M-1, JA:JA+N-1) (SRC/pdgetrf.f:178-186, TOOLS/infog2l.f): every
+// process holds a contiguous mloc x nloc window of its local array starting at (loff_r, loff_c), and sub(A) is itself a
+// block-cyclic matrix whose first block lives on process (rsrc, csrc).
+struct Window { int64_t loff_r, loff_c, mloc, nloc; int rsrc, csrc; };
+static Window window(int m, int n, int ia, int ja, const int *desc, int P, int Q, int myrow, int mycol)
+{
+    Window w;
+    const int mb = desc[MB_], nb = desc[NB_];
+    w.loff_r = numroc(ia - 1, mb, myrow, desc[RSRC_], P);
+    w.loff_c = numroc(ja - 1, nb, mycol, desc[CSRC_], Q);
+    w.rsrc = indxg2p(ia, mb, desc[RSRC_], P);
+    w.csrc = indxg2p(ja, nb, desc[CSRC_], Q);
+    w.mloc = numroc(m, mb, myrow, w.rsrc, P);
+    w.nloc = numroc(n, nb, mycol, w.csrc, Q);
+    return w;
+}
+
+// The window of a host- or device-resident local array as the device sees it.  Host-resident: a staging copy in HBM (even
+// leading dimension, so the 16-byte epilogues of the update stay aligned) reached through a HostLink; device-resident: in place.
+template <typename T>
+struct DevWindow {
+    T *dev = nullptr; int64_t ld = 1; bool staged = false;
+    HostMat hm; HostLink *link = nullptr;
+    DevWindow(const char *name, T *p, int64_t lld, int64_t loff_r, int64_t loff_c, int64_t rows, int64_t cols)
+    {
+        T *win = p + loff_r + loff_c * lld;
+        if (rows <= 0 || cols <= 0 || is_device_ptr(p)) { dev = win; ld = lld; return; }
+        staged = true;
+        ld = (rows + 1) & ~(int64_t)1;
+        dev = (T *)workspace(name, (size_t)ld * (size_t)cols * sizeof(T));
+        hm.p = win; hm.ld = lld; hm.rows = rows; hm.cols = cols; hm.elem = sizeof(T); hm.pinned = host_ptr_is_pinned(p);
+        link = new HostLink(hm, dev, ld);
+    }
+    void upload_all() { if (link) link->wait(link->upload(0, hm.rows, 0, hm.cols)); }
+    void download_all() { if (link) { link->download(0, hm.rows, 0, hm.cols, nullptr); link->finish(); } }
+    ~DevWindow() { delete link; }
+};
+
+// local IPIV(loff + il) <- global pivot (as a row index of A, not of sub(A)) of each locally owned row < mn (SRC/pdgetrf.f:118-121)
+static void fill_local_ipiv(const std::vector<int> &ipg, int mn, int nb, int rsrc, int P, int myrow, int *ipiv, int row0)
 {
     for (int gi = 0; gi < mn; ++gi) {
         if (indxg2p(gi + 1, nb, rsrc, P) != myrow) continue;
-        ipiv[indxg2l(gi + 1, nb, P) - 1] = ipg[gi];
+        ipiv[indxg2l(gi + 1, nb, P) - 1] = ipg[gi] + row0;
     }
 }
 
-// global pivot vector from the row-distributed IPIV (each process row holds the entries of its rows)
-static void gather_global_ipiv(Grid *g, int n, int nb, int rsrc, const int *ipiv_local, std::vector<int> &ipg)
+// pivot vector of sub(A) (1-based, relative to sub(A)) from the row-distributed IPIV (each process row holds the entries of its rows)
+static void gather_global_ipiv(Grid *g, int n, int nb, int rsrc, const int *ipiv_local, int row0, std::vector<int> &ipg)
 {
     const int P = g->nprow;
     ipg.assign((size_t)n, 0);
     std::vector<int> mine((size_t)n, 0);
     for (int gi = 0; gi < n; ++gi)
-        if (indxg2p(gi + 1, nb, rsrc, P) == g->myrow) mine[gi] = ipiv_local[indxg2l(gi + 1, nb, P) - 1];
+        if (indxg2p(gi + 1, nb, rsrc, P) == g->myrow) mine[gi] = ipiv_local[indxg2l(gi + 1, nb, P) - 1] - row0;
     if (P == 1) { ipg = mine; return; }
     std::vector<int> all((size_t)n * P);
     grid_allgather(g, 'C', mine.data(), all.data(), (size_t)n * sizeof(int));
@@ -92,26 +131,17 @@ static void getrf_entry(const char *name, const int *m, const int *n, T *a, cons
     if (*info != 0) { xerbla(ictxt, name, *info); return; }
     if (desca[M_] == 1) { ipiv[0] = 1; return; }
     if (*m == 0 || *n == 0) return;
-    if (*ia != 1 || *ja != 1) {
-        // Block-aligned sub-matrix offsets are legal in the reference (pdgetrf.f:180-185) but not implemented here.
-        fprintf(stderr, "[scalapack_b200] %s: IA/JA > 1 (sub-matrix factorisation) is not implemented; returning INFO=%d\n", name, *ia != 1 ? -4 : -5);
-        *info = *ia != 1 ? -4 : -5;
-        return;
-    }
     Grid *g = grid_of(ictxt);
-    const int nb = desca[NB_], rsrc = desca[RSRC_], csrc = desca[CSRC_];
+    const int nb = desca[NB_];
     const int64_t lld = desca[LLD_];
-    const int64_t nloc = numroc(desca[N_], nb, mycol, csrc, npcol);
+    const Window w = window(*m, *n, *ia, *ja, desca, nprow, npcol, myrow, mycol);
     const int mn = *m < *n ? *m : *n;
-    if (*m != desca[M_] || *n != desca[N_]) {
-        fprintf(stderr, "[scalapack_b200] %s: M,N smaller than the descriptor's matrix is not implemented; returning INFO=-1\n", name);
-        *info = -1; return;
-    }
-    Staged<T> A("stage_A", a, (size_t)lld * (size_t)nloc);
+    DevWindow<T> A("stage_A", a, lld, w.loff_r, w.loff_c, w.mloc, w.nloc);
     std::vector<int> ipg((size_t)mn);
-    getrf_device<T>(g, *m, *n, A.dev, lld, nb, rsrc, csrc, ipg.data(), info, A.staged ? A.host : nullptr);
-    if (!g_last_lu.host_written) A.writeback();
-    fill_local_ipiv(ipg, mn, nb, rsrc, nprow, myrow, ipiv);
+    getrf_device<T>(g, *m, *n, A.dev, A.ld, nb, w.rsrc, w.csrc, ipg.data(), info, A.link);
+    if (A.link && !g_last_lu.host_written) A.download_all();
+    fill_local_ipiv(ipg, mn, nb, w.rsrc, nprow, myrow, ipiv + w.loff_r, *ia - 1);
+    // INFO = k > 0: U(IA+k-1, JA+k-1) is exactly zero -- k is already relative to sub(A) (pdgetrf.f:129-132)
 }
 
 template <typename T>
@@ -156,6 +186,16 @@ static void getrs_checks(const char *name, int descpos_a, int descpos_b, const c
     (void)name;
 }
 
+// the right-hand sides sub(B) = B(IB:IB+N-1, JB:JB+NRHS-1): rows aligned with sub(A) (checked), columns anywhere in B
+struct RhsWindow { int64_t loff_r, nloc_all; };
+static RhsWindow rhs_window(int ib, const int *descb, int P, int Q, int myrow, int mycol)
+{
+    RhsWindow w;
+    w.loff_r = numroc(ib - 1, descb[MB_], myrow, descb[RSRC_], P);
+    w.nloc_all = numroc(descb[N_], descb[NB_], mycol, descb[CSRC_], Q);
+    return w;
+}
+
 template <typename T>
 static void getrs_entry(const char *name, const char *trans, const int *n, const int *nrhs, const T *a, const int *ia,
                         const int *ja, const int *desca, const int *ipiv, T *b, const int *ib, const int *jb, const int *descb,
@@ -165,26 +205,20 @@ static void getrs_entry(const char *name, const char *trans, const int *n, const
     getrs_checks<T>(name, 7, 12, trans, n, nrhs, ia, ja, desca, ib, jb, descb, info, true);
     if (*info != 0) { xerbla(ictxt, name, *info); return; }
     if (*n == 0 || *nrhs == 0) return;
-    char t = trans[0] & ~0x20;
-    if (t != 'N') {
-        fprintf(stderr, "[scalapack_b200] %s: TRANS='%c' is not implemented (only 'N'); returning INFO=-1\n", name, trans[0]);
-        *info = -1; return;
-    }
-    if (*ia != 1 || *ja != 1 || *ib != 1 || *jb != 1 || *n != desca[M_] || *n != desca[N_] || *nrhs != descb[N_]) {
-        fprintf(stderr, "[scalapack_b200] %s: sub-matrix operands are not implemented; returning INFO=-5\n", name);
-        *info = -5; return;
-    }
+    const char t = trans[0] & ~0x20;
     int nprow, npcol, myrow, mycol;
     blacs_gridinfo_(&ictxt, &nprow, &npcol, &myrow, &mycol);
     Grid *g = grid_of(ictxt);
-    const int nb = desca[NB_], rsrc = desca[RSRC_], csrc = desca[CSRC_];
-    const int64_t nlocA = numroc(*n, nb, mycol, csrc, npcol), nlocB = numroc(*nrhs, descb[NB_], mycol, descb[CSRC_], npcol);
+    const int nb = desca[NB_];
+    const Window w = window(*n, *n, *ia, *ja, desca, nprow, npcol, myrow, mycol);
+    const RhsWindow wb = rhs_window(*ib, descb, nprow, npcol, myrow, mycol);
     std::vector<int> ipg;
-    gather_global_ipiv(g, *n, nb, rsrc, ipiv, ipg);
-    Staged<T> A("stage_A", const_cast<T *>(a), (size_t)desca[LLD_] * (size_t)nlocA);
-    Staged<T> B("stage_B", b, (size_t)descb[LLD_] * (size_t)nlocB);
-    getrs_device<T>(g, *n, *nrhs, A.dev, desca[LLD_], nb, rsrc, csrc, ipg.data(), B.dev, descb[LLD_], descb[NB_], descb[CSRC_]);
-    B.writeback();
+    gather_global_ipiv(g, *n, nb, w.rsrc, ipiv + w.loff_r, *ia - 1, ipg);
+    DevWindow<T> A("stage_A", const_cast<T *>(a), desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
+    DevWindow<T> B("stage_B", b, descb[LLD_], wb.loff_r, 0, w.mloc, wb.nloc_all);
+    A.upload_all(); B.upload_all();
+    getrs_device<T>(g, t, *n, *nrhs, A.dev, A.ld, nb, w.rsrc, w.csrc, ipg.data(), B.dev, B.ld, descb[NB_], descb[CSRC_], *jb - 1, wb.nloc_all);
+    B.download_all();
 }
 
 template <typename T>
@@ -195,30 +229,29 @@ static void gesv_entry(const char *name, const int *n, const int *nrhs, T *a, co
     getrs_checks<T>(name, 6, 11, "N", n, nrhs, ia, ja, desca, ib, jb, descb, info, false);
     if (*info != 0) { xerbla(ictxt, name, *info); return; }
     if (*n == 0) return;
-    if (*ia != 1 || *ja != 1 || *ib != 1 || *jb != 1 || *n != desca[M_] || *n != desca[N_] || *nrhs != descb[N_]) {
-        fprintf(stderr, "[scalapack_b200] %s: sub-matrix operands are not implemented; returning INFO=-4\n", name);
-        *info = -4; return;
-    }
-    if (desca[M_] == 1) {      // 1 x 1 system: PDGETRF's quick return leaves A, IPIV(1)=1 (pdgetrf.f:201-203)
-        ipiv[0] = 1;
-    }
     int nprow, npcol, myrow, mycol;
     blacs_gridinfo_(&ictxt, &nprow, &npcol, &myrow, &mycol);
     Grid *g = grid_of(ictxt);
-    const int nb = desca[NB_], rsrc = desca[RSRC_], csrc = desca[CSRC_];
-    const int64_t nlocA = numroc(*n, nb, mycol, csrc, npcol), nlocB = numroc(*nrhs, descb[NB_], mycol, descb[CSRC_], npcol);
-    // one staging of A for factor + solve
-    Staged<T> A("stage_A", a, (size_t)desca[LLD_] * (size_t)nlocA);
+    const int nb = desca[NB_];
+    const Window w = window(*n, *n, *ia, *ja, desca, nprow, npcol, myrow, mycol);
+    const RhsWindow wb = rhs_window(*ib, descb, nprow, npcol, myrow, mycol);
+    // one staging of A for factor + solve: the factors go back to a host-resident caller during the factorisation and stay in HBM
+    DevWindow<T> A("stage_A", a, desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
     std::vector<int> ipg((size_t)*n);
-    if (desca[M_] == 1) { ipg[0] = 1; *info = 0; }
-    else getrf_device<T>(g, *n, *n, A.dev, desca[LLD_], nb, rsrc, csrc, ipg.data(), info);
-    fill_local_ipiv(ipg, *n, nb, rsrc, nprow, myrow, ipiv);
-    if (*info == 0 && *nrhs > 0) {                       // pdgesv.f:231
-        Staged<T> B("stage_B", b, (size_t)descb[LLD_] * (size_t)nlocB);
-        getrs_device<T>(g, *n, *nrhs, A.dev, desca[LLD_], nb, rsrc, csrc, ipg.data(), B.dev, descb[LLD_], descb[NB_], descb[CSRC_]);
-        B.writeback();
+    if (desca[M_] == 1) {      // 1 x 1 system: PDGETRF's quick return leaves A, IPIV(1)=1 (pdgetrf.f:201-203)
+        ipiv[0] = 1; ipg[0] = 1; *info = 0;
+        A.upload_all();
+    } else {
+        getrf_device<T>(g, *n, *n, A.dev, A.ld, nb, w.rsrc, w.csrc, ipg.data(), info, A.link);
+        if (A.link && !g_last_lu.host_written) A.download_all();
+        fill_local_ipiv(ipg, *n, nb, w.rsrc, nprow, myrow, ipiv + w.loff_r, *ia - 1);
     }
-    A.writeback();
+    if (*info == 0 && *nrhs > 0) {                       // pdgesv.f:231
+        DevWindow<T> B("stage_B", b, descb[LLD_], wb.loff_r, 0, w.mloc, wb.nloc_all);
+        B.upload_all();
+        getrs_device<T>(g, 'N', *n, *nrhs, A.dev, A.ld, nb, w.rsrc, w.csrc, ipg.data(), B.dev, B.ld, descb[NB_], descb[CSRC_], *jb - 1, wb.nloc_all);
+        B.download_all();
+    }
 }
 
 }  // namespace slb

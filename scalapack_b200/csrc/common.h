@@ -78,7 +78,9 @@ struct Runtime {
     cudaStream_t s_main = nullptr;     // trailing update / swaps
     cudaStream_t s_panel = nullptr;    // look-ahead panel stream (high priority)
     cudaStream_t s_copy = nullptr;     // staging copies
-    cudaStream_t s_d2h = nullptr;      // write-back of finished block rows to a host-resident caller (experimental, e2e_overlap)
+    cudaStream_t s_d2h = nullptr;      // copy engine, device -> host: finished block rows of a host-resident caller (stage.cu)
+    cudaStream_t s_h2d = nullptr;      // copy engine, host -> device: column slabs of a host-resident caller (stage.cu)
+    cudaStream_t s_aux = nullptr;      // carries no work: joins several events into one (cudaStreamWaitEvent x n + cudaEventRecord)
     cudaStream_t s_prep = nullptr;     // row interchanges + U12 solve of the next column half (above the update, below the panel)
 };
 Runtime &rt();                      // initialises CUDA lazily; fatal()s if no device (no CPU fallback)

@@ -40,6 +40,9 @@ __device__ __forceinline__ zcomplex t_add(zcomplex a, zcomplex b) { return make_
 __device__ __forceinline__ double t_sub(double a, double b) { return a - b; }
 __device__ __forceinline__ zcomplex t_sub(zcomplex a, zcomplex b) { return make_double2(a.x - b.x, a.y - b.y); }
 
+__device__ __forceinline__ double t_conj(double a) { return a; }
+__device__ __forceinline__ zcomplex t_conj(zcomplex a) { return make_double2(a.x, -a.y); }
+
 // L1-bypassing loads for data another CTA / GPU may have just written
 __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
 __device__ __forceinline__ zcomplex ld_cg(const zcomplex *p) { return __ldcg(p); }

@@ -379,9 +379,8 @@ zgemm_minus_kernel(int64_t M, int64_t N, int K, const zcomplex *__restrict__ A, 
 
 bool dgemm_takes_packed(int64_t M, int K, int flags)
 {
-    static int64_t packed = -1, min_m = 0;
-    if (packed < 0) { packed = opt("gemm_variant", 9) == 9; min_m = opt("gemm_packed_min", 3072); }   // SLB200_GEMM_VARIANT=7: cp.async kernel only
-    return packed && (flags & GEMM_MAIN) && M >= min_m && K >= 16;
+    // SLB200_GEMM_VARIANT=7: cp.async kernel only (options are read on every call so slb200_set_option takes effect)
+    return (flags & GEMM_MAIN) && K >= 16 && opt("gemm_variant", 9) == 9 && M >= opt("gemm_packed_min", 3072);
 }
 
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,

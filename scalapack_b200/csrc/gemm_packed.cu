@@ -309,12 +309,11 @@ void launch_dgemm_minus_packed(int64_t M, int64_t N, int K, const double *A, int
 {
     if (M <= 0 || N <= 0 || K <= 0) return;
     static bool attr_done = false;
-    static int epi = 0, lag = 0;
+    const int epi = (int)opt("gemm_epi", 0), lag = (int)opt("gemm_lag", 0);
     if (!attr_done) {
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
         SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
-        epi = (int)opt("gemm_epi", 0); lag = (int)opt("gemm_lag", 0);
         attr_done = true;
     }
     const int KT = (K + BK - 1) / BK;

@@ -104,6 +104,7 @@ static void server_loop(int listen_fd, int size)
         if (c < 0) { if (errno == EINTR) { --i; continue; } fatal("hostcomm accept failed: %s", strerror(errno)); }
         int one = 1; setsockopt(c, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
         int32_t r; if (!read_full(c, &r, sizeof(r))) fatal("hostcomm: handshake failed");
+        if (r < 0 || r >= size) { ::close(c); --i; continue; }      // not one of this job's ranks: drop the connection
         fds.push_back(c);
     }
     ::close(listen_fd);
@@ -119,6 +120,8 @@ static void server_loop(int listen_fd, int size)
             if (fds[i] < 0 || !(pfds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
             ReqHeader h;
             if (!read_full(fds[i], &h, sizeof(h))) { ::close(fds[i]); fds[i] = -1; --alive; continue; }
+            // bound what the wire may ask for: collectives of this control plane carry descriptors, ids and small vectors
+            if (h.len > ((uint64_t)256 << 20) || h.nmembers < 1 || h.nmembers > size) fatal("hostcomm: malformed request (len %llu, members %d)", (unsigned long long)h.len, h.nmembers);
             std::string payload(h.len, '\0');
             if (h.len && !read_full(fds[i], &payload[0], h.len)) { ::close(fds[i]); fds[i] = -1; --alive; continue; }
             Pending &p = pend[h.group];
@@ -151,7 +154,10 @@ static void bootstrap()
     if (g_hc.rank == 0) {
         int lf = ::socket(AF_INET, SOCK_STREAM, 0);
         int one = 1; setsockopt(lf, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-        sockaddr_in sa; memset(&sa, 0, sizeof(sa)); sa.sin_family = AF_INET; sa.sin_addr.s_addr = htonl(INADDR_ANY);
+        // single-node jobs (MASTER_ADDR is loopback or unset) listen on loopback only; SLB200_BIND_ANY=1 restores INADDR_ANY
+        sockaddr_in sa; memset(&sa, 0, sizeof(sa)); sa.sin_family = AF_INET;
+        const bool loop = strncmp(addr, "127.", 4) == 0 || strcmp(addr, "localhost") == 0;
+        sa.sin_addr.s_addr = htonl((loop && env_int("SLB200_BIND_ANY", nullptr, nullptr, 0) == 0) ? INADDR_LOOPBACK : INADDR_ANY);
         sa.sin_port = htons((uint16_t)port);
         if (::bind(lf, (sockaddr *)&sa, sizeof(sa)) != 0) fatal("hostcomm: cannot bind port %d: %s", port, strerror(errno));
         if (::listen(lf, g_hc.size + 8) != 0) fatal("hostcomm: listen failed: %s", strerror(errno));

@@ -68,11 +68,9 @@ void launch_swap_pack(int jb, int j0, SwapPlan plan, RowDist rd, const T *A, int
 template <typename T>
 void launch_swap_unpack_out(int jb, SwapPlan plan, RowDist rd, T *A, int64_t lda, int64_t c0, int64_t c1,
                             const T *Obuf, int64_t ldo, cudaStream_t s);
-// experimental one-pass variant of pack + unpack (+ top-row copy) for nprow == 1 (SLB200_SWAP_FUSED=1; swap.cu)
-bool swap_fused_enabled();
-template <typename T>
-void launch_swap_fused(int jb, int j0, SwapPlan plan, RowDist rd, T *A, int64_t lda, int64_t c0, int64_t c1, T *Ubuf, int64_t ldu,
-                       bool write_top, cudaStream_t s);
+// the interchange / copy kernels cap their grids (option swap_grid) so that they can run UNDER the trailing update; a caller
+// that runs them alone on a stream lifts the cap for its launches (cap = 0) and restores it with -1
+void swap_grid_override(int cap);
 // select: U[t + c*ldu] = Cbuf_{owner(top_src[t])}[t + c*ldc] where Cbuf_p = Call + p*stride_p (all-gathered packs)
 template <typename T>
 void launch_swap_select(int jb, SwapPlan plan, RowDist rd, const T *Call, int64_t ldc, int64_t stride_p, int64_t ncols,
@@ -96,14 +94,20 @@ void launch_gen_matvec(int64_t n, int nb, uint64_t aseed, int gen, int myrow, in
                        const double *xrow /* x for my local columns, nq */, double *r /* np */, double *rowabs /* np */,
                        cudaStream_t s);
 
-// ---- triangular solves of PDGETRS (SRC/pdgetrs.f:255-266) ----
-// x[k0:k0+kb] = tri(A[k0.., k0..])^-1 x[k0:k0+kb]  (unit lower or non-unit upper), nrhs columns
+// ---- triangular solves of PDGETRS (SRC/pdgetrs.f:255-284) ----
+// x[0:kb] = tri(op(Akk))^-1 x[0:kb], nrhs columns.  mode: TRSV_UPPER = the stored triangle is U (non-unit diagonal), else L
+// (unit diagonal); TRSV_TRANS / TRSV_CONJ: op = transpose / conjugate transpose.
+enum { TRSV_UPPER = 1, TRSV_TRANS = 2, TRSV_CONJ = 4 };
 template <typename T>
-void launch_trsv_block(int kb, const T *Akk, int64_t lda, T *X, int64_t ldx, int nrhs, int upper, cudaStream_t s);
+void launch_trsv_block(int kb, const T *Akk, int64_t lda, T *X, int64_t ldx, int nrhs, int mode, cudaStream_t s);
 // Y[rows] -= A[rows x kb] * X[kb] for nrhs columns (memory-bound GEMV-like)
 template <typename T>
 void launch_gemv_minus(int64_t rows, int kb, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs,
                        cudaStream_t s);
+// Y[ncols] -= op(A[kb x ncols])^T * X[kb] for nrhs columns (the transposed solves; conj: A^H)
+template <typename T>
+void launch_gemvt_minus(int kb, int64_t ncols, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs,
+                        bool conj, cudaStream_t s);
 
 // ---- micro-benchmarks (roofline denominators) ----
 double bench_dmma_peak_tflops(int iters);     // register-resident DMMA loop on all SMs

@@ -17,6 +17,9 @@
 #include "kernels.cuh"
 #include "ncclw.h"
 #include "lu.h"
+#include "stage.h"
+
+#include <algorithm>
 
 namespace slb {
 
@@ -57,17 +60,28 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // prep_k(near) runs under update_{k-1}(far), prep_k(far) under update_k(near): the HBM-latency-bound interchanges and the
 // launch-latency-bound U12 solve leave the critical path, which becomes  update_k(near) + update_k(far)  per step.
 // The boundary b only moves when near has shrunk below a quarter of the trailing columns (then one step waits for both halves).
+//
+// HOST-RESIDENT CALLER (link != nullptr; the drop-in case of an unmodified Fortran program): A arrives over
+// PCIe in column slabs while the sweep is already running, and leaves in block rows while it is still running:
+//   * upload: the sweep works on the columns [0, Np) that are PRESENT.  A slab that has arrived JOINS at the top of a step k:
+//     it is first taken through steps 0 .. k-1 ("replay": interchanges, U12 solve and update of exactly these columns with
+//     the kept plan and a kept copy of each panel in its step-time row order), then it is part of the trailing matrix.  Every
+//     element sees the same operations in the same order as in the device-resident sweep, so the factors are bit-identical.
+//     Which slabs join when follows their ACTUAL arrival (the host stays one step ahead of the device while slabs are
+//     pending), except that the columns of the next panel are waited for.
+//   * download: rows [0, j0 + jb) never change after step k (later interchanges only touch rows below), so block row k goes
+//     back to the caller as soon as its interchanges and U12 solve are done.
 template <typename T>
-static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host, T *hA)
+static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipiv_glob_host, int *info_host, HostLink *link)
 {
     Runtime &r = rt();
-    cudaStream_t sg = r.s_main, sp = r.s_panel, sc = r.s_copy, sq = r.s_prep;
+    cudaStream_t sg = r.s_main, sp = r.s_panel, sc = r.s_copy, sq = r.s_prep, sx = r.s_aux;
     const int mn = M < N ? M : N;
     const int nsteps = (mn + nb - 1) / nb;
     int *ipiv_dev = (int *)workspace("lu_ipiv", (size_t)(mn + nb + 16) * sizeof(int));
     int *info_dev = (int *)workspace("lu_info", 64);
-    int *plan_mem = (int *)workspace("lu_plan", (size_t)6 * nb * sizeof(int));
-    SwapPlan plans[2] = { { plan_mem, plan_mem + nb, plan_mem + 2 * nb }, { plan_mem + 3 * nb, plan_mem + 4 * nb, plan_mem + 5 * nb } };
+    int *plan_mem = (int *)workspace("lu_plan", (size_t)3 * nb * (nsteps + 1) * sizeof(int));     // one plan per step (the replay re-reads them)
+    auto plan_of = [&](int k) { int *p = plan_mem + (size_t)3 * nb * k; return SwapPlan{ p, p + nb, p + 2 * nb }; };
     void *panel_work = workspace("lu_panelwork", panel_work_bytes(nb), true);
     T *Ubuf = (T *)workspace("lu_U", (size_t)nb * N * sizeof(T));
     T *Obuf = (T *)workspace("lu_O", (size_t)nb * N * sizeof(T));
@@ -76,31 +90,45 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     const bool pipe = opt("la_pipeline", 1) != 0;
     const int64_t split_min = opt("la_split_min", 6144);      // fewer trailing columns: the step is not split
     const bool trace = opt("la_trace", 0) != 0;               // per-step timeline on stderr
-    const bool fused = swap_fused_enabled();                  // experimental one-pass interchanges (swap.cu)
-    // experimental (default off until validated on hardware): block row k of the factors -- the L11/U11 block and U12, final once
-    // step k's prep is done -- goes back to a host-resident caller during the factorisation; only the L21 parts (final
-    // after the last left interchange) are left for the end.  Halves the serial D2H of the end-to-end path.
-    if (hA != nullptr && opt("e2e_overlap", 0) == 0) hA = nullptr;
-    if (hA != nullptr) {     // pageable memory would make every async copy block the enqueueing thread: pinned callers only
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, hA) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); hA = nullptr; }
-    }
-    cudaStream_t sd = r.s_d2h;
-    auto rows_to_host = [&](int64_t r0, int64_t nr, int64_t c0, int64_t c1) {
-        if (nr <= 0 || c1 <= c0) return;
-        SLB_CUDA(cudaMemcpy2DAsync(hA + r0 + c0 * lld, (size_t)lld * sizeof(T), A + r0 + c0 * lld, (size_t)lld * sizeof(T),
-                                   (size_t)nr * sizeof(T), (size_t)(c1 - c0), cudaMemcpyDeviceToHost, sd));
-        counter_add("d2h_bytes", (int64_t)((size_t)nr * (size_t)(c1 - c0) * sizeof(T)));
-    };
 
     auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
-    cudaEvent_t ev0, ev1, evs;
+    cudaEvent_t ev0, ev1, evs, rj;
     SLB_CUDA(cudaEventCreate(&ev0)); SLB_CUDA(cudaEventCreate(&ev1)); SLB_CUDA(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
-    std::vector<cudaEvent_t> evp, evn, evl, pdp, pdn, pdf, gdn, gdf;
+    SLB_CUDA(cudaEventCreateWithFlags(&rj, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> evp, evn, evl, pdp, pdn, pdf, gdn, gdf, dlev;
     mkev(evp, (size_t)nsteps + 1); mkev(evn, (size_t)nsteps + 1); mkev(evl, (size_t)nsteps + 1);
     mkev(pdp, (size_t)nsteps); mkev(pdn, (size_t)nsteps); mkev(pdf, (size_t)nsteps); mkev(gdn, (size_t)nsteps); mkev(gdf, (size_t)nsteps);
     std::vector<cudaEvent_t> gev((size_t)6 * nsteps, nullptr), eva((size_t)nsteps, nullptr);
+    std::vector<char> evn_set((size_t)nsteps + 1, 0);
     std::vector<double> gflops((size_t)nsteps, 0.0);
+
+    // ---- host-resident caller: queue the upload of every column slab now (narrow slabs first: the first panels start early) ----
+    struct Slab { int64_t c0, c1; int ticket; };
+    std::vector<Slab> slabs;
+    size_t next_slab = 0;
+    int64_t Np = N;                                            // columns [0, Np) take part in the sweep
+    int ksave = 0; T *Lsave = nullptr;
+    bool dl_started = false, rj_set = false;
+    if (link) {
+        const int64_t wmax = std::max<int64_t>(nb, (int64_t)((size_t)opt("e2e_slab_mb", 1024) << 20) / ((int64_t)M * (int64_t)sizeof(T)) / nb * nb);
+        int64_t c = 0, w = nb; int i = 0;
+        while (c < N) {
+            const int64_t c1 = std::min<int64_t>(N, c + w);
+            slabs.push_back({ c, c1, link->upload(0, M, c, c1) });
+            c = c1;
+            if (i++ >= 1 && w < wmax) w = std::min(wmax, 2 * w);
+        }
+        // the panels of the first ksave steps are kept (step-time row order) for the replay of late slabs
+        const size_t panel_bytes = (size_t)M * nb * sizeof(T);
+        size_t free_b = 0, total_b = 0; SLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = std::min<size_t>((size_t)opt("e2e_save_mb", 16384) << 20, free_b > ((size_t)4 << 30) ? free_b - ((size_t)4 << 30) : 0);
+        ksave = (int)std::min<size_t>((size_t)nsteps, budget / panel_bytes);
+        if (slabs.size() <= 1) ksave = 0;
+        if (ksave > 0) Lsave = (T *)workspace("lu_Lsave", (size_t)ksave * panel_bytes);
+        Np = 0;
+        counter_add("e2e_upload_overlapped", 1); counter_add("e2e_download_overlapped", 1);
+    }
+    auto pending = [&]() { return link != nullptr && next_slab < slabs.size(); };
 
     SLB_CUDA(cudaEventRecord(ev0, sg));
     SLB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), sg));
@@ -108,16 +136,42 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     SLB_CUDA(cudaEventRecord(evs, sg));
     SLB_CUDA(cudaStreamWaitEvent(sp, evs, 0)); SLB_CUDA(cudaStreamWaitEvent(sq, evs, 0)); SLB_CUDA(cudaStreamWaitEvent(sc, evs, 0));
     RowDist rd{ nb, 1, 0, 0, 0 };
-    // panel k and its interchange plan; plan buffer k&1 was last read by step k-2 (prep on sq: ordered before this
-    // through pdf/pdn -> sg -> evn[k-1] -> sp; left interchanges on sc: evl[k-2])
+    // panel k and its interchange plan (+ the kept copy while slabs are pending)
     auto run_panel = [&](int k, int gmax) {
         const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
         PanelRowMap map{ j0, nb, 1, 0 };
-        Ops<T>::panel(M - j0, jb, A + j0 + (int64_t)j0 * lld, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, sp, gmax);
-        if (k >= 2) SLB_CUDA(cudaStreamWaitEvent(sp, evl[k - 2], 0));
-        launch_swap_plan(j0, jb, ipiv_dev + j0, plans[k & 1], sp);
+        T *Wp = A + j0 + (int64_t)j0 * lld;
+        Ops<T>::panel(M - j0, jb, Wp, lld, map, ipiv_dev + j0, info_dev, j0, panel_work, sp, gmax);
+        if (pending() && k < ksave) launch_copy2d<T>(M - j0, jb, Wp, lld, Lsave + (size_t)k * M * nb, M - j0, sp);
+        launch_swap_plan(j0, jb, ipiv_dev + j0, plan_of(k), sp);
         SLB_CUDA(cudaEventRecord(evp[k], sp));
     };
+    // columns [a, b) through steps 0 .. k-1 on the update stream (the interchange kernels run alone here: uncapped grids)
+    auto replay = [&](int64_t a, int64_t b, int k) {
+        swap_grid_override(0);
+        for (int kk = 0; kk < k; ++kk) {
+            const int j0 = kk * nb, jb = nb;
+            const int64_t cr = j0 + jb, ldl = M - j0;
+            const T *Ls = Lsave + (size_t)kk * M * nb;
+            SwapPlan plan = plan_of(kk);
+            T *Ur = Ubuf + a * jb, *Or = Obuf + a * jb;
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, a, b, Ur, jb, Or, jb, sg);
+            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, a, b, Or, jb, sg);
+            Ops<T>::trsm(jb, b - a, Ls, ldl, Ur, jb, sg);
+            launch_copy2d<T>(jb, b - a, Ur, jb, A + j0 + a * lld, lld, sg);
+            if (M > cr) Ops<T>::gemm(M - cr, b - a, jb, Ls + jb, ldl, Ur, jb, A + cr + a * lld, lld, sg, 0, GEMM_MAIN);
+        }
+        swap_grid_override(-1);
+    };
+    // one event that completes when all of `evs` have (the aux stream carries no work)
+    auto all_of = [&](std::initializer_list<cudaEvent_t> list) {
+        for (cudaEvent_t e : list) if (e) SLB_CUDA(cudaStreamWaitEvent(sx, e, 0));
+        cudaEvent_t o; SLB_CUDA(cudaEventCreateWithFlags(&o, cudaEventDisableTiming));
+        SLB_CUDA(cudaEventRecord(o, sx));
+        dlev.push_back(o);
+        return o;
+    };
+    if (link) { link->stream_wait(slabs[0].ticket, sp); next_slab = 1; Np = slabs[0].c1; }
     run_panel(0, 0);
     int64_t b = -1;                 // absolute column of the near | far boundary of the previous step (-1: none yet)
     bool far_prev = false;          // the previous step had a far half
@@ -125,8 +179,27 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     for (int k = 0; k < nsteps; ++k) {
         const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
         T *Wp = A + j0 + (int64_t)j0 * lld;
-        SwapPlan plan = plans[k & 1];
-        const int64_t cr = j0 + jb, nright = N - cr;
+        SwapPlan plan = plan_of(k);
+        const int64_t cr = j0 + jb;
+        // ---- slabs that have arrived (or must be waited for) join the sweep ----
+        bool joined = false;
+        if (pending()) {
+            if (k >= 1 && evn_set[k - 1]) SLB_CUDA(cudaEventSynchronize(evn[k - 1]));       // stay one step ahead of the device, not more
+            const int64_t need = std::min<int64_t>(N, cr + nb);
+            const bool force = k >= ksave || k == nsteps - 1;
+            const size_t first = next_slab;
+            while (next_slab < slabs.size() && (force || slabs[next_slab].c0 < need || link->done(slabs[next_slab].ticket))) {
+                link->stream_wait(slabs[next_slab].ticket, sg);
+                ++next_slab;
+            }
+            if (next_slab > first) {
+                replay(slabs[first].c0, slabs[next_slab - 1].c1, k);
+                Np = slabs[next_slab - 1].c1;
+                SLB_CUDA(cudaEventRecord(rj, sg)); rj_set = true;
+                joined = true;
+            }
+        }
+        const int64_t nright = Np - cr;
         const int64_t mrows = M - cr;
         const bool have_next = k + 1 < nsteps && mrows > 0 && nright > 0;
         const int jbn = have_next ? ((mn - (int)cr) < nb ? (mn - (int)cr) : nb) : 0;
@@ -136,34 +209,34 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             SLB_CUDA(cudaStreamWaitEvent(sc, evp[k], 0));
             if (last_gemm) SLB_CUDA(cudaStreamWaitEvent(sc, last_gemm, 0));
             if (have_next) SLB_CUDA(cudaStreamWaitEvent(sc, evn[k], 0));
-            if (fused) launch_swap_fused<T>(jb, j0, plan, rd, A, lld, 0, j0, (T *)nullptr, 0, true, sc);
-            else {
-                launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
-                launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
-                launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
-            }
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, 0, j0, Ubuf, jb, Obuf, jb, sc);
+            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, 0, j0, Obuf, jb, sc);
+            launch_copy2d<T>(jb, j0, Ubuf, jb, A + j0, lld, sc);
             SLB_CUDA(cudaEventRecord(evl[k], sc));
+        };
+        // block row k (and, the first time, every block row above it) is final: back to the host-resident caller
+        auto block_row_home = [&](cudaEvent_t e1, cudaEvent_t e2) {
+            if (!link || pending()) return;
+            link->download(dl_started ? j0 : 0, j0 + jb, 0, N, all_of({ e1, e2, evl[k], rj_set ? rj : nullptr }));
+            dl_started = true;
         };
         if (nright <= 0) {
             left_swaps();
-            if (hA) { SLB_CUDA(cudaStreamWaitEvent(sd, evp[k], 0)); rows_to_host(j0, jb, j0, N); }
+            block_row_home(evp[k], nullptr);
             continue;
         }
         // ---- near | far boundary ----
-        int64_t bk = N;
+        int64_t bk = Np;
         bool resplit = false;
         if (pipe && have_next && nright >= split_min) {
-            if (b < 0 || b - cr < nright / 4 || b >= N) { bk = cr + ((nright / 2 + nb - 1) / nb) * nb; resplit = true; }
+            if (b < 0 || b - cr < nright / 4 || b >= Np) { bk = cr + ((nright / 2 + nb - 1) / nb) * nb; resplit = true; }
             else bk = b;
-            if (bk >= N) bk = N;
+            if (bk >= Np) bk = Np;
         }
         if (bk > b || b < 0) resplit = true;          // near grows into the previous far half (or there was no split)
         auto prep = [&](int64_t c_lo, int64_t c_hi) {
-            if (fused) launch_swap_fused<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, false, sq);
-            else {
-                launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, Obuf + c_lo * jb, jb, sq);
-                launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c_lo, c_hi, Obuf + c_lo * jb, jb, sq);
-            }
+            launch_swap_pack<T>(jb, j0, plan, rd, A, lld, c_lo, c_hi, Ubuf + c_lo * jb, jb, Obuf + c_lo * jb, jb, sq);
+            launch_swap_unpack_out<T>(jb, plan, rd, A, lld, c_lo, c_hi, Obuf + c_lo * jb, jb, sq);
             Ops<T>::trsm(jb, c_hi - c_lo, Wp, lld, Ubuf + c_lo * jb, jb, sq);
             launch_copy2d<T>(jb, c_hi - c_lo, Ubuf + c_lo * jb, jb, A + j0 + c_lo * lld, lld, sq);
         };
@@ -185,6 +258,7 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
         SLB_CUDA(cudaStreamWaitEvent(sq, evp[k], 0));
         if (k > 0) SLB_CUDA(cudaStreamWaitEvent(sq, gdn[k - 1], 0));
         if (k > 0 && far_prev && resplit) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+        if (joined) SLB_CUDA(cudaStreamWaitEvent(sq, rj, 0));           // the new columns are in HBM and caught up
         if (jbn > 0 && cr + jbn < bk) {
             prep(cr, cr + jbn);
             SLB_CUDA(cudaEventRecord(pdp[k], sq));
@@ -201,35 +275,31 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             const double rest_ms = 2.0 * (double)mrows * (double)(nright - jbn) * jb * Ops<T>::flop_mul / 30e12 * 1e3;
             const bool overlap = nright - jbn > 0 && rest_ms >= overlap_min_ms;
             timed_gemm(0, cr, cr + jbn, false);
-            SLB_CUDA(cudaEventRecord(evn[k], sg));
+            SLB_CUDA(cudaEventRecord(evn[k], sg)); evn_set[k] = 1;
             SLB_CUDA(cudaStreamWaitEvent(sp, evn[k], 0));
             run_panel(k + 1, overlap ? gmax_opt : 0);
         }
         // ---- (c) sc: left interchanges; (d) sq: prep of the far half -- both only after g0 (they would take its SMs) ----
         left_swaps();
-        if (bk < N) {
+        if (bk < Np) {
             if (k > 0 && far_prev) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
             if (have_next) SLB_CUDA(cudaStreamWaitEvent(sq, evn[k], 0));
-            prep(bk, N);
+            prep(bk, Np);
             SLB_CUDA(cudaEventRecord(pdf[k], sq));
         }
-        if (hA) {                                                      // block row k is final: panel block + U12
-            SLB_CUDA(cudaStreamWaitEvent(sd, pdn[k], 0));
-            rows_to_host(j0, jb, j0, bk);
-            if (bk < N) { SLB_CUDA(cudaStreamWaitEvent(sd, pdf[k], 0)); rows_to_host(j0, jb, bk, N); }
-        }
+        block_row_home(pdn[k], bk < Np ? pdf[k] : nullptr);
         // ---- (e) sg: rest of near, far ----
         SLB_CUDA(cudaStreamWaitEvent(sg, pdn[k], 0));
         timed_gemm(2, cr + jbn, bk, have_next);
         SLB_CUDA(cudaEventRecord(gdn[k], sg));
         last_gemm = gdn[k];
-        if (bk < N) {
+        if (bk < Np) {
             SLB_CUDA(cudaStreamWaitEvent(sg, pdf[k], 0));
-            timed_gemm(4, bk, N, true);
+            timed_gemm(4, bk, Np, true);
             SLB_CUDA(cudaEventRecord(gdf[k], sg));
             last_gemm = gdf[k];
         }
-        far_prev = bk < N;
+        far_prev = bk < Np;
         b = bk;
     }
     SLB_CUDA(cudaStreamWaitEvent(sg, evp[nsteps - 1], 0));
@@ -241,13 +311,9 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     int info_local = 0;
     SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sg));
     g_last_lu.host_written = false;
-    if (hA) {                                                          // what is left: the L21 part of every block column
-        SLB_CUDA(cudaStreamWaitEvent(sd, ev1, 0));
-        for (int k = 0; k < nsteps; ++k) {
-            const int j0 = k * nb, jb = (mn - j0) < nb ? (mn - j0) : nb;
-            rows_to_host(j0 + jb, M - (j0 + jb), j0, j0 + jb);
-        }
-        SLB_CUDA(cudaStreamSynchronize(sd));
+    if (link) {                                                        // rows below the last block row (M > N): final only now
+        if (M > mn) link->download(mn, M, 0, N, ev1);
+        link->finish();
         g_last_lu.host_written = true;
     }
     SLB_CUDA(cudaStreamSynchronize(sg));
@@ -269,7 +335,7 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
                 if (gev[6 * k + 2 * q]) { SLB_CUDA(cudaEventElapsedTime(&g[q], gev[6 * k + 2 * q], gev[6 * k + 2 * q + 1])); last = gev[6 * k + 2 * q + 1]; }
             prev_end = last;
             t_gap += gap; t_g0 += g[0]; t_gn += g[1]; t_gf += g[2];
-            if (k % 8 == 0 || k >= nsteps - 8) fprintf(stderr, "la_trace: %d %d %.3f %.3f %.3f %.3f\n", k, M - k * nb, gap, g[0], g[1], g[2]);
+            if (k % 8 == 0 || k >= nsteps - 8 || (link && k < 24)) fprintf(stderr, "la_trace: %d %d %.3f %.3f %.3f %.3f\n", k, M - k * nb, gap, g[0], g[1], g[2]);
         }
         fprintf(stderr, "la_trace: total %.1f ms = gap %.1f + g0 %.1f + gnear %.1f + gfar %.1f (+ waits inside the update stream)\n", ms, t_gap, t_g0, t_gn, t_gf);
         for (auto &e : eva) if (e) cudaEventDestroy(e);
@@ -283,23 +349,30 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
             }
         g_last_lu.update_flops += gflops[k];
     }
-    for (auto *v : { &evp, &evn, &evl, &pdp, &pdn, &pdf, &gdn, &gdf }) for (auto &e : *v) cudaEventDestroy(e);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs);
+    for (auto *v : { &evp, &evn, &evl, &pdp, &pdn, &pdf, &gdn, &gdf, &dlev }) for (auto &e : *v) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs); cudaEventDestroy(rj);
     *info_host = info_local;
     return 0;
 }
 
 template <typename T>
-int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host, T *host_out)
+int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host, HostLink *link)
 {
     g_last_lu.host_written = false;
     const bool prof = opt("profile", 0) != 0;
-    if (g->nprow * g->npcol == 1 && opt("lookahead", 1) != 0 && !prof)
-        return getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host, host_out);
     Runtime &r = rt();
     const int P = g->nprow, Q = g->npcol, myrow = g->myrow, mycol = g->mycol;
     const int mn = M < N ? M : N;
     const int64_t mloc = numroc(M, nb, myrow, rsrc, P), nloc = numroc(N, nb, mycol, csrc, Q);
+    // small host-resident problems are not worth the slab / block-row machinery: one copy in, one copy out
+    const bool stream_io = link != nullptr && opt("e2e_overlap", 1) != 0 &&
+                           (size_t)mloc * (size_t)nloc * sizeof(T) >= ((size_t)opt("e2e_overlap_min_mb", 256) << 20);
+    if (link && !(stream_io && P * Q == 1 && opt("lookahead", 1) != 0 && !prof)) link->wait(link->upload(0, mloc, 0, nloc));
+    if (P * Q == 1 && opt("lookahead", 1) != 0 && !prof) {
+        int rc = getrf_lookahead_1x1<T>(M, N, A, lld, nb, ipiv_glob_host, info_host, stream_io ? link : nullptr);
+        if (link && !stream_io) { link->download(0, mloc, 0, nloc, nullptr); link->finish(); g_last_lu.host_written = true; }
+        return rc;
+    }
     const bool multi = P * Q > 1;
     if (multi && !g->nccl) g->nccl = nccl_create(g);
     NcclComms *nc = g->nccl;
@@ -446,6 +519,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
 
     panel_phase(0, 0);
     const bool pipe = la && opt("la_pipeline", 1) != 0;
+    std::vector<cudaEvent_t> dlev;
     if (pipe) {
         // ===== two-half software pipeline on P x Q grids (same idea as getrf_lookahead_1x1) =====
         // sq carries the "prep" of a column range: pack -> column all-gather + broadcast (NCCL, nc->col) -> select ->
@@ -546,6 +620,11 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             prep_range(bk, nloc, true);
             SLB_CUDA(cudaEventRecord(pdf[k], sq));
             prep_range(0, lcl, false);
+            if (stream_io && myrow == pr) {      // block row k never changes again (later interchanges touch rows below): back to the host caller
+                cudaEvent_t e; SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                SLB_CUDA(cudaEventRecord(e, sq)); dlev.push_back(e);
+                link->download(lr0, lr0 + jb, 0, nloc, e);
+            }
             // ---- (d) sg: rest of near, far ----
             SLB_CUDA(cudaStreamWaitEvent(sg, pdn[k], 0));
             timed_gemm(2, lcr + nfirst, bk, true);
@@ -651,6 +730,14 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     SLB_CUDA(cudaMemcpyAsync(&info_local, info_dev, sizeof(int), cudaMemcpyDeviceToHost, sm));
     SLB_CUDA(cudaStreamSynchronize(sm));
     if (sp != sm) SLB_CUDA(cudaStreamSynchronize(sp));
+    if (link) {
+        if (stream_io && pipe) { const int64_t l0 = numroc(mn, nb, myrow, rsrc, P); link->download(l0, mloc, 0, nloc, nullptr); }
+        else link->download(0, mloc, 0, nloc, nullptr);
+        link->finish();
+        g_last_lu.host_written = true;
+        for (auto &e : dlev) cudaEventDestroy(e);
+        if (stream_io && pipe) counter_add("e2e_download_overlapped", 1);
+    }
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g_last_lu.factor_ms = ms;
     g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
@@ -683,7 +770,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     return 0;
 }
 
-template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *, double *);
-template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *, zcomplex *);
+template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *, HostLink *);
+template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *, HostLink *);
 
 }  // namespace slb

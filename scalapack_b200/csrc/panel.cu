@@ -258,6 +258,8 @@ panel_leaf_kernel(int m, int w, T *__restrict__ Wp, int64_t ldw, PanelRowMap map
         for (int i = tid; i < nrows; i += PT) Wp[(base + i) + (int64_t)c * ldw] = S[i * LS + c];
 }
 
+inline unsigned &leaf_epoch() { static unsigned e = 0; return e; }
+
 template <typename T, int W>
 size_t leaf_smem_bytes(int rpb)
 {
@@ -292,8 +294,9 @@ void launch_leaf(int m, int w, T *Wp, int64_t ldw, const PanelRowMap &map, int *
         attr_done = true;
     }
     unsigned char *wk = (unsigned char *)work;
-    // mailbox tags = (launch epoch << 8) + column + 1: never equal to a stale tag of an earlier launch
-    static unsigned epoch = 0;
+    // mailbox tags = (launch epoch << 8) + column + 1: never equal to a stale tag of an earlier launch.  ONE counter for
+    // every instantiation (real / complex, every leaf width): they all share the mailbox.
+    unsigned &epoch = leaf_epoch();
     if ((++epoch & 0x7fffffu) == 0) { SLB_CUDA(cudaMemsetAsync(wk, 0, panel_work_bytes(0), s)); ++epoch; }
     unsigned tagbase = (epoch & 0x7fffffu) << 8;
     unsigned long long *dbg = opt("panel_debug", 0) ? (unsigned long long *)workspace("panel_dbg", 2 * 4096 * 8 * 8, true) : nullptr;
@@ -357,7 +360,6 @@ void panel_swap(PanelCtx<T> &c, int p0, int p1, int c0, int c1)
     RowDist rd{ 1 << 30, 1, 0, 0, c.map.g0 };            // rows of Wp are global rows g0, g0+1, ...
     const int j0 = c.map.g0 + p0;
     launch_swap_plan(j0, jb, c.ipiv + p0, c.plan, c.s);
-    if (swap_fused_enabled()) { launch_swap_fused<T>(jb, j0, c.plan, rd, c.Wp, c.ldw, c0, c1, (T *)nullptr, 0, true, c.s); return; }
     launch_swap_pack<T>(jb, j0, c.plan, rd, c.Wp, c.ldw, c0, c1, c.U, jb, c.O, jb, c.s);
     launch_swap_unpack_out<T>(jb, c.plan, rd, c.Wp, c.ldw, c0, c1, c.O, jb, c.s);
     launch_copy2d<T>(jb, nc, c.U, jb, c.Wp + p0 + (int64_t)c0 * c.ldw, c.ldw, c.s);
@@ -391,8 +393,12 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
     if (m <= 0 || jb <= 0) return;
     PanelCtx<T> c;
     // look-ahead mode caps the CTAs; if the slabs of so few CTAs cannot hold m rows, allow more (0 = whole GPU)
-    c.coop = gmax == 0;                 // whole GPU to itself: cooperative launch (the runtime checks co-residency)
+    const bool lookahead = gmax > 0;
     while (gmax > 0 && leaf_rpb<T, 8>(m, gmax) == 0) gmax = (2 * gmax >= rt().sm_count) ? 0 : 2 * gmax;
+    // A capped panel is launched plainly and its CTAs become resident as the chunked update's CTAs retire; a panel that
+    // needs (nearly) every SM cannot rely on that: it is launched cooperatively, so the runtime guarantees co-residency
+    // (it then starts once the kernels ahead of it have drained).
+    c.coop = !lookahead || gmax == 0 || gmax > rt().sm_count / 2;
     // a panel that fits the slabs of G1 CTAs at the widest leaf uses no more: the one-phase exchange (one L2 round
     // trip per column) needs G <= G1, and per-column latency, not bandwidth, bounds a panel of this size
     if ((gmax == 0 || gmax > G1) && leaf_rpb<T, LeafCfg<T>::W0>(m, G1) != 0) gmax = G1;

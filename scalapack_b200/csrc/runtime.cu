@@ -22,7 +22,12 @@ bool cuda_available()
 Runtime &rt()
 {
     std::lock_guard<std::mutex> lk(g_rtmu);
-    if (g_rt.cuda_ok) return g_rt;
+    if (g_rt.cuda_ok) {
+        // a caller's other thread may not have this process's GPU current yet
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != g_rt.device) SLB_CUDA(cudaSetDevice(g_rt.device));
+        return g_rt;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)
@@ -42,6 +47,8 @@ Runtime &rt()
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_panel, cudaStreamNonBlocking, hi));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_copy, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_d2h, cudaStreamNonBlocking, lo));
+    SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_h2d, cudaStreamNonBlocking, lo));
+    SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_aux, cudaStreamNonBlocking, hi));
     SLB_CUDA(cudaStreamCreateWithPriority(&g_rt.s_prep, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
     g_rt.cuda_ok = true;
     return g_rt;

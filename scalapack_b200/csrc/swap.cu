@@ -113,56 +113,6 @@ swap_unpack_out_kernel(int jb, const int *__restrict__ out_dst, RowDist rd, T *_
     }
 }
 
-// ---- experimental (SLB200_SWAP_FUSED=1, default off until validated on hardware) ------------------------------
-// pack + unpack (+ the copy of the permuted block into the top rows) in ONE pass for rows that are all local (nprow == 1):
-// a CTA stages the 2*jb row segments of FUSED_COLS columns in shared memory (all reads before any write), then writes
-// the top block rows (write_top) and/or Ubuf, and the displaced top rows into their outside destinations.  Against the
-// three-kernel version: one launch instead of three, no O buffer round trip, and the scattered writes hit sectors the
-// gather has just brought into L2 (no fill reads).
-constexpr int FUSED_COLS = 4;
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-swap_fused_kernel(int jb, int j0, const int *__restrict__ top_src, const int *__restrict__ out_dst,
-                  const int *__restrict__ out_src, RowDist rd, T *__restrict__ A, int64_t lda, int64_t c0, int64_t c1,
-                  T *__restrict__ Ubuf, int64_t ldu, int write_top)
-{
-    extern __shared__ __align__(16) unsigned char fused_smem[];
-    T *u = reinterpret_cast<T *>(fused_smem);            // [FUSED_COLS][jb]
-    T *o = u + (size_t)FUSED_COLS * jb;                  // [FUSED_COLS][jb]
-    for (int64_t cb = c0 + (int64_t)blockIdx.x * FUSED_COLS; cb < c1; cb += (int64_t)gridDim.x * FUSED_COLS) {
-        const int nc = (int)min((int64_t)FUSED_COLS, c1 - cb);
-        for (int t = threadIdx.x; t < jb; t += blockDim.x) {
-            const T *ap = A + row_local(rd, top_src[t]) + cb * lda;
-#pragma unroll
-            for (int c = 0; c < FUSED_COLS; ++c) if (c < nc) u[c * jb + t] = ap[(int64_t)c * lda];
-            if (out_dst[t] >= 0) {
-                const T *bp = A + row_local(rd, j0 + out_src[t]) + cb * lda;
-#pragma unroll
-                for (int c = 0; c < FUSED_COLS; ++c) if (c < nc) o[c * jb + t] = bp[(int64_t)c * lda];
-            }
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < jb; t += blockDim.x) {
-            T *tp = A + row_local(rd, j0 + t) + cb * lda;
-#pragma unroll
-            for (int c = 0; c < FUSED_COLS; ++c)
-                if (c < nc) {
-                    const T v = u[c * jb + t];
-                    if (Ubuf != nullptr) Ubuf[t + (cb - c0 + c) * ldu] = v;
-                    if (write_top) tp[(int64_t)c * lda] = v;
-                }
-            const int d = out_dst[t];
-            if (d >= 0) {
-                T *dp = A + row_local(rd, d) + cb * lda;
-#pragma unroll
-                for (int c = 0; c < FUSED_COLS; ++c) if (c < nc) dp[(int64_t)c * lda] = o[c * jb + t];
-            }
-        }
-        __syncthreads();
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 swap_select_kernel(int jb, const int *__restrict__ top_src, RowDist rd, const T *__restrict__ Call, int64_t ldc,
@@ -218,10 +168,11 @@ void launch_rows_bc(int64_t rows, int cols, T *L, int64_t ldl, int64_t l0, T *G,
 
 // The gather / scatter kernels are memory-latency bound: a few hundred CTAs keep the HBM queues full, and a capped
 // grid leaves the other SMs to the trailing update running underneath (lu.cu pipelines the two).  SLB200_SWAP_GRID=0: uncapped.
+static thread_local int g_grid_override = -1;      // >= 0: replaces the swap_grid option (0 = uncapped)
+void swap_grid_override(int cap) { g_grid_override = cap; }
 static unsigned capped_grid(int64_t groups)
 {
-    static int64_t cap = -1;
-    if (cap < 0) cap = opt("swap_grid", 48);
+    const int64_t cap = g_grid_override >= 0 ? g_grid_override : opt("swap_grid", 48);
     return (unsigned)((cap > 0 && groups > cap) ? cap : groups);
 }
 
@@ -251,32 +202,6 @@ void launch_swap_unpack_out(int jb, SwapPlan plan, RowDist rd, T *A, int64_t lda
     if (c1 <= c0 || jb <= 0) return;
     unsigned grid = capped_grid((c1 - c0 + SWAP_COLS - 1) / SWAP_COLS);
     swap_unpack_out_kernel<T><<<grid, 256, 0, s>>>(jb, plan.out_dst, rd, A, lda, c0, c1, Obuf, ldo);
-    SLB_CUDA(cudaGetLastError());
-    counter_add("kernel_launches", 1);
-}
-bool swap_fused_enabled()
-{
-    static int64_t on = -1;
-    if (on < 0) on = opt("swap_fused", 0);
-    return on != 0;
-}
-// Interchanges of columns [c0, c1) in one pass; requires rd.nprow == 1.  Ubuf may be null; write_top: also store the
-// permuted block into the top rows j0 .. j0+jb-1 of A (false when a U12 solve on Ubuf follows and writes them later).
-template <typename T>
-void launch_swap_fused(int jb, int j0, SwapPlan plan, RowDist rd, T *A, int64_t lda, int64_t c0, int64_t c1, T *Ubuf, int64_t ldu,
-                       bool write_top, cudaStream_t s)
-{
-    if (c1 <= c0 || jb <= 0) return;
-    if (rd.nprow != 1) fatal("launch_swap_fused needs all rows local (nprow == 1)");
-    const size_t smem = (size_t)2 * FUSED_COLS * jb * sizeof(T);
-    static size_t attr_bytes[2] = { 0, 0 };
-    const int ti = sizeof(T) == 8 ? 0 : 1;
-    if (smem > 48 * 1024 && smem > attr_bytes[ti]) {
-        SLB_CUDA(cudaFuncSetAttribute(swap_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_bytes[ti] = smem;
-    }
-    unsigned grid = capped_grid((c1 - c0 + FUSED_COLS - 1) / FUSED_COLS);
-    swap_fused_kernel<T><<<grid, 256, smem, s>>>(jb, j0, plan.top_src, plan.out_dst, plan.out_src, rd, A, lda, c0, c1, Ubuf, ldu, write_top ? 1 : 0);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);
 }
@@ -311,7 +236,6 @@ void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst
     template void launch_swap_select<T>(int, SwapPlan, RowDist, const T *, int64_t, int64_t, int64_t, T *, int64_t,    \
                                         cudaStream_t);                                                                \
     template void launch_copy2d<T>(int64_t, int64_t, const T *, int64_t, T *, int64_t, cudaStream_t);                  \
-    template void launch_swap_fused<T>(int, int, SwapPlan, RowDist, T *, int64_t, int64_t, int64_t, T *, int64_t, bool, cudaStream_t); \
     template void launch_rows_bc<T>(int64_t, int, T *, int64_t, int64_t, T *, int64_t, int64_t, int, int, int, int, cudaStream_t);
 INST(double)
 INST(zcomplex)

@@ -107,12 +107,9 @@ void slb200_test_laswp(int m, int64_t n, double *A, int64_t lda, int j0, int jb,
     double *U = (double *)workspace("lu_U", (size_t)jb * n * 8), *O = (double *)workspace("lu_O", (size_t)jb * n * 8);
     RowDist rd{ m > 0 ? m : 1, 1, 0, 0, 0 };
     launch_swap_plan(j0, jb, dp, plan, s);
-    if (swap_fused_enabled()) launch_swap_fused<double>(jb, j0, plan, rd, (double *)a.d, lda, 0, n, nullptr, 0, true, s);
-    else {
-        launch_swap_pack<double>(jb, j0, plan, rd, (double *)a.d, lda, 0, n, U, jb, O, jb, s);
-        launch_swap_unpack_out<double>(jb, plan, rd, (double *)a.d, lda, 0, n, O, jb, s);
-        launch_copy2d<double>(jb, n, U, jb, (double *)a.d + j0, lda, s);
-    }
+    launch_swap_pack<double>(jb, j0, plan, rd, (double *)a.d, lda, 0, n, U, jb, O, jb, s);
+    launch_swap_unpack_out<double>(jb, plan, rd, (double *)a.d, lda, 0, n, O, jb, s);
+    launch_copy2d<double>(jb, n, U, jb, (double *)a.d + j0, lda, s);
     SLB_CUDA(cudaStreamSynchronize(s));
     a.back();
 }

@@ -2,6 +2,7 @@
 // Pure host integer code re-exported under the reference's Fortran symbols.
 #include "common.h"
 
+#include <cctype>
 #include <map>
 #include <mutex>
 
@@ -154,7 +155,9 @@ void pxerbla_(const int *ictxt, const char *srname, const int *info)
     int nprow, npcol, myrow, mycol;
     blacs_gridinfo_(ictxt, &nprow, &npcol, &myrow, &mycol);
     char name[32]; int i = 0;
-    for (; i < 31 && srname[i] && srname[i] != ' '; ++i) name[i] = srname[i];
+    // a Fortran CHARACTER has no terminator (its hidden length is not part of this C prototype): routine names are
+    // [A-Z0-9_], at most 12 characters
+    for (; i < 12 && (isalnum((unsigned char)srname[i]) || srname[i] == '_'); ++i) name[i] = srname[i];
     name[i] = 0;
     fprintf(stderr, "{%5d,%5d}:  On entry to %s parameter number%4d had an illegal value\n", myrow, mycol, name, *info);
     fflush(stderr);

@@ -76,6 +76,17 @@ def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False, split=0):
             res["x_err"] = e2
             if not e2 < 1e-8:
                 res["ok"] = False; res["msgs"].append(f"x_err {e2}")
+        for trans in (("T", "C") if cplx else ("T",)):           # transposed solves (pdgetrs.f:268-284)
+            blt = O.scatter(b0, nb, nbr, P, Q, r, c, lld=max(1, mloc))
+            inft = g(trans, n, nrhs, al, 1, 1, desca, ipiv, blt, 1, 1, descb)
+            xt = b0.copy(order="F"); O.getrs(ref, ipr, xt, trans)
+            xtl = O.scatter(xt, nb, nbr, P, Q, r, c, lld=max(1, mloc))
+            if inft != 0:
+                res["ok"] = False; res["msgs"].append(f"getrs {trans} info {inft}")
+            if mloc and nlocb:
+                e3 = float(np.abs(blt[:mloc, :nlocb] - xtl[:mloc, :nlocb]).max() / max(1e-300, np.abs(xt).max()))
+                if not e3 < 1e-8:
+                    res["ok"] = False; res["msgs"].append(f"x_err[{trans}] {e3}")
         # PDGESV in one call on fresh copies
         al2 = O.scatter(a0, nb, nb, P, Q, r, c, lld=lld); bl2 = O.scatter(b0, nb, nbr, P, Q, r, c, lld=max(1, mloc))
         ip2 = np.zeros(mloc + nb, np.int32)
@@ -83,6 +94,69 @@ def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False, split=0):
         inf3 = h(n, nrhs, al2, 1, 1, desca, ip2, bl2, 1, 1, descb)
         if inf3 != 0 or (mloc and nlocb and not np.allclose(bl2[:mloc, :nlocb], bl[:mloc, :nlocb], rtol=0, atol=1e-300)):
             res["ok"] = False; res["msgs"].append(f"pdgesv differs from pdgetrf+pdgetrs (info {inf3})")
+    return res
+
+
+def run_case_general(ctx, P, Q, cs):
+    """Sub-matrix operands on a grid with non-zero source processes: sub(A) = A(ia:ia+m-1, ja:ja+n-1) of an mg x ng matrix
+    distributed from (rsrc, csrc); PDGETRF, then PDGETRS with TRANS in N/T on sub(B) rows aligned with sub(A)."""
+    mg, ng, nb, ia, ja, m, n = cs["mg"], cs["ng"], cs["nb"], cs["ia"], cs["ja"], cs["m"], cs["n"]
+    rsrc, csrc, nrhs = cs.get("rsrc", 0), cs.get("csrc", 0), cs.get("nrhs", 2)
+    _, _, r, c = S.blacs_gridinfo(ctx)
+    res = {"case": f"{P}x{Q} general {cs}", "ok": True, "msgs": []}
+    if r < 0:
+        return res
+    def fail(msg):
+        res["ok"] = False; res["msgs"].append(msg)
+    ag = O.pdmatgen(mg, ng, 100)
+    sub0 = np.asfortranarray(ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n])
+    ref = sub0.copy(order="F"); ipr, infr = O.getrf(ref, nb)
+    G = ag.copy(order="F"); G[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n] = ref
+    mloc, nloc = S.numroc(mg, nb, r, rsrc, P), S.numroc(ng, nb, c, csrc, Q)
+    lld = max(1, mloc) + 1
+    al = O.scatter(ag, nb, nb, P, Q, r, c, rsrc=rsrc, csrc=csrc, lld=lld); al[mloc:, :] = -9923.0
+    exp = O.scatter(G, nb, nb, P, Q, r, c, rsrc=rsrc, csrc=csrc, lld=lld); exp[mloc:, :] = -9923.0
+    desca, info = S.descinit(mg, ng, nb, nb, rsrc, csrc, ctx, lld)
+    ipiv = np.full(mloc + nb, -77, np.int32)
+    info = S.pdgetrf(m, n, al, ia, ja, desca, ipiv)
+    if info != infr:
+        fail(f"info {info} != {infr}")
+    ipe = np.full(mloc + nb, -77, np.int32)
+    for i in range(min(m, n)):
+        gi = ia + i                                              # 1-based global row of A
+        if S.indxg2p(gi, nb, r, rsrc, P) == r:
+            ipe[S.indxg2l(gi, nb, r, rsrc, P) - 1] = ipr[i] + ia - 1
+    if not np.array_equal(ipiv, ipe):
+        bad = np.nonzero(ipiv != ipe)[0]
+        fail(f"ipiv mismatch at local idx {bad[:5].tolist()} got {ipiv[bad[:5]].tolist()} want {ipe[bad[:5]].tolist()}")
+    anorm = np.abs(sub0).sum(axis=1).max()
+    err = float(np.abs(al - exp).max() / (anorm * max(m, n) * EPS))
+    res["lu_err"] = err
+    if not err < 1.0:
+        fail(f"lu_err {err}")
+    # outside sub(A): untouched bits.  Mask = positions whose global index lies inside the window.
+    Mk = np.zeros((mg, ng), order="F"); Mk[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n] = 1.0
+    mk = O.scatter(Mk, nb, nb, P, Q, r, c, rsrc=rsrc, csrc=csrc, lld=lld)
+    if not np.array_equal(al[mk == 0.0], exp[mk == 0.0]):
+        fail("something outside sub(A) was written")
+    if m == n and nrhs > 0 and res["ok"]:
+        nbb, csrcb = 2, (csrc + 1) % Q
+        bg = O.pdmatgen(mg, nrhs, 200)
+        b0 = np.asfortranarray(bg[ia - 1:ia - 1 + n, :])
+        descb, _ = S.descinit(mg, nrhs, nb, nbb, rsrc, csrcb, ctx, max(1, mloc))
+        for trans in ("N", "T"):
+            bl = O.scatter(bg, nb, nbb, P, Q, r, c, rsrc=rsrc, csrc=csrcb, lld=max(1, mloc))
+            inf2 = S.pdgetrs(trans, n, nrhs, al, ia, ja, desca, ipiv, bl, ia, 1, descb)
+            xr = b0.copy(order="F"); O.getrs(ref, ipr, xr, trans)
+            XG = bg.copy(order="F"); XG[ia - 1:ia - 1 + n, :] = xr
+            xl = O.scatter(XG, nb, nbb, P, Q, r, c, rsrc=rsrc, csrc=csrcb, lld=max(1, mloc))
+            nlocb = S.numroc(nrhs, nbb, c, csrcb, Q)
+            if inf2 != 0:
+                fail(f"getrs {trans} info {inf2}")
+            if mloc and nlocb:
+                e2 = float(np.abs(bl[:mloc, :nlocb] - xl[:mloc, :nlocb]).max() / max(1e-300, np.abs(xr).max()))
+                if not e2 < 1e-8:
+                    fail(f"x_err[{trans}] {e2}")
     return res
 
 
@@ -98,7 +172,10 @@ def main():
         if key not in grids:
             grids[key] = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", cs["P"], cs["Q"])
         print(f"[rank {me}] case {cs}", file=sys.stderr, flush=True)
-        out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False), cs.get("split", 0)))
+        if "ia" in cs:
+            out.append(run_case_general(grids[key], cs["P"], cs["Q"], cs))
+        else:
+            out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False), cs.get("split", 0)))
     S.blacs_exit(0)
     print("RESULT" + json.dumps({"rank": me, "results": out}), flush=True)
 

@@ -278,27 +278,51 @@ def test_full_size_properties_n65536(S, ctx11):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.skipif(not os.environ.get("SLB200_TEST_EXPERIMENTAL"), reason="experimental path (SLB200_E2E_OVERLAP), enabled once validated on hardware")
-@pytest.mark.parametrize("m,n,nb", [(3072, 3072, 256), (2000, 1500, 128), (1500, 2000, 128)])
-def test_e2e_overlap_writes_the_same_factors(S, O, ctx11, m, n, nb):
-    """Block rows written back to a pinned host array during the factorisation (e2e_overlap) must give exactly the
-    array the plain staged path gives, guard rows included."""
+def _host_array(a0, lld, pinned):
+    """(lld, n) column-major host copy of a0 with PADVAL guard rows, page-locked or pageable."""
     import torch
+    m, n = a0.shape
+    host = torch.full((n, lld), PADVAL, dtype=torch.float64)
+    if pinned:
+        host = host.pin_memory()
+    host[:, :m] = torch.from_numpy(np.ascontiguousarray(a0.T))
+    return host
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("m,n,nb,slab_mb,save_mb", [(3072, 3072, 256, 0, 16384), (2000, 1500, 128, 0, 16384), (1500, 2000, 128, 0, 16384),
+                                                    (4096, 4096, 512, 0, 40), (4096, 4096, 256, 4, 16384), (2048, 2048, 128, 0, 0)])
+def test_host_resident_streaming_is_bit_identical(S, O, ctx11, m, n, nb, slab_mb, save_mb, pinned):
+    """A host-resident caller (pinned or pageable memory): A is uploaded in column slabs that join the sweep as they arrive
+    (replay of the steps they missed) and the factors go back in block rows during the factorisation.  The host array must
+    end up bit-identical to the device-resident factorisation, guard rows untouched.  slab_mb=0: one slab per block column
+    (a join in almost every step); small save_mb: the kept-panel budget runs out and the remaining slabs are waited for."""
     a0 = O.matgen64_tile(max(m, n), 4321, 0, m, 0, n)
     lld = m + 3
-    outs = []
-    for ov in (0, 1):
-        S.set_option("e2e_overlap", ov)
-        S.set_option("la_split_min", 512); S.set_option("lookahead_min_us", 0)
-        try:
-            host = torch.full((n, lld), PADVAL, dtype=torch.float64).pin_memory()      # (lld, n) column-major
-            host[:, :m] = torch.from_numpy(np.ascontiguousarray(a0.T))
-            desc, info = S.descinit(m, n, nb, nb, 0, 0, ctx11, lld)
-            ipiv = np.zeros(m + nb, np.int32)
-            assert S.pdgetrf(m, n, host.numpy(), 1, 1, desc, ipiv) == 0
-        finally:
-            S.set_option("e2e_overlap", 0); S.set_option("la_split_min", 6144); S.set_option("lookahead_min_us", 4000)
-        outs.append((host.numpy().copy(), ipiv.copy()))
-    assert np.array_equal(outs[0][1], outs[1][1])
-    assert np.array_equal(outs[0][0], outs[1][0])
-    assert np.all(outs[1][0][:, m:] == PADVAL)
+    lu_dev, ipiv_dev, info_dev, _ = run_getrf(S, O, ctx11, a0, nb, pad=0, device=True)
+    S.set_option("e2e_overlap_min_mb", 0); S.set_option("e2e_slab_mb", slab_mb); S.set_option("e2e_save_mb", save_mb)
+    S.set_option("la_split_min", 512); S.set_option("lookahead_min_us", 0)
+    try:
+        host = _host_array(a0, lld, pinned)
+        desc, info = S.descinit(m, n, nb, nb, 0, 0, ctx11, lld)
+        ipiv = np.zeros(m + nb, np.int32)
+        S.reset_counters()
+        assert S.pdgetrf(m, n, host.numpy(), 1, 1, desc, ipiv) == info_dev == 0
+        assert S.get_counter("e2e_upload_overlapped") == 1
+        assert S.get_counter("h2d_bytes") == m * n * 8 and S.get_counter("d2h_bytes") == m * n * 8
+    finally:
+        S.set_option("e2e_overlap_min_mb", 256); S.set_option("e2e_slab_mb", 1024); S.set_option("e2e_save_mb", 16384)
+        S.set_option("la_split_min", 6144); S.set_option("lookahead_min_us", 4000)
+    out = host.numpy().T                                        # (lld, n)
+    assert np.array_equal(ipiv[:min(m, n)], ipiv_dev)
+    assert np.array_equal(out[:m, :], lu_dev)
+    assert np.all(out[m:, :] == PADVAL)
+
+
+def test_host_resident_small_matrix_takes_the_one_copy_path(S, O, ctx11):
+    n, nb = 600, 64
+    a0 = O.pdmatgen(n, n, 100)
+    S.reset_counters()
+    lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, nb, pad=2)
+    assert S.get_counter("e2e_upload_overlapped") == 0
+    check_against_oracle(O, a0, lu, ipiv, info, nb)

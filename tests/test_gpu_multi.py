@@ -55,6 +55,13 @@ def spawn(world, cases, timeout=600):
 
 
 SMALL = [dict(m=m, n=n, nb=nb, nrhs=3) for (m, n) in [(4, 4), (10, 12), (17, 13), (13, 13)] for nb in (2, 3, 4)]
+# sub-matrix operands (IA, JA > 1, M, N < descriptor) on grids whose first block does not live on process (0, 0)
+GENERAL = [dict(mg=40, ng=40, nb=4, ia=9, ja=5, m=20, n=20, rsrc=0, csrc=0), dict(mg=300, ng=260, nb=32, ia=65, ja=33, m=200, n=200, rsrc=1, csrc=1),
+           dict(mg=500, ng=500, nb=64, ia=1, ja=1, m=500, n=500, rsrc=1, csrc=0), dict(mg=640, ng=640, nb=64, ia=129, ja=65, m=300, n=400, rsrc=0, csrc=1)]
+
+
+def general(P, Q):
+    return [dict(c, P=P, Q=Q, rsrc=c["rsrc"] % P, csrc=c["csrc"] % Q) for c in GENERAL]
 
 
 @pytest.mark.parametrize("P,Q", [(1, 2), (2, 1)])
@@ -65,7 +72,7 @@ def test_two_gpus(P, Q):
                                                    dict(P=P, Q=Q, m=300, n=200, nb=64, nrhs=0), dict(P=P, Q=Q, m=1536, n=1536, nb=512, nrhs=1),
                                                    dict(P=P, Q=Q, m=120, n=120, nb=16, nrhs=2, z=True),
                                                    dict(P=P, Q=Q, m=3072, n=3072, nb=128, nrhs=1, dev=True, split=256)]   # pipelined halves
-    spawn(2, cases)
+    spawn(2, cases + general(P, Q))
 
 
 @pytest.mark.parametrize("P,Q", [(2, 2), (1, 4), (4, 1)])
@@ -76,12 +83,13 @@ def test_four_gpus(P, Q):
                                                    dict(P=P, Q=Q, m=777, n=513, nb=100, nrhs=0), dict(P=P, Q=Q, m=2048, n=2048, nb=512, nrhs=2, dev=True),
                                                    dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2, z=True),
                                                    dict(P=P, Q=Q, m=4096, n=4096, nb=128, nrhs=1, dev=True, split=256)]  # pipelined halves
-    spawn(4, cases)
+    spawn(4, cases + general(P, Q))
 
 
 def test_eight_gpus():
     if ngpus() < 8:
         pytest.skip("needs 8 GPUs")
     cases = [dict(P=2, Q=4, m=2000, n=2000, nb=64, nrhs=1), dict(P=2, Q=4, m=4096, n=4096, nb=512, nrhs=1, dev=True), dict(P=2, Q=4, m=13, n=13, nb=2, nrhs=3),
-             dict(P=4, Q=2, m=1000, n=1000, nb=64, nrhs=2), dict(P=2, Q=4, m=512, n=512, nb=64, nrhs=1, z=True)]
-    spawn(8, cases)
+             dict(P=4, Q=2, m=1000, n=1000, nb=64, nrhs=2), dict(P=2, Q=4, m=512, n=512, nb=64, nrhs=1, z=True),
+             dict(P=2, Q=4, m=8192, n=8192, nb=256, nrhs=1, dev=True, split=512), dict(P=2, Q=4, m=2048, n=2048, nb=128, nrhs=2, z=True)]
+    spawn(8, cases + general(2, 4))
