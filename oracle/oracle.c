@@ -725,7 +725,27 @@ static inline zdouble zdiv(zdouble a, zdouble b) { return zmul(a, zrecip(b)); }
 void orc_zgetrs(char trans, int n, int nrhs, const zdouble *a, int64_t lda, const int *ipiv, zdouble *b, int64_t ldb)
 {
     if (n == 0 || nrhs == 0) return;
-    if (!(trans == 'N' || trans == 'n')) { fprintf(stderr, "orc_zgetrs: only TRANS='N' restated\n"); return; }
+    if (!(trans == 'N' || trans == 'n')) {
+        /* SRC/pzgetrs.f:268-284: op(U)^-1 (forward), op(L)^-1 unit (backward), PZLAPIV backward; op = ^T or ^H ('C') */
+        const int cj = (trans == 'C' || trans == 'c');
+        for (int c = 0; c < nrhs; ++c) {
+            zdouble *x = b + c * ldb;
+            for (int k = 0; k < n; ++k) {
+                zdouble s = x[k];
+                for (int i = 0; i < k; ++i) { zdouble e = a[i + k * lda]; if (cj) e.im = -e.im; zdouble t = zmul(e, x[i]); s.re -= t.re; s.im -= t.im; }
+                zdouble d = a[k + k * lda]; if (cj) d.im = -d.im;
+                x[k] = zdiv(s, d);
+            }
+            for (int k = n - 1; k >= 0; --k) {
+                zdouble s = x[k];
+                for (int i = k + 1; i < n; ++i) { zdouble e = a[i + k * lda]; if (cj) e.im = -e.im; zdouble t = zmul(e, x[i]); s.re -= t.re; s.im -= t.im; }
+                x[k] = s;
+            }
+        }
+        for (int i = n - 1; i >= 0; --i) { int p = ipiv[i] - 1;
+            if (p != i) for (int c = 0; c < nrhs; ++c) { zdouble t = b[i + c * ldb]; b[i + c * ldb] = b[p + c * ldb]; b[p + c * ldb] = t; } }
+        return;
+    }
     for (int i = 0; i < n; ++i) { int p = ipiv[i] - 1;
         if (p != i) for (int c = 0; c < nrhs; ++c) { zdouble t = b[i + c * ldb]; b[i + c * ldb] = b[p + c * ldb]; b[p + c * ldb] = t; } }
     for (int c = 0; c < nrhs; ++c) {

@@ -227,3 +227,16 @@ def test_slab_left_looking_schedule_is_the_same_factorisation(O, m, n, nb, ws):
     ipr, info = O.getrf(ref, nb)
     assert info == 0 and np.array_equal(ipr - 1, piv_r)
     assert np.allclose(ref, lu_r, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("trans", ["N", "T", "C"])
+def test_oracle_getrs_trans_against_numpy(O, cplx, trans):
+    """The restated PDGETRS / PZGETRS (SRC/pdgetrs.f:255-284) for every TRANS against an independent dense solve."""
+    n, nb = 70, 8
+    a0 = (O.pzmatgen if cplx else O.pdmatgen)(n, n, 100); b0 = (O.pzmatgen if cplx else O.pdmatgen)(n, 4, 200)
+    ref = a0.copy(order="F"); ipiv, info = O.getrf(ref, nb)
+    assert info == 0
+    x = b0.copy(order="F"); O.getrs(ref, ipiv, x, trans)
+    aop = {"N": a0, "T": a0.T, "C": a0.conj().T}[trans]
+    assert np.abs(x - np.linalg.solve(aop, b0)).max() < 1e-11
