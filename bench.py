@@ -217,7 +217,7 @@ def parity_preflight(S, ctx, P, Q, dist, cplx, cases=None):
         lug = np.zeros((n, n), dtype=a0.dtype, order="F")
         O.gather_into(lug, np.asfortranarray(al), nb, nb, P, Q, r, c)
         if dist is not None:
-            t = torch.from_numpy(lug.view(np.float64).reshape(-1)).cuda()
+            t = torch.from_numpy(lug.ravel(order="K").view(np.float64)).cuda()      # memory (column-major) order
             dist.all_reduce(t); lug = t.cpu().numpy().view(a0.dtype).reshape((n, n), order="F")
         fres = float(O.fresid(np.asfortranarray(lug), ipr, a0)) if ipiv_exact else float("nan")
         v = torch.tensor([0.0 if ipiv_exact and inf2 == 0 else 1.0, lu_err, x_err], dtype=torch.float64, device="cuda")
