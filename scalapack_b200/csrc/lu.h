@@ -31,6 +31,10 @@ template <typename T>
 int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv_glob_host,
                  T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all);
 
+// 1 x 1 grid, TRANS = 'N', nb <= 512, few right-hand sides: the two sweeps at HBM speed (solve_fast.cu)
+bool getrs_fast_applies(int P, int Q, char trans, int nb, int nrhs);
+void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg);
+
 template <typename T>
 void launch_gather_rows(int64_t n, const int *perm, const T *src, int64_t lds, T *dst, int64_t ldd, int nrhs, cudaStream_t s,
                         bool scatter = false);

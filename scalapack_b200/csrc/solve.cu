@@ -96,7 +96,14 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
     else Xw = X0;
 
     const int nblk = (N + nb - 1) / nb;
-    for (int pass = 0; pass < 2; ++pass) {
+    bool fast = false;
+    if constexpr (sizeof(T) == sizeof(double)) {
+        if (getrs_fast_applies(P, Q, trans, nb, nrhs)) {
+            getrs_fast_device(N, nrhs, reinterpret_cast<const double *>(A), lld, nb, reinterpret_cast<double *>(Xg));
+            fast = true;
+        }
+    }
+    for (int pass = 0; pass < 2 && !fast; ++pass) {
         // 'N': pass 0 = L forward, pass 1 = U backward.  'T'/'C': pass 0 = U^T forward, pass 1 = L^T backward.
         const bool use_u = tr ? pass == 0 : pass == 1;
         const bool fwd = pass == 0;
