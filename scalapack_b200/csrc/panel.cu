@@ -392,11 +392,16 @@ void launch_panel(int m, int jb, T *Wp, int64_t ldw, const PanelRowMap &map, int
 {
     if (m <= 0 || jb <= 0) return;
     PanelCtx<T> c;
-    // look-ahead mode caps the CTAs; if the slabs of so few CTAs cannot hold m rows, allow more (0 = whole GPU)
+    // The CTA count (and with it the leaf width W and the recursion tree, i.e. the ARITHMETIC of the panel) is a function of m
+    // and the panel_gmax option only -- never of whether this panel happens to overlap a trailing update: a host-resident
+    // caller's schedule follows the arrival of its column slabs (lu.cu), and the factors must not depend on that.
     const bool lookahead = gmax > 0;
+    gmax = (int)opt("panel_gmax", 32);
+    if (gmax <= 0) gmax = G1;
+    // if the slabs of so few CTAs cannot hold m rows, allow more (0 = whole GPU)
     while (gmax > 0 && leaf_rpb<T, 8>(m, gmax) == 0) gmax = (2 * gmax >= rt().sm_count) ? 0 : 2 * gmax;
-    // A capped panel is launched plainly and its CTAs become resident as the chunked update's CTAs retire; a panel that
-    // needs (nearly) every SM cannot rely on that: it is launched cooperatively, so the runtime guarantees co-residency
+    // A capped look-ahead panel is launched plainly and its CTAs become resident as the chunked update's CTAs retire; a panel
+    // that needs (nearly) every SM cannot rely on that: it is launched cooperatively, so the runtime guarantees co-residency
     // (it then starts once the kernels ahead of it have drained).
     c.coop = !lookahead || gmax == 0 || gmax > rt().sm_count / 2;
     // a panel that fits the slabs of G1 CTAs at the widest leaf uses no more: the one-phase exchange (one L2 round

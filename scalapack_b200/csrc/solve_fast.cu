@@ -27,19 +27,69 @@ namespace {
 
 constexpr int SUB = 32;            // rows per sub-block of the diagonal solve
 constexpr int MAXSUB = 16;         // nb <= 512
-constexpr int KSPLIT = 8;          // K slices of top()
+constexpr int KSPLIT = 32;         // K slices of top()
 constexpr int MAXRHS = 8;
 
 __device__ __forceinline__ int ld_flag(volatile int *p) { return *p; }
 
+// Inverses of the 32 x 32 diagonal triangles of every nb x nb diagonal block (one warp each; lane = row, the 32 columns of the
+// inverse in registers, row k broadcast by shuffles): Dinv[((which*nblk + k)*MAXSUB + s)*1024 + c*32 + i] = inv(T)(i, c), which = 0:
+// unit lower triangle of L, 1: upper triangle of U.  ~20 us for N = 65536, re-done per solve (the factors are the caller's).
+__global__ void __launch_bounds__(128)
+inv32_kernel(int N, int nb, int nblk, const double *__restrict__ A, int64_t lda, double *__restrict__ Dinv)
+{
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * 4 + (threadIdx.x >> 5);                // (which, k, s)
+    if (task >= 2 * nblk * MAXSUB) return;
+    const int which = task / (nblk * MAXSUB), k = (task / MAXSUB) % nblk, s = task % MAXSUB;
+    const int kb = min(nb, N - k * nb), sb = s * SUB;
+    if (sb >= kb) return;
+    const int bs = min(SUB, kb - sb);
+    const double *T = A + ((int64_t)k * nb + sb) * (lda + 1);
+    double t[SUB], inv[SUB];
+#pragma unroll
+    for (int c = 0; c < SUB; ++c) {
+        t[c] = (lane < bs && c < bs) ? T[lane + (int64_t)c * lda] : (lane == c ? 1.0 : 0.0);
+        inv[c] = lane == c ? 1.0 : 0.0;
+    }
+    if (which == 0) {                                                    // unit lower: forward
+#pragma unroll
+        for (int kk = 0; kk < SUB; ++kk) {
+#pragma unroll
+            for (int c = 0; c < SUB; ++c) {
+                const double r = __shfl_sync(0xffffffffu, inv[c], kk);
+                if (lane > kk) inv[c] = fma(-t[kk], r, inv[c]);
+            }
+        }
+    } else {                                                             // upper, non-unit: backward
+#pragma unroll
+        for (int q = 0; q < SUB; ++q) {
+            const int kk = SUB - 1 - q;
+            const double d = __shfl_sync(0xffffffffu, t[kk], kk);
+#pragma unroll
+            for (int c = 0; c < SUB; ++c) {
+                if (lane == kk) inv[c] = inv[c] / d;
+                const double r = __shfl_sync(0xffffffffu, inv[c], kk);
+                if (lane < kk) inv[c] = fma(-t[kk], r, inv[c]);
+            }
+        }
+    }
+    double *out = Dinv + (size_t)task * (SUB * SUB);
+#pragma unroll
+    for (int c = 0; c < SUB; ++c) out[c * SUB + lane] = inv[c];
+}
+
 // x[0:kb] = tri(A)^-1 (b + acc + sum_s P[s]);  FORWARD: unit lower triangle (L), else non-unit upper triangle (U).
 // A: kb x kb diagonal block (ld = lda).  Xk, Acc: this block's rows of X and acc (ld = ldx).  P: [nparts][nrhs][kb].
-// NW warps; warp w owns the sub-blocks w, w + NW, ... of the sweep order (its second sub-block comes up long after its first).
+// Dk: the inverted 32 x 32 diagonal triangles of this block.  NW warps; warp w owns the sub-blocks w, w + NW, ... of the sweep
+// order (its second sub-block comes up long after its first).  Per sub-block the serial chain is: flag -> 32 FMAs in four
+// independent chains (fold of the sub-block just solved) -> 32 shuffles + FMAs with the inverted triangle -> flag.
 constexpr int NW = 8;
 template <bool FORWARD>
 __global__ void __launch_bounds__(SUB * NW, 1)
 diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__restrict__ Xk, const double *__restrict__ Acc,
-                  int64_t ldx, const double *__restrict__ P, int nparts, int nrhs, const double *__restrict__ pf, int pf_cols)
+                  int64_t ldx, const double *__restrict__ P, int nparts, int nrhs, const double *__restrict__ Dk,
+                  const double *__restrict__ pf, int pf_cols)
 {
     __shared__ double xs[SUB * MAXSUB];
     __shared__ int flag[MAXSUB];
@@ -55,13 +105,13 @@ diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__r
     if (tid < MAXSUB) flag[tid] = 0;
     __syncthreads();
     for (int q = w; q < nsub; q += NW) {
-        const int sb = (FORWARD ? q : nsub - 1 - q) * SUB;               // first row of sub-block q of the sweep
+        const int sq = FORWARD ? q : nsub - 1 - q;                       // sub-block q of the sweep
+        const int sb = sq * SUB;
         const int i = sb + lane;
         const bool valid = i < kb;
-        const int bs = min(SUB, kb - sb);
-        double lrow[SUB];                                                // my row of the diagonal 32 x 32 triangle
+        double dinv[SUB];                                                // my row of the inverted diagonal triangle
 #pragma unroll
-        for (int k = 0; k < SUB; ++k) lrow[k] = (valid && k < bs) ? A[i + (int64_t)(sb + k) * lda] : 0.0;
+        for (int c = 0; c < SUB; ++c) dinv[c] = Dk[(size_t)sq * (SUB * SUB) + c * SUB + lane];
         double v = 0.0;
         if (valid) {
             v = Xk[i + (int64_t)rhs * ldx] + Acc[i + (int64_t)rhs * ldx];
@@ -78,8 +128,13 @@ diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__r
             const int pb = (FORWARD ? p : nsub - 1 - p) * SUB;
             while (ld_flag(&flag[p]) == 0) { }
             __syncwarp();
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int k = 0; k < SUB; ++k) v = fma(-a[k], xs[pb + k], v);
+            for (int k = 0; k < SUB; k += 4) {
+                s0 = fma(a[k], xs[pb + k], s0); s1 = fma(a[k + 1], xs[pb + k + 1], s1);
+                s2 = fma(a[k + 2], xs[pb + k + 2], s2); s3 = fma(a[k + 3], xs[pb + k + 3], s3);
+            }
+            v -= (s0 + s1) + (s2 + s3);
         };
         double a0[SUB], a1[SUB];
         if (q > 0) load_blk(a0, 0);
@@ -91,22 +146,14 @@ diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__r
                 fold(a1, p + 1);
             }
         }
-        // my triangle: warp-shuffle substitution
-        if (FORWARD) {
+        // my triangle: x = inv(T) v, the 32 values of v broadcast by shuffles, four independent chains
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int k = 0; k < SUB; ++k) {
-                const double xk = __shfl_sync(0xffffffffu, v, k);
-                if (lane > k && k < bs) v = fma(-lrow[k], xk, v);
-            }
-        } else {
-#pragma unroll
-            for (int kk = 0; kk < SUB; ++kk) {
-                const int k = SUB - 1 - kk;
-                if (valid && lane == k) v = v / lrow[k];
-                const double xk = __shfl_sync(0xffffffffu, v, k);
-                if (lane < k && k < bs) v = fma(-lrow[k], xk, v);
-            }
+        for (int c = 0; c < SUB; c += 4) {
+            s0 = fma(dinv[c], __shfl_sync(0xffffffffu, v, c), s0); s1 = fma(dinv[c + 1], __shfl_sync(0xffffffffu, v, c + 1), s1);
+            s2 = fma(dinv[c + 2], __shfl_sync(0xffffffffu, v, c + 2), s2); s3 = fma(dinv[c + 3], __shfl_sync(0xffffffffu, v, c + 3), s3);
         }
+        v = (s0 + s1) + (s2 + s3);
         if (valid) { xs[i] = v; Xk[i + (int64_t)rhs * ldx] = v; }
         __threadfence_block();
         __syncwarp();
@@ -116,7 +163,7 @@ diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__r
 
 // rows [0, nr) of Y (-)= A[nr x kb] X[kb] for nrhs right-hand sides.  blockIdx.x: 256-row chunk, blockIdx.y: K slice.
 // PARTIAL: the slice's product (negated) is WRITTEN to P[slice][rhs][row] (top); else Y[row + rhs*ldy] -= product (bulk, one slice).
-template <bool VEC, bool PARTIAL, int NR>
+template <bool VEC, bool PARTIAL, int NR, int UNR>
 __global__ void __launch_bounds__(128)
 gemv_rows_kernel(int64_t nr, int kb, const double *__restrict__ A, int64_t lda, const double *__restrict__ X, int64_t ldx,
                  double *__restrict__ Y, int64_t ldy, int nrhs, int kslice)
@@ -138,16 +185,16 @@ gemv_rows_kernel(int64_t nr, int kb, const double *__restrict__ A, int64_t lda, 
     const double *ap = A + row + (int64_t)k0 * lda;
     const int kn = k1 - k0;
     int k = 0;
-    for (; k + 8 <= kn; k += 8) {
-        double2 a[8];
+    for (; k + UNR <= kn; k += UNR) {
+        double2 a[UNR];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const double *p = ap + (int64_t)(k + u) * lda;
             if (VEC) a[u] = __ldcs(reinterpret_cast<const double2 *>(p));
             else { a[u].x = __ldcs(p); a[u].y = two ? __ldcs(p + 1) : 0.0; }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < UNR; ++u)
 #pragma unroll
             for (int r = 0; r < NR; ++r) { const double x = xs[r * (SUB * MAXSUB) + k + u]; acc0[r] = fma(a[u].x, x, acc0[r]); acc1[r] = fma(a[u].y, x, acc1[r]); }
     }
@@ -174,16 +221,20 @@ template <int NR>
 void launch_gemv_rows_nr(int64_t nr, int kb, const double *A, int64_t lda, const double *X, int64_t ldx, double *Y, int64_t ldy, int nrhs,
                          bool partial, cudaStream_t s)
 {
+    constexpr int UNR = NR <= 2 ? 16 : 8;                              // 16-byte loads in flight per thread
     const bool vec = (((uintptr_t)A) & 15) == 0 && lda % 2 == 0 && nr % 2 == 0;
-    const unsigned gx = (unsigned)((nr + 255) / 256);
+    // enough CTAs to fill the GPU also when few rows are left: 256, 128 or 64 rows per CTA
+    const int sms = rt().sm_count;
+    const int threads = partial ? 128 : (nr >= (int64_t)sms * 512 ? 128 : (nr >= (int64_t)sms * 256 ? 64 : 32));
+    const unsigned gx = (unsigned)((nr + 2 * threads - 1) / (2 * threads));
     if (partial) {
         const int kslice = (kb + KSPLIT - 1) / KSPLIT;
-        dim3 grid(gx, KSPLIT);
-        if (vec) gemv_rows_kernel<true, true, NR><<<grid, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
-        else gemv_rows_kernel<false, true, NR><<<grid, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
+        dim3 grid(gx, (unsigned)((kb + kslice - 1) / kslice));
+        if (vec) gemv_rows_kernel<true, true, NR, UNR><<<grid, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
+        else gemv_rows_kernel<false, true, NR, UNR><<<grid, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
     } else {
-        if (vec) gemv_rows_kernel<true, false, NR><<<gx, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
-        else gemv_rows_kernel<false, false, NR><<<gx, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
+        if (vec) gemv_rows_kernel<true, false, NR, UNR><<<gx, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
+        else gemv_rows_kernel<false, false, NR, UNR><<<gx, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
     }
 }
 void launch_gemv_rows(int64_t nr, int kb, const double *A, int64_t lda, const double *X, int64_t ldx, double *Y, int64_t ldy, int nrhs,
@@ -220,13 +271,17 @@ void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, do
         SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evb.push_back(e);
     }
     cudaEvent_t fork, join; SLB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)); SLB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    double *Dinv = (double *)workspace("rs_fast_dinv", (size_t)2 * nblk * MAXSUB * SUB * SUB * sizeof(double));
     SLB_CUDA(cudaEventRecord(fork, sb));
     SLB_CUDA(cudaStreamWaitEvent(sa, fork, 0));
+    inv32_kernel<<<(unsigned)((2 * nblk * MAXSUB + 3) / 4), 128, 0, sa>>>(N, nb, nblk, A, lld, Dinv);
+    SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
     for (int pass = 0; pass < 2; ++pass) {
         const bool fwd = pass == 0;
         SLB_CUDA(cudaMemsetAsync(acc, 0, (size_t)N * nrhs * sizeof(double), sa));
         SLB_CUDA(cudaEventRecord(fork, sa));
         SLB_CUDA(cudaStreamWaitEvent(sb, fork, 0));
+        int nparts_prev = 0;                                                  // K slices top(q-1) wrote
         for (int q = 0; q < nblk; ++q) {
             const int k = fwd ? q : nblk - 1 - q;
             const int64_t j0 = (int64_t)k * nb; const int kb = (int)std::min<int64_t>(nb, N - j0);
@@ -237,14 +292,16 @@ void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, do
             if (q >= 2) SLB_CUDA(cudaStreamWaitEvent(sa, evb[q - 2], 0));         // bulk(q-2) has folded x into my rows
             const double *Pk = part + (size_t)(q & 1) * KSPLIT * MAXRHS * nb;     // written by top(q-1)
             const double *pf = have_next ? A + jn + jn * lld : nullptr;
-            if (fwd) diag_solve_kernel<true><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, q > 0 ? KSPLIT : 0, nrhs, pf, kbn);
-            else diag_solve_kernel<false><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, q > 0 ? KSPLIT : 0, nrhs, pf, kbn);
+            const double *Dk = Dinv + ((size_t)(fwd ? 0 : 1) * nblk + k) * MAXSUB * SUB * SUB;
+            if (fwd) diag_solve_kernel<true><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn);
+            else diag_solve_kernel<false><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn);
             SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
             SLB_CUDA(cudaEventRecord(evd[q], sa));
             if (!have_next) break;
             // ---- top(k): x_k into the rows of the next block, K-split partial sums ----
             double *Pn = part + (size_t)((q + 1) & 1) * KSPLIT * MAXRHS * nb;
             launch_gemv_rows(kbn, kb, A + jn + j0 * lld, lld, Xg + j0, N, Pn, 0, nrhs, true, sa);
+            { const int kslice = (kb + KSPLIT - 1) / KSPLIT; nparts_prev = (kb + kslice - 1) / kslice; }
             // ---- bulk(k): x_k into the rows beyond the next block ----
             SLB_CUDA(cudaStreamWaitEvent(sb, evd[q], 0));
             if (fwd) {

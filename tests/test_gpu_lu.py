@@ -291,7 +291,8 @@ def _host_array(a0, lld, pinned):
 
 @pytest.mark.parametrize("pinned", [True, False])
 @pytest.mark.parametrize("m,n,nb,slab_mb,save_mb", [(3072, 3072, 256, 0, 16384), (2000, 1500, 128, 0, 16384), (1500, 2000, 128, 0, 16384),
-                                                    (4096, 4096, 512, 0, 40), (4096, 4096, 256, 4, 16384), (2048, 2048, 128, 0, 0)])
+                                                    (4096, 4096, 512, 0, 40), (4096, 4096, 256, 4, 16384), (2048, 2048, 128, 0, 0),
+                                                    (4096, 4096, 128, 16, 16384), (8192, 8192, 256, 64, 16384)])
 def test_host_resident_streaming_is_bit_identical(S, O, ctx11, m, n, nb, slab_mb, save_mb, pinned):
     """A host-resident caller (pinned or pageable memory): A is uploaded in column slabs that join the sweep as they arrive
     (replay of the steps they missed) and the factors go back in block rows during the factorisation.  The host array must
