@@ -413,10 +413,19 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
     counter_add("gemm_launches", 1);
 }
 
+bool zgemm_takes_packed(int64_t M, int K, int flags)
+{
+    return (flags & GEMM_MAIN) && K >= 16 && opt("zgemm_packed", 1) != 0 && M >= opt("zgemm_packed_min", 2048);
+}
+
 void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
-                        zcomplex *C, int64_t ldc, cudaStream_t s)
+                        zcomplex *C, int64_t ldc, cudaStream_t s, int chunk, int flags)
 {
     if (M <= 0 || N <= 0 || K <= 0) return;
+    if (zgemm_takes_packed(M, K, flags)) {
+        launch_zgemm_minus_packed(M, N, K, A, lda, B, ldb, C, ldc, s, chunk, (flags & GEMM_REUSE_A) != 0);
+        return;
+    }
     static bool attr_done = false;
     const size_t smem_bytes = (size_t)ZSTAGES * (ZAS_STAGE + ZBS_STAGE) * sizeof(zcomplex);
     if (!attr_done) {

@@ -80,6 +80,54 @@ __global__ void __launch_bounds__(256) pack_b_kernel(int64_t N, int K, const dou
     for (int i = threadIdx.x; i < BLK; i += 256) dst[i] = t[i];
 }
 
+// ---- complex operands (PZGEMM, SRC/pzgetrf.f:288) on the same real kernel ------------------------------------------------
+// C -= A B with A = Ar + i Ai, B = Br + i Bi becomes ONE real product with K doubled and the columns of C interleaved:
+//     [Cr | Ci] -= [Ar | Ai] * [ Br  Bi ]
+//                              [-Bi  Br ]
+// A' = [Ar | Ai] is M x 2K' (K' = K rounded up to the 16-wide k-tile, zero padded); B' has 2N "virtual" columns, column
+// 2n = (Br(:,n); -Bi(:,n)), column 2n+1 = (Bi(:,n); Br(:,n)); virtual column n' of C is the real (n' even) or imaginary (n' odd)
+// plane of complex column n'/2, i.e. exactly the interleaved COMPLEX*16 storage with row stride 2 (CMODE = 1 in the kernel).
+__global__ void __launch_bounds__(256) pack_a_z_kernel(int64_t M, int K, const double2 *__restrict__ A, int64_t lda, double *__restrict__ Ap, int KTh)
+{
+    __shared__ double t[BLK];
+    const int KT = 2 * KTh;
+    const int kt = blockIdx.x % KT; const int64_t tm = blockIdx.x / KT;
+    const bool imag = kt >= KTh;
+    const int64_t m0 = tm * BM; const int k0 = (imag ? kt - KTh : kt) * BK;
+    for (int i = threadIdx.x; i < BLK; i += 256) {
+        int m = i & 127, k = i >> 7;
+        double v = 0.0;
+        if (m0 + m < M && k0 + k < K) { const double2 z = A[m0 + m + (int64_t)(k0 + k) * lda]; v = imag ? z.y : z.x; }
+        t[a_slot(m, k)] = v;
+    }
+    __syncthreads();
+    double *dst = Ap + (int64_t)blockIdx.x * BLK;
+    for (int i = threadIdx.x; i < BLK; i += 256) dst[i] = t[i];
+}
+// N2 = 2 N virtual columns
+__global__ void __launch_bounds__(256) pack_b_z_kernel(int64_t N2, int K, const double2 *__restrict__ B, int64_t ldb, double *__restrict__ Bp, int KTh)
+{
+    __shared__ double t[BLK];
+    const int KT = 2 * KTh;
+    const int kt = blockIdx.x % KT; const int64_t tn = blockIdx.x / KT;
+    const bool lower = kt >= KTh;                                      // the half of B' that multiplies Ai
+    const int64_t n0 = tn * BN; const int k0 = (lower ? kt - KTh : kt) * BK;
+    for (int i = threadIdx.x; i < BLK; i += 256) {
+        int k = i & 15, n = i >> 4;
+        double v = 0.0;
+        const int64_t nv = n0 + n;
+        if (nv < N2 && k0 + k < K) {
+            const double2 z = B[k0 + k + (nv >> 1) * ldb];
+            const bool im_col = nv & 1;
+            v = !lower ? (im_col ? z.y : z.x) : (im_col ? z.x : -z.y);
+        }
+        t[b_slot(n, k)] = v;
+    }
+    __syncthreads();
+    double *dst = Bp + (int64_t)blockIdx.x * BLK;
+    for (int i = threadIdx.x; i < BLK; i += 256) dst[i] = t[i];
+}
+
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
@@ -122,7 +170,13 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 }
 
 // EPI: 0 = load / subtract / store (16-byte when VEC == 2), 1 = fire-and-forget red.global.add.f64 of -acc
-template <int VEC, int EPI>
+// CMODE: 0 = C is a real column-major matrix (ldc in doubles); 1 = C is an interleaved COMPLEX*16 matrix seen as 2N virtual real
+// columns (see pack_b_z_kernel): element (m, n') lives at 2 m + (n' & 1) + (n' >> 1) * ldc with ldc = 2 x the complex leading dimension
+template <int CMODE>
+__device__ __forceinline__ int64_t c_index(int64_t m, int64_t n, int64_t ldc)
+{ return CMODE ? 2 * m + (n & 1) + (n >> 1) * ldc : m + n * ldc; }
+
+template <int VEC, int EPI, int CMODE = 0>
 __global__ void __launch_bounds__(PK_THREADS, 1)
 dgemm_minus_packed(int64_t M, int64_t N, int KT, const double *__restrict__ Ap, const double *__restrict__ Bp,
                    double *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int tn_off, int chunk, int lag)
@@ -155,9 +209,16 @@ dgemm_minus_packed(int64_t M, int64_t N, int KT, const double *__restrict__ Ap, 
             int tm, tn; tile_coords(t_first + lt * t_stride, tiles_m, tiles_n, tm, tn);
             {   // C tile -> L2: 128 columns x 8 lines of 128 B
                 const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-                for (int i = lane; i < BN * 8; i += 32) {
-                    int64_t n = n0 + (i >> 3), m = m0 + (i & 7) * 16;
-                    if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
+                if (CMODE == 0) {
+                    for (int i = lane; i < BN * 8; i += 32) {
+                        int64_t n = n0 + (i >> 3), m = m0 + (i & 7) * 16;
+                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + m + n * ldc));
+                    }
+                } else {                                                // 64 complex columns x 16 lines of 128 B (8 complex rows)
+                    for (int i = lane; i < (BN / 2) * 16; i += 32) {
+                        int64_t n = n0 + 2 * (i >> 4), m = m0 + (i & 15) * 8;
+                        if (n < N && m < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + c_index<1>(m, n, ldc)));
+                    }
                 }
             }
             if (lane == 0) {
@@ -251,12 +312,11 @@ dgemm_minus_packed(int64_t M, int64_t N, int KT, const double *__restrict__ Ap, 
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int64_t n = n0 + wn0 + nf * 16 + g + h * 8;
-                        double *cp = C + n * ldc;
 #pragma unroll
                         for (int mf = 0; mf < 8; ++mf) {
                             const int64_t m = m0 + wm0 + mf * 8 + 2 * tig;
-                            if (n < N && m < M) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(cp + m), "d"(-acc[nf][mf][2 * h]) : "memory");
-                            if (n < N && m + 1 < M) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(cp + m + 1), "d"(-acc[nf][mf][2 * h + 1]) : "memory");
+                            if (n < N && m < M) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(C + c_index<CMODE>(m, n, ldc)), "d"(-acc[nf][mf][2 * h]) : "memory");
+                            if (n < N && m + 1 < M) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(C + c_index<CMODE>(m + 1, n, ldc)), "d"(-acc[nf][mf][2 * h + 1]) : "memory");
                         }
                     }
             } else {
@@ -272,7 +332,7 @@ dgemm_minus_packed(int64_t M, int64_t N, int KT, const double *__restrict__ Ap, 
                             for (int q = 0; q < 4; ++q) {
                                 const int64_t m = m0 + wm0 + (mh * 4 + q) * 8 + 2 * tig;
                                 if (VEC == 2 && n < N && m + 1 < M) cv[h][q] = *reinterpret_cast<const double2 *>(C + m + n * ldc);
-                                else if (n < N && m < M) cv[h][q] = make_double2(C[m + n * ldc], (m + 1 < M) ? C[m + 1 + n * ldc] : 0.0);
+                                else if (n < N && m < M) cv[h][q] = make_double2(C[c_index<CMODE>(m, n, ldc)], (m + 1 < M) ? C[c_index<CMODE>(m + 1, n, ldc)] : 0.0);
                                 else cv[h][q] = make_double2(0.0, 0.0);
                             }
                         }
@@ -285,7 +345,7 @@ dgemm_minus_packed(int64_t M, int64_t N, int KT, const double *__restrict__ Ap, 
                                 double2 c = cv[h][q];
                                 c.x -= acc[nf][mh * 4 + q][2 * h]; c.y -= acc[nf][mh * 4 + q][2 * h + 1];
                                 if (VEC == 2 && n < N && m + 1 < M) *reinterpret_cast<double2 *>(C + m + n * ldc) = c;
-                                else if (n < N && m < M) { C[m + n * ldc] = c.x; if (m + 1 < M) C[m + 1 + n * ldc] = c.y; }
+                                else if (n < N && m < M) { C[c_index<CMODE>(m, n, ldc)] = c.x; if (m + 1 < M) C[c_index<CMODE>(m + 1, n, ldc)] = c.y; }
                             }
                         }
                     }
@@ -336,6 +396,36 @@ void launch_dgemm_minus_packed(int64_t M, int64_t N, int K, const double *A, int
         dgemm_minus_packed<2, 0><<<grid, PK_THREADS, PK_SMEM, s>>>(M, N, KT, Ap, Bp, C, ldc, tiles_m, tiles_n, 0, chunk, lag);
     else
         dgemm_minus_packed<1, 0><<<grid, PK_THREADS, PK_SMEM, s>>>(M, N, KT, Ap, Bp, C, ldc, tiles_m, tiles_n, 0, chunk, lag);
+    SLB_CUDA(cudaGetLastError());
+    counter_add("kernel_launches", 2);
+    counter_add("gemm_launches", 1);
+}
+
+// PZGEMM 'N','N' (alpha = -1, beta = 1) through the packed real kernel: one launch, K doubled, C interleaved (see pack_b_z_kernel).
+void launch_zgemm_minus_packed(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
+                               zcomplex *C, int64_t ldc, cudaStream_t s, int chunk, bool reuse_a)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SLB_CUDA(cudaFuncSetAttribute(dgemm_minus_packed<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM));
+        attr_done = true;
+    }
+    const int KTh = (K + BK - 1) / BK, KT = 2 * KTh;
+    const int64_t N2 = 2 * N;
+    const int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N2 + BN - 1) / BN);
+    const int64_t ntiles = (int64_t)tiles_m * tiles_n;
+    if (ntiles * KT > 0x7fffffffLL) fatal("zgemm(packed): too many tile stages");
+    double *Ap = (double *)workspace("zgemm_Apack", (size_t)tiles_m * KT * BLK * sizeof(double));
+    double *Bp = (double *)workspace("zgemm_Bpack", (size_t)tiles_n * KT * BLK * sizeof(double));
+    if (!reuse_a) {
+        pack_a_z_kernel<<<(unsigned)(tiles_m * KT), 256, 0, s>>>(M, K, A, lda, Ap, KTh);
+        counter_add("kernel_launches", 1);
+    }
+    pack_b_z_kernel<<<(unsigned)(tiles_n * KT), 256, 0, s>>>(N2, K, B, ldb, Bp, KTh);
+    unsigned grid = (unsigned)(ntiles < rt().sm_count ? ntiles : rt().sm_count);
+    if (chunk > 0 && ntiles > rt().sm_count) grid = (unsigned)((ntiles + chunk - 1) / chunk); else chunk = 0;
+    dgemm_minus_packed<1, 0, 1><<<grid, PK_THREADS, PK_SMEM, s>>>(M, N2, KT, Ap, Bp, reinterpret_cast<double *>(C), 2 * ldc, tiles_m, tiles_n, 0, chunk, 0);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 2);
     counter_add("gemm_launches", 1);

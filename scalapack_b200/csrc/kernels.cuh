@@ -19,8 +19,13 @@ void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t ld
 bool dgemm_takes_packed(int64_t M, int K, int flags);   // the decision launch_dgemm_minus makes (depends on M, K only)
 void launch_dgemm_minus_packed(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb,
                                double *C, int64_t ldc, cudaStream_t s, int chunk, bool reuse_a);
+// complex update: flags = GEMM_MAIN routes large products through the packed real kernel (K doubled, interleaved C;
+// gemm_packed.cu), everything else through the 64 x 64 complex DMMA kernel of gemm.cu
 void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
-                        zcomplex *C, int64_t ldc, cudaStream_t s);
+                        zcomplex *C, int64_t ldc, cudaStream_t s, int chunk = 0, int flags = 0);
+bool zgemm_takes_packed(int64_t M, int K, int flags);
+void launch_zgemm_minus_packed(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb,
+                               zcomplex *C, int64_t ldc, cudaStream_t s, int chunk, bool reuse_a);
 
 // ---- U12 triangular solve (replaces PDTRSM 'L','L','N','U'; PBLAS/SRC/PTOOLS/PB_CptrsmAB.c:359-416) ----
 // B[jb x n] <- unit_lower(L[jb x jb])^-1 B, blocked: 64-row diagonal solves + DMMA updates.

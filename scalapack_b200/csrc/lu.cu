@@ -35,8 +35,8 @@ template <> struct Ops<double> {
 };
 template <> struct Ops<zcomplex> {
     static void gemm(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc, cudaStream_t s, int chunk = 0, int flags = 0)
-    { (void)chunk; (void)flags; launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s); }
-    static bool packs(int64_t, int) { return false; }
+    { launch_zgemm_minus(M, N, K, A, lda, B, ldb, C, ldc, s, chunk, flags); }
+    static bool packs(int64_t M, int K) { return zgemm_takes_packed(M, K, GEMM_MAIN); }
     static void trsm(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t s) { launch_ztrsm_llnu(jb, n, L, ldl, B, ldb, s); }
     static void panel(int m, int jb, zcomplex *W, int64_t ldw, const PanelRowMap &map, int *ipiv, int *info, int off, void *work, cudaStream_t s, int gmax = 0)
     { launch_zpanel(m, jb, W, ldw, map, ipiv, info, off, work, s, gmax); }

@@ -256,22 +256,12 @@ bool getrs_fast_applies(int P, int Q, char trans, int nb, int nrhs)
     return P * Q == 1 && trans == 'N' && nb <= SUB * MAXSUB && nrhs >= 1 && nrhs <= MAXRHS && opt("solve_fast", 1) != 0;
 }
 
-// Xg: N x nrhs (ld = N), holds P b on entry and x on return.  Everything is enqueued on s_main (critical) and s_prep (bulk);
-// on return s_main has waited for the bulk stream.
-void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg)
+// The two sweeps as a fork/join of the critical stream sa and the bulk stream sb (sb is the origin: on return it has waited for sa).
+static void enqueue_sweeps(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg, double *acc, double *part, double *Dinv,
+                           cudaStream_t sa, cudaStream_t sb, std::vector<cudaEvent_t> &evd, std::vector<cudaEvent_t> &evb,
+                           cudaEvent_t fork, cudaEvent_t join)
 {
-    Runtime &r = rt();
-    cudaStream_t sa = r.s_panel, sb = r.s_main;      // critical chain on the high-priority stream, the HBM stream on the low one
     const int nblk = (N + nb - 1) / nb;
-    double *acc = (double *)workspace("rs_fast_acc", (size_t)N * nrhs * sizeof(double));
-    double *part = (double *)workspace("rs_fast_part", (size_t)2 * KSPLIT * MAXRHS * nb * sizeof(double));
-    static std::vector<cudaEvent_t> evd, evb;
-    while ((int)evd.size() < nblk + 2) {
-        cudaEvent_t e; SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evd.push_back(e);
-        SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evb.push_back(e);
-    }
-    cudaEvent_t fork, join; SLB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)); SLB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    double *Dinv = (double *)workspace("rs_fast_dinv", (size_t)2 * nblk * MAXSUB * SUB * SUB * sizeof(double));
     SLB_CUDA(cudaEventRecord(fork, sb));
     SLB_CUDA(cudaStreamWaitEvent(sa, fork, 0));
     inv32_kernel<<<(unsigned)((2 * nblk * MAXSUB + 3) / 4), 128, 0, sa>>>(N, nb, nblk, A, lld, Dinv);
@@ -318,7 +308,43 @@ void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, do
     }
     SLB_CUDA(cudaEventRecord(join, sa));
     SLB_CUDA(cudaStreamWaitEvent(sb, join, 0));
-    cudaEventDestroy(fork); cudaEventDestroy(join);
+}
+
+// Xg: N x nrhs (ld = N), holds P b on entry and x on return.  The ~4 launches per block step are recorded ONCE into a CUDA
+// graph (stream capture of the two-stream fork/join) and replayed: issued one by one from the host they cost more host time
+// (~30 us per block step) than the device needs to execute them.  The graph is kept for the next solve with the same factors
+// (same pointers and sizes: PDGETRS is typically called again and again on one factorisation).
+void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg)
+{
+    Runtime &r = rt();
+    cudaStream_t sa = r.s_panel, sb = r.s_main;      // critical chain on the high-priority stream, the HBM stream on the low one
+    const int nblk = (N + nb - 1) / nb;
+    double *acc = (double *)workspace("rs_fast_acc", (size_t)N * nrhs * sizeof(double));
+    double *part = (double *)workspace("rs_fast_part", (size_t)2 * KSPLIT * MAXRHS * nb * sizeof(double));
+    double *Dinv = (double *)workspace("rs_fast_dinv", (size_t)2 * nblk * MAXSUB * SUB * SUB * sizeof(double));
+    static std::vector<cudaEvent_t> evd, evb;
+    static cudaEvent_t fork = nullptr, join = nullptr;
+    if (!fork) { SLB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)); SLB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming)); }
+    while ((int)evd.size() < nblk + 2) {
+        cudaEvent_t e; SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evd.push_back(e);
+        SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evb.push_back(e);
+    }
+    if (opt("solve_graph", 1) == 0) { enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, sa, sb, evd, evb, fork, join); return; }
+    struct Key { int64_t N, nrhs, nb, lld; const void *A, *Xg, *acc, *part, *Dinv; };      // no padding: compared with memcmp
+    static Key key{}; static cudaGraphExec_t exec = nullptr;
+    const Key now{ N, nrhs, nb, lld, A, Xg, acc, part, Dinv };
+    if (exec == nullptr || memcmp(&key, &now, sizeof(Key)) != 0) {
+        if (exec) { SLB_CUDA(cudaGraphExecDestroy(exec)); exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        SLB_CUDA(cudaStreamBeginCapture(sb, cudaStreamCaptureModeRelaxed));
+        enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, sa, sb, evd, evb, fork, join);
+        SLB_CUDA(cudaStreamEndCapture(sb, &graph));
+        SLB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        SLB_CUDA(cudaGraphDestroy(graph));
+        key = now;
+        counter_add("solve_graph_builds", 1);
+    }
+    SLB_CUDA(cudaGraphLaunch(exec, sb));
 }
 
 }  // namespace slb

@@ -40,7 +40,7 @@ double slb200_test_gemm(int64_t M, int64_t N, int K, const void *A, int64_t lda,
     cudaEvent_t e0, e1; SLB_CUDA(cudaEventCreate(&e0)); SLB_CUDA(cudaEventCreate(&e1));
     SLB_CUDA(cudaEventRecord(e0, r.s_main));
     for (int i = 0; i < (reps > 0 ? reps : 1); ++i) {
-        if (is_complex) launch_zgemm_minus(M, N, K, (const zcomplex *)a.d, lda, (const zcomplex *)b.d, ldb, (zcomplex *)c.d, ldc, r.s_main);
+        if (is_complex) launch_zgemm_minus(M, N, K, (const zcomplex *)a.d, lda, (const zcomplex *)b.d, ldb, (zcomplex *)c.d, ldc, r.s_main, (int)opt("gemm_test_chunk", 0), GEMM_MAIN);
         else launch_dgemm_minus(M, N, K, (const double *)a.d, lda, (const double *)b.d, ldb, (double *)c.d, ldc, r.s_main, (int)opt("gemm_test_chunk", 0), GEMM_MAIN);
     }
     SLB_CUDA(cudaEventRecord(e1, r.s_main));

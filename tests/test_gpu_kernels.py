@@ -30,15 +30,19 @@ def test_dgemm_update(S, M, N, K, pad):
     assert np.array_equal(out[M:, :], Cm[M:, :])          # rows beyond M untouched
 
 
-@pytest.mark.parametrize("M,N,K", [(5, 3, 2), (64, 64, 16), (100, 130, 33), (256, 192, 256)])
+@pytest.mark.parametrize("M,N,K", [(5, 3, 2), (64, 64, 16), (100, 130, 33), (256, 192, 256),
+                                   (2048, 300, 256), (2500, 1031, 100), (4096, 129, 37), (3000, 64, 16)])   # M >= 2048: packed real kernel
 def test_zgemm_update(S, M, N, K):
     rng = np.random.default_rng(M + N + K)
     cz = lambda r, c: _f(rng.uniform(-1, 1, (r, c)) + 1j * rng.uniform(-1, 1, (r, c)))
     A, B, Cm = cz(M, K), cz(K, N), cz(M, N)
     ref = Cm - A @ B
     out = Cm.copy(order="F")
-    S.lib().slb200_test_gemm(I64(M), I64(N), K, S.api._ptr(A), I64(M), S.api._ptr(B), I64(K), S.api._ptr(out), I64(M), 1, 1)
-    assert np.abs(out - ref).max() <= 64 * K * 2.0 ** -53
+    ldc = M + 3                                                  # guard rows below C
+    outp = np.full((ldc, N), -9923.0 + 0j, order="F"); outp[:M, :] = Cm
+    S.lib().slb200_test_gemm(I64(M), I64(N), K, S.api._ptr(A), I64(M), S.api._ptr(B), I64(K), S.api._ptr(outp), I64(ldc), 1, 1)
+    assert np.abs(outp[:M, :] - ref).max() <= 64 * K * 2.0 ** -53
+    assert np.all(outp[M:, :] == -9923.0)
 
 
 @pytest.mark.parametrize("jb,n,cplx", [(2, 5, 0), (3, 1, 0), (64, 100, 0), (65, 33, 0), (200, 300, 0), (512, 1000, 0), (40, 50, 1), (256, 64, 1)])
