@@ -34,6 +34,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
 // 1 x 1 grid, TRANS = 'N', nb <= 512, few right-hand sides: the two sweeps at HBM speed (solve_fast.cu)
 bool getrs_fast_applies(int P, int Q, char trans, int nb, int nrhs);
 void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg);
+double solve_fast_probe(int which, int nb, int64_t nr, const double *A, int64_t lld, int N, int reps);
 
 template <typename T>
 void launch_gather_rows(int64_t n, const int *perm, const T *src, int64_t lds, T *dst, int64_t ldd, int nrhs, cudaStream_t s,

@@ -29,8 +29,15 @@ constexpr int SUB = 32;            // rows per sub-block of the diagonal solve
 constexpr int MAXSUB = 16;         // nb <= 512
 constexpr int KSPLIT = 32;         // K slices of top()
 constexpr int MAXRHS = 8;
+constexpr int BULK_MAXS = 8;         // K slices of bulk()
 
-__device__ __forceinline__ int ld_flag(volatile int *p) { return *p; }
+// Loads and polls as volatile asm: the compiler keeps volatile asm statements in program order, so a load written BEFORE a poll
+// is issued before the poll (left to itself it sinks the loads to their first use, i.e. behind the wait, and every fold then
+// pays a full L2 round trip on the critical path -- measured: 0.66 us per fold instead of 0.1 us).
+__device__ __forceinline__ double ldg_early(const double *p)
+{ double v; asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ld_flag(const int *p)
+{ int v; asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
 
 // Inverses of the 32 x 32 diagonal triangles of every nb x nb diagonal block (one warp each; lane = row, the 32 columns of the
 // inverse in registers, row k broadcast by shuffles): Dinv[((which*nblk + k)*MAXSUB + s)*1024 + c*32 + i] = inv(T)(i, c), which = 0:
@@ -85,23 +92,35 @@ inv32_kernel(int N, int nb, int nblk, const double *__restrict__ A, int64_t lda,
 // order (its second sub-block comes up long after its first).  Per sub-block the serial chain is: flag -> 32 FMAs in four
 // independent chains (fold of the sub-block just solved) -> 32 shuffles + FMAs with the inverted triangle -> flag.
 constexpr int NW = 8;
+constexpr size_t DIAG_SMEM = (size_t)NW * 3 * SUB * SUB * sizeof(double);      // per warp: two staged 32 x 32 blocks + the inverted triangle
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool pred)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = pred ? 8 : 0;                                     // 0: the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// The 32 x 32 blocks a warp works on (the off-diagonal blocks it folds, one ahead, and its inverted triangle) are STAGED IN
+// SHARED MEMORY by cp.async: held in registers they take > 190 registers per thread, and the compiler then funnels every
+// shared-memory load of x through the same four registers -- one load latency per FMA (measured: 0.66 us per fold).
 template <bool FORWARD>
 __global__ void __launch_bounds__(SUB * NW, 1)
 diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__restrict__ Xk, const double *__restrict__ Acc,
                   int64_t ldx, const double *__restrict__ P, int nparts, int nrhs, const double *__restrict__ Dk,
-                  const double *__restrict__ pf, int pf_cols)
+                  const double *__restrict__ pf, int pf_cols, unsigned sleep_ns, long long *__restrict__ dbg = nullptr)
 {
+    extern __shared__ __align__(16) double stage[];                     // [NW][3][SUB (k)][SUB (lane)]
     __shared__ double xs[SUB * MAXSUB];
     __shared__ int flag[MAXSUB];
+    const long long t_begin = dbg ? clock64() : 0;
+    auto stamp = [&](int q, int k) { if (dbg && (threadIdx.x & 31) == 0) dbg[q * 8 + k] = clock64() - t_begin; };
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nsub = (kb + SUB - 1) / SUB;
     const int rhs = blockIdx.x;
-    // the next diagonal block -> L2 while this one is being solved (pf_cols columns of pf_cols doubles, 128-byte lines)
-    if (pf != nullptr) {
-        const int lines = (pf_cols * 8 + 127) / 128;
-        for (int e = blockIdx.x * blockDim.x + tid; e < pf_cols * lines; e += gridDim.x * blockDim.x)
-            asm volatile("prefetch.global.L2 [%0];\n" ::"l"((const char *)(pf + (int64_t)(e / lines) * lda) + (e % lines) * 128));
-    }
+    double *mybuf = stage + (size_t)w * 3 * SUB * SUB;
     if (tid < MAXSUB) flag[tid] = 0;
     __syncthreads();
     for (int q = w; q < nsub; q += NW) {
@@ -109,55 +128,95 @@ diag_solve_kernel(int kb, const double *__restrict__ A, int64_t lda, double *__r
         const int sb = sq * SUB;
         const int i = sb + lane;
         const bool valid = i < kb;
-        double dinv[SUB];                                                // my row of the inverted diagonal triangle
-#pragma unroll
-        for (int c = 0; c < SUB; ++c) dinv[c] = Dk[(size_t)sq * (SUB * SUB) + c * SUB + lane];
+        stamp(q, 0);
+        // block p of my rows -> staging buffer p & 1 (a rolled loop with a running pointer: 32 unrolled 64-bit addresses
+        // would cost the registers the FMA pipelines below need)
+        auto load_blk = [&](int p) {
+            const int pb = (FORWARD ? p : nsub - 1 - p) * SUB;
+            const int pbs = min(SUB, kb - pb);
+            double *dst = mybuf + (size_t)(p & 1) * SUB * SUB + lane;
+            const double *src = A + (valid ? i : 0) + (int64_t)pb * lda;
+#pragma unroll 2
+            for (int k = 0; k < SUB; ++k) { cp_async8(dst, src, valid && k < pbs); dst += SUB; if (k + 1 < pbs) src += lda; }
+            cp_async_commit();
+        };
+        {   // my row of the inverted diagonal triangle -> third staging buffer (needed last)
+            double *dst = mybuf + (size_t)2 * SUB * SUB + lane;
+            const double *src = Dk + (size_t)sq * (SUB * SUB) + lane;
+#pragma unroll 2
+            for (int c = 0; c < SUB; ++c) { cp_async8(dst, src, true); dst += SUB; src += SUB; }
+            cp_async_commit();
+        }
+        if (q > 0) load_blk(0);
+        // right-hand side of my rows: b + acc + the K slices of top() in a FIXED order; the loads are issued 16 at a time
+        // (a loop of dependent load + add pairs would cost one L2 round trip per slice)
         double v = 0.0;
         if (valid) {
             v = Xk[i + (int64_t)rhs * ldx] + Acc[i + (int64_t)rhs * ldx];
-            for (int s = 0; s < nparts; ++s) v += P[((int64_t)s * nrhs + rhs) * kb + i];
-        }
-        // fold the sub-blocks solved before mine, in sweep order, as their x appears; the loads run one sub-block ahead
-        auto load_blk = [&](double (&a)[SUB], int p) {
-            const int pb = (FORWARD ? p : nsub - 1 - p) * SUB;
-            const int pbs = min(SUB, kb - pb);
 #pragma unroll
-            for (int k = 0; k < SUB; ++k) a[k] = (valid && k < pbs) ? A[i + (int64_t)(pb + k) * lda] : 0.0;
-        };
-        auto fold = [&](const double (&a)[SUB], int p) {
-            const int pb = (FORWARD ? p : nsub - 1 - p) * SUB;
-            while (ld_flag(&flag[p]) == 0) { }
+            for (int s0 = 0; s0 < KSPLIT; s0 += 16) {
+                double pv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) pv[u] = (s0 + u < nparts) ? ldg_early(P + ((int64_t)(s0 + u) * nrhs + rhs) * kb + i) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v += pv[u];
+            }
+        }
+        stamp(q, 1);
+        // fold the sub-blocks solved before mine, in sweep order, as their x appears
+        for (int p = 0; p < q; ++p) {
+            if (p + 1 < q) { load_blk(p + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+            if (lane == 0) while (ld_flag(&flag[p]) == 0) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
+            if (p == q - 1) stamp(q, 4);
             __syncwarp();
+            if (p == q - 1) stamp(q, 5);
+            const int pb = (FORWARD ? p : nsub - 1 - p) * SUB;
+            const double *a = mybuf + (size_t)(p & 1) * SUB * SUB + lane;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int k = 0; k < SUB; k += 4) {
-                s0 = fma(a[k], xs[pb + k], s0); s1 = fma(a[k + 1], xs[pb + k + 1], s1);
-                s2 = fma(a[k + 2], xs[pb + k + 2], s2); s3 = fma(a[k + 3], xs[pb + k + 3], s3);
+            for (int k0 = 0; k0 < SUB; k0 += 8) {                        // 16 shared-memory loads in flight, then 8 FMAs
+                double av[8], xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { av[u] = a[(k0 + u) * SUB]; xv[u] = xs[pb + k0 + u]; }
+                s0 = fma(av[0], xv[0], s0); s1 = fma(av[1], xv[1], s1); s2 = fma(av[2], xv[2], s2); s3 = fma(av[3], xv[3], s3);
+                s0 = fma(av[4], xv[4], s0); s1 = fma(av[5], xv[5], s1); s2 = fma(av[6], xv[6], s2); s3 = fma(av[7], xv[7], s3);
             }
             v -= (s0 + s1) + (s2 + s3);
-        };
-        double a0[SUB], a1[SUB];
-        if (q > 0) load_blk(a0, 0);
-        for (int p = 0; p < q; p += 2) {
-            if (p + 1 < q) load_blk(a1, p + 1);
-            fold(a0, p);
-            if (p + 1 < q) {
-                if (p + 2 < q) load_blk(a0, p + 2);
-                fold(a1, p + 1);
-            }
+            __syncwarp();                                                // buffer p & 1 is free for block p + 2
         }
+        if (q == 0) cp_async_wait<0>();
+        stamp(q, 2);
         // my triangle: x = inv(T) v, the 32 values of v broadcast by shuffles, four independent chains
+        const double *dinv = mybuf + (size_t)2 * SUB * SUB + lane;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int c = 0; c < SUB; c += 4) {
-            s0 = fma(dinv[c], __shfl_sync(0xffffffffu, v, c), s0); s1 = fma(dinv[c + 1], __shfl_sync(0xffffffffu, v, c + 1), s1);
-            s2 = fma(dinv[c + 2], __shfl_sync(0xffffffffu, v, c + 2), s2); s3 = fma(dinv[c + 3], __shfl_sync(0xffffffffu, v, c + 3), s3);
+        for (int c0 = 0; c0 < SUB; c0 += 8) {
+            double dv[8], vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { dv[u] = dinv[(c0 + u) * SUB]; vv[u] = __shfl_sync(0xffffffffu, v, c0 + u); }
+            s0 = fma(dv[0], vv[0], s0); s1 = fma(dv[1], vv[1], s1); s2 = fma(dv[2], vv[2], s2); s3 = fma(dv[3], vv[3], s3);
+            s0 = fma(dv[4], vv[4], s0); s1 = fma(dv[5], vv[5], s1); s2 = fma(dv[6], vv[6], s2); s3 = fma(dv[7], vv[7], s3);
         }
         v = (s0 + s1) + (s2 + s3);
-        if (valid) { xs[i] = v; Xk[i + (int64_t)rhs * ldx] = v; }
-        __threadfence_block();
+        stamp(q, 6);
+        // publish: shared memory first (the fence then only has shared-memory stores to order), the global copy afterwards
+        if (valid) xs[i] = v;
         __syncwarp();
-        if (lane == 0) *((volatile int *)&flag[q]) = 1;
+        stamp(q, 7);
+        if (lane == 0) {
+            __threadfence_block();
+            asm volatile("st.volatile.shared.s32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&flag[q])), "r"(1) : "memory");
+        }
+        stamp(q, 3);
+        if (valid) Xk[i + (int64_t)rhs * ldx] = v;
+    }
+    // the next diagonal block -> L2 for the next launch of this kernel (a few us away): one 128-byte line per thread and
+    // column, by the warps as they run out of work
+    if (pf != nullptr && blockIdx.x == 0) {
+        const int lines = (pf_cols * 8 + 127) >> 7;
+        for (int c = w; c < pf_cols; c += NW)
+            for (int l = lane; l < lines; l += 32)
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"((const char *)(pf + (int64_t)c * lda) + l * 128));
     }
 }
 
@@ -217,15 +276,101 @@ gemv_rows_kernel(int64_t nr, int kb, const double *__restrict__ A, int64_t lda, 
     }
 }
 
+// bulk(): Y[row] -= A[nr x kb] X[kb] with the K range cut into S slices (blockIdx.y) so that few remaining rows still put
+// enough loads in flight to stream at HBM speed.  Slices write their partial products to `scratch`; the LAST slice CTA of a
+// row chunk to arrive (counter) adds them up in slice order 0 .. S-1 and updates Y: the result does not depend on arrival order.
+template <bool VEC, int NR, int UNR>
+__global__ void __launch_bounds__(128)
+gemv_bulk_kernel(int64_t nr, int kb, const double *__restrict__ A, int64_t lda, const double *__restrict__ X, int64_t ldx,
+                 double *__restrict__ Y, int64_t ldy, int nrhs, int kslice, int S, double *__restrict__ scratch,
+                 unsigned *__restrict__ counters)
+{
+    __shared__ double xs[NR * SUB * MAXSUB];
+    __shared__ int is_last;
+    const int k0 = blockIdx.y * kslice, k1 = min(kb, k0 + kslice), kn = k1 - k0;
+    for (int e = threadIdx.x; e < NR * kn; e += blockDim.x) {
+        const int r = e / kn, k = e % kn;
+        xs[r * (SUB * MAXSUB) + k] = r < nrhs ? X[k0 + k + (int64_t)r * ldx] : 0.0;
+    }
+    __syncthreads();
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const bool active = row < nr, two = row + 1 < nr;
+    double acc0[NR], acc1[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { acc0[r] = 0.0; acc1[r] = 0.0; }
+    if (active) {
+        const double *ap = A + row + (int64_t)k0 * lda;
+        int k = 0;
+        for (; k + UNR <= kn; k += UNR) {
+            double2 a[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const double *p = ap + (int64_t)(k + u) * lda;
+                if (VEC) a[u] = __ldcs(reinterpret_cast<const double2 *>(p));
+                else { a[u].x = __ldcs(p); a[u].y = two ? __ldcs(p + 1) : 0.0; }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) { const double x = xs[r * (SUB * MAXSUB) + k + u]; acc0[r] = fma(a[u].x, x, acc0[r]); acc1[r] = fma(a[u].y, x, acc1[r]); }
+        }
+        for (; k < kn; ++k) {
+            const double *p = ap + (int64_t)k * lda;
+            const double ax = p[0], ay = two ? p[1] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { const double x = xs[r * (SUB * MAXSUB) + k]; acc0[r] = fma(ax, x, acc0[r]); acc1[r] = fma(ay, x, acc1[r]); }
+        }
+    }
+    if (S == 1) {
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (r >= nrhs) continue;
+                double *yp = Y + row + (int64_t)r * ldy;
+                yp[0] -= acc0[r]; if (two) yp[1] -= acc1[r];
+            }
+        }
+        return;
+    }
+    const int64_t nrp = (nr + 1) & ~(int64_t)1;
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double *sp = scratch + ((int64_t)blockIdx.y * NR + r) * nrp + row;
+            __stcg(sp, acc0[r]); __stcg(sp + 1, acc1[r]);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1u) == (unsigned)(S - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (r >= nrhs) continue;
+            double s0 = 0.0, s1 = 0.0;
+            for (int sl = 0; sl < S; ++sl) {
+                const double *sp = scratch + ((int64_t)sl * NR + r) * nrp + row;
+                s0 += __ldcg(sp); s1 += __ldcg(sp + 1);
+            }
+            double *yp = Y + row + (int64_t)r * ldy;
+            yp[0] -= s0; if (two) yp[1] -= s1;
+        }
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+}
+
 template <int NR>
 void launch_gemv_rows_nr(int64_t nr, int kb, const double *A, int64_t lda, const double *X, int64_t ldx, double *Y, int64_t ldy, int nrhs,
-                         bool partial, cudaStream_t s)
+                         bool partial, cudaStream_t s, double *scratch, unsigned *counters)
 {
     constexpr int UNR = NR <= 2 ? 16 : 8;                              // 16-byte loads in flight per thread
     const bool vec = (((uintptr_t)A) & 15) == 0 && lda % 2 == 0 && nr % 2 == 0;
     // enough CTAs to fill the GPU also when few rows are left: 256, 128 or 64 rows per CTA
     const int sms = rt().sm_count;
-    const int threads = partial ? 128 : (nr >= (int64_t)sms * 512 ? 128 : (nr >= (int64_t)sms * 256 ? 64 : 32));
+    const int threads = 128;
     const unsigned gx = (unsigned)((nr + 2 * threads - 1) / (2 * threads));
     if (partial) {
         const int kslice = (kb + KSPLIT - 1) / KSPLIT;
@@ -233,18 +378,25 @@ void launch_gemv_rows_nr(int64_t nr, int kb, const double *A, int64_t lda, const
         if (vec) gemv_rows_kernel<true, true, NR, UNR><<<grid, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
         else gemv_rows_kernel<false, true, NR, UNR><<<grid, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice);
     } else {
-        if (vec) gemv_rows_kernel<true, false, NR, UNR><<<gx, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
-        else gemv_rows_kernel<false, false, NR, UNR><<<gx, threads, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kb);
+        // K slices: enough CTAs (4 per SM) also when few rows are left; slices are multiples of the load batch
+        const unsigned chunks = (unsigned)((nr + 255) / 256);
+        int S = 1;
+        while (S < BULK_MAXS && (int64_t)chunks * S < (int64_t)sms * 4 && kb / (2 * S) >= UNR) S *= 2;
+        const int kslice = ((kb + S - 1) / S + UNR - 1) / UNR * UNR;
+        S = (kb + kslice - 1) / kslice;
+        dim3 grid(chunks, (unsigned)S);
+        if (vec) gemv_bulk_kernel<true, NR, UNR><<<grid, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice, S, scratch, counters);
+        else gemv_bulk_kernel<false, NR, UNR><<<grid, 128, 0, s>>>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, kslice, S, scratch, counters);
     }
 }
 void launch_gemv_rows(int64_t nr, int kb, const double *A, int64_t lda, const double *X, int64_t ldx, double *Y, int64_t ldy, int nrhs,
-                      bool partial, cudaStream_t s)
+                      bool partial, cudaStream_t s, double *scratch = nullptr, unsigned *counters = nullptr)
 {
     if (nr <= 0 || kb <= 0) return;
-    if (nrhs == 1) launch_gemv_rows_nr<1>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s);
-    else if (nrhs == 2) launch_gemv_rows_nr<2>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s);
-    else if (nrhs <= 4) launch_gemv_rows_nr<4>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s);
-    else launch_gemv_rows_nr<8>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s);
+    if (nrhs == 1) launch_gemv_rows_nr<1>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s, scratch, counters);
+    else if (nrhs == 2) launch_gemv_rows_nr<2>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s, scratch, counters);
+    else if (nrhs <= 4) launch_gemv_rows_nr<4>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s, scratch, counters);
+    else launch_gemv_rows_nr<8>(nr, kb, A, lda, X, ldx, Y, ldy, nrhs, partial, s, scratch, counters);
     SLB_CUDA(cudaGetLastError());
     counter_add("kernel_launches", 1);
 }
@@ -258,10 +410,11 @@ bool getrs_fast_applies(int P, int Q, char trans, int nb, int nrhs)
 
 // The two sweeps as a fork/join of the critical stream sa and the bulk stream sb (sb is the origin: on return it has waited for sa).
 static void enqueue_sweeps(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg, double *acc, double *part, double *Dinv,
-                           cudaStream_t sa, cudaStream_t sb, std::vector<cudaEvent_t> &evd, std::vector<cudaEvent_t> &evb,
+                           double *scratch, unsigned *counters, cudaStream_t sa, cudaStream_t sb, std::vector<cudaEvent_t> &evd, std::vector<cudaEvent_t> &evb,
                            cudaEvent_t fork, cudaEvent_t join)
 {
     const int nblk = (N + nb - 1) / nb;
+    const unsigned sleep_ns = (unsigned)opt("solve_poll_ns", 40);
     SLB_CUDA(cudaEventRecord(fork, sb));
     SLB_CUDA(cudaStreamWaitEvent(sa, fork, 0));
     inv32_kernel<<<(unsigned)((2 * nblk * MAXSUB + 3) / 4), 128, 0, sa>>>(N, nb, nblk, A, lld, Dinv);
@@ -283,8 +436,8 @@ static void enqueue_sweeps(int N, int nrhs, const double *A, int64_t lld, int nb
             const double *Pk = part + (size_t)(q & 1) * KSPLIT * MAXRHS * nb;     // written by top(q-1)
             const double *pf = have_next ? A + jn + jn * lld : nullptr;
             const double *Dk = Dinv + ((size_t)(fwd ? 0 : 1) * nblk + k) * MAXSUB * SUB * SUB;
-            if (fwd) diag_solve_kernel<true><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn);
-            else diag_solve_kernel<false><<<nrhs, SUB * NW, 0, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn);
+            if (fwd) diag_solve_kernel<true><<<nrhs, SUB * NW, DIAG_SMEM, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn, sleep_ns);
+            else diag_solve_kernel<false><<<nrhs, SUB * NW, DIAG_SMEM, sa>>>(kb, A + j0 + j0 * lld, lld, Xg + j0, acc + j0, N, Pk, nparts_prev, nrhs, Dk, pf, kbn, sleep_ns);
             SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
             SLB_CUDA(cudaEventRecord(evd[q], sa));
             if (!have_next) break;
@@ -296,9 +449,9 @@ static void enqueue_sweeps(int N, int nrhs, const double *A, int64_t lld, int nb
             SLB_CUDA(cudaStreamWaitEvent(sb, evd[q], 0));
             if (fwd) {
                 const int64_t r0 = jn + kbn;
-                launch_gemv_rows(N - r0, kb, A + r0 + j0 * lld, lld, Xg + j0, N, acc + r0, N, nrhs, false, sb);
+                launch_gemv_rows(N - r0, kb, A + r0 + j0 * lld, lld, Xg + j0, N, acc + r0, N, nrhs, false, sb, scratch, counters);
             } else {
-                launch_gemv_rows(jn, kb, A + j0 * lld, lld, Xg + j0, N, acc, N, nrhs, false, sb);
+                launch_gemv_rows(jn, kb, A + j0 * lld, lld, Xg + j0, N, acc, N, nrhs, false, sb, scratch, counters);
             }
             SLB_CUDA(cudaEventRecord(evb[q], sb));
         }
@@ -314,14 +467,33 @@ static void enqueue_sweeps(int N, int nrhs, const double *A, int64_t lld, int nb
 // graph (stream capture of the two-stream fork/join) and replayed: issued one by one from the host they cost more host time
 // (~30 us per block step) than the device needs to execute them.  The graph is kept for the next solve with the same factors
 // (same pointers and sizes: PDGETRS is typically called again and again on one factorisation).
+static void diag_attr()
+{
+    static bool done = false;
+    if (done) return;
+    SLB_CUDA(cudaFuncSetAttribute(diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    SLB_CUDA(cudaFuncSetAttribute(diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    // the kernels that alternate with diag() on the same SMs ask for the same shared-memory carve-out: no L1 / shared
+    // reconfiguration between consecutive launches of the critical chain
+    if (opt("solve_carveout", 0)) {      // measured: no gain (profiles/r02_solve.md)
+        SLB_CUDA(cudaFuncSetAttribute(gemv_rows_kernel<true, true, 1, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SLB_CUDA(cudaFuncSetAttribute(gemv_bulk_kernel<true, 1, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SLB_CUDA(cudaFuncSetAttribute(inv32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    done = true;
+}
+
 void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, double *Xg)
 {
     Runtime &r = rt();
+    diag_attr();
     cudaStream_t sa = r.s_panel, sb = r.s_main;      // critical chain on the high-priority stream, the HBM stream on the low one
     const int nblk = (N + nb - 1) / nb;
     double *acc = (double *)workspace("rs_fast_acc", (size_t)N * nrhs * sizeof(double));
     double *part = (double *)workspace("rs_fast_part", (size_t)2 * KSPLIT * MAXRHS * nb * sizeof(double));
     double *Dinv = (double *)workspace("rs_fast_dinv", (size_t)2 * nblk * MAXSUB * SUB * SUB * sizeof(double));
+    double *scratch = (double *)workspace("rs_fast_scratch", (size_t)BULK_MAXS * MAXRHS * (N + 2) * sizeof(double));
+    unsigned *counters = (unsigned *)workspace("rs_fast_counters", (size_t)(N / 256 + 2) * sizeof(unsigned), true);
     static std::vector<cudaEvent_t> evd, evb;
     static cudaEvent_t fork = nullptr, join = nullptr;
     if (!fork) { SLB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)); SLB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming)); }
@@ -329,15 +501,15 @@ void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, do
         cudaEvent_t e; SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evd.push_back(e);
         SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evb.push_back(e);
     }
-    if (opt("solve_graph", 1) == 0) { enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, sa, sb, evd, evb, fork, join); return; }
-    struct Key { int64_t N, nrhs, nb, lld; const void *A, *Xg, *acc, *part, *Dinv; };      // no padding: compared with memcmp
+    if (opt("solve_graph", 1) == 0) { enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, scratch, counters, sa, sb, evd, evb, fork, join); return; }
+    struct Key { int64_t N, nrhs, nb, lld; const void *A, *Xg, *acc, *part, *Dinv, *scratch, *counters; };      // no padding: compared with memcmp
     static Key key{}; static cudaGraphExec_t exec = nullptr;
-    const Key now{ N, nrhs, nb, lld, A, Xg, acc, part, Dinv };
+    const Key now{ N, nrhs, nb, lld, A, Xg, acc, part, Dinv, scratch, counters };
     if (exec == nullptr || memcmp(&key, &now, sizeof(Key)) != 0) {
         if (exec) { SLB_CUDA(cudaGraphExecDestroy(exec)); exec = nullptr; }
         cudaGraph_t graph = nullptr;
         SLB_CUDA(cudaStreamBeginCapture(sb, cudaStreamCaptureModeRelaxed));
-        enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, sa, sb, evd, evb, fork, join);
+        enqueue_sweeps(N, nrhs, A, lld, nb, Xg, acc, part, Dinv, scratch, counters, sa, sb, evd, evb, fork, join);
         SLB_CUDA(cudaStreamEndCapture(sb, &graph));
         SLB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         SLB_CUDA(cudaGraphDestroy(graph));
@@ -345,6 +517,76 @@ void getrs_fast_device(int N, int nrhs, const double *A, int64_t lld, int nb, do
         counter_add("solve_graph_builds", 1);
     }
     SLB_CUDA(cudaGraphLaunch(exec, sb));
+}
+
+
+__global__ void lat_probe_kernel(long long *out, double seed)
+{
+    double v = seed, w = seed + 1.0; const double a = 1.0000001, b = 1e-9;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v = fma(v, a, b);
+    }
+    long long t1 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) w = w + b;
+    }
+    long long t2 = clock64();
+    double s = v;
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s = __shfl_sync(0xffffffffu, s, (u + 1) & 31);
+    }
+    long long t3 = clock64();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[3] = (long long)(v + w + s); }
+}
+
+// test / tuning hook: `reps` back-to-back launches of one kernel of the sweep on the factors' first diagonal block (which: 0 = diag
+// forward, 1 = diag backward, 2 = top, 3 = bulk over nr rows); returns the mean time per launch in microseconds
+double solve_fast_probe(int which, int nb, int64_t nr, const double *A, int64_t lld, int N, int reps)
+{
+    Runtime &r = rt(); cudaStream_t s = r.s_main;
+    diag_attr();
+    const int nblk = (N + nb - 1) / nb;
+    double *acc = (double *)workspace("rs_fast_acc", (size_t)N * sizeof(double));
+    double *part = (double *)workspace("rs_fast_part", (size_t)2 * KSPLIT * MAXRHS * nb * sizeof(double));
+    double *Dinv = (double *)workspace("rs_fast_dinv", (size_t)2 * nblk * MAXSUB * SUB * SUB * sizeof(double));
+    double *scratch = (double *)workspace("rs_fast_scratch", (size_t)BULK_MAXS * MAXRHS * (N + 2) * sizeof(double));
+    unsigned *counters = (unsigned *)workspace("rs_fast_counters", (size_t)(N / 256 + 2) * sizeof(unsigned), true);
+    double *X = (double *)workspace("rs_Xg", (size_t)N * sizeof(double));
+    SLB_CUDA(cudaMemsetAsync(X, 0, (size_t)N * sizeof(double), s)); SLB_CUDA(cudaMemsetAsync(acc, 0, (size_t)N * sizeof(double), s));
+    SLB_CUDA(cudaMemsetAsync(part, 0, (size_t)2 * KSPLIT * MAXRHS * nb * sizeof(double), s));
+    inv32_kernel<<<(unsigned)((2 * nblk * MAXSUB + 3) / 4), 128, 0, s>>>(N, nb, nblk, A, lld, Dinv);
+    cudaEvent_t e0, e1; SLB_CUDA(cudaEventCreate(&e0)); SLB_CUDA(cudaEventCreate(&e1));
+    if (which == 4) {       // per-warp timeline of one diag launch (clock64 ticks since kernel start)
+        long long *dbg = (long long *)workspace("rs_fast_dbg", MAXSUB * 8 * sizeof(long long), true);
+        for (int it = 0; it < 3; ++it)
+            diag_solve_kernel<true><<<1, SUB * NW, DIAG_SMEM, s>>>(nb, A, lld, X, acc, N, part, KSPLIT, 1, Dinv, A + nb + (int64_t)nb * lld, nb, (unsigned)opt("solve_poll_ns", 40), dbg);
+        long long h[MAXSUB * 8];
+        SLB_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, s)); SLB_CUDA(cudaStreamSynchronize(s));
+        lat_probe_kernel<<<1, 32, 0, s>>>(dbg, 1.5);
+        long long l[4]; SLB_CUDA(cudaMemcpyAsync(l, dbg, sizeof(l), cudaMemcpyDeviceToHost, s)); SLB_CUDA(cudaStreamSynchronize(s));
+        fprintf(stderr, "diag latency probe (1 warp, dependent chains of 1024): DFMA %.1f DADD %.1f SHFL.64 %.1f ticks per op\n", l[0] / 1024.0, l[1] / 1024.0, l[2] / 1024.0);
+        for (int q = 0; q < MAXSUB; ++q) fprintf(stderr, "diag timeline q=%2d: start %6lld rhs %6lld | flag seen %6lld synced %6lld folds %6lld | tri done %6lld synced %6lld published %6lld\n", q, h[q * 8], h[q * 8 + 1], h[q * 8 + 4], h[q * 8 + 5], h[q * 8 + 2], h[q * 8 + 6], h[q * 8 + 7], h[q * 8 + 3]);
+        return 0.0;
+    }
+    for (int it = 0; it < reps + 3; ++it) {
+        if (it == 3) SLB_CUDA(cudaEventRecord(e0, s));
+        if (which == 0) diag_solve_kernel<true><<<1, SUB * NW, DIAG_SMEM, s>>>(nb, A, lld, X, acc, N, part, KSPLIT, 1, Dinv, A + nb + (int64_t)nb * lld, nb, (unsigned)opt("solve_poll_ns", 40));
+        else if (which == 1) diag_solve_kernel<false><<<1, SUB * NW, DIAG_SMEM, s>>>(nb, A, lld, X, acc, N, part, KSPLIT, 1, Dinv + (size_t)nblk * MAXSUB * SUB * SUB, A + nb + (int64_t)nb * lld, nb, (unsigned)opt("solve_poll_ns", 40));
+        else if (which == 2) launch_gemv_rows(nb, nb, A + nb, lld, X, N, part, 0, 1, true, s);
+        else launch_gemv_rows(nr, nb, A + (N - nr), lld, X, N, acc + (N - nr), N, 1, false, s, scratch, counters);
+    }
+    SLB_CUDA(cudaEventRecord(e1, s));
+    SLB_CUDA(cudaStreamSynchronize(s));
+    float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return (double)ms * 1e3 / reps;
 }
 
 }  // namespace slb

@@ -114,4 +114,8 @@ void slb200_test_laswp(int m, int64_t n, double *A, int64_t lda, int j0, int jb,
     a.back();
 }
 
+// standalone timing of the PDGETRS fast-path kernels (solve_fast.cu); A: device pointer to N x N factors
+double slb200_test_solve_probe(int which, int nb, int64_t nr, const double *A, int64_t lld, int N, int reps)
+{ return solve_fast_probe(which, nb, nr, A, lld, N, reps); }
+
 }  // extern "C"

@@ -47,3 +47,18 @@ elif mode == "solve":
         S.matgen64(ctx, n, 1, nb, 1, X, n, 777)
         assert S.pdgetrs("N", n, 1, A, 1, 1, desca, ipiv, X, 1, 1, descb) == 0
     print(f"solve n={n}: {S.last_solve_ms():.3f} ms = {8.0 * n * n / S.last_solve_ms() / 1e6:.1f} GB/s of 8 N^2 bytes; sresid {S.pdlaschk(ctx, n, 1, X, descb, desca, 20261017, 777, gen=64):.2e}")
+elif mode == "probe":
+    n, nb = (arg + [16384, 512])[:2] if len(arg) >= 2 else (16384, 512)
+    desca, _ = S.descinit(n, n, nb, nb, 0, 0, ctx, n)
+    A = torch.empty(n * n, dtype=torch.float64, device="cuda"); ipiv = np.zeros(n + nb, np.int32)
+    S.matgen64(ctx, n, n, nb, nb, A, n, 20261017)
+    assert S.pdgetrf(n, n, A, 1, 1, desca, ipiv) == 0
+    L.slb200_test_solve_probe.restype = C.c_double
+    for ns in (0, 40, 200):
+        S.set_option("solve_poll_ns", ns)
+        print("poll", ns, "ns:", " ".join("%s %.2f us" % (name, L.slb200_test_solve_probe(which, nb, I64(0), S.api._ptr(A), I64(n), n, 50)) for which, name in ((0, "diag fwd"), (1, "diag bwd"), (2, "top"))))
+    S.set_option("solve_poll_ns", 40)
+    L.slb200_test_solve_probe(4, nb, I64(0), S.api._ptr(A), I64(n), n, 1)
+    for nr in (n - 1024, n // 2, n // 4, n // 16):
+        us = L.slb200_test_solve_probe(3, nb, I64(nr), S.api._ptr(A), I64(n), n, 50)
+        print(f"bulk nr={nr}: {us:.2f} us = {nr * nb * 8 / us / 1e3:.1f} GB/s")
