@@ -429,9 +429,19 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     auto rows_before = [&](int prow, int gidx) { return (int64_t)numroc(gidx, nb, prow, rsrc, P); };
     auto mloc_of = [&](int prow) { return (int64_t)numroc(M, nb, prow, rsrc, P); };
 
+    // per-step timeline (SLB200_LA_TRACE=1): timed events on the panel stream (start | panel gathered + factored + scattered down
+    // the column | row broadcast done) and on the prep stream (near start | near done | far + left done); printed by every rank
+    const bool trace = opt("la_trace", 0) != 0;
+    std::vector<cudaEvent_t> tev;                                 // [nsteps][8]
+    if (trace) { tev.assign((size_t)8 * ((M < N ? M : N) / nb + 2), nullptr); }
+    auto tmark = [&](int k, int slot, cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e; SLB_CUDA(cudaEventCreate(&e)); SLB_CUDA(cudaEventRecord(e, st)); tev[(size_t)8 * k + slot] = e;
+    };
     // =============== panel phase of step k (stream sp) ===============
     auto panel_phase = [&](int k, int gmax) {
         cudaStream_t s = sp;
+        tmark(k, 0, s);
         const int j0 = k * nb;
         const int jb = (mn - j0) < nb ? (mn - j0) : nb;
         const int pr = (rsrc + k) % P, pc = (csrc + k) % Q;
@@ -508,7 +518,9 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                     }
                 }
             }
+            tmark(k, 1, s);
             if (Q > 1) nccl_bcast(nc->row, Pbuf, my_pbytes, NT_U8, pc, s);
+            tmark(k, 2, s);
             if (!(mycol == pc && myrow == pr))
                 SLB_CUDA(cudaMemcpyAsync(ipiv_dev + j0, pIpiv, (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
         }
@@ -597,6 +609,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             SLB_CUDA(cudaStreamWaitEvent(sq, evp[k], 0));
             if (k > 0) SLB_CUDA(cudaStreamWaitEvent(sq, gdn[k - 1], 0));
             if (k > 0 && far_prev && resplit) SLB_CUDA(cudaStreamWaitEvent(sq, gdf[k - 1], 0));
+            tmark(k, 3, sq);
             if (nfirst > 0 && lcr + nfirst < bk) {
                 prep_range(lcr, lcr + nfirst, true);
                 SLB_CUDA(cudaEventRecord(pdp[k], sq));
@@ -606,6 +619,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
                 SLB_CUDA(cudaEventRecord(pdp[k], sq));
             }
             SLB_CUDA(cudaEventRecord(pdn[k], sq));
+            tmark(k, 4, sq);
             // ---- (b) sg: next panel's columns, hand-over to the panel stream ----
             SLB_CUDA(cudaStreamWaitEvent(sg, pdp[k], 0));
             if (have_next) {
@@ -620,6 +634,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
             prep_range(bk, nloc, true);
             SLB_CUDA(cudaEventRecord(pdf[k], sq));
             prep_range(0, lcl, false);
+            tmark(k, 5, sq);
             if (stream_io && myrow == pr) {      // block row k never changes again (later interchanges touch rows below): back to the host caller
                 cudaEvent_t e; SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 SLB_CUDA(cudaEventRecord(e, sq)); dlev.push_back(e);
@@ -741,6 +756,31 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
     float ms = 0; SLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g_last_lu.factor_ms = ms;
     g_last_lu.update_ms = 0; g_last_lu.update_flops = 0; g_last_lu.update_launches = 0;
+    if (trace && pipe) {
+        // per step: update launches (g0 | near | far) on the update stream, the gaps before them, panel-phase pieces, prep pieces
+        double t_upd = 0, t_gap = 0, t_pf = 0, t_pb = 0, t_pn = 0, t_pfar = 0;
+        cudaEvent_t prev_end = ev0;
+        fprintf(stderr, "la_trace[%d,%d]: k | gap g0 near far | panel: factor+col bcast_row | prep: near far+left  (ms)\n", myrow, mycol);
+        for (int k = 0; k < nsteps; ++k) {
+            float g[3] = { 0, 0, 0 }, gap = 0, pf = 0, pbr = 0, pn = 0, pfar = 0;
+            cudaEvent_t first = nullptr, last = nullptr;
+            for (int q = 0; q < 3; ++q)
+                if (gev[(size_t)6 * k + 2 * q]) {
+                    SLB_CUDA(cudaEventElapsedTime(&g[q], gev[(size_t)6 * k + 2 * q], gev[(size_t)6 * k + 2 * q + 1]));
+                    if (!first) first = gev[(size_t)6 * k + 2 * q];
+                    last = gev[(size_t)6 * k + 2 * q + 1];
+                }
+            if (first) { SLB_CUDA(cudaEventElapsedTime(&gap, prev_end, first)); prev_end = last; }
+            auto el = [&](int a, int b) { float t = 0; if (tev[(size_t)8 * k + a] && tev[(size_t)8 * k + b]) SLB_CUDA(cudaEventElapsedTime(&t, tev[(size_t)8 * k + a], tev[(size_t)8 * k + b])); return t; };
+            pf = el(0, 1); pbr = el(1, 2); pn = el(3, 4); pfar = el(4, 5);
+            t_upd += g[0] + g[1] + g[2]; t_gap += gap; t_pf += pf; t_pb += pbr; t_pn += pn; t_pfar += pfar;
+            if (k % 16 == 0 || k >= nsteps - 4)
+                fprintf(stderr, "la_trace[%d,%d]: %d | %.2f %.2f %.2f %.2f | %.2f %.2f | %.2f %.2f\n", myrow, mycol, k, gap, g[0], g[1], g[2], pf, pbr, pn, pfar);
+        }
+        fprintf(stderr, "la_trace[%d,%d]: total %.1f ms: update launches %.1f + gaps on the update stream %.1f; panel phases: factor+column %.1f, row broadcast %.1f; prep: near %.1f, far+left %.1f\n",
+                myrow, mycol, ms, t_upd, t_gap, t_pf, t_pb, t_pn, t_pfar);
+    }
+    for (auto &e : tev) if (e) cudaEventDestroy(e);
     for (size_t i = 0; i + 1 < gev.size(); i += 2)
         if (gev[i]) {
             float t = 0; SLB_CUDA(cudaEventElapsedTime(&t, gev[i], gev[i + 1]));

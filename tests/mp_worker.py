@@ -15,12 +15,14 @@ import scalapack_b200 as S  # noqa: E402
 EPS = 2.0 ** -53
 
 
-def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False, split=0):
+def run_case(ctx, P, Q, m, n, nb, nrhs, cplx=False, device=False, split=0, hoststream=False):
     # split > 0: force the near | far column pipeline (and look-ahead overlap) at this small size
     S.set_option("la_split_min", split if split else 6144)
     S.set_option("lookahead_min_us", 0 if split else 4000)
+    # hoststream: a host-resident caller takes the streaming path (block rows written back during the factorisation) at this size
+    S.set_option("e2e_overlap_min_mb", 0 if hoststream else 256)
     _, _, r, c = S.blacs_gridinfo(ctx)
-    res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)} split={split}", "ok": True, "msgs": []}
+    res = {"case": f"{P}x{Q} m={m} n={n} nb={nb} nrhs={nrhs} z={int(cplx)} dev={int(device)} split={split} hoststream={int(hoststream)}", "ok": True, "msgs": []}
     if r < 0:
         return res
     gen = O.pzmatgen if cplx else O.pdmatgen
@@ -175,7 +177,7 @@ def main():
         if "ia" in cs:
             out.append(run_case_general(grids[key], cs["P"], cs["Q"], cs))
         else:
-            out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False), cs.get("split", 0)))
+            out.append(run_case(grids[key], cs["P"], cs["Q"], cs["m"], cs["n"], cs["nb"], cs.get("nrhs", 1), cs.get("z", False), cs.get("dev", False), cs.get("split", 0), cs.get("hoststream", False)))
     S.blacs_exit(0)
     print("RESULT" + json.dumps({"rank": me, "results": out}), flush=True)
 

@@ -71,7 +71,9 @@ def test_two_gpus(P, Q):
     cases = [dict(c, P=P, Q=Q) for c in SMALL] + [dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2), dict(P=P, Q=Q, m=1000, n=1000, nb=64, nrhs=1, dev=True),
                                                    dict(P=P, Q=Q, m=300, n=200, nb=64, nrhs=0), dict(P=P, Q=Q, m=1536, n=1536, nb=512, nrhs=1),
                                                    dict(P=P, Q=Q, m=120, n=120, nb=16, nrhs=2, z=True),
-                                                   dict(P=P, Q=Q, m=3072, n=3072, nb=128, nrhs=1, dev=True, split=256)]   # pipelined halves
+                                                   dict(P=P, Q=Q, m=3072, n=3072, nb=128, nrhs=1, dev=True, split=256),   # pipelined halves
+                                                   dict(P=P, Q=Q, m=3072, n=3072, nb=128, nrhs=1, split=256, hoststream=True),
+                                                   dict(P=P, Q=Q, m=2000, n=1500, nb=64, nrhs=0, split=128, hoststream=True)]
     spawn(2, cases + general(P, Q))
 
 
@@ -82,7 +84,9 @@ def test_four_gpus(P, Q):
     cases = [dict(c, P=P, Q=Q) for c in SMALL] + [dict(P=P, Q=Q, m=2000, n=2000, nb=64, nrhs=1),           # BASELINE config 1
                                                    dict(P=P, Q=Q, m=777, n=513, nb=100, nrhs=0), dict(P=P, Q=Q, m=2048, n=2048, nb=512, nrhs=2, dev=True),
                                                    dict(P=P, Q=Q, m=200, n=200, nb=32, nrhs=2, z=True),
-                                                   dict(P=P, Q=Q, m=4096, n=4096, nb=128, nrhs=1, dev=True, split=256)]  # pipelined halves
+                                                   dict(P=P, Q=Q, m=4096, n=4096, nb=128, nrhs=1, dev=True, split=256),  # pipelined halves
+                                                   dict(P=P, Q=Q, m=4096, n=4096, nb=128, nrhs=1, split=256, hoststream=True),
+                                                   dict(P=P, Q=Q, m=1500, n=2000, nb=64, nrhs=0, split=128, hoststream=True)]
     spawn(4, cases + general(P, Q))
 
 
@@ -91,5 +95,6 @@ def test_eight_gpus():
         pytest.skip("needs 8 GPUs")
     cases = [dict(P=2, Q=4, m=2000, n=2000, nb=64, nrhs=1), dict(P=2, Q=4, m=4096, n=4096, nb=512, nrhs=1, dev=True), dict(P=2, Q=4, m=13, n=13, nb=2, nrhs=3),
              dict(P=4, Q=2, m=1000, n=1000, nb=64, nrhs=2), dict(P=2, Q=4, m=512, n=512, nb=64, nrhs=1, z=True),
-             dict(P=2, Q=4, m=8192, n=8192, nb=256, nrhs=1, dev=True, split=512), dict(P=2, Q=4, m=2048, n=2048, nb=128, nrhs=2, z=True)]
+             dict(P=2, Q=4, m=8192, n=8192, nb=256, nrhs=1, dev=True, split=512), dict(P=2, Q=4, m=2048, n=2048, nb=128, nrhs=2, z=True),
+             dict(P=2, Q=4, m=8192, n=8192, nb=256, nrhs=1, split=512, hoststream=True)]
     spawn(8, cases + general(2, 4))
