@@ -164,6 +164,8 @@ def run_case_general(ctx, P, Q, cs):
 
 def main():
     me, np_ = S.blacs_pinfo()
+    # every rank runs the oracle's BLAS: share the host cores (8 ranks x all-core OpenBLAS pools spin against each other)
+    O.set_threads(max(1, (os.cpu_count() or 1) // max(1, np_)))
     cases = json.loads(sys.argv[1])
     out = []
     grids = {}                      # one BLACS grid (and one set of NCCL communicators) per (P, Q)
