@@ -42,6 +42,47 @@ def test_tools_match_oracle(S, O, ctx11):
     assert S.iceil(7, 3) == 3 and S.ilcm(4, 6) == 12
 
 
+def test_index_tools_against_the_block_cyclic_definition(S, O):
+    """NUMROC / INDXG2P / INDXG2L / INDXL2G / INFOG2L of the product AND of the oracle against a brute-force enumeration of the
+    2D block-cyclic map itself (global index g, 0-based, lives on process (isrc + g // nb) % P; its local index is its rank among the
+    indices that process owns) -- independent of both restatements of TOOLS/*.f, plus literal values worked by hand from the
+    Fortran (TOOLS/numroc.f, indxg2l.f examples: N=10, NB=2, P=3)."""
+    for impl in (S, O):
+        assert [impl.numroc(10, 2, p, 0, 3) for p in range(3)] == [4, 4, 2]
+        assert [impl.numroc(10, 2, p, 1, 3) for p in range(3)] == [2, 4, 4]
+        assert impl.numroc(0, 4, 0, 0, 2) == 0 and impl.numroc(7, 8, 0, 0, 2) == 7 and impl.numroc(7, 8, 1, 0, 2) == 0
+        assert [impl.indxg2p(g, 2, 0, 0, 3) for g in range(1, 11)] == [0, 0, 1, 1, 2, 2, 0, 0, 1, 1]
+        assert [impl.indxg2l(g, 2, 0, 0, 3) for g in range(1, 11)] == [1, 2, 1, 2, 1, 2, 3, 4, 3, 4]
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        n, nb, P = int(rng.integers(1, 150)), int(rng.integers(1, 12)), int(rng.integers(1, 6))
+        src = int(rng.integers(0, P))
+        owner = [(src + g // nb) % P for g in range(n)]
+        local = []                                               # 1-based local index of global index g+1
+        cnt = [0] * P
+        for g in range(n):
+            cnt[owner[g]] += 1; local.append(cnt[owner[g]])
+        for impl in (S, O):
+            for p in range(P):
+                assert impl.numroc(n, nb, p, src, P) == cnt[p]
+            for g in range(n):
+                assert impl.indxg2p(g + 1, nb, 0, src, P) == owner[g]
+                assert impl.indxg2l(g + 1, nb, 0, 0, P) == local[g]
+                assert impl.indxl2g(local[g], nb, owner[g], src, P) == g + 1
+        # INFOG2L: (local row, local column) of the first element at or after (gr, gc) on every process, and its owner
+        Q = int(rng.integers(1, 5)); csrc = int(rng.integers(0, Q)); m = int(rng.integers(1, 150))
+        cown = [(csrc + g // nb) % Q for g in range(m)]
+        desc = [1, 0, n, m, nb, nb, src, csrc, max(1, n)]
+        gr, gc = int(rng.integers(1, n + 1)), int(rng.integers(1, m + 1))
+        for pr in range(P):
+            for pc in range(Q):
+                want_lr = 1 + sum(1 for g in range(gr - 1) if owner[g] == pr)
+                want_lc = 1 + sum(1 for g in range(gc - 1) if cown[g] == pc)
+                for impl in (S, O):
+                    lr, lc, rs, cs = impl.infog2l(gr, gc, desc, P, Q, pr, pc)
+                    assert (lr, lc, rs, cs) == (want_lr, want_lc, owner[gr - 1], cown[gc - 1]), (impl.__name__, n, m, nb, P, Q, src, csrc, gr, gc, pr, pc)
+
+
 def test_descinit_and_chk1mat(S, O, ctx11):
     d, info = S.descinit(10, 12, 4, 4, 0, 0, ctx11, 10)
     assert info == 0 and d == [1, ctx11, 10, 12, 4, 4, 0, 0, 10]
@@ -127,6 +168,13 @@ out["incons"] = S.pdgetrf(10, 10 if me == 0 else 9, a, 1, 1, d, ipiv)
 c1 = S.blacs_gridinit(S.blacs_get(-1, 0), "R", 1, 1)
 out["solo_ctx_valid"] = c1 >= 0
 out["solo_info"] = S.blacs_gridinfo(c1)
+# a grid created AFTER one that only rank 0 belongs to: the context handles now differ between the ranks (as in the reference,
+# where a handle is an index into the process's own table, blacs_map_.c:72-77,127) -- collectives must not depend on them
+ctx3 = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 2, 1)
+out["ctx3"] = ctx3; out["grid3"] = S.blacs_gridinfo(ctx3)
+S.blacs_barrier(ctx3, "All")
+d3, _ = S.descinit(10, 10, 2, 2, 0, 0, ctx3, 6)
+out["incons3"] = S.pdgetrf(10 if me == 0 else 8, 10, np.zeros((6, 10), order="F"), 1, 1, d3, np.zeros(10, np.int32))
 import ctypes as C
 v = (C.c_int * 2)(me + 5, 10 - me)
 S.lib().igamn2d_(C.byref(C.c_int(ctx)), b"All", b" ", C.byref(C.c_int(2)), C.byref(C.c_int(1)), v, C.byref(C.c_int(2)),
@@ -160,6 +208,8 @@ def test_two_process_control_plane(S):
     assert [r["incons"] for r in res] == [-2, -2]
     assert res[0]["solo_ctx_valid"] and not res[1]["solo_ctx_valid"] and res[1]["solo_info"] == [-1, -1, -1, -1]
     assert res[0]["igamn"] == [5, 9] and res[1]["igamn"] == [5, 9]
+    assert res[0]["ctx3"] != res[1]["ctx3"] and res[0]["grid3"] == [2, 1, 0, 0] and res[1]["grid3"] == [2, 1, 1, 0]
+    assert [r["incons3"] for r in res] == [-1, -1]                      # PCHK1MAT on the later grid: M differs -> -1 on both
 
 
 def test_bench_reference_arm_rank_contract():
