@@ -386,7 +386,10 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs") or 6546.9
     solve_bytes = esz * float(n) * n / world                   # L and U read once, this GPU's share
     solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
-    roof_solve = {"bound": "hbm", "kernel": "PDGETRS block substitution (solve_kernels.cu)", "achieved": solve_gbs, "peak": hbm_peak,
+    solve_kernel = ("PDGETRS 'N' two-stream sweep: diag_solve_kernel -> gemv_rows_kernel (top) beside gemv_bulk_kernel (solve_fast.cu)"
+                    if (world == 1 and not cplx and nb <= 512) else
+                    "PDGETRS block substitution with NCCL reductions / broadcasts per block (solve.cu, solve_kernels.cu)")
+    roof_solve = {"bound": "hbm", "kernel": solve_kernel, "achieved": solve_gbs, "peak": hbm_peak,
                   "unit": "GB/s", "frac": solve_gbs / hbm_peak if solve_gbs else None, "traffic": None,
                   "algorithmic_bytes_per_gpu": solve_bytes, "solve_ms": solve_ms,
                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6546.9 GB/s (B200_PROFILING.md)"}
@@ -396,11 +399,11 @@ def run_ours(args):
     dmma_peak = S.lib().slb200_bench_dmma_tflops(20000)
     dfma_peak = S.lib().slb200_bench_dfma_tflops(20000)
     achieved = u_fl / (u_ms * 1e-3) / 1e12 if u_ms > 0 else None
-    # DRAM traffic of the update kernel: one `ncu --set full` capture (profiles/r01_gemm_v9_ncu.md, M=N=32768, K=512) read
+    # DRAM traffic of the update kernel: one `ncu --set full` capture (profiles/r02_gemm_ncu.md, M=N=32768, K=512) read
     # 11.48 GB and wrote 8.54 GB for 17.45 GB of algorithmic bytes (16*m*n for C + the operands) = 1.147x; scaled here to
     # the average launch of this run (algorithmic C bytes of a launch = its flops * 8 / NB).  Not a live counter.
     traffic = (u_fl / u_n) * 8.0 / nb * 1.147 if (u_n and not cplx) else None
-    kern = ("zgemm_minus (complex FP64 DMMA trailing update, gemm.cu)" if cplx else
+    kern = ("dgemm_minus_packed<CMODE=1> (complex update on the real FP64 DMMA kernel: K doubled, interleaved C; gemm_packed.cu)" if cplx else
             "dgemm_minus_packed (FP64 DMMA trailing update, gemm_packed.cu; dgemm_minus_p8b for m < 3072)")
     roof = {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": dmma_peak,
             "unit": "TFLOP/s", "frac": (achieved / dmma_peak) if achieved else None, "traffic": traffic,

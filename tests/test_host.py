@@ -228,3 +228,23 @@ def test_bench_reference_arm_rank_contract():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "TFLOP/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_bench_config_table():
+    """bench.py's BASELINE config table: sizes, grids, flop models (pdludriver.f:913-918) and the shared workload string."""
+    import argparse
+    import bench as B
+    def cfg(gpus, config="", n=0, nb=0):
+        return B.pick_config(argparse.Namespace(gpus=gpus, config=config, n=n, nb=nb))
+    assert cfg(1)["name"] == "c2" and cfg(1)["n"] == 65536 and cfg(1)["nb"] == 512
+    assert cfg(8)["name"] == "weak" and cfg(8)["n"] == int(65536 * 8 ** 0.5) // 512 * 512 == 185344
+    assert cfg(4)["n"] == 131072 and cfg(2)["n"] == 92672
+    c3, c4, c5 = cfg(8, "c3"), cfg(8, "c4"), cfg(8, "c5")
+    assert (c3["routine"], c3["n"], c3["scaling"]) == ("pdgesv", 131072, "strong")
+    assert (c4["routine"], c4["n"]) == ("pdgetrf", 262144) and (c5["routine"], c5["n"], c5["nb"], c5["cplx"]) == ("pzgetrf", 65536, 256, True)
+    n = 131072.0
+    head, ref = B.flop_counts(c3)
+    assert head == 2.0 / 3.0 * n ** 3 + 2 * n * n and ref == 2.0 / 3.0 * n ** 3 - 0.5 * n * n + 2 * n * n
+    assert B.flop_counts(c5)[0] == 4 * 2.0 / 3.0 * 65536.0 ** 3
+    assert "grid 2x4" in B.workload_string(c4, 8) and "64.0 GiB" in B.workload_string(c4, 8)
+    assert cfg(1, "c5", n=8192)["n"] == 8192 and set(B.METRIC) == {"pdgetrf", "pdgesv", "pzgetrf"}
