@@ -30,7 +30,7 @@ extern "C" {
 
 typedef struct { double re, im; } slb200_z;   /* COMPLEX*16 */
 
-/* ---- BLACS setup API (BLACS/SRC/*.c) ------------------------------------ */
+/* ---- BLACS setup API (BLACS/SRC/<name>.c) ------------------------------------ */
 void blacs_pinfo_(int *mypnum, int *nprocs);                                  /* BLACS/SRC/blacs_pinfo_.c:3-28 */
 void blacs_get_(const int *ictxt, const int *what, int *val);                 /* BLACS/SRC/blacs_get_.c */
 void blacs_set_(const int *ictxt, const int *what, const int *val);           /* BLACS/SRC/blacs_set_.c (accepted, ignored) */
@@ -43,7 +43,7 @@ void blacs_abort_(const int *ictxt, const int *errnum);                       /*
 void blacs_barrier_(const int *ictxt, const char *scope);                     /* BLACS/SRC/blacs_barr_.c:16-26 */
 int  blacs_pnum_(const int *ictxt, const int *prow, const int *pcol);         /* BLACS/SRC/blacs_pnum_.c */
 void blacs_pcoord_(const int *ictxt, const int *pnum, int *prow, int *pcol);  /* BLACS/SRC/blacs_pcoord_.c */
-/* C twins (BLACS/SRC/*.c compile both bindings from one file, dgebs2d_.c:3-8) */
+/* C twins (BLACS/SRC/<name>.c compile both bindings from one file, dgebs2d_.c:3-8) */
 void Cblacs_pinfo(int *mypnum, int *nprocs);
 void Cblacs_get(int ictxt, int what, int *val);
 void Cblacs_gridinit(int *ictxt, const char *order, int nprow, int npcol);
@@ -59,7 +59,7 @@ void igamn2d_(const int *ictxt, const char *scope, const char *top, const int *m
 void igamx2d_(const int *ictxt, const char *scope, const char *top, const int *m, const int *n, int *a,
               const int *lda, int *ra, int *ca, const int *rcflag, const int *rdest, const int *cdest); /* BLACS/SRC/igamx2d_.c */
 
-/* ---- TOOLS (TOOLS/*.f, SL_init.f) ---------------------------------------- */
+/* ---- TOOLS (TOOLS/<name>.f, SL_init.f) ---------------------------------------- */
 void sl_init_(int *ictxt, const int *nprow, const int *npcol);                /* TOOLS/SL_init.f */
 void descinit_(int *desc, const int *m, const int *n, const int *mb, const int *nb, const int *irsrc,
                const int *icsrc, const int *ictxt, const int *lld, int *info);                  /* TOOLS/descinit.f:1-2 */

@@ -248,3 +248,20 @@ def test_bench_config_table():
     assert B.flop_counts(c5)[0] == 4 * 2.0 / 3.0 * 65536.0 ** 3
     assert "grid 2x4" in B.workload_string(c4, 8) and "64.0 GiB" in B.workload_string(c4, 8)
     assert cfg(1, "c5", n=8192)["n"] == 8192 and set(B.METRIC) == {"pdgetrf", "pdgesv", "pzgetrf"}
+
+
+def test_compiled_c_caller_links_against_the_boundary(S, tmp_path):
+    """examples/pdgesv_example.c (the flow of EXAMPLE/pdscaex.f written against include/scalapack_b200.h) compiles with plain gcc
+    and links against the shared library -- the drop-in boundary needs nothing but the header and the .so.  Without a GPU the program
+    must stop loudly (no CPU fallback); with one it solves the reference's 6 x 6 tutorial system below the example's threshold."""
+    exe = str(tmp_path / "pdgesv_example")
+    libdir = os.path.join(ROOT, "scalapack_b200", "lib")
+    cc = subprocess.run(["gcc", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "examples", "pdgesv_example.c"), "-I" + os.path.join(ROOT, "include"),
+                         "-L" + libdir, "-lscalapack_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True, timeout=120)
+    assert cc.returncode == 0, cc.stderr
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    if S.has_cuda():
+        assert run.returncode == 0 and "scaled residual" in run.stdout, run.stderr
+    else:
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr

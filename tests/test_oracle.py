@@ -229,6 +229,77 @@ def test_slab_left_looking_schedule_is_the_same_factorisation(O, m, n, nb, ws):
     assert np.allclose(ref, lu_r, rtol=0, atol=1e-12)
 
 
+def _rl_step_exact(a, piv, j0, jb, c0, c1, panel=None):
+    """Block step (j0, jb) applied to columns [c0, c1) with ELEMENTWISE-deterministic arithmetic (rank-1 updates in k order, no
+    BLAS): interchanges, U12 = L11^-1 A12, A22 -= L21 U12.  panel: the step's panel in its step-time row order (rows j0..)."""
+    pan = a[j0:, j0:j0 + jb] if panel is None else panel
+    for j in range(j0, j0 + jb):
+        p = piv[j]
+        if p != j:
+            a[[j, p], c0:c1] = a[[p, j], c0:c1]
+    for kk in range(jb):                                                # forward substitution with the unit lower L11, row by row
+        a[j0 + kk + 1:j0 + jb, c0:c1] -= np.outer(pan[kk + 1:jb, kk], a[j0 + kk, c0:c1])
+    for kk in range(jb):                                                # trailing update, one rank-1 term at a time
+        a[j0 + jb:, c0:c1] -= np.outer(pan[jb:, kk], a[j0 + kk, c0:c1])
+
+
+def _panel_exact(a, piv, j0, jb):
+    for j in range(j0, j0 + jb):
+        p = j + int(np.argmax(np.abs(a[j:, j])))
+        piv[j] = p
+        if p != j:
+            a[[j, p], j0:j0 + jb] = a[[p, j], j0:j0 + jb]
+        if a[j, j] != 0.0:
+            a[j + 1:, j] *= 1.0 / a[j, j]
+        a[j + 1:, j + 1:j0 + jb] -= np.outer(a[j + 1:, j], a[j, j + 1:j0 + jb])
+
+
+def _streamed_right_looking(a0, nb, present):
+    """The schedule lu.cu runs for a HOST-RESIDENT caller: the right-looking sweep works on the columns [0, Np) that
+    have arrived; columns that arrive later JOIN at the top of a step k and are first taken through steps 0 .. k-1 with the KEPT
+    copy of each panel (step-time row order: the in-place panel has since been permuted by later left interchanges).
+    present(k) = number of columns that have arrived when step k starts."""
+    m, n = a0.shape; mn = min(m, n)
+    a = np.full_like(a0, np.nan, order="F")
+    piv = np.zeros(mn, np.int64); kept = {}
+    nsteps = (mn + nb - 1) // nb
+    Np = 0
+    for k in range(nsteps):
+        j0 = k * nb; jb = min(nb, mn - j0)
+        want = max(present(k), min(n, j0 + jb + nb))                     # the next panel's columns are waited for
+        if k == nsteps - 1:
+            want = n
+        if want > Np:
+            a[:, Np:want] = a0[:, Np:want]
+            for kk in range(k):                                          # replay, in step order, with the kept panels
+                _rl_step_exact(a, piv, kk * nb, nb, Np, want, panel=kept[kk])
+            Np = want
+        _panel_exact(a, piv, j0, jb)
+        kept[k] = a[j0:, j0:j0 + jb].copy()
+        for j in range(j0, j0 + jb):                                     # left interchanges
+            p = piv[j]
+            if p != j:
+                a[[j, p], :j0] = a[[p, j], :j0]
+        _rl_step_exact(a, piv, j0, jb, j0 + jb, Np)
+    return a, piv
+
+
+@pytest.mark.parametrize("m,n,nb", [(96, 96, 8), (120, 90, 16), (70, 110, 8)])
+@pytest.mark.parametrize("rate", [0, 5, 23, 10 ** 6])
+def test_streamed_schedule_is_bit_identical_to_the_resident_sweep(O, m, n, nb, rate):
+    """Host-resident callers: whatever the arrival order of the column slabs (rate = columns arriving per step; 0 = only the
+    columns that are waited for, 10^6 = everything at once), the streamed schedule with replay performs, for every element, the
+    same operations in the same order as the device-resident right-looking sweep -- so with elementwise-deterministic arithmetic
+    the factors are BIT-identical (the GPU kernels have that property: one accumulation chain per element in k order)."""
+    a0 = O.matgen64_tile(max(m, n), 78, 0, m, 0, n)
+    ref, pr = _streamed_right_looking(a0, nb, lambda k: n)             # everything present from the start = the resident sweep
+    lu, piv = _streamed_right_looking(a0, nb, lambda k: min(n, nb + rate * (k + 1)))
+    assert np.array_equal(piv, pr)
+    assert np.array_equal(lu, ref)
+    orc = a0.copy(order="F"); ipr, info = O.getrf(orc, nb)
+    assert info == 0 and np.array_equal(ipr - 1, pr) and np.allclose(orc, ref, rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("trans", ["N", "T", "C"])
 def test_oracle_getrs_trans_against_numpy(O, cplx, trans):
