@@ -398,6 +398,14 @@ double slb200_pdlaschk(const int *ictxt, const int *n_, const int *nrhs_, const 
     return resid;
 }
 
+// test hook (host integer code only, no GPU): the local window of sub(A) as the entry points compute it
+// out = { loff_r, loff_c, mloc, nloc, rsrc, csrc }
+void slb200_test_window(int m, int n, int ia, int ja, const int *desc, int nprow, int npcol, int myrow, int mycol, int64_t *out)
+{
+    const Window w = window(m, n, ia, ja, desc, nprow, npcol, myrow, mycol);
+    out[0] = w.loff_r; out[1] = w.loff_c; out[2] = w.mloc; out[3] = w.nloc; out[4] = w.rsrc; out[5] = w.csrc;
+}
+
 // micro-benchmarks exported for bench.py (roofline denominators)
 double slb200_bench_dmma_tflops(int iters) { return bench_dmma_peak_tflops(iters); }
 double slb200_bench_dfma_tflops(int iters) { return bench_dfma_peak_tflops(iters); }

@@ -173,6 +173,13 @@ struct Ticket {
 
 }  // namespace
 
+// test hook (pure host code): one 2-D copy through a worker pool of `threads` threads (the pageable-memory path of HostLink)
+void test_copy2d(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, int64_t n, int threads)
+{
+    CopyPool pool(threads > 1 ? threads - 1 : 0);
+    for (int rep = 0; rep < 3; ++rep) pool.copy2d(dst, dpitch, src, spitch, width, n);       // the pool is reused job after job
+}
+
 struct HostLink::Impl {
     std::deque<Ticket> tickets;       // stable addresses; only the issuing thread appends
 };
@@ -319,3 +326,7 @@ void HostLink::finish()
 }
 
 }  // namespace slb
+
+extern "C" void slb200_test_copy2d(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, int64_t n, int threads)
+{ slb::test_copy2d(dst, dpitch, src, spitch, width, n, threads); }
+

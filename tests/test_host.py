@@ -265,3 +265,50 @@ def test_compiled_c_caller_links_against_the_boundary(S, tmp_path):
         assert run.returncode == 0 and "scaled residual" in run.stdout, run.stderr
     else:
         assert run.returncode != 0 and "no CPU fallback" in run.stderr
+
+
+def test_submatrix_window_against_infog2l_and_enumeration(S):
+    """The local window of a block-aligned sub(A) = A(IA:IA+M-1, JA:JA+N-1) that PDGETRF / PDGETRS work on (api.cu `window`): offsets
+    equal INFOG2L's local indices (TOOLS/infog2l.f, which pdgetrf.f:202 uses), the window's source process is the owner of (IA, JA),
+    and its extent equals a brute-force count of the owned rows / columns -- on every process of random P x Q grids."""
+    import ctypes as C
+    L = S.lib()
+    rng = np.random.default_rng(11)
+    out = (C.c_int64 * 6)()
+    for _ in range(150):
+        P, Q, nb = int(rng.integers(1, 5)), int(rng.integers(1, 5)), int(rng.integers(1, 9))
+        M, N = int(rng.integers(nb, 12 * nb)), int(rng.integers(nb, 12 * nb))
+        rs, cs = int(rng.integers(0, P)), int(rng.integers(0, Q))
+        ia = 1 + nb * int(rng.integers(0, (M - 1) // nb + 1)); ja = 1 + nb * int(rng.integers(0, (N - 1) // nb + 1))
+        m = int(rng.integers(1, M - ia + 2)); n = int(rng.integers(1, N - ja + 2))
+        desc = [1, 0, M, N, nb, nb, rs, cs, M]
+        for pr in range(P):
+            for pc in range(Q):
+                L.slb200_test_window(m, n, ia, ja, (C.c_int * 9)(*desc), P, Q, pr, pc, out)
+                lr, lc, orow, ocol = S.infog2l(ia, ja, desc, P, Q, pr, pc)
+                rows = [g for g in range(ia - 1, ia - 1 + m) if (rs + g // nb) % P == pr]
+                cols = [g for g in range(ja - 1, ja - 1 + n) if (cs + g // nb) % Q == pc]
+                assert list(out) == [lr - 1, lc - 1, len(rows), len(cols), orow, ocol], (P, Q, nb, M, N, rs, cs, ia, ja, m, n, pr, pc, list(out))
+                # the window's rows are CONTIGUOUS in the local array: local index of the k-th owned row = offset + k
+                if rows:
+                    before = sum(1 for g in range(rows[0]) if (rs + g // nb) % P == pr)
+                    assert before == out[0] and [S.indxg2l(g + 1, nb, 0, 0, P) - 1 for g in rows] == list(range(before, before + len(rows)))
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_worker_pool_2d_copy(S, threads):
+    """The pageable-memory path of the host <-> HBM link moves the caller's array with a pool of memcpy threads (stage.cu): 2-D copies
+    of every shape it cuts (many short columns grouped, long columns split along their length, contiguous blocks) equal numpy's."""
+    import ctypes as C
+    L = S.lib()
+    rng = np.random.default_rng(threads)
+    for width, n, spitch, dpitch in [(8, 1000, 24, 8), (4096, 300, 8192, 4096), (1 << 20, 5, (1 << 20) + 64, 1 << 20), (700000, 3, 700000, 700008),
+                                     (1 << 16, 64, 1 << 16, 1 << 16), (1, 1, 1, 1), (333, 0, 400, 333)]:
+        src = rng.integers(0, 255, size=max(1, spitch * max(n, 1)), dtype=np.uint8)
+        dst = np.full(max(1, dpitch * max(n, 1)), 7, np.uint8)
+        L.slb200_test_copy2d(dst.ctypes.data_as(C.c_void_p), C.c_size_t(dpitch), src.ctypes.data_as(C.c_void_p), C.c_size_t(spitch),
+                             C.c_size_t(width), C.c_int64(n), threads)
+        want = np.full_like(dst, 7)
+        for j in range(n):
+            want[j * dpitch:j * dpitch + width] = src[j * spitch:j * spitch + width]
+        assert np.array_equal(dst, want), (width, n, spitch, dpitch)
