@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
 A_SEED, B_SEED = 20261017, 777
 EPS = 2.0 ** -53
-CPU_SAMPLE_N = 16384            # the reference arm's bounded sample: a full factorisation at this fixed N (see cpu_sample)
+CPU_SAMPLE_N = int(os.environ.get("SLB200_BENCH_CPU_SAMPLE_N", 16384))   # the reference arm's bounded sample: a full factorisation at this
+                                                                          # fixed N (see cpu_sample; the variable exists for the CPU test suite)
 
 # BASELINE.json configs.  "weak" is the driver's default scaling run: 32 GiB of A per GPU at every grid.
 CONFIGS = {

@@ -220,7 +220,7 @@ def test_bench_reference_arm_rank_contract():
     p1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         cwd=ROOT, env=env1, capture_output=True, text=True, timeout=120)
     assert p1.returncode == 0 and p1.stdout.strip() == ""
-    env0 = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", SLB200_BENCH_CPU_TARGET_S="1")
+    env0 = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", SLB200_BENCH_CPU_SAMPLE_N="4096")
     p0 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         cwd=ROOT, env=env0, capture_output=True, text=True, timeout=300)
     assert p0.returncode == 0, p0.stderr[-2000:]
