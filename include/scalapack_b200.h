@@ -102,6 +102,29 @@ void pzgetrs_(const char *trans, const int *n, const int *nrhs, const slb200_z *
 void pzgesv_(const int *n, const int *nrhs, slb200_z *a, const int *ia, const int *ja, const int *desca,
              int *ipiv, slb200_z *b, const int *ib, const int *jb, const int *descb, int *info); /* SRC/pzgesv.f:1-2 */
 
+/* ---- around the factors: norms, equilibration, condition estimate, refinement, expert driver ----
+ * WORK / IWORK keep the reference's workspace protocol (LWORK = -1 queries the minimal sizes into WORK(1) / IWORK(1));
+ * the library allocates its own device scratch and does not touch them otherwise. */
+double pdlange_(const char *norm, const int *m, const int *n, const double *a, const int *ia, const int *ja,
+                const int *desca, double *work);                              /* SRC/pdlange.f:1-2 */
+void pdgeequ_(const int *m, const int *n, const double *a, const int *ia, const int *ja, const int *desca, double *r,
+              double *c, double *rowcnd, double *colcnd, double *amax, int *info);             /* SRC/pdgeequ.f:1-2 */
+void pdlaqge_(const int *m, const int *n, double *a, const int *ia, const int *ja, const int *desca, const double *r,
+              const double *c, const double *rowcnd, const double *colcnd, const double *amax, char *equed); /* SRC/pdlaqge.f:1-2 */
+void pdgecon_(const char *norm, const int *n, const double *a, const int *ia, const int *ja, const int *desca,
+              const double *anorm, double *rcond, double *work, const int *lwork, int *iwork, const int *liwork,
+              int *info);                                                     /* SRC/pdgecon.f:1-2 */
+void pdgerfs_(const char *trans, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja,
+              const int *desca, const double *af, const int *iaf, const int *jaf, const int *descaf, const int *ipiv,
+              const double *b, const int *ib, const int *jb, const int *descb, double *x, const int *ix, const int *jx,
+              const int *descx, double *ferr, double *berr, double *work, const int *lwork, int *iwork,
+              const int *liwork, int *info);                                  /* SRC/pdgerfs.f:1-4 */
+void pdgesvx_(const char *fact, const char *trans, const int *n, const int *nrhs, double *a, const int *ia, const int *ja,
+              const int *desca, double *af, const int *iaf, const int *jaf, const int *descaf, int *ipiv, char *equed,
+              double *r, double *c, double *b, const int *ib, const int *jb, const int *descb, double *x, const int *ix,
+              const int *jx, const int *descx, double *rcond, double *ferr, double *berr, double *work, const int *lwork,
+              int *iwork, const int *liwork, int *info);                      /* SRC/pdgesvx.f:1-5 */
+
 /* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
 /* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
  * a may be host or device. */

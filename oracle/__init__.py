@@ -26,8 +26,8 @@ c_dbl_p = C.POINTER(C.c_double)
 def build(force: bool = False) -> str:
     """Compile oracle.c with gcc (no GPU, no reference sources needed)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_next.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so
 
@@ -48,7 +48,7 @@ def lib():
         L = C.CDLL(build())
         L.orc_wtime.restype = C.c_double
         L.orc_dlange_inf.restype = C.c_double
-        for f in ("orc_fresid", "orc_sresid", "orc_zfresid", "orc_zsresid"):
+        for f in ("orc_fresid", "orc_sresid", "orc_zfresid", "orc_zsresid", "orcn_dlange", "orcn_dgecon"):
             getattr(L, f).restype = C.c_double
         p = _find_openblas()
         if p is not None:
@@ -234,3 +234,61 @@ def lu_tolerance_ok(lu_test, lu_ref, a0):
     anorm = np.abs(a0).sum(axis=1).max()
     err = np.abs(lu_test - lu_ref).max() / (anorm * n * 2.0 ** -53)
     return err, err < 1.0
+
+
+# ---------------------------------------------------------------- SURVEY 8(f) rows (oracle_next.c)
+def _f(a):
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and (a.flags.f_contiguous or a.ndim == 1)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def dlange(norm, a):
+    """SRC/pdlange.f on the global matrix."""
+    m, n = a.shape
+    return float(lib().orcn_dlange(C.c_char(norm.encode()), m, n, _f(a), C.c_int64(a.strides[1] // 8)))
+
+
+def dgeequ(a):
+    """SRC/pdgeequ.f: returns (r, c, rowcnd, colcnd, amax, info)."""
+    m, n = a.shape
+    r, c = np.zeros(m), np.zeros(n)
+    rc, cc, am = C.c_double(1.0), C.c_double(1.0), C.c_double(0.0)
+    info = lib().orcn_dgeequ(m, n, _f(a), C.c_int64(a.strides[1] // 8), _f(r), _f(c), C.byref(rc), C.byref(cc), C.byref(am))
+    return r, c, rc.value, cc.value, am.value, int(info)
+
+
+def dlaqge(a, r, c, rowcnd, colcnd, amax):
+    """SRC/pdlaqge.f: scales a in place, returns EQUED."""
+    m, n = a.shape
+    L = lib(); L.orcn_dlaqge.restype = C.c_char
+    return L.orcn_dlaqge(m, n, _f(a), C.c_int64(a.strides[1] // 8), _f(r), _f(c), C.c_double(rowcnd), C.c_double(colcnd),
+                         C.c_double(amax)).decode()
+
+
+def dgecon(norm, lu, anorm):
+    """SRC/pdgecon.f + pdlacon.f on the factors of getrf(); returns RCOND."""
+    n = lu.shape[0]
+    return float(lib().orcn_dgecon(C.c_char(norm.encode()), n, _f(lu), C.c_int64(lu.strides[1] // 8), C.c_double(anorm)))
+
+
+def dgerfs(trans, a, af, ipiv, b, x):
+    """SRC/pdgerfs.f: refines x in place; returns (ferr, berr)."""
+    n, nrhs = b.shape
+    ferr, berr = np.zeros(nrhs), np.zeros(nrhs)
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    lib().orcn_dgerfs(C.c_char(trans.encode()), n, nrhs, _f(a), C.c_int64(a.strides[1] // 8), _f(af), C.c_int64(af.strides[1] // 8), _p(ip),
+                      _f(b), C.c_int64(b.strides[1] // 8), _f(x), C.c_int64(x.strides[1] // 8), _f(ferr), _f(berr))
+    return ferr, berr
+
+
+def dgesvx(fact, trans, a, af, ipiv, equed, r, c, b, x, nb=64):
+    """SRC/pdgesvx.f (IA = JA = 1): a, af, ipiv, r, c, b, x in / out; returns (equed, rcond, ferr, berr, info)."""
+    n, nrhs = b.shape
+    ferr, berr = np.zeros(nrhs), np.zeros(nrhs)
+    rcond = C.c_double(0.0)
+    eq = C.c_char(equed.encode())
+    assert ipiv.dtype == np.int32
+    info = lib().orcn_dgesvx(C.c_char(fact.encode()), C.c_char(trans.encode()), n, nrhs, _f(a), C.c_int64(a.strides[1] // 8), _f(af),
+                             C.c_int64(af.strides[1] // 8), _p(ipiv), C.byref(eq), _f(r), _f(c), _f(b), C.c_int64(b.strides[1] // 8), _f(x),
+                             C.c_int64(x.strides[1] // 8), C.byref(rcond), _f(ferr), _f(berr), nb)
+    return eq.value.decode(), rcond.value, ferr, berr, int(info)

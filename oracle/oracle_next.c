@@ -1,0 +1,270 @@
+/*
+ * oracle_next.c -- CPU restatement of the SURVEY 8(f) "next" rows: the routines around the LU factors
+ * (PDLANGE, PDGEEQU, PDLAQGE, PDLACON, PDGECON, PDGERFS, PDGESVX), Cholesky (PDPOTRF / PDPOTRS), the inverse
+ * (PDTRTRI / PDGETRI) and the redistribution PDGEMR2D.
+ *
+ * TEST INFRASTRUCTURE ONLY, like oracle.c: serial programs on the GLOBAL matrix, plain loops (no BLAS), each
+ * function citing the reference file:line it follows.  The distributed routines of the reference compute the
+ * same quantities with the vectors block-cyclically distributed; the order of the floating-point sums differs
+ * from any distributed run, so parity is to a stated tolerance, and the discrete decisions (sign vectors,
+ * arg-max of PDLACON, the refinement stopping rule) are the same on tie-free data.
+ *
+ * Pinning: every routine here has a LAPACK twin (dlange, dgeequ, dlaqge, dlacon, dgecon, dgerfs, dgesvx,
+ * dpotrf, dpotrs, dtrtri, dgetri); tests/test_oracle_next.py checks each against scipy's LAPACK.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* from oracle.c */
+int orc_dgetrf(int m, int n, double *a, int64_t lda, int nb, int *ipiv, double *phase_times);
+void orc_dgetrs(char trans, int n, int nrhs, const double *a, int64_t lda, const int *ipiv, double *b, int64_t ldb);
+
+#define A_(i, j) a[(i) + (int64_t)(j) * lda]
+
+static const double EPS = DBL_EPSILON * 0.5;   /* PDLAMCH 'Epsilon' (TOOLS/pdlamch -> dlamch 'E'): 2^-53 */
+static const double SAFMIN = DBL_MIN;          /* 'Safe minimum' */
+static const double PREC = DBL_EPSILON;        /* 'Precision' = eps * base */
+
+/* SRC/pdlange.f:196-329 */
+double orcn_dlange(char norm, int m, int n, const double *a, int64_t lda)
+{
+    double value = 0.0;
+    if (m == 0 || n == 0) return 0.0;
+    if (norm == 'M') {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) { double t = fabs(A_(i, j)); if (t > value) value = t; }
+    } else if (norm == 'O' || norm == '1') {
+        for (int j = 0; j < n; ++j) { double s = 0.0; for (int i = 0; i < m; ++i) s += fabs(A_(i, j)); if (s > value) value = s; }
+    } else if (norm == 'I') {
+        for (int i = 0; i < m; ++i) { double s = 0.0; for (int j = 0; j < n; ++j) s += fabs(A_(i, j)); if (s > value) value = s; }
+    } else {  /* 'F' / 'E': DLASSQ's scaled sum of squares (pdlange.f:303-316) */
+        double scale = 0.0, ssq = 1.0;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < m; ++i) {
+                double t = fabs(A_(i, j));
+                if (t != 0.0) {
+                    if (scale < t) { ssq = 1.0 + ssq * (scale / t) * (scale / t); scale = t; }
+                    else ssq += (t / scale) * (t / scale);
+                }
+            }
+        value = scale * sqrt(ssq);
+    }
+    return value;
+}
+
+/* SRC/pdgeequ.f:213-365.  INFO: i <= m: row i is exactly zero; > m: column info-m. */
+int orcn_dgeequ(int m, int n, const double *a, int64_t lda, double *r, double *c, double *rowcnd, double *colcnd, double *amax)
+{
+    const double smlnum = SAFMIN, bignum = 1.0 / smlnum;
+    if (m == 0 || n == 0) { *rowcnd = 1.0; *colcnd = 1.0; *amax = 0.0; return 0; }
+    for (int i = 0; i < m; ++i) r[i] = 0.0;
+    for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) { double t = fabs(A_(i, j)); if (t > r[i]) r[i] = t; }
+    double rcmin = bignum, rcmax = 0.0;
+    for (int i = 0; i < m; ++i) { if (r[i] > rcmax) rcmax = r[i]; if (r[i] < rcmin) rcmin = r[i]; }
+    *amax = rcmax;
+    if (rcmin == 0.0) { for (int i = 0; i < m; ++i) if (r[i] == 0.0) return i + 1; }
+    for (int i = 0; i < m; ++i) r[i] = 1.0 / fmin(fmax(r[i], smlnum), bignum);
+    *rowcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+    for (int j = 0; j < n; ++j) c[j] = 0.0;
+    for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) { double t = fabs(A_(i, j)) * r[i]; if (t > c[j]) c[j] = t; }
+    rcmin = bignum; rcmax = 0.0;
+    for (int j = 0; j < n; ++j) { if (c[j] < rcmin) rcmin = c[j]; if (c[j] > rcmax) rcmax = c[j]; }
+    if (rcmin == 0.0) { for (int j = 0; j < n; ++j) if (c[j] == 0.0) return m + j + 1; }
+    for (int j = 0; j < n; ++j) c[j] = 1.0 / fmin(fmax(c[j], smlnum), bignum);
+    *colcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+    return 0;
+}
+
+/* SRC/pdlaqge.f:214-268; returns EQUED */
+char orcn_dlaqge(int m, int n, double *a, int64_t lda, const double *r, const double *c, double rowcnd, double colcnd, double amax)
+{
+    const double thresh = 0.1, small_ = SAFMIN / PREC, large_ = 1.0 / small_;
+    if (m <= 0 || n <= 0) return 'N';
+    if (rowcnd >= thresh && amax >= small_ && amax <= large_) {
+        if (colcnd >= thresh) return 'N';
+        for (int j = 0; j < n; ++j) { double cj = c[j]; for (int i = 0; i < m; ++i) A_(i, j) = cj * A_(i, j); }
+        return 'C';
+    } else if (colcnd >= thresh) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) A_(i, j) = r[i] * A_(i, j);
+        return 'R';
+    }
+    for (int j = 0; j < n; ++j) { double cj = c[j]; for (int i = 0; i < m; ++i) A_(i, j) = cj * r[i] * A_(i, j); }
+    return 'B';
+}
+
+/* SRC/pdlacon.f:186-387 in its own reverse-communication form: the SAVEd locals live in `st` */
+typedef struct { int jump, iter, j, jlast; double estold; } lacon_state;
+static double sign1(double x) { return signbit(x) ? -1.0 : 1.0; }
+static double asum(int n, const double *x) { double s = 0.0; for (int i = 0; i < n; ++i) s += fabs(x[i]); return s; }
+static int iamax1(int n, const double *x) { int j = 0; for (int i = 1; i < n; ++i) if (fabs(x[i]) > fabs(x[j])) j = i; return j + 1; }
+static void lacon_rc(int n, double *v, double *x, int *isgn, double *est, int *kase, lacon_state *st)
+{
+    if (*kase == 0) {                                                /* pdlacon.f:205-212 */
+        for (int i = 0; i < n; ++i) x[i] = 1.0 / (double)n;
+        *kase = 1; st->jump = 1; return;
+    }
+    switch (st->jump) {
+    case 1:                                                          /* label 20 */
+        if (n == 1) { v[0] = x[0]; *est = fabs(v[0]); goto L150; }
+        *est = asum(n, x);
+        for (int i = 0; i < n; ++i) { x[i] = sign1(x[i]); isgn[i] = (int)lround(x[i]); }
+        *kase = 2; st->jump = 2; return;
+    case 2:                                                          /* label 40 */
+        st->j = iamax1(n, x); st->iter = 2;
+        goto L50;
+    case 3: {                                                        /* label 70 */
+        memcpy(v, x, (size_t)n * sizeof(double));
+        st->estold = *est;
+        *est = asum(n, v);
+        int iflag = 0;
+        for (int i = 0; i < n; ++i) if ((int)lround(sign1(x[i])) != isgn[i]) { iflag = 1; break; }
+        if (iflag == 0 || *est <= st->estold) goto L120;
+        for (int i = 0; i < n; ++i) { x[i] = sign1(x[i]); isgn[i] = (int)lround(x[i]); }
+        *kase = 2; st->jump = 4; return;
+    }
+    case 4: {                                                        /* label 110 */
+        st->jlast = st->j;
+        st->j = iamax1(n, x);
+        double xmax = x[st->j - 1], jlmax = x[st->jlast - 1];
+        if (jlmax != fabs(xmax) && st->iter < 5) { st->iter++; goto L50; }
+        goto L120;
+    }
+    case 5: {                                                        /* label 140 */
+        double temp = 2.0 * (asum(n, x) / (double)(3 * n));
+        if (temp > *est) { memcpy(v, x, (size_t)n * sizeof(double)); *est = temp; }
+        goto L150;
+    }
+    }
+L50:
+    for (int i = 0; i < n; ++i) x[i] = 0.0;
+    x[st->j - 1] = 1.0;
+    *kase = 1; st->jump = 3; return;
+L120:
+    for (int i = 0; i < n; ++i) { int k = i + 1; double alt = (k % 2 == 0) ? -1.0 : 1.0; x[i] = alt * (1.0 + (double)(k - 1) / (double)(n - 1)); }
+    *kase = 1; st->jump = 5; return;
+L150:
+    *kase = 0;
+}
+
+/* solves with the triangles of the factors, no interchanges (the two PDLATRS calls of pdgecon.f:337-373) */
+static void solve_lu(char trans, int n, const double *a, int64_t lda, double *x)
+{
+    if (trans == 'N') {
+        for (int k = 0; k < n; ++k) for (int i = k + 1; i < n; ++i) x[i] -= A_(i, k) * x[k];                       /* inv(L), unit */
+        for (int k = n - 1; k >= 0; --k) { x[k] /= A_(k, k); for (int i = 0; i < k; ++i) x[i] -= A_(i, k) * x[k]; } /* inv(U) */
+    } else {
+        for (int k = 0; k < n; ++k) { for (int i = 0; i < k; ++i) x[k] -= A_(i, k) * x[i]; x[k] /= A_(k, k); }      /* inv(U') */
+        for (int k = n - 1; k >= 0; --k) for (int i = k + 1; i < n; ++i) x[k] -= A_(i, k) * x[i];                   /* inv(L') */
+    }
+}
+
+/* SRC/pdgecon.f:288-404.  norm: '1' / 'O' or 'I'.  Returns RCOND. */
+double orcn_dgecon(char norm, int n, const double *a, int64_t lda, double anorm)
+{
+    if (n == 0) return 1.0;
+    if (anorm == 0.0) return 0.0;
+    if (n == 1) return 1.0;
+    const int onenrm = norm == '1' || norm == 'O';
+    const int kase1 = onenrm ? 1 : 2;
+    double *v = malloc((size_t)n * sizeof(double)), *x = malloc((size_t)n * sizeof(double));
+    int *isgn = malloc((size_t)n * sizeof(int));
+    double ainvnm = 0.0, rcond = 0.0;
+    int kase = 0; lacon_state st; memset(&st, 0, sizeof(st));
+    for (;;) {
+        lacon_rc(n, v, x, isgn, &ainvnm, &kase, &st);
+        if (kase == 0) break;
+        solve_lu(kase == kase1 ? 'N' : 'T', n, a, lda, x);
+    }
+    if (ainvnm != 0.0) rcond = (1.0 / ainvnm) / anorm;
+    free(v); free(x); free(isgn);
+    return rcond;
+}
+
+/* SRC/pdgerfs.f:466-660 (one right-hand side after the other; trans 'N' or 'T') */
+void orcn_dgerfs(char trans, int n, int nrhs, const double *a, int64_t lda, const double *af, int64_t ldaf, const int *ipiv,
+                 const double *b, int64_t ldb, double *x, int64_t ldx, double *ferr, double *berr)
+{
+    const int itmax = 5, nz = n + 1;
+    const double safe1 = nz * SAFMIN, safe2 = safe1 / EPS;
+    const int notran = trans == 'N';
+    const char transt = notran ? 'T' : 'N';
+    if (n <= 1 || nrhs == 0) { for (int k = 0; k < nrhs; ++k) { ferr[k] = 0.0; berr[k] = 0.0; } return; }
+    double *r = malloc((size_t)n * sizeof(double)), *w = malloc((size_t)n * sizeof(double)), *v = malloc((size_t)n * sizeof(double));
+    int *isgn = malloc((size_t)n * sizeof(int));
+    for (int k = 0; k < nrhs; ++k) {
+        const double *bk = b + (int64_t)k * ldb; double *xk = x + (int64_t)k * ldx;
+        int count = 1; double lstres = 3.0, s;
+        for (;;) {
+            for (int i = 0; i < n; ++i) { r[i] = bk[i]; w[i] = fabs(bk[i]); }
+            if (notran) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { r[i] -= A_(i, j) * xk[j]; w[i] += fabs(A_(i, j)) * fabs(xk[j]); }
+            else for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { r[j] -= A_(i, j) * xk[i]; w[j] += fabs(A_(i, j)) * fabs(xk[i]); }
+            s = 0.0;
+            for (int i = 0; i < n; ++i) { double q = w[i] > safe2 ? fabs(r[i]) / w[i] : (fabs(r[i]) + safe1) / (w[i] + safe1); if (q > s) s = q; }
+            berr[k] = s;
+            if (s > EPS && 2.0 * s <= lstres && count <= itmax) {
+                orc_dgetrs(trans, n, 1, af, ldaf, ipiv, r, n);
+                for (int i = 0; i < n; ++i) xk[i] += r[i];
+                lstres = s; ++count;
+            } else break;
+        }
+        for (int i = 0; i < n; ++i) w[i] = w[i] > safe2 ? fabs(r[i]) + nz * EPS * w[i] : fabs(r[i]) + nz * EPS * w[i] + safe1;
+        int kase = 0; double est = 0.0; lacon_state st; memset(&st, 0, sizeof(st));
+        for (;;) {
+            lacon_rc(n, v, r, isgn, &est, &kase, &st);
+            if (kase == 0) break;
+            if (kase == 1) { orc_dgetrs(transt, n, 1, af, ldaf, ipiv, r, n); for (int i = 0; i < n; ++i) r[i] = w[i] * r[i]; }
+            else { for (int i = 0; i < n; ++i) r[i] = w[i] * r[i]; orc_dgetrs(trans, n, 1, af, ldaf, ipiv, r, n); }
+        }
+        double xmax = 0.0; for (int i = 0; i < n; ++i) if (fabs(xk[i]) > xmax) xmax = fabs(xk[i]);
+        ferr[k] = xmax != 0.0 ? est / xmax : 0.0;
+    }
+    free(r); free(w); free(v); free(isgn);
+}
+
+/* SRC/pdgesvx.f:660-812 (IA = JA = 1).  equed is in/out.  Returns INFO. */
+int orcn_dgesvx(char fact, char trans, int n, int nrhs, double *a, int64_t lda, double *af, int64_t ldaf, int *ipiv, char *equed,
+                double *r, double *c, double *b, int64_t ldb, double *x, int64_t ldx, double *rcond, double *ferr, double *berr, int nb)
+{
+    const int nofact = fact == 'N', equil = fact == 'E', notran = trans == 'N';
+    int rowequ = 0, colequ = 0, info = 0;
+    double rowcnd = 1.0, colcnd = 1.0, amax = 0.0;
+    const double smlnum = SAFMIN, bignum = 1.0 / smlnum;
+    if (nofact || equil) *equed = 'N';
+    else {
+        rowequ = *equed == 'R' || *equed == 'B'; colequ = *equed == 'C' || *equed == 'B';
+        if (rowequ) {
+            double mn = bignum, mx = 0.0;
+            for (int i = 0; i < n; ++i) { mn = fmin(mn, r[i]); mx = fmax(mx, r[i]); }
+            if (mn <= 0.0) return -14;
+            rowcnd = n > 0 ? fmax(mn, smlnum) / fmin(mx, bignum) : 1.0;
+        }
+        if (colequ) {
+            double mn = bignum, mx = 0.0;
+            for (int i = 0; i < n; ++i) { mn = fmin(mn, c[i]); mx = fmax(mx, c[i]); }
+            if (mn <= 0.0) return -15;
+            colcnd = n > 0 ? fmax(mn, smlnum) / fmin(mx, bignum) : 1.0;
+        }
+    }
+    if (equil) {
+        int infequ = orcn_dgeequ(n, n, a, lda, r, c, &rowcnd, &colcnd, &amax);
+        if (infequ == 0) { *equed = orcn_dlaqge(n, n, a, lda, r, c, rowcnd, colcnd, amax); rowequ = *equed == 'R' || *equed == 'B'; colequ = *equed == 'C' || *equed == 'B'; }
+    }
+    if (notran) { if (rowequ) for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) b[i + (int64_t)j * ldb] *= r[i]; }
+    else if (colequ) for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) b[i + (int64_t)j * ldb] *= c[i];
+    if (nofact || equil) {
+        for (int j = 0; j < n; ++j) memcpy(af + (int64_t)j * ldaf, a + (int64_t)j * lda, (size_t)n * sizeof(double));
+        info = orc_dgetrf(n, n, af, ldaf, nb, ipiv, NULL);
+        if (info != 0) { if (info > 0) *rcond = 0.0; return info; }
+    }
+    const double anorm = orcn_dlange(notran ? '1' : 'I', n, n, a, lda);
+    *rcond = orcn_dgecon(notran ? '1' : 'I', n, af, ldaf, anorm);
+    if (*rcond < EPS) return n + 1;                                    /* pdgesvx.f:738-741: INFO = IA + N with IA = 1 */
+    for (int j = 0; j < nrhs; ++j) memcpy(x + (int64_t)j * ldx, b + (int64_t)j * ldb, (size_t)n * sizeof(double));
+    orc_dgetrs(trans, n, nrhs, af, ldaf, ipiv, x, ldx);
+    orcn_dgerfs(trans, n, nrhs, a, lda, af, ldaf, ipiv, b, ldb, x, ldx, ferr, berr);
+    if (notran) { if (colequ) { for (int j = 0; j < nrhs; ++j) { for (int i = 0; i < n; ++i) x[i + (int64_t)j * ldx] *= c[i]; ferr[j] /= colcnd; } } }
+    else if (rowequ) { for (int j = 0; j < nrhs; ++j) { for (int i = 0; i < n; ++i) x[i + (int64_t)j * ldx] *= r[i]; ferr[j] /= rowcnd; } }
+    return 0;
+}

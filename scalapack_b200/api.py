@@ -222,6 +222,88 @@ def pzgesv(n, nrhs, a, ia, ja, desca, ipiv, b, ib, jb, descb):
     return info.value
 
 
+# ------------------------------------------------------------------ consumers of the factors
+def _d(v):
+    return C.byref(C.c_double(float(v)))
+
+
+def _dptr(a):
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pdlange(norm, m, n, a, ia, ja, desca):
+    """SRC/pdlange.f: 'M', '1' / 'O', 'I', 'F' / 'E' norm of sub(A)."""
+    L = lib()
+    L.pdlange_.restype = C.c_double
+    return float(L.pdlange_(norm.encode(), _i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), C.c_void_p(0)))
+
+
+def pdgeequ(m, n, a, ia, ja, desca, r, c):
+    """SRC/pdgeequ.f: fills the local arrays R (LOCr(M_A)) and C (LOCc(N_A)); returns (rowcnd, colcnd, amax, info)."""
+    rc, cc, am, info = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+    lib().pdgeequ_(_i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _dptr(r), _dptr(c), C.byref(rc), C.byref(cc), C.byref(am),
+                   C.byref(info))
+    return rc.value, cc.value, am.value, info.value
+
+
+def pdlaqge(m, n, a, ia, ja, desca, r, c, rowcnd, colcnd, amax):
+    """SRC/pdlaqge.f: scales sub(A) in place; returns EQUED."""
+    eq = C.create_string_buffer(b"N", 2)
+    lib().pdlaqge_(_i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _dptr(r), _dptr(c), _d(rowcnd), _d(colcnd), _d(amax), eq)
+    return eq.value[:1].decode()
+
+
+def pdgecon(norm, n, a, ia, ja, desca, anorm, lwork=None, liwork=None):
+    """SRC/pdgecon.f: returns (rcond, info); lwork / liwork default to the sizes a workspace query reports."""
+    rcond, info = C.c_double(), C.c_int()
+    w1, iw1 = np.zeros(1), np.zeros(1, np.int32)
+    lib().pdgecon_(norm.encode(), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _d(anorm), C.byref(rcond), _dptr(w1), _i(-1),
+                   _ipiv_ptr(iw1), _i(-1), C.byref(info))
+    if info.value != 0:
+        return rcond.value, info.value
+    lw = int(w1[0]) if lwork is None else lwork
+    liw = int(iw1[0]) if liwork is None else liwork
+    work, iwork = np.zeros(max(1, lw)), np.zeros(max(1, liw), np.int32)
+    lib().pdgecon_(norm.encode(), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _d(anorm), C.byref(rcond), _dptr(work), _i(lw),
+                   _ipiv_ptr(iwork), _i(liw), C.byref(info))
+    return rcond.value, info.value
+
+
+def pdgerfs(trans, n, nrhs, a, ia, ja, desca, af, iaf, jaf, descaf, ipiv, b, ib, jb, descb, x, ix, jx, descx, ferr, berr):
+    """SRC/pdgerfs.f: refines X in place, fills the local arrays FERR / BERR (LOCc(N_B)); returns info."""
+    info = C.c_int()
+    args = lambda work, lw, iwork, liw: (trans.encode(), _i(n), _i(nrhs), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(af), _i(iaf),  # noqa: E731
+                                         _i(jaf), _desc(descaf), _ipiv_ptr(ipiv), _ptr(b), _i(ib), _i(jb), _desc(descb), _ptr(x), _i(ix),
+                                         _i(jx), _desc(descx), _dptr(ferr), _dptr(berr), _dptr(work), _i(lw), _ipiv_ptr(iwork), _i(liw),
+                                         C.byref(info))
+    w1, iw1 = np.zeros(1), np.zeros(1, np.int32)
+    lib().pdgerfs_(*args(w1, -1, iw1, -1))
+    if info.value != 0:
+        return info.value
+    work, iwork = np.zeros(max(1, int(w1[0]))), np.zeros(max(1, int(iw1[0])), np.int32)
+    lib().pdgerfs_(*args(work, work.size, iwork, iwork.size))
+    return info.value
+
+
+def pdgesvx(fact, trans, n, nrhs, a, ia, ja, desca, af, iaf, jaf, descaf, ipiv, equed, r, c, b, ib, jb, descb, x, ix, jx, descx,
+            ferr, berr):
+    """SRC/pdgesvx.f: returns (equed, rcond, info)."""
+    rcond, info = C.c_double(), C.c_int()
+    eq = C.create_string_buffer(equed.encode()[:1], 2)
+    args = lambda work, lw, iwork, liw: (fact.encode(), trans.encode(), _i(n), _i(nrhs), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(af),  # noqa: E731
+                                         _i(iaf), _i(jaf), _desc(descaf), _ipiv_ptr(ipiv), eq, _dptr(r), _dptr(c), _ptr(b), _i(ib), _i(jb),
+                                         _desc(descb), _ptr(x), _i(ix), _i(jx), _desc(descx), C.byref(rcond), _dptr(ferr), _dptr(berr),
+                                         _dptr(work), _i(lw), _ipiv_ptr(iwork), _i(liw), C.byref(info))
+    w1, iw1 = np.zeros(1), np.zeros(1, np.int32)
+    lib().pdgesvx_(*args(w1, -1, iw1, -1))
+    if info.value != 0:
+        return eq.value[:1].decode(), rcond.value, info.value
+    work, iwork = np.zeros(max(1, int(w1[0]))), np.zeros(max(1, int(iw1[0])), np.int32)
+    lib().pdgesvx_(*args(work, work.size, iwork, iwork.size))
+    return eq.value[:1].decode(), rcond.value, info.value
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

@@ -6,21 +6,11 @@
 #include "lu.h"
 #include "ncclw.h"
 #include "stage.h"
+#include "entry.h"
 
 #include <cmath>
 
 namespace slb {
-
-static bool is_device_ptr(const void *p)
-{
-    cudaPointerAttributes at;
-    cudaError_t e = cudaPointerGetAttributes(&at, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    if (at.type == cudaMemoryTypeDevice && at.device != rt().device)
-        fatal("a device-resident operand lives on GPU %d but this BLACS process drives GPU %d (LOCAL_RANK): allocate it on the "
-              "process's own GPU", at.device, rt().device);
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
 
 // A host-resident 1-D / small array staged through HBM in one piece (test-driver helpers); a device-resident one is used in place.
 template <typename T>
@@ -45,25 +35,6 @@ struct Staged {
     }
 };
 
-static void xerbla(int ictxt, const char *name, int info) { int p = -info; pxerbla_(&ictxt, name, &p); }
-
-// Local window of a block-aligned sub-matrix sub(A) = A(IA:IA+M-1, JA:JA+N-1) (SRC/pdgetrf.f:178-186, TOOLS/infog2l.f): every
-// process holds a contiguous mloc x nloc window of its local array starting at (loff_r, loff_c), and sub(A) is itself a
-// block-cyclic matrix whose first block lives on process (rsrc, csrc).
-struct Window { int64_t loff_r, loff_c, mloc, nloc; int rsrc, csrc; };
-static Window window(int m, int n, int ia, int ja, const int *desc, int P, int Q, int myrow, int mycol)
-{
-    Window w;
-    const int mb = desc[MB_], nb = desc[NB_];
-    w.loff_r = numroc(ia - 1, mb, myrow, desc[RSRC_], P);
-    w.loff_c = numroc(ja - 1, nb, mycol, desc[CSRC_], Q);
-    w.rsrc = indxg2p(ia, mb, desc[RSRC_], P);
-    w.csrc = indxg2p(ja, nb, desc[CSRC_], Q);
-    w.mloc = numroc(m, mb, myrow, w.rsrc, P);
-    w.nloc = numroc(n, nb, mycol, w.csrc, Q);
-    return w;
-}
-
 // The window of a host- or device-resident local array as the device sees it.  Host-resident: a staging copy in HBM (even
 // leading dimension, so the 16-byte epilogues of the update stay aligned) reached through a HostLink; device-resident: in place.
 template <typename T>
@@ -84,29 +55,6 @@ struct DevWindow {
     void download_all() { if (link) { link->download(0, hm.rows, 0, hm.cols, nullptr); link->finish(); } }
     ~DevWindow() { delete link; }
 };
-
-// local IPIV(loff + il) <- global pivot (as a row index of A, not of sub(A)) of each locally owned row < mn (SRC/pdgetrf.f:118-121)
-static void fill_local_ipiv(const std::vector<int> &ipg, int mn, int nb, int rsrc, int P, int myrow, int *ipiv, int row0)
-{
-    for (int gi = 0; gi < mn; ++gi) {
-        if (indxg2p(gi + 1, nb, rsrc, P) != myrow) continue;
-        ipiv[indxg2l(gi + 1, nb, P) - 1] = ipg[gi] + row0;
-    }
-}
-
-// pivot vector of sub(A) (1-based, relative to sub(A)) from the row-distributed IPIV (each process row holds the entries of its rows)
-static void gather_global_ipiv(Grid *g, int n, int nb, int rsrc, const int *ipiv_local, int row0, std::vector<int> &ipg)
-{
-    const int P = g->nprow;
-    ipg.assign((size_t)n, 0);
-    std::vector<int> mine((size_t)n, 0);
-    for (int gi = 0; gi < n; ++gi)
-        if (indxg2p(gi + 1, nb, rsrc, P) == g->myrow) mine[gi] = ipiv_local[indxg2l(gi + 1, nb, P) - 1] - row0;
-    if (P == 1) { ipg = mine; return; }
-    std::vector<int> all((size_t)n * P);
-    grid_allgather(g, 'C', mine.data(), all.data(), (size_t)n * sizeof(int));
-    for (int p = 0; p < P; ++p) for (int gi = 0; gi < n; ++gi) if (all[(size_t)p * n + gi] > ipg[gi]) ipg[gi] = all[(size_t)p * n + gi];
-}
 
 template <typename T>
 static void getrf_entry(const char *name, const int *m, const int *n, T *a, const int *ia, const int *ja, const int *desca,
@@ -184,16 +132,6 @@ static void getrs_checks(const char *name, int descpos_a, int descpos_b, const c
     int da = DA, db = DB;
     pchk2mat_(n, &pn, n, &pn, ia, ja, desca, &da, n, &pn, nrhs, &pnrhs, ib, jb, descb, &db, &nextra, ex, expos, info);
     (void)name;
-}
-
-// the right-hand sides sub(B) = B(IB:IB+N-1, JB:JB+NRHS-1): rows aligned with sub(A) (checked), columns anywhere in B
-struct RhsWindow { int64_t loff_r, nloc_all; };
-static RhsWindow rhs_window(int ib, const int *descb, int P, int Q, int myrow, int mycol)
-{
-    RhsWindow w;
-    w.loff_r = numroc(ib - 1, descb[MB_], myrow, descb[RSRC_], P);
-    w.nloc_all = numroc(descb[N_], descb[NB_], mycol, descb[CSRC_], Q);
-    return w;
 }
 
 template <typename T>

@@ -29,7 +29,10 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
 // global columns [jb0, jb0 + nrhs) of B.  ipiv_glob_host: N ints, 1-based, relative to sub(A).
 template <typename T>
 int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv_glob_host,
-                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all);
+                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all,
+                 const T *Xrep_in = nullptr, T *Xrep_out = nullptr);
+// Xrep_in / Xrep_out (device, N x nrhs, ld = N, global row order, identical on every process): when given, the right-hand
+// sides are taken from / the solutions are left in these replicated blocks instead of the block-cyclic B (which may be null).
 
 // 1 x 1 grid, TRANS = 'N', nb <= 512, few right-hand sides: the two sweeps at HBM speed (solve_fast.cu)
 bool getrs_fast_applies(int P, int Q, char trans, int nb, int nrhs);

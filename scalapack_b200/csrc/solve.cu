@@ -49,7 +49,7 @@ __global__ void add_block_kernel(int kb, int nrhs, const T *__restrict__ xg, int
 
 template <typename T>
 int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv_glob_host,
-                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all)
+                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all, const T *Xrep_in, T *Xrep_out)
 {
     Runtime &r = rt();
     cudaStream_t s = r.s_main;
@@ -83,6 +83,10 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
     // ---- replicate sub(B) in global order ----
     const int myr_rel = (P + myrow - rsrc) % P, myc_relb = (Q + mycol - csrcb) % Q;
     unsigned gyb = (unsigned)(nlocB_all < 65535 ? (nlocB_all > 0 ? nlocB_all : 1) : 65535);
+    if (Xrep_in) {
+        // the caller already holds the right-hand sides replicated in global row order (PDGECON / PDGERFS work vectors)
+        SLB_CUDA(cudaMemcpyAsync(X0, Xrep_in, (size_t)N * nrhs * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    } else {
     SLB_CUDA(cudaMemsetAsync(X0, 0, (size_t)N * nrhs * sizeof(T), s));
     if (mloc > 0 && nlocB_all > 0) {
         dim3 grid((unsigned)((mloc + 255) / 256), gyb);
@@ -90,6 +94,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
         SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
     }
     if (multi) nccl_allreduce_sum_f64(nc->all, X0, X0, (size_t)N * nrhs * nelem, s);
+    }
     // ---- 'N': x = U^-1 L^-1 (P b) (pdgetrs.f:255-266);  'T','C': x = P^T (L^-T (U^-T b)) (pdgetrs.f:268-284) ----
     T *Xw = Xg;
     if (!tr) launch_gather_rows<T>(N, perm_dev, X0, N, Xg, N, nrhs, s);
@@ -159,8 +164,9 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
         }
     }
     if (tr) { launch_gather_rows<T>(N, perm_dev, X0, N, Xg, N, nrhs, s, true); }   // x = P^T z: row perm[i] of x is row i of z
-    // ---- back into the caller's block-cyclic sub(B) ----
-    if (mloc > 0 && nlocB_all > 0) {
+    // ---- back into the caller's block-cyclic sub(B) (or to the caller's replicated copy) ----
+    if (Xrep_out) SLB_CUDA(cudaMemcpyAsync(Xrep_out, Xg, (size_t)N * nrhs * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    else if (mloc > 0 && nlocB_all > 0) {
         dim3 grid((unsigned)((mloc + 255) / 256), gyb);
         rhs_scatter_kernel<T><<<grid, 256, 0, s>>>(mloc, nlocB_all, nb, nbb, P, Q, myr_rel, myc_relb, B, lldb, Xg, N, jb0, nrhs, 0);
         SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
@@ -173,7 +179,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
     return 0;
 }
 
-template int getrs_device<double>(Grid *, char, int, int, const double *, int64_t, int, int, int, const int *, double *, int64_t, int, int, int, int64_t);
-template int getrs_device<zcomplex>(Grid *, char, int, int, const zcomplex *, int64_t, int, int, int, const int *, zcomplex *, int64_t, int, int, int, int64_t);
+template int getrs_device<double>(Grid *, char, int, int, const double *, int64_t, int, int, int, const int *, double *, int64_t, int, int, int, int64_t, const double *, double *);
+template int getrs_device<zcomplex>(Grid *, char, int, int, const zcomplex *, int64_t, int, int, int, const int *, zcomplex *, int64_t, int, int, int, int64_t, const zcomplex *, zcomplex *);
 
 }  // namespace slb

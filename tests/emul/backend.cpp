@@ -1,0 +1,276 @@
+// backend.cpp -- TEST INFRASTRUCTURE (see tests/emul/cuda_runtime.h).  Stands in, by documented contract, for the pieces of
+// the product that only exist on a GPU, so that the host logic of the SURVEY 8(f) files can be exercised on a CPU-only machine:
+//   * runtime.cu            -> rt(), workspace(): "device" memory is host memory
+//   * gemm*.cu / trsm.cu    -> launch_dgemm_minus (C -= A B), launch_dtrsm_llnu (B <- unit_lower(L)^-1 B), launch_copy2d
+//   * lu.cu / solve.cu      -> getrf_device / getrs_device on a P x Q grid: gather, serial LAPACK-style algorithm, scatter
+//   * ncclw.cpp             -> broadcast / all-gather / all-reduce over the TCP control plane (hostcomm.cpp), same call order
+// Nothing here is linked into libscalapack_b200.so, and nothing here is timed or shipped.
+#include "common.h"
+#include "kernels.cuh"
+#include "lu.h"
+#include "ncclw.h"
+
+#include <cmath>
+#include <map>
+
+namespace slb {
+
+struct ncclComm { Grid *g; char scope; };
+
+static Runtime g_rt;
+Runtime &rt() { g_rt.cuda_ok = true; g_rt.device = 0; g_rt.sm_count = 148; g_rt.smem_optin = 227 * 1024; return g_rt; }
+bool cuda_available() { return true; }
+
+struct WsEntry { void *p = nullptr; size_t bytes = 0; };
+static std::map<std::string, WsEntry> g_ws;
+void *workspace(const char *name, size_t bytes, bool zero_on_alloc)
+{
+    WsEntry &e = g_ws[name];
+    if (e.bytes < bytes) {
+        free(e.p);
+        e.bytes = bytes + 64;
+        e.p = malloc(e.bytes);
+        memset(e.p, zero_on_alloc ? 0 : 0xA5, e.bytes);      // poison: a read of never-written workspace shows up as garbage
+    }
+    return e.p;
+}
+void workspace_release_all() { for (auto &kv : g_ws) free(kv.second.p); g_ws.clear(); }
+
+LuStats g_last_lu;
+
+// ---- arithmetic helpers on double / zcomplex ---------------------------------------------------------------------------
+static inline double cmul_sub(double c, double a, double b) { return c - a * b; }
+static inline zcomplex cmul_sub(zcomplex c, zcomplex a, zcomplex b)
+{ return make_double2(c.x - (a.x * b.x - a.y * b.y), c.y - (a.x * b.y + a.y * b.x)); }
+static inline double cabs1(double a) { return fabs(a); }
+static inline double cabs1(zcomplex a) { return fabs(a.x) + fabs(a.y); }
+static inline bool is0(double a) { return a == 0.0; }
+static inline bool is0(zcomplex a) { return a.x == 0.0 && a.y == 0.0; }
+static inline double cdiv(double a, double b) { return a / b; }
+static inline zcomplex cdiv(zcomplex a, zcomplex b)
+{ double d = b.x * b.x + b.y * b.y; return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
+static inline double cconj(double a) { return a; }
+static inline zcomplex cconj(zcomplex a) { return make_double2(a.x, -a.y); }
+
+template <typename T>
+static void gemm_minus(int64_t M, int64_t N, int K, const T *A, int64_t lda, const T *B, int64_t ldb, T *C, int64_t ldc)
+{
+    for (int64_t j = 0; j < N; ++j)
+        for (int k = 0; k < K; ++k) {
+            const T b = B[k + j * ldb];
+            for (int64_t i = 0; i < M; ++i) C[i + j * ldc] = cmul_sub(C[i + j * ldc], A[i + (int64_t)k * lda], b);
+        }
+}
+void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+                        cudaStream_t, int, int)
+{ gemm_minus<double>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
+void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc,
+                        cudaStream_t, int, int)
+{ gemm_minus<zcomplex>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
+
+template <typename T>
+static void trsm_llnu(int jb, int64_t n, const T *L, int64_t ldl, T *B, int64_t ldb)
+{
+    for (int64_t j = 0; j < n; ++j)
+        for (int k = 0; k < jb; ++k) {
+            const T x = B[k + j * ldb];
+            for (int i = k + 1; i < jb; ++i) B[i + j * ldb] = cmul_sub(B[i + j * ldb], L[i + (int64_t)k * ldl], x);
+        }
+}
+void launch_dtrsm_llnu(int jb, int64_t n, const double *L, int64_t ldl, double *B, int64_t ldb, cudaStream_t)
+{ trsm_llnu<double>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
+void launch_ztrsm_llnu(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t)
+{ trsm_llnu<zcomplex>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
+
+template <typename T>
+void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst, int64_t ldd, cudaStream_t)
+{
+    for (int64_t c = 0; c < cols; ++c) for (int64_t i = 0; i < rows; ++i) dst[i + c * ldd] = src[i + c * lds];
+    counter_add("kernel_launches", 1);
+}
+template void launch_copy2d<double>(int64_t, int64_t, const double *, int64_t, double *, int64_t, cudaStream_t);
+template void launch_copy2d<zcomplex>(int64_t, int64_t, const zcomplex *, int64_t, zcomplex *, int64_t, cudaStream_t);
+
+// ---- block-cyclic gather / scatter of an M x N matrix over the grid (local windows start at A, first block on (rsrc, csrc)) ----
+template <typename T>
+static std::vector<T> gather_bc(Grid *g, int M, int N, const T *A, int64_t lld, int nb, int rsrc, int csrc)
+{
+    const int P = g->nprow, Q = g->npcol, np = P * Q;
+    const int64_t mmax = numroc(M, nb, 0, 0, P), nmax = numroc(N, nb, 0, 0, Q);      // process 0 of a dimension holds the most
+    const int64_t mloc = numroc(M, nb, g->myrow, rsrc, P), nloc = numroc(N, nb, g->mycol, csrc, Q);
+    std::vector<T> mine((size_t)(mmax * nmax)), all((size_t)(mmax * nmax) * np);
+    memset(mine.data(), 0, mine.size() * sizeof(T));
+    for (int64_t c = 0; c < nloc; ++c) for (int64_t i = 0; i < mloc; ++i) mine[(size_t)(i + c * mmax)] = A[i + c * lld];
+    if (np > 1) grid_allgather(g, 'A', mine.data(), all.data(), mine.size() * sizeof(T)); else all = mine;
+    std::vector<T> G((size_t)M * N);
+    for (int64_t j = 0; j < N; ++j) {
+        const int pc = indxg2p((int)j + 1, nb, csrc, Q); const int64_t jl = indxg2l((int)j + 1, nb, Q) - 1;
+        for (int64_t i = 0; i < M; ++i) {
+            const int pr = indxg2p((int)i + 1, nb, rsrc, P); const int64_t il = indxg2l((int)i + 1, nb, P) - 1;
+            G[(size_t)(i + j * M)] = all[(size_t)(pr * Q + pc) * (size_t)(mmax * nmax) + (size_t)(il + jl * mmax)];
+        }
+    }
+    return G;
+}
+template <typename T>
+static void scatter_bc(Grid *g, int M, int N, const std::vector<T> &G, T *A, int64_t lld, int nb, int rsrc, int csrc)
+{
+    const int P = g->nprow, Q = g->npcol;
+    for (int64_t j = 0; j < N; ++j) {
+        if (indxg2p((int)j + 1, nb, csrc, Q) != g->mycol) continue;
+        const int64_t jl = indxg2l((int)j + 1, nb, Q) - 1;
+        for (int64_t i = 0; i < M; ++i) {
+            if (indxg2p((int)i + 1, nb, rsrc, P) != g->myrow) continue;
+            A[(indxg2l((int)i + 1, nb, P) - 1) + jl * lld] = G[(size_t)(i + j * M)];
+        }
+    }
+}
+
+// PDGETRF by contract: partial pivoting with the reference's rule (first maximal |a|, complex |Re|+|Im|), reciprocal scaling
+template <typename T>
+int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host, HostLink *)
+{
+    std::vector<T> G = gather_bc<T>(g, M, N, A, lld, nb, rsrc, csrc);
+    const int mn = M < N ? M : N;
+    int info = 0;
+    for (int j = 0; j < mn; ++j) {
+        int p = j; double best = cabs1(G[(size_t)(j + (int64_t)j * M)]);
+        for (int i = j + 1; i < M; ++i) { const double v = cabs1(G[(size_t)(i + (int64_t)j * M)]); if (v > best) { best = v; p = i; } }
+        ipiv_glob_host[j] = p + 1;
+        if (!is0(G[(size_t)(p + (int64_t)j * M)])) {
+            if (p != j) for (int c = 0; c < N; ++c) { T t = G[(size_t)(j + (int64_t)c * M)]; G[(size_t)(j + (int64_t)c * M)] = G[(size_t)(p + (int64_t)c * M)]; G[(size_t)(p + (int64_t)c * M)] = t; }
+            const T piv = G[(size_t)(j + (int64_t)j * M)];
+            for (int i = j + 1; i < M; ++i) G[(size_t)(i + (int64_t)j * M)] = cdiv(G[(size_t)(i + (int64_t)j * M)], piv);
+        } else if (info == 0) info = j + 1;
+        for (int c = j + 1; c < N; ++c) {
+            const T u = G[(size_t)(j + (int64_t)c * M)];
+            for (int i = j + 1; i < M; ++i) G[(size_t)(i + (int64_t)c * M)] = cmul_sub(G[(size_t)(i + (int64_t)c * M)], G[(size_t)(i + (int64_t)j * M)], u);
+        }
+    }
+    scatter_bc<T>(g, M, N, G, A, lld, nb, rsrc, csrc);
+    *info_host = info;
+    g_last_lu.host_written = false;
+    return 0;
+}
+template int getrf_device<double>(Grid *, int, int, double *, int64_t, int, int, int, int *, int *, HostLink *);
+template int getrf_device<zcomplex>(Grid *, int, int, zcomplex *, int64_t, int, int, int, int *, int *, HostLink *);
+
+// PDGETRS by contract, replicated or block-cyclic right-hand sides
+template <typename T>
+int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv,
+                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all, const T *Xin, T *Xout)
+{
+    std::vector<T> G = gather_bc<T>(g, N, N, A, lld, nb, rsrc, csrc);
+    const int P = g->nprow, Q = g->npcol;
+    std::vector<T> X((size_t)N * nrhs);
+    memset(X.data(), 0, X.size() * sizeof(T));
+    const int64_t mloc = numroc(N, nb, g->myrow, rsrc, P);
+    auto bcol = [&](int64_t jl) { return (int64_t)indxl2g((int)jl + 1, nbb, g->mycol, csrcb, Q) - 1 - jb0; };
+    if (Xin) memcpy(X.data(), Xin, X.size() * sizeof(T));
+    else {
+        for (int64_t jl = 0; jl < nlocB_all; ++jl) {
+            const int64_t jg = bcol(jl); if (jg < 0 || jg >= nrhs) continue;
+            for (int64_t il = 0; il < mloc; ++il) X[(size_t)(indxl2g((int)il + 1, nb, g->myrow, rsrc, P) - 1 + jg * N)] = B[il + jl * lldb];
+        }
+        if (P * Q > 1) {
+            std::vector<T> all(X.size() * (size_t)(P * Q));
+            grid_allgather(g, 'A', X.data(), all.data(), X.size() * sizeof(T));
+            const size_t nd = X.size() * sizeof(T) / sizeof(double);
+            double *x = reinterpret_cast<double *>(X.data()); const double *a = reinterpret_cast<const double *>(all.data());
+            for (size_t e = 0; e < nd; ++e) { double v = 0; for (int p = 0; p < P * Q; ++p) v += a[(size_t)p * nd + e]; x[e] = v; }
+        }
+    }
+    const bool cj = trans == 'C';
+    auto el = [&](int i, int k) { return G[(size_t)(i + (int64_t)k * N)]; };
+    for (int c = 0; c < nrhs; ++c) {
+        T *x = X.data() + (size_t)c * N;
+        if (trans == 'N') {
+            for (int i = 0; i < N; ++i) { const int p = ipiv[i] - 1; if (p != i) { T t = x[i]; x[i] = x[p]; x[p] = t; } }
+            for (int k = 0; k < N; ++k) for (int i = k + 1; i < N; ++i) x[i] = cmul_sub(x[i], el(i, k), x[k]);
+            for (int k = N - 1; k >= 0; --k) { x[k] = cdiv(x[k], el(k, k)); for (int i = 0; i < k; ++i) x[i] = cmul_sub(x[i], el(i, k), x[k]); }
+        } else {
+            for (int k = 0; k < N; ++k) {                      // U^T (U^H) forward
+                for (int i = 0; i < k; ++i) x[k] = cmul_sub(x[k], cj ? cconj(el(i, k)) : el(i, k), x[i]);
+                x[k] = cdiv(x[k], cj ? cconj(el(k, k)) : el(k, k));
+            }
+            for (int k = N - 1; k >= 0; --k)                   // L^T (L^H) backward, unit diagonal
+                for (int i = k + 1; i < N; ++i) x[k] = cmul_sub(x[k], cj ? cconj(el(i, k)) : el(i, k), x[i]);
+            for (int i = N - 1; i >= 0; --i) { const int p = ipiv[i] - 1; if (p != i) { T t = x[i]; x[i] = x[p]; x[p] = t; } }
+        }
+    }
+    if (Xout) memcpy(Xout, X.data(), X.size() * sizeof(T));
+    else
+        for (int64_t jl = 0; jl < nlocB_all; ++jl) {
+            const int64_t jg = bcol(jl); if (jg < 0 || jg >= nrhs) continue;
+            for (int64_t il = 0; il < mloc; ++il) B[il + jl * lldb] = X[(size_t)(indxl2g((int)il + 1, nb, g->myrow, rsrc, P) - 1 + jg * N)];
+        }
+    g_last_lu.solve_ms = 0;
+    return 0;
+}
+template int getrs_device<double>(Grid *, char, int, int, const double *, int64_t, int, int, int, const int *, double *, int64_t, int, int, int, int64_t, const double *, double *);
+template int getrs_device<zcomplex>(Grid *, char, int, int, const zcomplex *, int64_t, int, int, int, const int *, zcomplex *, int64_t, int, int, int, int64_t, const zcomplex *, zcomplex *);
+
+// ---- NCCL wrappers over the TCP control plane ------------------------------------------------------------------------------
+static size_t tsize(NcclType t) { return t == NT_F64 ? 8 : (t == NT_I32 ? 4 : 1); }
+NcclComms *nccl_create(Grid *g)
+{
+    NcclComms *c = new NcclComms();
+    c->all = new ncclComm{ g, 'A' }; c->row = new ncclComm{ g, 'R' }; c->col = new ncclComm{ g, 'C' }; c->colp = new ncclComm{ g, 'C' };
+    return c;
+}
+void nccl_destroy(NcclComms *c) { if (!c) return; delete c->all; delete c->row; delete c->col; delete c->colp; delete c; }
+void nccl_group_start() {}
+void nccl_group_end() {}
+void nccl_bcast(ncclComm_t_ comm, void *buf, size_t count, NcclType t, int root, cudaStream_t)
+{
+    const int np = grid_scope_size(comm->g, comm->scope);
+    const size_t len = count * tsize(t);
+    if (np <= 1 || len == 0) return;
+    std::vector<char> all(len * (size_t)np);
+    grid_allgather(comm->g, comm->scope, buf, all.data(), len);
+    memcpy(buf, all.data() + (size_t)root * len, len);
+}
+void nccl_send(ncclComm_t_, const void *, size_t, NcclType, int, cudaStream_t) { fatal("emulation: nccl_send is not modelled"); }
+void nccl_recv(ncclComm_t_, void *, size_t, NcclType, int, cudaStream_t) { fatal("emulation: nccl_recv is not modelled"); }
+void nccl_allgather(ncclComm_t_ comm, const void *send, void *recv, size_t sendcount, NcclType t, cudaStream_t)
+{
+    const size_t len = sendcount * tsize(t);
+    if (grid_scope_size(comm->g, comm->scope) <= 1) { if (recv != send) memmove(recv, send, len); return; }
+    std::vector<char> tmp((const char *)send, (const char *)send + len);
+    grid_allgather(comm->g, comm->scope, tmp.data(), recv, len);
+}
+template <typename T, typename F>
+static void allreduce(ncclComm_t_ comm, const void *send, void *recv, size_t count, F f)
+{
+    const int np = grid_scope_size(comm->g, comm->scope);
+    std::vector<T> mine((const T *)send, (const T *)send + count);
+    if (np > 1) {
+        std::vector<T> all(count * (size_t)np);
+        grid_allgather(comm->g, comm->scope, mine.data(), all.data(), count * sizeof(T));
+        for (size_t e = 0; e < count; ++e) { T v = all[e]; for (int p = 1; p < np; ++p) v = f(v, all[(size_t)p * count + e]); mine[e] = v; }
+    }
+    memcpy(recv, mine.data(), count * sizeof(T));
+}
+void nccl_allreduce_min_i32(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<int>(c, s, r, n, [](int a, int b) { return a < b ? a : b; }); }
+void nccl_allreduce_sum_f64(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<double>(c, s, r, n, [](double a, double b) { return a + b; }); }
+void nccl_allreduce_max_f64(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<double>(c, s, r, n, [](double a, double b) { return a > b ? a : b; }); }
+const char *nccl_version_string() { return "emulated"; }
+
+}  // namespace slb
+
+extern "C" {
+int slb200_has_cuda(void) { return 0; }       // the emulation library never claims a GPU
+int slb200_device(void) { return -1; }
+int slb200_is_emulation(void) { return 1; }
+double slb200_last_factor_ms(void) { return 0; }
+double slb200_last_solve_ms(void) { return 0; }
+double slb200_last_update_ms(void) { return 0; }
+double slb200_last_update_flops(void) { return 0; }
+int64_t slb200_last_update_launches(void) { return 0; }
+// hooks of the GPU-only test drivers that scalapack_b200/api.py resolves at load time: present, never callable here
+double slb200_pdlaschk(const int *, const int *, const int *, const double *, const int *, const int *, const uint64_t *, const uint64_t *, const int *)
+{ slb::fatal("slb200_pdlaschk is not part of the host-logic emulation"); }
+#define NOT_EMULATED(name) double name(void) { slb::fatal(#name " is not part of the host-logic emulation"); }
+NOT_EMULATED(slb200_test_gemm) NOT_EMULATED(slb200_test_panel)
+NOT_EMULATED(slb200_bench_dmma_tflops) NOT_EMULATED(slb200_bench_dfma_tflops) NOT_EMULATED(slb200_bench_copy_gbs)
+}

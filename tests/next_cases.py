@@ -1,0 +1,251 @@
+"""Parity cases of the SURVEY 8(f) rows, written once against the reference's interface and run three ways:
+on the GPU through libscalapack_b200.so (tests/test_gpu_next.py, multi-GPU via tests/mp_worker.py) and, for the host logic
+only, on the CPU through the emulation library (tests/emul; tests/test_emul_next.py).  Every rank of a P x Q grid builds the
+global test matrix, takes its block-cyclic piece, calls the routine and compares its local result with the oracle's."""
+import numpy as np
+
+import oracle as O
+
+EPS = 2.0 ** -53
+
+
+class Grid:
+    def __init__(self, S, ctx):
+        self.S, self.ctx = S, ctx
+        self.P, self.Q, self.r, self.c = S.blacs_gridinfo(ctx)
+
+    def dist(self, ag, nb, rsrc=0, csrc=0, extra=0, nbc=None):
+        """(local array with `extra` guard rows, descriptor) of the global matrix ag"""
+        S = self.S
+        nbc = nb if nbc is None else nbc
+        m, n = ag.shape
+        mloc = S.numroc(m, nb, self.r, rsrc, self.P)
+        lld = max(1, mloc) + extra
+        al = O.scatter(ag, nb, nbc, self.P, self.Q, self.r, self.c, rsrc=rsrc, csrc=csrc, lld=lld)
+        if extra:
+            al[mloc:, :] = -9923.0
+        desc, info = S.descinit(m, n, nb, nbc, rsrc, csrc, self.ctx, lld)
+        assert info == 0
+        return al, desc
+
+    def local_of(self, ag, nb, rsrc=0, csrc=0, lld=None, nbc=None):
+        return O.scatter(ag, nb, nb if nbc is None else nbc, self.P, self.Q, self.r, self.c, rsrc=rsrc, csrc=csrc, lld=lld)
+
+    def rows_of(self, v, nb, rsrc=0):
+        """local entries (LOCr) of a vector aligned with the rows of a distributed matrix"""
+        return self.local_of(np.asfortranarray(v.reshape(-1, 1)), nb, rsrc=rsrc, nbc=1)[:, 0] if self.c == 0 or True else None
+
+
+def matrix(n, m=None, seed=100, cond=None):
+    a = O.pdmatgen(n, m or n, seed)
+    if cond:
+        rng = np.random.default_rng(seed)
+        a = (10.0 ** rng.uniform(-cond, cond, (n, 1))) * a * (10.0 ** rng.uniform(-cond, cond, (1, m or n)))
+    return np.asfortranarray(a)
+
+
+def _close(msgs, what, got, want, rtol, atol=0.0):
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    if got.shape != want.shape or not np.allclose(got, want, rtol=rtol, atol=atol):
+        err = np.abs(got - want).max() if got.shape == want.shape and got.size else None
+        msgs.append(f"{what}: max abs diff {err} (rtol {rtol})")
+
+
+def case_lange(G, cs):
+    """PDLANGE on a general (not block-aligned) sub-matrix"""
+    S, msgs = G.S, []
+    mg, ng, nb, ia, ja, m, n = cs["mg"], cs["ng"], cs["nb"], cs["ia"], cs["ja"], cs["m"], cs["n"]
+    rsrc, csrc = cs.get("rsrc", 0) % G.P, cs.get("csrc", 0) % G.Q
+    ag = matrix(mg, ng)
+    al, desc = G.dist(ag, nb, rsrc, csrc, extra=1)
+    sub = np.asfortranarray(ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n])
+    for nm in ("M", "1", "O", "I", "F", "E"):
+        got, want = S.pdlange(nm, m, n, al, ia, ja, desc), O.dlange(nm, sub)
+        if not abs(got - want) <= 1e-13 * max(1.0, want):
+            msgs.append(f"pdlange {nm}: {got} != {want}")
+    return msgs
+
+
+def case_equ(G, cs):
+    """PDGEEQU + PDLAQGE"""
+    S, msgs = G.S, []
+    n, m, nb, cond = cs["n"], cs.get("m", cs["n"]), cs["nb"], cs.get("cond")
+    ag = matrix(m, n, cond=cond)
+    if cs.get("zero_row") is not None:
+        ag[cs["zero_row"], :] = 0.0
+    al, desc = G.dist(ag, nb, extra=1)
+    mloc, nloc = S.numroc(m, nb, G.r, 0, G.P), S.numroc(n, nb, G.c, 0, G.Q)
+    r, c = np.full(max(1, mloc), -1.0), np.full(max(1, nloc), -1.0)
+    rowcnd, colcnd, amax, info = S.pdgeequ(m, n, al, 1, 1, desc, r, c)
+    r0, c0, rowcnd0, colcnd0, amax0, info0 = O.dgeequ(ag)
+    if cs.get("zero_row") is not None:
+        if info != info0:
+            msgs.append(f"pdgeequ info {info} != {info0}")
+        return msgs
+    if info != info0 or not np.allclose([rowcnd, colcnd, amax], [rowcnd0, colcnd0, amax0], rtol=1e-14):
+        msgs.append(f"pdgeequ scalars {(rowcnd, colcnd, amax, info)} != {(rowcnd0, colcnd0, amax0, info0)}")
+    rl = G.local_of(np.asfortranarray(r0.reshape(-1, 1)), nb, nbc=1)[:mloc, 0] if G.c == 0 else None
+    rl = O.scatter(np.asfortranarray(r0.reshape(-1, 1)), nb, 1, G.P, 1, G.r, 0)[:mloc, 0]
+    cl = O.scatter(np.asfortranarray(c0.reshape(1, -1)), 1, nb, 1, G.Q, 0, G.c)[0, :nloc]
+    _close(msgs, "R", r[:mloc], rl, 1e-15); _close(msgs, "C", c[:nloc], cl, 1e-15)
+    eq = S.pdlaqge(m, n, al, 1, 1, desc, r, c, rowcnd, colcnd, amax)
+    a2 = ag.copy(order="F")
+    eq0 = O.dlaqge(a2, r0, c0, rowcnd0, colcnd0, amax0)
+    if eq != eq0:
+        msgs.append(f"pdlaqge equed {eq} != {eq0}")
+    exp = G.local_of(a2, nb, lld=al.shape[0])
+    _close(msgs, "scaled A", al[:mloc, :nloc], exp[:mloc, :nloc], 1e-15)
+    if not np.all(al[mloc:, :] == -9923.0):
+        msgs.append("guard row overwritten")
+    return msgs
+
+
+def _factored(G, ag, nb, rsrc=0, csrc=0):
+    """oracle factors of ag distributed over the grid: (local LU, descriptor, local IPIV, global LU, global ipiv)"""
+    S = G.S
+    lu = ag.copy(order="F"); ipg, info = O.getrf(lu, nb)
+    assert info == 0
+    n = ag.shape[0]
+    ll, desc = G.dist(lu, nb, rsrc, csrc)
+    mloc = S.numroc(n, nb, G.r, rsrc, G.P)
+    ipl = O.ipiv_local(n, n, nb, G.P, G.r, ipg, mloc + nb, rsrc=rsrc, fill=-77)
+    return ll, desc, ipl, lu, ipg
+
+
+def case_gecon(G, cs):
+    """PDGECON on the oracle's factors"""
+    S, msgs = G.S, []
+    n, nb = cs["n"], cs["nb"]
+    ag = matrix(n, cond=cs.get("cond"))
+    ll, desc, ipl, lu, ipg = _factored(G, ag, nb)
+    for nm in ("1", "I"):
+        anorm = O.dlange(nm, ag)
+        rc, info = S.pdgecon(nm, n, ll, 1, 1, desc, anorm)
+        want = O.dgecon(nm, lu, anorm)
+        if info != 0 or not abs(rc - want) <= 1e-9 * want:
+            msgs.append(f"pdgecon {nm}: rcond {rc} info {info}, oracle {want}")
+    rc, info = S.pdgecon("X", n, ll, 1, 1, desc, 1.0)
+    if info != -1:
+        msgs.append(f"pdgecon bad NORM: info {info}")
+    rc, info = S.pdgecon("1", n, ll, 1, 1, desc, 1.0, lwork=1)
+    if info != -10:
+        msgs.append(f"pdgecon short LWORK: info {info}")
+    return msgs
+
+
+def case_gerfs(G, cs):
+    """PDGERFS: a perturbed solution is refined; X, FERR, BERR against the oracle"""
+    S, msgs = G.S, []
+    n, nb, nrhs, trans = cs["n"], cs["nb"], cs.get("nrhs", 2), cs.get("trans", "N")
+    nbr = cs.get("nbr", 1)
+    ag = matrix(n, cond=cs.get("cond")); bg = matrix(n, nrhs, seed=200)
+    ll, desc, ipl, lu, ipg = _factored(G, ag, nb)
+    al, desca = G.dist(ag, nb)
+    xg = bg.copy(order="F"); O.getrs(lu, ipg, xg, trans)
+    xg *= 1.0 + 1e-8 * np.sin(np.arange(n))[:, None]
+    xg = np.asfortranarray(xg)
+    bl, descb = G.dist(bg, nb, nbc=nbr); xl, descx = G.dist(xg, nb, extra=1, nbc=nbr)
+    nlocb = S.numroc(nrhs, nbr, G.c, 0, G.Q); mloc = S.numroc(n, nb, G.r, 0, G.P)
+    ferr, berr = np.full(max(1, nlocb), -1.0), np.full(max(1, nlocb), -1.0)
+    info = S.pdgerfs(trans, n, nrhs, al, 1, 1, desca, ll, 1, 1, desc, ipl, bl, 1, 1, descb, xl, 1, 1, descx, ferr, berr)
+    ferr0, berr0 = O.dgerfs(trans, ag, lu, ipg, bg, xg)
+    if info != 0:
+        msgs.append(f"pdgerfs info {info}")
+    xe = G.local_of(xg, nb, lld=xl.shape[0], nbc=nbr)
+    _close(msgs, "X", xl[:mloc, :nlocb], xe[:mloc, :nlocb], 1e-9, atol=1e-13 * np.abs(xg).max())
+    fl = O.scatter(np.asfortranarray(ferr0.reshape(1, -1)), 1, nbr, 1, G.Q, 0, G.c)[0, :nlocb]
+    blc = O.scatter(np.asfortranarray(berr0.reshape(1, -1)), 1, nbr, 1, G.Q, 0, G.c)[0, :nlocb]
+    _close(msgs, "FERR", ferr[:nlocb], fl, 0.05)
+    if nlocb and not (np.all(berr[:nlocb] >= 0) and np.all(berr[:nlocb] < 1e-14) and np.all(blc < 1e-14)):
+        msgs.append(f"BERR {berr[:nlocb]} vs {blc}")
+    if not np.all(xl[mloc:, :] == -9923.0):
+        msgs.append("guard row of X overwritten")
+    xt = np.linalg.solve(ag if trans == "N" else ag.T, bg)
+    for k in range(nrhs):                                       # FERR bounds the true error
+        if not np.abs(xg[:, k] - xt[:, k]).max() / np.abs(xt[:, k]).max() <= ferr0[k] * 1.001:
+            msgs.append(f"oracle FERR[{k}] is not a bound")
+    return msgs
+
+
+def case_gesvx(G, cs):
+    """PDGESVX: FACT = N / E (then F on the result), TRANS = N / T"""
+    S, msgs = G.S, []
+    n, nb, nrhs, fact, trans = cs["n"], cs["nb"], cs.get("nrhs", 2), cs.get("fact", "E"), cs.get("trans", "N")
+    ag = matrix(n, cond=cs.get("cond")); bg = matrix(n, nrhs, seed=200)
+    if cs.get("singular"):
+        ag[:, 3] = ag[:, 2]
+    al, desca = G.dist(ag, nb, extra=1); bl, descb = G.dist(bg, nb, nbc=1)
+    mloc, nloc, nlocb = S.numroc(n, nb, G.r, 0, G.P), S.numroc(n, nb, G.c, 0, G.Q), S.numroc(nrhs, 1, G.c, 0, G.Q)
+    afl = np.zeros_like(al); xl = np.zeros_like(bl)
+    ipiv = np.full(mloc + nb, -77, np.int32)
+    r, c = np.zeros(max(1, mloc)), np.zeros(max(1, nloc))
+    ferr, berr = np.full(max(1, nlocb), -1.0), np.full(max(1, nlocb), -1.0)
+    eq, rcond, info = S.pdgesvx(fact, trans, n, nrhs, al, 1, 1, desca, afl, 1, 1, desca, ipiv, "N", r, c, bl, 1, 1, descb, xl, 1, 1,
+                                descb, ferr, berr)
+    a1, b1 = ag.copy(order="F"), bg.copy(order="F")
+    af0, x0 = np.zeros((n, n), order="F"), np.zeros((n, nrhs), order="F")
+    ip0, r0, c0 = np.zeros(n, np.int32), np.zeros(n), np.zeros(n)
+    eq0, rcond0, ferr0, berr0, info0 = O.dgesvx(fact, trans, a1, af0, ip0, "N", r0, c0, b1, x0, nb=nb)
+    if (eq, info) != (eq0, info0):
+        msgs.append(f"pdgesvx equed/info {(eq, info)} != {(eq0, info0)}")
+        return msgs
+    if info0 != 0:
+        if info0 <= n and rcond != 0.0:
+            msgs.append(f"singular: rcond {rcond}")
+        return msgs
+    if not abs(rcond - rcond0) <= 1e-8 * rcond0:
+        msgs.append(f"rcond {rcond} != {rcond0}")
+    ipl = O.ipiv_local(n, n, nb, G.P, G.r, ip0, mloc + nb, fill=-77)
+    own = ipl != -77
+    if not np.array_equal(ipiv[own], ipl[own]):
+        msgs.append("IPIV differs")
+    _close(msgs, "A (equilibrated)", al[:mloc, :nloc], G.local_of(a1, nb)[:mloc, :nloc], 1e-15)
+    _close(msgs, "B (scaled)", bl[:mloc, :nlocb], G.local_of(b1, nb, nbc=1)[:mloc, :nlocb], 1e-15)
+    anorm = np.abs(a1).sum(axis=1).max()
+    lerr = np.abs(afl[:mloc, :nloc] - G.local_of(af0, nb)[:mloc, :nloc]).max() / (anorm * n * EPS) if mloc and nloc else 0.0
+    if not lerr < 1.0:
+        msgs.append(f"AF lu_err {lerr}")
+    _close(msgs, "X", xl[:mloc, :nlocb], G.local_of(x0, nb, nbc=1)[:mloc, :nlocb], 1e-8, atol=1e-12 * np.abs(x0).max())
+    _close(msgs, "FERR", ferr[:nlocb], O.scatter(np.asfortranarray(ferr0.reshape(1, -1)), 1, 1, 1, G.Q, 0, G.c)[0, :nlocb], 0.1)
+    if not np.all(al[mloc:, :] == -9923.0):
+        msgs.append("guard row of A overwritten")
+    # FACT = 'F': the factors and scalings just returned reproduce X
+    bl2 = G.local_of(bg, nb, nbc=1); xl2 = np.zeros_like(bl2)
+    eq2, rcond2, info2 = S.pdgesvx("F", trans, n, nrhs, al, 1, 1, desca, afl, 1, 1, desca, ipiv, eq, r, c, bl2, 1, 1, descb, xl2, 1, 1,
+                                   descb, ferr, berr)
+    if info2 != 0 or eq2 != eq or not abs(rcond2 - rcond) <= 1e-10 * rcond:
+        msgs.append(f"FACT=F: {(eq2, rcond2, info2)}")
+    _close(msgs, "X (FACT=F)", xl2[:mloc, :nlocb], xl[:mloc, :nlocb], 1e-9, atol=1e-13 * np.abs(x0).max())
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx}
+
+
+def run(S, ctx, cases):
+    G = Grid(S, ctx)
+    out = []
+    for cs in cases:
+        res = {"case": str(cs), "ok": True, "msgs": []}
+        if G.r >= 0:
+            try:
+                res["msgs"] = CASES[cs["kind"]](G, cs)
+            except Exception as e:          # noqa: BLE001 - a rank must report, not vanish
+                import traceback
+                res["msgs"] = [f"exception {e!r}", traceback.format_exc()[-1500:]]
+            res["ok"] = not res["msgs"]
+        out.append(res)
+    return out
+
+
+# the default case lists: small enough for the serial emulation, shaped to hit partial blocks, P != Q ownership and non-aligned windows
+F1_CASES = [
+    dict(kind="lange", mg=45, ng=37, nb=4, ia=6, ja=3, m=30, n=29, rsrc=1, csrc=1),
+    dict(kind="lange", mg=64, ng=64, nb=8, ia=1, ja=1, m=64, n=64),
+    dict(kind="lange", mg=20, ng=20, nb=32, ia=2, ja=2, m=1, n=7),
+    dict(kind="equ", n=37, m=45, nb=4, cond=6), dict(kind="equ", n=64, nb=8), dict(kind="equ", n=30, nb=4, cond=1, zero_row=7),
+    dict(kind="gecon", n=64, nb=8), dict(kind="gecon", n=45, nb=4, cond=2), dict(kind="gecon", n=2, nb=2),
+    dict(kind="gerfs", n=64, nb=8, nrhs=3), dict(kind="gerfs", n=45, nb=4, nrhs=2, trans="T", cond=2), dict(kind="gerfs", n=30, nb=4, nrhs=5, nbr=2),
+    dict(kind="gesvx", n=64, nb=8, fact="N"), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5, trans="T"),
+    dict(kind="gesvx", n=40, nb=8, fact="E"), dict(kind="gesvx", n=24, nb=4, fact="N", singular=True),
+]

@@ -1,0 +1,48 @@
+"""Host logic of the SURVEY 8(f) entry points on the CPU: the product's own sources (refine.cu, ...) built against the stub CUDA
+runtime of tests/emul, run on 1x1, 1x2, 2x1, 2x2 and 2x3 process grids over the TCP control plane, checked against the oracle.
+This covers what a GPU-less machine can: index arithmetic of the simple kernels, argument checks, block loops, the order of
+collectives.  The GPU tests (tests/test_gpu_next.py) run the same cases through the real library."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="session")
+def emul_lib():
+    subprocess.check_call(["make", "-C", EMUL, "-s", "-j8"])
+    return os.path.join(EMUL, "libslb_emul.so")
+
+
+def spawn(P, Q, cases, timeout=300):
+    world = P * Q
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   SLB200_PORT_OFFSET="0", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", SLB200_EMUL="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "next_worker.py"), json.dumps(dict(P=P, Q=Q, cases=cases))],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=timeout)
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("RESULT")][0][6:]))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    bad = [(o["rank"], r["case"], r["msgs"]) for o in outs for r in o["results"] if not r["ok"]]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
+def test_refinement_family(emul_lib, P, Q):
+    spawn(P, Q, "F1_CASES")

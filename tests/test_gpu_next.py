@@ -1,0 +1,75 @@
+"""GPU parity of the SURVEY 8(f) rows through the C-ABI: PDLANGE / PDGEEQU / PDLAQGE / PDGECON / PDGERFS / PDGESVX (row 1), ...
+against the oracle (tests/next_cases.py).  Each group runs in its own process (one rank per GPU), like tests/test_gpu_multi.py."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import next_cases  # noqa: E402
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def spawn(P, Q, cases, timeout=600):
+    world = P * Q
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   SLB200_PORT_OFFSET="0", OPENBLAS_NUM_THREADS="2", OMP_NUM_THREADS="2")
+        env.pop("SLB200_EMUL", None)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "next_worker.py"), json.dumps(dict(P=P, Q=Q, cases=cases))],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs, tails = [], []
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=timeout)
+            tails.append(e[-3000:])
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("RESULT")][0][6:]))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    bad = [(o["rank"], r["case"], r["msgs"]) for o in outs for r in o["results"] if not r["ok"]]
+    assert not bad, bad
+
+
+# larger cases than the emulation's: the 1x1 solves take the two-stream fast path (nb <= 512), the matrix passes fill the GPU
+F1_GPU = [
+    dict(kind="lange", mg=3000, ng=2500, nb=128, ia=130, ja=7, m=2000, n=2200),
+    dict(kind="equ", n=2000, m=2300, nb=128, cond=6),
+    dict(kind="gecon", n=2048, nb=256), dict(kind="gecon", n=1500, nb=64, cond=2), dict(kind="gecon", n=1000, nb=1024),
+    dict(kind="gerfs", n=2048, nb=256, nrhs=2), dict(kind="gerfs", n=1500, nb=64, nrhs=2, trans="T", cond=1),
+    dict(kind="gesvx", n=2048, nb=256, fact="N"), dict(kind="gesvx", n=1500, nb=128, fact="E", cond=4),
+    dict(kind="gesvx", n=1000, nb=64, fact="E", cond=4, trans="T"),
+]
+
+
+def test_refinement_family_1x1():
+    spawn(1, 1, next_cases.F1_CASES + F1_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 1)])
+def test_refinement_family_2gpus(P, Q):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    spawn(P, Q, next_cases.F1_CASES + F1_GPU)
+
+
+def test_refinement_family_2x2():
+    if ngpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    spawn(2, 2, next_cases.F1_CASES + F1_GPU)
