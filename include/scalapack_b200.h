@@ -125,6 +125,17 @@ void pdgesvx_(const char *fact, const char *trans, const int *n, const int *nrhs
               const int *jx, const int *descx, double *rcond, double *ferr, double *berr, double *work, const int *lwork,
               int *iwork, const int *liwork, int *info);                      /* SRC/pdgesvx.f:1-5 */
 
+/* ---- redistribution between block-cyclic layouts / grids.  ictxt: a context containing every process of
+ * both grids; all of its processes call; a process outside A's (B's) grid passes DESCA(CTXT_) (DESCB(CTXT_)) = -1. */
+void pdgemr2d_(const int *m, const int *n, const double *a, const int *ia, const int *ja, const int *desca, double *b,
+               const int *ib, const int *jb, const int *descb, const int *ictxt);             /* REDIST/SRC/pdgemr.c:253-260 */
+void pzgemr2d_(const int *m, const int *n, const slb200_z *a, const int *ia, const int *ja, const int *desca, slb200_z *b,
+               const int *ib, const int *jb, const int *descb, const int *ictxt);             /* REDIST/SRC/pzgemr.c */
+void Cpdgemr2d(int m, int n, const double *a, int ia, int ja, const int *desca, double *b, int ib, int jb,
+               const int *descb, int gcontext);                                               /* REDIST/SRC/pdgemr.c:286-296 */
+void Cpzgemr2d(int m, int n, const slb200_z *a, int ia, int ja, const int *desca, slb200_z *b, int ib, int jb,
+               const int *descb, int gcontext);
+
 /* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
 /* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
  * a may be host or device. */

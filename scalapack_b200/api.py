@@ -304,6 +304,16 @@ def pdgesvx(fact, trans, n, nrhs, a, ia, ja, desca, af, iaf, jaf, descaf, ipiv, 
     return eq.value[:1].decode(), rcond.value, info.value
 
 
+# ------------------------------------------------------------------ redistribution
+def pdgemr2d(m, n, a, ia, ja, desca, b, ib, jb, descb, ictxt):
+    """REDIST/SRC/pdgemr.c: sub(B) <- sub(A) across layouts / grids; every process of context ictxt calls."""
+    lib().pdgemr2d_(_i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb), _i(ictxt))
+
+
+def pzgemr2d(m, n, a, ia, ja, desca, b, ib, jb, descb, ictxt):
+    lib().pzgemr2d_(_i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb), _i(ictxt))
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

@@ -117,4 +117,20 @@ void nccl_allreduce_sum_f64(ncclComm_t_ comm, const void *send, void *recv, size
 void nccl_allreduce_max_f64(ncclComm_t_ comm, const void *send, void *recv, size_t count, cudaStream_t s)
 { NCHECK(N.AllReduce(send, recv, count, (int)NT_F64, 2, comm, s)); counter_add("nccl_calls", 1); }
 
+void nccl_alltoallv(ncclComm_t_ comm, int np, int me, const void *send, const size_t *scount, const size_t *sdispl, void *recv,
+                    const size_t *rcount, const size_t *rdispl, cudaStream_t s)
+{
+    if (scount[me] != rcount[me]) fatal("nccl_alltoallv: own part %zu != %zu", scount[me], rcount[me]);
+    if (scount[me]) SLB_CUDA(cudaMemcpyAsync((char *)recv + rdispl[me], (const char *)send + sdispl[me], scount[me], cudaMemcpyDeviceToDevice, s));
+    if (np <= 1) return;
+    NCHECK(N.GroupStart());
+    for (int p = 0; p < np; ++p) {
+        if (p == me) continue;
+        if (scount[p]) NCHECK(N.Send((const char *)send + sdispl[p], scount[p], (int)NT_U8, p, comm, s));
+        if (rcount[p]) NCHECK(N.Recv((char *)recv + rdispl[p], rcount[p], (int)NT_U8, p, comm, s));
+    }
+    NCHECK(N.GroupEnd());
+    counter_add("nccl_calls", 1);
+}
+
 }  // namespace slb

@@ -30,6 +30,11 @@ void nccl_allgather(ncclComm_t_ comm, const void *send, void *recv, size_t sendc
 void nccl_allreduce_min_i32(ncclComm_t_ comm, const void *send, void *recv, size_t count, cudaStream_t s);
 void nccl_allreduce_sum_f64(ncclComm_t_ comm, const void *send, void *recv, size_t count, cudaStream_t s);
 void nccl_allreduce_max_f64(ncclComm_t_ comm, const void *send, void *recv, size_t count, cudaStream_t s);
+// personalised all-to-all in BYTES (PDGEMR2D): peer p receives send[sdispl[p], sdispl[p] + scount[p]) and its part lands in
+// recv[rdispl[p], rdispl[p] + rcount[p]); one group of ncclSend / ncclRecv, the own part is a device copy.  np / me: size of the
+// communicator and my rank in it.
+void nccl_alltoallv(ncclComm_t_ comm, int np, int me, const void *send, const size_t *scount, const size_t *sdispl, void *recv,
+                    const size_t *rcount, const size_t *rdispl, cudaStream_t s);
 const char *nccl_version_string();
 
 }  // namespace slb

@@ -254,6 +254,25 @@ static void allreduce(ncclComm_t_ comm, const void *send, void *recv, size_t cou
 void nccl_allreduce_min_i32(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<int>(c, s, r, n, [](int a, int b) { return a < b ? a : b; }); }
 void nccl_allreduce_sum_f64(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<double>(c, s, r, n, [](double a, double b) { return a + b; }); }
 void nccl_allreduce_max_f64(ncclComm_t_ c, const void *s, void *r, size_t n, cudaStream_t) { allreduce<double>(c, s, r, n, [](double a, double b) { return a > b ? a : b; }); }
+void nccl_alltoallv(ncclComm_t_ comm, int np, int me, const void *send, const size_t *scount, const size_t *sdispl, void *recv,
+                    const size_t *rcount, const size_t *rdispl, cudaStream_t)
+{
+    // every rank publishes its counts / displacements and its whole send buffer (padded to the largest); each picks its parts
+    size_t mytot = 0; for (int p = 0; p < np; ++p) if (sdispl[p] + scount[p] > mytot) mytot = sdispl[p] + scount[p];
+    std::vector<size_t> meta((size_t)2 * np + 1), allmeta(((size_t)2 * np + 1) * np);
+    for (int p = 0; p < np; ++p) { meta[(size_t)p] = scount[p]; meta[(size_t)np + p] = sdispl[p]; }
+    meta[(size_t)2 * np] = mytot;
+    if (np > 1) grid_allgather(comm->g, comm->scope, meta.data(), allmeta.data(), meta.size() * sizeof(size_t)); else allmeta = meta;
+    size_t maxtot = 1; for (int p = 0; p < np; ++p) if (allmeta[(size_t)p * (2 * np + 1) + 2 * np] > maxtot) maxtot = allmeta[(size_t)p * (2 * np + 1) + 2 * np];
+    std::vector<char> mine(maxtot, 0), all(maxtot * (size_t)np);
+    if (mytot) memcpy(mine.data(), send, mytot);
+    if (np > 1) grid_allgather(comm->g, comm->scope, mine.data(), all.data(), maxtot); else all = mine;
+    for (int p = 0; p < np; ++p) {
+        const size_t cnt = allmeta[(size_t)p * (2 * np + 1) + me], dsp = allmeta[(size_t)p * (2 * np + 1) + np + me];
+        if (cnt != rcount[p]) fatal("emulated alltoallv: rank %d sends %zu bytes to %d which expects %zu", p, cnt, me, rcount[p]);
+        if (cnt) memcpy((char *)recv + rdispl[p], all.data() + (size_t)p * maxtot + dsp, cnt);
+    }
+}
 const char *nccl_version_string() { return "emulated"; }
 
 }  // namespace slb

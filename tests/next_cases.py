@@ -219,7 +219,60 @@ def case_gesvx(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx}
+def _subgrid(G, Pn, Qn, cache={}):
+    """a context on the first Pn*Qn processes (every process of the main grid calls; outsiders get -1)"""
+    key = (id(G.S), G.ctx, Pn, Qn)
+    if key not in cache:
+        cache[key] = G.S.blacs_gridinit(G.S.blacs_get(-1, 0), "Row-major", Pn, Qn)
+    return cache[key]
+
+
+def case_gemr2d(G, cs):
+    """PDGEMR2D / PZGEMR2D: sub(A) on grid ga (block mba x nba, source (rsa, csa)) -> sub(B) on grid gb (any other layout)"""
+    S, msgs = G.S, []
+    z = cs.get("z", False)
+    (Pa, Qa), (Pb, Qb) = cs.get("ga", (G.P, G.Q)), cs.get("gb", (G.P, G.Q))
+    if Pa * Qa > G.P * G.Q or Pb * Qb > G.P * G.Q:
+        return msgs
+    ca, cb = _subgrid(G, Pa, Qa), _subgrid(G, Pb, Qb)
+    m, n, ia, ja, ib, jb = cs["m"], cs["n"], cs.get("ia", 1), cs.get("ja", 1), cs.get("ib", 1), cs.get("jb", 1)
+    (mga, nga), (mgb, ngb) = cs["shape_a"], cs["shape_b"]
+    (mba, nba), (mbb, nbb) = cs["blk_a"], cs["blk_b"]
+    (rsa, csa), (rsb, csb) = cs.get("src_a", (0, 0)), cs.get("src_b", (0, 0))
+    rsa, csa, rsb, csb = rsa % Pa, csa % Qa, rsb % Pb, csb % Qb
+    gen = O.pzmatgen if z else O.pdmatgen
+    ag = np.asfortranarray(gen(mga, nga, 100))
+    bg = np.full((mgb, ngb), -9923.0, dtype=ag.dtype, order="F")
+    want = bg.copy(order="F"); want[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n] = ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]
+
+    def local(ctx, Pn, Qn, glob, mb, nb, rs, cs_):
+        _, _, r, c = S.blacs_gridinfo(ctx) if ctx >= 0 else (0, 0, -1, -1)
+        if r < 0:
+            return None, [1, -1, glob.shape[0], glob.shape[1], mb, nb, rs, cs_, 1], None
+        lld = max(1, S.numroc(glob.shape[0], mb, r, rs, Pn)) + 1
+        al = O.scatter(glob, mb, nb, Pn, Qn, r, c, rsrc=rs, csrc=cs_, lld=lld)
+        al[lld - 1:, :] = -555.0
+        desc, info = S.descinit(glob.shape[0], glob.shape[1], mb, nb, rs, cs_, ctx, lld)
+        assert info == 0
+        return al, desc, (r, c)
+    al, desca, _ = local(ca, Pa, Qa, ag, mba, nba, rsa, csa)
+    bl, descb, rc = local(cb, Pb, Qb, bg, mbb, nbb, rsb, csb)
+    a_before = None if al is None else al.copy()
+    f = S.pzgemr2d if z else S.pdgemr2d
+    f(m, n, al if al is not None else np.zeros(1, dtype=ag.dtype), ia, ja, desca, bl if bl is not None else np.zeros(1, dtype=ag.dtype), ib, jb,
+      descb, G.ctx)
+    if al is not None and not np.array_equal(al, a_before):
+        msgs.append("A was modified")
+    if bl is not None:
+        exp = O.scatter(want, mbb, nbb, Pb, Qb, rc[0], rc[1], rsrc=rsb, csrc=csb, lld=bl.shape[0])
+        exp[bl.shape[0] - 1:, :] = -555.0
+        if not np.array_equal(bl, exp):
+            bad = np.argwhere(bl != exp)
+            msgs.append(f"B differs at {len(bad)} local entries, first {bad[0].tolist()}: got {bl[tuple(bad[0])]} want {exp[tuple(bad[0])]}")
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d}
 
 
 def run(S, ctx, cases):
@@ -248,4 +301,19 @@ F1_CASES = [
     dict(kind="gerfs", n=64, nb=8, nrhs=3), dict(kind="gerfs", n=45, nb=4, nrhs=2, trans="T", cond=2), dict(kind="gerfs", n=30, nb=4, nrhs=5, nbr=2),
     dict(kind="gesvx", n=64, nb=8, fact="N"), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5, trans="T"),
     dict(kind="gesvx", n=40, nb=8, fact="E"), dict(kind="gesvx", n=24, nb=4, fact="N", singular=True),
+]
+
+# PDGEMR2D: other block sizes (the NB=64 -> NB=512 use), rectangular blocks, shifted source processes, non-aligned sub-matrices,
+# other grids (1 x np line, a single process, a transposed grid); ga / gb cases are skipped when the run has too few processes
+F2_CASES = [
+    dict(kind="gemr2d", m=50, n=40, shape_a=(50, 40), shape_b=(50, 40), blk_a=(4, 4), blk_b=(16, 16)),
+    dict(kind="gemr2d", m=33, n=29, ia=5, ja=8, ib=2, jb=11, shape_a=(45, 41), shape_b=(37, 50), blk_a=(4, 3), blk_b=(7, 5), src_a=(1, 0), src_b=(0, 1)),
+    dict(kind="gemr2d", m=64, n=64, shape_a=(64, 64), shape_b=(64, 64), blk_a=(8, 8), blk_b=(8, 8), src_b=(1, 1)),
+    dict(kind="gemr2d", m=40, n=30, shape_a=(40, 30), shape_b=(40, 30), blk_a=(4, 4), blk_b=(5, 5), gb=(1, 1)),
+    dict(kind="gemr2d", m=40, n=30, shape_a=(40, 30), shape_b=(40, 30), blk_a=(40, 30), blk_b=(3, 3), ga=(1, 1)),
+    dict(kind="gemr2d", m=37, n=41, shape_a=(37, 41), shape_b=(37, 41), blk_a=(4, 4), blk_b=(6, 2), ga=(1, 2), gb=(2, 1)),
+    dict(kind="gemr2d", m=37, n=41, ia=2, shape_a=(40, 41), shape_b=(37, 41), blk_a=(4, 4), blk_b=(6, 2), ga=(2, 2), gb=(1, 4)),
+    dict(kind="gemr2d", m=37, n=41, shape_a=(37, 41), shape_b=(37, 41), blk_a=(4, 4), blk_b=(6, 2), ga=(1, 3), gb=(3, 2)),
+    dict(kind="gemr2d", m=20, n=25, ja=3, shape_a=(20, 30), shape_b=(25, 25), ib=6, blk_a=(2, 2), blk_b=(4, 4), z=True),
+    dict(kind="gemr2d", m=1, n=1, ia=7, ja=9, ib=3, jb=2, shape_a=(10, 10), shape_b=(5, 5), blk_a=(2, 2), blk_b=(3, 3)),
 ]

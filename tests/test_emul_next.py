@@ -46,3 +46,8 @@ def spawn(P, Q, cases, timeout=300):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
 def test_refinement_family(emul_lib, P, Q):
     spawn(P, Q, "F1_CASES")
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 2), (2, 3)])
+def test_redistribution(emul_lib, P, Q):
+    spawn(P, Q, "F2_CASES")

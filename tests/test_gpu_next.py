@@ -73,3 +73,25 @@ def test_refinement_family_2x2():
     if ngpus() < 4:
         pytest.skip("needs 4 GPUs")
     spawn(2, 2, next_cases.F1_CASES + F1_GPU)
+
+
+# ---- row 2: PDGEMR2D ----
+F2_GPU = [
+    dict(kind="gemr2d", m=4096, n=4096, shape_a=(4096, 4096), shape_b=(4096, 4096), blk_a=(64, 64), blk_b=(512, 512)),     # NB 64 -> 512
+    dict(kind="gemr2d", m=3000, n=2000, ia=65, ja=130, ib=7, jb=3, shape_a=(3100, 2200), shape_b=(3010, 2005), blk_a=(64, 32), blk_b=(100, 256),
+         src_a=(1, 1), src_b=(0, 1)),
+    dict(kind="gemr2d", m=1500, n=1500, shape_a=(1500, 1500), shape_b=(1500, 1500), blk_a=(128, 128), blk_b=(32, 32), z=True),
+    dict(kind="gemr2d", m=2048, n=2048, shape_a=(2048, 2048), shape_b=(2048, 2048), blk_a=(64, 64), blk_b=(512, 512), ga=(1, 2), gb=(2, 1)),
+    dict(kind="gemr2d", m=2048, n=2048, shape_a=(2048, 2048), shape_b=(2048, 2048), blk_a=(64, 64), blk_b=(512, 512), ga=(2, 2), gb=(1, 1)),
+]
+
+
+def test_redistribution_1x1():
+    spawn(1, 1, next_cases.F2_CASES + F2_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 2)])
+def test_redistribution_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.F2_CASES + F2_GPU)
