@@ -136,6 +136,13 @@ void Cpdgemr2d(int m, int n, const double *a, int ia, int ja, const int *desca, 
 void Cpzgemr2d(int m, int n, const slb200_z *a, int ia, int ja, const int *desca, slb200_z *b, int ib, int jb,
                const int *descb, int gcontext);
 
+/* ---- Cholesky: only the UPLO triangle of sub(A) is referenced / written ---- */
+void pdpotrf_(const char *uplo, const int *n, double *a, const int *ia, const int *ja, const int *desca, int *info);   /* SRC/pdpotrf.f:1 */
+void pdpotrs_(const char *uplo, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja, const int *desca,
+              double *b, const int *ib, const int *jb, const int *descb, int *info);                                /* SRC/pdpotrs.f:1-2 */
+void pdposv_(const char *uplo, const int *n, const int *nrhs, double *a, const int *ia, const int *ja, const int *desca,
+             double *b, const int *ib, const int *jb, const int *descb, int *info);                                 /* SRC/pdposv.f:1-2 */
+
 /* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
 /* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
  * a may be host or device. */

@@ -292,3 +292,15 @@ def dgesvx(fact, trans, a, af, ipiv, equed, r, c, b, x, nb=64):
                              C.c_int64(af.strides[1] // 8), _p(ipiv), C.byref(eq), _f(r), _f(c), _f(b), C.c_int64(b.strides[1] // 8), _f(x),
                              C.c_int64(x.strides[1] // 8), C.byref(rcond), _f(ferr), _f(berr), nb)
     return eq.value.decode(), rcond.value, ferr, berr, int(info)
+
+
+def dpotrf(uplo, a, nb):
+    """SRC/pdpotrf.f on the global matrix (only the UPLO triangle is referenced); returns INFO."""
+    n = a.shape[0]
+    return int(lib().orcn_dpotrf(C.c_char(uplo.encode()), n, _f(a), C.c_int64(a.strides[1] // 8), nb))
+
+
+def dpotrs(uplo, a, b):
+    """SRC/pdpotrs.f: b <- inv(A) b from the Cholesky factor."""
+    n, nrhs = b.shape
+    lib().orcn_dpotrs(C.c_char(uplo.encode()), n, nrhs, _f(a), C.c_int64(a.strides[1] // 8), _f(b), C.c_int64(b.strides[1] // 8))

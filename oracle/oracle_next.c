@@ -268,3 +268,60 @@ int orcn_dgesvx(char fact, char trans, int n, int nrhs, double *a, int64_t lda, 
     else if (rowequ) { for (int j = 0; j < nrhs; ++j) { for (int i = 0; i < n; ++i) x[i + (int64_t)j * ldx] *= r[i]; ferr[j] /= rowcnd; } }
     return 0;
 }
+
+/* ---- Cholesky ------------------------------------------------------------------------------------------ */
+/* SRC/pdpotf2.f:208-262: unblocked, left-looking; the other triangle is not referenced.  Returns INFO (1-based). */
+static int potf2_ref(int upper, int n, double *a, int64_t lda)
+{
+    for (int j = 0; j < n; ++j) {
+        double ajj = A_(j, j);
+        if (upper) { for (int k = 0; k < j; ++k) ajj -= A_(k, j) * A_(k, j); }
+        else { for (int k = 0; k < j; ++k) ajj -= A_(j, k) * A_(j, k); }
+        if (!(ajj > 0.0)) { A_(j, j) = ajj; return j + 1; }
+        ajj = sqrt(ajj); A_(j, j) = ajj;
+        const double r = 1.0 / ajj;
+        if (upper) for (int c = j + 1; c < n; ++c) { double s = A_(j, c); for (int k = 0; k < j; ++k) s -= A_(k, c) * A_(k, j); A_(j, c) = s * r; }
+        else for (int i = j + 1; i < n; ++i) { double s = A_(i, j); for (int k = 0; k < j; ++k) s -= A_(i, k) * A_(j, k); A_(i, j) = s * r; }
+    }
+    return 0;
+}
+
+/* SRC/pdpotrf.f:226-352 with IA = JA = 1: PDPOTF2 on the diagonal block, PDTRSM on the panel, PDSYRK on the trailing triangle */
+int orcn_dpotrf(char uplo, int n, double *a, int64_t lda, int nb)
+{
+    const int upper = uplo == 'U';
+    for (int j0 = 0; j0 < n; j0 += nb) {
+        const int jb = n - j0 < nb ? n - j0 : nb, t0 = j0 + jb;
+        int info = potf2_ref(upper, jb, &A_(j0, j0), lda);
+        if (info != 0) return info + j0;
+        if (t0 >= n) break;
+        if (upper) {
+            /* A12 <- U11^-T A12 (pdpotrf.f:261), then A22 -= A12^T A12 on the upper triangle (:264) */
+            for (int c = t0; c < n; ++c)
+                for (int k = 0; k < jb; ++k) { double s = A_(j0 + k, c); for (int q = 0; q < k; ++q) s -= A_(j0 + q, j0 + k) * A_(j0 + q, c); A_(j0 + k, c) = s / A_(j0 + k, j0 + k); }
+            for (int c = t0; c < n; ++c) for (int i = t0; i <= c; ++i) { double s = A_(i, c); for (int k = 0; k < jb; ++k) s -= A_(j0 + k, i) * A_(j0 + k, c); A_(i, c) = s; }
+        } else {
+            /* A21 <- A21 L11^-T (pdpotrf.f:318), then A22 -= A21 A21^T on the lower triangle (:321) */
+            for (int i = t0; i < n; ++i)
+                for (int k = 0; k < jb; ++k) { double s = A_(i, j0 + k); for (int q = 0; q < k; ++q) s -= A_(i, j0 + q) * A_(j0 + k, j0 + q); A_(i, j0 + k) = s / A_(j0 + k, j0 + k); }
+            for (int c = t0; c < n; ++c) for (int i = c; i < n; ++i) { double s = A_(i, c); for (int k = 0; k < jb; ++k) s -= A_(i, j0 + k) * A_(c, j0 + k); A_(i, c) = s; }
+        }
+    }
+    return 0;
+}
+
+/* SRC/pdpotrs.f:249-263: two triangular solves with the factor */
+void orcn_dpotrs(char uplo, int n, int nrhs, const double *a, int64_t lda, double *b, int64_t ldb)
+{
+    const int upper = uplo == 'U';
+    for (int c = 0; c < nrhs; ++c) {
+        double *x = b + (int64_t)c * ldb;
+        if (upper) {
+            for (int k = 0; k < n; ++k) { for (int i = 0; i < k; ++i) x[k] -= A_(i, k) * x[i]; x[k] /= A_(k, k); }                   /* U' y = b */
+            for (int k = n - 1; k >= 0; --k) { x[k] /= A_(k, k); for (int i = 0; i < k; ++i) x[i] -= A_(i, k) * x[k]; }             /* U x = y  */
+        } else {
+            for (int k = 0; k < n; ++k) { x[k] /= A_(k, k); for (int i = k + 1; i < n; ++i) x[i] -= A_(i, k) * x[k]; }              /* L y = b  */
+            for (int k = n - 1; k >= 0; --k) { for (int i = k + 1; i < n; ++i) x[k] -= A_(i, k) * x[i]; x[k] /= A_(k, k); }         /* L' x = y */
+        }
+    }
+}

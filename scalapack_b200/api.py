@@ -314,6 +314,25 @@ def pzgemr2d(m, n, a, ia, ja, desca, b, ib, jb, descb, ictxt):
     lib().pzgemr2d_(_i(m), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb), _i(ictxt))
 
 
+# ------------------------------------------------------------------ Cholesky
+def pdpotrf(uplo, n, a, ia, ja, desca):
+    info = C.c_int()
+    lib().pdpotrf_(uplo.encode(), _i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), C.byref(info))
+    return info.value
+
+
+def pdpotrs(uplo, n, nrhs, a, ia, ja, desca, b, ib, jb, descb):
+    info = C.c_int()
+    lib().pdpotrs_(uplo.encode(), _i(n), _i(nrhs), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb), C.byref(info))
+    return info.value
+
+
+def pdposv(uplo, n, nrhs, a, ia, ja, desca, b, ib, jb, descb):
+    info = C.c_int()
+    lib().pdposv_(uplo.encode(), _i(n), _i(nrhs), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb), C.byref(info))
+    return info.value
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

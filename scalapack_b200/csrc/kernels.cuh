@@ -102,7 +102,7 @@ void launch_gen_matvec(int64_t n, int nb, uint64_t aseed, int gen, int myrow, in
 // ---- triangular solves of PDGETRS (SRC/pdgetrs.f:255-284) ----
 // x[0:kb] = tri(op(Akk))^-1 x[0:kb], nrhs columns.  mode: TRSV_UPPER = the stored triangle is U (non-unit diagonal), else L
 // (unit diagonal); TRSV_TRANS / TRSV_CONJ: op = transpose / conjugate transpose.
-enum { TRSV_UPPER = 1, TRSV_TRANS = 2, TRSV_CONJ = 4 };
+enum { TRSV_UPPER = 1, TRSV_TRANS = 2, TRSV_CONJ = 4, TRSV_NONUNIT_L = 8 };   // NONUNIT_L: the stored L has a general diagonal (Cholesky)
 template <typename T>
 void launch_trsv_block(int kb, const T *Akk, int64_t lda, T *X, int64_t ldx, int nrhs, int mode, cudaStream_t s);
 // Y[rows] -= A[rows x kb] * X[kb] for nrhs columns (memory-bound GEMV-like)

@@ -4,7 +4,8 @@
 // Host-logic test build (tests/emul, g++ with a stub cuda_runtime.h that defines SLB_EMUL): the same kernel body is run
 // thread by thread in a serial loop, so the index arithmetic of these kernels and of the drivers above them is checked
 // on a CPU-only machine.  Kernels launched through SLB_LAUNCH therefore use no shared memory, barriers, shuffles or
-// atomics, and no thread reads an element another thread of the same launch writes.  The emulation is test
+// atomics, and no thread reads an element another thread of the same launch writes; SLB_LAUNCH_SYNC additionally allows
+// __syncthreads() and static __shared__ arrays (small blocks: the emulation spends one OS thread per CUDA thread).  The emulation is test
 // infrastructure only: the product library contains no CPU path and aborts without a GPU (runtime.cu).
 #pragma once
 #include "common.h"
@@ -16,6 +17,8 @@
         SLB_CUDA(cudaGetLastError());                                     \
         ::slb::counter_add("kernel_launches", 1);                         \
     } while (0)
+// a kernel that uses __syncthreads() / static __shared__ arrays: the emulation runs one OS thread per CUDA thread of a block
+#define SLB_LAUNCH_SYNC SLB_LAUNCH
 #endif
 
 namespace slb {

@@ -172,7 +172,11 @@ void launch_trsv_block(int kb, const T *Akk, int64_t lda, T *X, int64_t ldx, int
     if (sm > 48 * 1024) fatal("block size %d too large for the diagonal solve", kb);
     const unsigned g = rhs_grid(nrhs);
     const bool upper = mode & TRSV_UPPER, trans = mode & TRSV_TRANS, conj = (mode & TRSV_CONJ) && sizeof(T) == 16;
-    if (!trans) {
+    if (!upper && (mode & TRSV_NONUNIT_L)) {                     // Cholesky factor: lower triangle with a general diagonal
+        if (!trans) trsv_block_kernel<T, true, false, false, false><<<g, 256, sm, s>>>(kb, Akk, lda, X, ldx, nrhs);
+        else if (!conj) trsv_block_kernel<T, false, false, true, false><<<g, 256, sm, s>>>(kb, Akk, lda, X, ldx, nrhs);
+        else trsv_block_kernel<T, false, false, true, true><<<g, 256, sm, s>>>(kb, Akk, lda, X, ldx, nrhs);
+    } else if (!trans) {
         if (upper) trsv_block_kernel<T, false, false, false, false><<<g, 256, sm, s>>>(kb, Akk, lda, X, ldx, nrhs);
         else trsv_block_kernel<T, true, true, false, false><<<g, 256, sm, s>>>(kb, Akk, lda, X, ldx, nrhs);
     } else if (!conj) {

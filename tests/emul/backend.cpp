@@ -91,6 +91,48 @@ void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst
 template void launch_copy2d<double>(int64_t, int64_t, const double *, int64_t, double *, int64_t, cudaStream_t);
 template void launch_copy2d<zcomplex>(int64_t, int64_t, const zcomplex *, int64_t, zcomplex *, int64_t, cudaStream_t);
 
+// ---- PDGETRS kernels by contract (kernels.cuh) ------------------------------------------------------------------------------
+template <typename T>
+void launch_trsv_block(int kb, const T *A, int64_t lda, T *X, int64_t ldx, int nrhs, int mode, cudaStream_t)
+{
+    const bool upper = mode & TRSV_UPPER, trans = mode & TRSV_TRANS, cj = (mode & TRSV_CONJ) != 0;
+    const bool unit = !upper && !(mode & TRSV_NONUNIT_L);
+    auto op = [&](int i, int k) { T v = trans ? A[k + (int64_t)i * lda] : A[i + (int64_t)k * lda]; return cj ? cconj(v) : v; };   // element (i, k) of op(A)
+    const bool fwd = upper == trans;
+    for (int c = 0; c < nrhs; ++c) {
+        T *x = X + (int64_t)c * ldx;
+        for (int q = 0; q < kb; ++q) {
+            const int i = fwd ? q : kb - 1 - q;
+            T v = x[i];
+            if (fwd) for (int k = 0; k < i; ++k) v = cmul_sub(v, op(i, k), x[k]);
+            else for (int k = i + 1; k < kb; ++k) v = cmul_sub(v, op(i, k), x[k]);
+            x[i] = unit ? v : cdiv(v, op(i, i));
+        }
+    }
+    counter_add("kernel_launches", 1);
+}
+template <typename T>
+void launch_gemv_minus(int64_t rows, int kb, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs, cudaStream_t)
+{
+    for (int c = 0; c < nrhs; ++c) for (int k = 0; k < kb; ++k) for (int64_t i = 0; i < rows; ++i)
+        Y[i + (int64_t)c * ldy] = cmul_sub(Y[i + (int64_t)c * ldy], A[i + (int64_t)k * lda], X[k + (int64_t)c * ldx]);
+    counter_add("kernel_launches", 1);
+}
+template <typename T>
+void launch_gemvt_minus(int kb, int64_t ncols, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs, bool conj, cudaStream_t)
+{
+    for (int c = 0; c < nrhs; ++c) for (int64_t j = 0; j < ncols; ++j) for (int i = 0; i < kb; ++i)
+        Y[j + (int64_t)c * ldy] = cmul_sub(Y[j + (int64_t)c * ldy], conj ? cconj(A[i + j * lda]) : A[i + j * lda], X[i + (int64_t)c * ldx]);
+    counter_add("kernel_launches", 1);
+}
+#define INST(T)                                                                                                  \
+    template void launch_trsv_block<T>(int, const T *, int64_t, T *, int64_t, int, int, cudaStream_t);           \
+    template void launch_gemv_minus<T>(int64_t, int, const T *, int64_t, const T *, int64_t, T *, int64_t, int, cudaStream_t); \
+    template void launch_gemvt_minus<T>(int, int64_t, const T *, int64_t, const T *, int64_t, T *, int64_t, int, bool, cudaStream_t);
+INST(double)
+INST(zcomplex)
+#undef INST
+
 // ---- block-cyclic gather / scatter of an M x N matrix over the grid (local windows start at A, first block on (rsrc, csrc)) ----
 template <typename T>
 static std::vector<T> gather_bc(Grid *g, int M, int N, const T *A, int64_t lld, int nb, int rsrc, int csrc)

@@ -13,6 +13,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
@@ -73,5 +77,44 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
                 kernel(__VA_ARGS__);                                                                         \
             }                                                                                                \
         }                                                                                                    \
+        ::slb::counter_add("kernel_launches", 1);                                                            \
+    } while (0)
+
+// ---- kernels with block-wide barriers and static shared memory (SLB_LAUNCH_SYNC) -------------------------------------------
+// One OS thread per CUDA thread of a block, blocks one after the other; __syncthreads() is a real barrier between them and a
+// `__shared__` array is a function-static one (shared by the threads of the running block).  Meant for SMALL blocks in tests.
+#define __shared__ static
+struct emul_barrier {
+    std::mutex mu; std::condition_variable cv; unsigned n = 1, waiting = 0, phase = 0;
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned ph = phase;
+        if (++waiting == n) { waiting = 0; ++phase; cv.notify_all(); }
+        else cv.wait(lk, [&] { return phase != ph; });
+    }
+};
+inline emul_barrier emul_block_barrier;
+static inline void __syncthreads() { emul_block_barrier.wait(); }
+template <typename F>
+static inline void emul_run_block(const dim3 &g, const dim3 &b, unsigned bx, unsigned by, unsigned bz, F body)
+{
+    const unsigned nt = b.x * b.y * b.z;
+    emul_block_barrier.n = nt; emul_block_barrier.waiting = 0;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([=] {
+            gridDim = g; blockDim = b; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            threadIdx.x = t % b.x; threadIdx.y = (t / b.x) % b.y; threadIdx.z = t / (b.x * b.y);
+            body();
+        });
+    for (auto &t : th) t.join();
+}
+#define SLB_LAUNCH_SYNC(kernel, grid, block, stream, ...)                                                    \
+    do {                                                                                                     \
+        const dim3 g_ = (grid), b_ = (block);                                                                \
+        (void)(stream);                                                                                      \
+        for (unsigned bz_ = 0; bz_ < g_.z; ++bz_) for (unsigned by_ = 0; by_ < g_.y; ++by_) for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) \
+            emul_run_block(g_, b_, bx_, by_, bz_, [&] { kernel(__VA_ARGS__); });                               \
         ::slb::counter_add("kernel_launches", 1);                                                            \
     } while (0)

@@ -272,7 +272,72 @@ def case_gemr2d(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d}
+def spd(n, seed=100):
+    """symmetric positive definite test matrix (the reference's PDMATGEN 'S' + diagonal dominance idea, pdlltdriver.f): A0 + A0' + 2 n I"""
+    a = O.pdmatgen(n, n, seed)
+    return np.asfortranarray(a + a.T + 2.0 * n * np.eye(n))
+
+
+def case_potrf(G, cs):
+    """PDPOTRF ('L' / 'U') on a sub-matrix, then PDPOTRS, then PDPOSV; the other triangle and the guard rows stay untouched"""
+    S, msgs = G.S, []
+    n, nb, uplo, nrhs = cs["n"], cs["nb"], cs.get("uplo", "L"), cs.get("nrhs", 2)
+    off = cs.get("off", 0)                                       # sub(A) = A(off*nb+1 : , off*nb+1 : ) of a larger matrix
+    rsrc, csrc = cs.get("rsrc", 0) % G.P, cs.get("csrc", 0) % G.Q
+    ng = n + off * nb
+    ag = O.pdmatgen(ng, ng, 77); a0 = spd(n)
+    if cs.get("notpd") is not None:
+        a0[cs["notpd"], cs["notpd"]] = -1.0
+    ag[off * nb:, off * nb:] = a0
+    ag = np.asfortranarray(ag)
+    al, desca = G.dist(ag, nb, rsrc, csrc, extra=1)
+    ia = off * nb + 1
+    info = S.pdpotrf(uplo, n, al, ia, ia, desca)
+    ref = a0.copy(order="F"); info0 = O.dpotrf(uplo, ref, nb)
+    if info != info0:
+        msgs.append(f"pdpotrf info {info} != {info0}")
+        return msgs
+    if info0 != 0:
+        return msgs                                              # same INFO; the partially factored matrix is not compared
+    want = ag.copy(order="F"); want[off * nb:, off * nb:] = ref
+    mloc, nloc = S.numroc(ng, nb, G.r, rsrc, G.P), S.numroc(ng, nb, G.c, csrc, G.Q)
+    exp = G.local_of(want, nb, rsrc, csrc, lld=al.shape[0])
+    anorm = np.abs(a0).sum(axis=1).max()
+    if mloc and nloc:
+        err = np.abs(al[:mloc, :nloc] - exp[:mloc, :nloc]).max() / (anorm * n * EPS)
+        if not err < 1.0:
+            msgs.append(f"factor error {err} (x ||A|| n eps)")
+        # everything outside the UPLO triangle of sub(A) is bit-identical to the input
+        gi = np.array([S.indxl2g(i + 1, nb, G.r, rsrc, G.P) - 1 for i in range(mloc)]); gj = np.array([S.indxl2g(j + 1, nb, G.c, csrc, G.Q) - 1 for j in range(nloc)])
+        I, J = np.meshgrid(gi, gj, indexing="ij")
+        insub = (I >= off * nb) & (J >= off * nb)
+        tri = (I >= J) if uplo == "L" else (I <= J)
+        untouched = ~(insub & tri)
+        orig = G.local_of(ag, nb, rsrc, csrc, lld=al.shape[0])
+        if not np.array_equal(al[:mloc, :nloc][untouched], orig[:mloc, :nloc][untouched]):
+            msgs.append("elements outside the triangle were modified")
+    if not np.all(al[mloc:, :] == -9923.0):
+        msgs.append("guard row overwritten")
+    if off or rsrc or csrc:
+        return msgs
+    # PDPOTRS on the factor, PDPOSV from scratch
+    bg = matrix(n, nrhs, seed=200)
+    bl, descb = G.dist(bg, nb, nbc=1); nlocb = S.numroc(nrhs, 1, G.c, 0, G.Q)
+    info = S.pdpotrs(uplo, n, nrhs, al, 1, 1, desca, bl, 1, 1, descb)
+    xg = bg.copy(order="F"); O.dpotrs(uplo, ref, xg)
+    xe = G.local_of(xg, nb, nbc=1)
+    if info != 0:
+        msgs.append(f"pdpotrs info {info}")
+    _close(msgs, "X (PDPOTRS)", bl[:mloc, :nlocb], xe[:mloc, :nlocb], 1e-10, atol=1e-14 * np.abs(xg).max())
+    al2, _ = G.dist(np.asfortranarray(a0), nb); bl2, _ = G.dist(bg, nb, nbc=1)
+    info = S.pdposv(uplo, n, nrhs, al2, 1, 1, desca[:8] + [al2.shape[0]], bl2, 1, 1, descb)
+    if info != 0:
+        msgs.append(f"pdposv info {info}")
+    _close(msgs, "X (PDPOSV)", bl2[:mloc, :nlocb], xe[:mloc, :nlocb], 1e-10, atol=1e-14 * np.abs(xg).max())
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf}
 
 
 def run(S, ctx, cases):
@@ -316,4 +381,15 @@ F2_CASES = [
     dict(kind="gemr2d", m=37, n=41, shape_a=(37, 41), shape_b=(37, 41), blk_a=(4, 4), blk_b=(6, 2), ga=(1, 3), gb=(3, 2)),
     dict(kind="gemr2d", m=20, n=25, ja=3, shape_a=(20, 30), shape_b=(25, 25), ib=6, blk_a=(2, 2), blk_b=(4, 4), z=True),
     dict(kind="gemr2d", m=1, n=1, ia=7, ja=9, ib=3, jb=2, shape_a=(10, 10), shape_b=(5, 5), blk_a=(2, 2), blk_b=(3, 3)),
+]
+
+# Cholesky: both triangles, partial last blocks, blocks wider than 32 (the diagonal block's inner loop), sub-matrices, shifted sources,
+# a matrix that is not positive definite
+F3_CASES = [
+    dict(kind="potrf", n=64, nb=8, uplo="L"), dict(kind="potrf", n=64, nb=8, uplo="U"),
+    dict(kind="potrf", n=45, nb=4, uplo="L", nrhs=3), dict(kind="potrf", n=45, nb=4, uplo="U", nrhs=3),
+    dict(kind="potrf", n=150, nb=40, uplo="L"), dict(kind="potrf", n=150, nb=40, uplo="U"),
+    dict(kind="potrf", n=100, nb=100, uplo="L"), dict(kind="potrf", n=7, nb=16, uplo="U"),
+    dict(kind="potrf", n=40, nb=8, uplo="L", off=2, rsrc=1, csrc=1), dict(kind="potrf", n=40, nb=8, uplo="U", off=1, csrc=1),
+    dict(kind="potrf", n=64, nb=8, uplo="L", notpd=37), dict(kind="potrf", n=64, nb=8, uplo="U", notpd=0), dict(kind="potrf", n=90, nb=40, uplo="L", notpd=75),
 ]

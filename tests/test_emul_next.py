@@ -20,7 +20,7 @@ def emul_lib():
     return os.path.join(EMUL, "libslb_emul.so")
 
 
-def spawn(P, Q, cases, timeout=300):
+def spawn(P, Q, cases, timeout=150):
     world = P * Q
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
@@ -51,3 +51,8 @@ def test_refinement_family(emul_lib, P, Q):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 2), (2, 3)])
 def test_redistribution(emul_lib, P, Q):
     spawn(P, Q, "F2_CASES")
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
+def test_cholesky(emul_lib, P, Q):
+    spawn(P, Q, "F3_CASES")

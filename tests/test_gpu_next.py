@@ -95,3 +95,22 @@ def test_redistribution_multi(P, Q):
     if ngpus() < P * Q:
         pytest.skip(f"needs {P * Q} GPUs")
     spawn(P, Q, next_cases.F2_CASES + F2_GPU)
+
+
+# ---- row 3: PDPOTRF / PDPOTRS / PDPOSV ----
+F3_GPU = [
+    dict(kind="potrf", n=2048, nb=256, uplo="L"), dict(kind="potrf", n=2048, nb=256, uplo="U"),
+    dict(kind="potrf", n=3000, nb=512, uplo="L", nrhs=1), dict(kind="potrf", n=1500, nb=64, uplo="U", nrhs=3),
+    dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
+]
+
+
+def test_cholesky_1x1():
+    spawn(1, 1, next_cases.F3_CASES + F3_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 1), (2, 2)])
+def test_cholesky_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.F3_CASES + F3_GPU)
