@@ -143,6 +143,10 @@ void pdpotrs_(const char *uplo, const int *n, const int *nrhs, const double *a, 
 void pdposv_(const char *uplo, const int *n, const int *nrhs, double *a, const int *ia, const int *ja, const int *desca,
              double *b, const int *ib, const int *jb, const int *descb, int *info);                                 /* SRC/pdposv.f:1-2 */
 
+/* ---- inverse from the factors of PDGETRF; WORK / IWORK: the reference's workspace protocol ---- */
+void pdgetri_(const int *n, double *a, const int *ia, const int *ja, const int *desca, const int *ipiv, double *work,
+              const int *lwork, int *iwork, const int *liwork, int *info);                                         /* SRC/pdgetri.f:1-2 */
+
 /* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
 /* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
  * a may be host or device. */

@@ -304,3 +304,10 @@ def dpotrs(uplo, a, b):
     """SRC/pdpotrs.f: b <- inv(A) b from the Cholesky factor."""
     n, nrhs = b.shape
     lib().orcn_dpotrs(C.c_char(uplo.encode()), n, nrhs, _f(a), C.c_int64(a.strides[1] // 8), _f(b), C.c_int64(b.strides[1] // 8))
+
+
+def dgetri(lu, ipiv, nb):
+    """SRC/pdgetri.f: the inverse in place from the factors of getrf(); returns INFO."""
+    n = lu.shape[0]
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    return int(lib().orcn_dgetri(n, _f(lu), C.c_int64(lu.strides[1] // 8), _p(ip), nb))

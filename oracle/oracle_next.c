@@ -325,3 +325,37 @@ void orcn_dpotrs(char uplo, int n, int nrhs, const double *a, int64_t lda, doubl
         }
     }
 }
+
+/* ---- inverse from the factors --------------------------------------------------------------------------- */
+/* SRC/pdgetri.f:300-372 with IA = JA = 1: PDTRTRI on U (INFO = i when U(i,i) is exactly zero), then for each block column from
+ * the right: save the strictly lower part of the block column (the L factor) into WORK and zero it, A(:, j:j+jb) -=
+ * A(:, j+jb:) WORK(j+jb:, :), A(:, j:j+jb) <- A(:, j:j+jb) inv(unit_lower(WORK(j:j+jb, :))); last the column interchanges
+ * backwards (PDLAPIV 'Backward', 'Columns').  Returns INFO. */
+int orcn_dgetri(int n, double *a, int64_t lda, const int *ipiv, int nb)
+{
+    for (int i = 0; i < n; ++i) if (A_(i, i) == 0.0) return i + 1;
+    /* inv(U) in place, column by column (DTRTI2 'Upper', 'Non-unit': SRC/pdtrti2.f -> dtrti2) */
+    for (int j = 0; j < n; ++j) {
+        A_(j, j) = 1.0 / A_(j, j);
+        const double ajj = -A_(j, j);
+        /* x = U(0:j, 0:j)^-1(already inverted) * a(0:j, j): DTRMV 'Upper', 'No transpose' */
+        for (int i = 0; i < j; ++i) { double s = 0.0; for (int k = i; k < j; ++k) s += A_(i, k) * A_(k, j); A_(i, j) = s; }
+        for (int i = 0; i < j; ++i) A_(i, j) *= ajj;
+    }
+    double *work = malloc((size_t)n * (size_t)nb * sizeof(double));
+    const int nn = ((n - 1) / nb) * nb;                              /* first column of the last block */
+    for (int j = nn; j >= 0; j -= nb) {
+        const int jb = n - j < nb ? n - j : nb;
+        for (int c = 0; c < jb; ++c) for (int i = j + c + 1; i < n; ++i) { work[i + (size_t)c * n] = A_(i, j + c); A_(i, j + c) = 0.0; }
+        for (int c = 0; c < jb; ++c)                                  /* PDGEMM: A(:, j+c) -= A(:, j+jb:) WORK(j+jb:, c) */
+            for (int k = j + jb; k < n; ++k) { const double wv = work[k + (size_t)c * n]; for (int i = 0; i < n; ++i) A_(i, j + c) -= A_(i, k) * wv; }
+        for (int c = jb - 1; c >= 0; --c)                             /* PDTRSM 'Right','Lower','No transpose','Unit': X L = B */
+            for (int k = c + 1; k < jb; ++k) { const double wv = work[(j + k) + (size_t)c * n]; for (int i = 0; i < n; ++i) A_(i, j + c) -= A_(i, j + k) * wv; }
+    }
+    free(work);
+    for (int j = n - 1; j >= 0; --j) {                                /* column interchanges, backwards */
+        const int p = ipiv[j] - 1;
+        if (p != j) for (int i = 0; i < n; ++i) { double t = A_(i, j); A_(i, j) = A_(i, p); A_(i, p) = t; }
+    }
+    return 0;
+}

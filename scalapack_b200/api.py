@@ -333,6 +333,21 @@ def pdposv(uplo, n, nrhs, a, ia, ja, desca, b, ib, jb, descb):
     return info.value
 
 
+# ------------------------------------------------------------------ inverse
+def pdgetri(n, a, ia, ja, desca, ipiv, lwork=None, liwork=None):
+    """SRC/pdgetri.f: sub(A) <- inv(sub(A)) from the factors of PDGETRF; returns INFO."""
+    info = C.c_int()
+    w1, iw1 = np.zeros(1), np.zeros(1, np.int32)
+    lib().pdgetri_(_i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _ipiv_ptr(ipiv), _dptr(w1), _i(-1), _ipiv_ptr(iw1), _i(-1), C.byref(info))
+    if info.value != 0:
+        return info.value
+    lw = int(w1[0]) if lwork is None else lwork
+    liw = int(iw1[0]) if liwork is None else liwork
+    work, iwork = np.zeros(max(1, lw)), np.zeros(max(1, liw), np.int32)
+    lib().pdgetri_(_i(n), _ptr(a), _i(ia), _i(ja), _desc(desca), _ipiv_ptr(ipiv), _dptr(work), _i(lw), _ipiv_ptr(iwork), _i(liw), C.byref(info))
+    return info.value
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

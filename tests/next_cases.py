@@ -337,7 +337,45 @@ def case_potrf(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf}
+def case_getri(G, cs):
+    """PDGETRI on the oracle's factors (optionally of a sub-matrix with shifted source processes)"""
+    S, msgs = G.S, []
+    n, nb, off = cs["n"], cs["nb"], cs.get("off", 0)
+    rsrc, csrc = cs.get("rsrc", 0) % G.P, cs.get("csrc", 0) % G.Q
+    ng = n + off * nb
+    a0 = matrix(n, cond=cs.get("cond"))
+    lu = a0.copy(order="F"); ipg, info = O.getrf(lu, nb)
+    if cs.get("singular") is not None:
+        lu[cs["singular"], cs["singular"]] = 0.0
+    big = O.pdmatgen(ng, ng, 55); big[off * nb:, off * nb:] = lu; big = np.asfortranarray(big)
+    al, desca = G.dist(big, nb, rsrc, csrc, extra=1)
+    mloc, nloc = S.numroc(ng, nb, G.r, rsrc, G.P), S.numroc(ng, nb, G.c, csrc, G.Q)
+    ipfull = np.concatenate([np.arange(1, off * nb + 1, dtype=np.int32), ipg + off * nb]).astype(np.int32)
+    ipl = O.ipiv_local(ng, ng, nb, G.P, G.r, ipfull, mloc + nb, rsrc=rsrc, fill=-77)
+    ia = off * nb + 1
+    info = S.pdgetri(n, al, ia, ia, desca, ipl)
+    inv = lu.copy(order="F"); info0 = O.dgetri(inv, ipg, nb)
+    if info != info0:
+        msgs.append(f"pdgetri info {info} != {info0}")
+        return msgs
+    want = big.copy(order="F")
+    if info0 == 0:
+        want[off * nb:, off * nb:] = inv
+    exp = G.local_of(want, nb, rsrc, csrc, lld=al.shape[0])
+    if mloc and nloc:
+        scale = np.abs(inv).max() if info0 == 0 else 1.0
+        cond = np.linalg.cond(a0)
+        err = np.abs(al[:mloc, :nloc] - exp[:mloc, :nloc]).max() / scale
+        if not err < 50 * n * EPS * cond:
+            msgs.append(f"inverse differs: {err} (cond {cond:.3g})")
+    if not np.all(al[mloc:, :] == -9923.0):
+        msgs.append("guard row overwritten")
+    if S.pdgetri(n, al, ia, ia, desca, ipl, lwork=0) != -8:
+        msgs.append("short LWORK not reported")
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri}
 
 
 def run(S, ctx, cases):
@@ -392,4 +430,9 @@ F3_CASES = [
     dict(kind="potrf", n=100, nb=100, uplo="L"), dict(kind="potrf", n=7, nb=16, uplo="U"),
     dict(kind="potrf", n=40, nb=8, uplo="L", off=2, rsrc=1, csrc=1), dict(kind="potrf", n=40, nb=8, uplo="U", off=1, csrc=1),
     dict(kind="potrf", n=64, nb=8, uplo="L", notpd=37), dict(kind="potrf", n=64, nb=8, uplo="U", notpd=0), dict(kind="potrf", n=90, nb=40, uplo="L", notpd=75),
+]
+
+F4_CASES = [
+    dict(kind="getri", n=64, nb=8), dict(kind="getri", n=45, nb=4, cond=2), dict(kind="getri", n=150, nb=40), dict(kind="getri", n=7, nb=16),
+    dict(kind="getri", n=100, nb=100), dict(kind="getri", n=40, nb=8, off=2, rsrc=1, csrc=1), dict(kind="getri", n=64, nb=8, singular=37),
 ]

@@ -56,3 +56,8 @@ def test_redistribution(emul_lib, P, Q):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
 def test_cholesky(emul_lib, P, Q):
     spawn(P, Q, "F3_CASES")
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
+def test_inverse(emul_lib, P, Q):
+    spawn(P, Q, "F4_CASES")

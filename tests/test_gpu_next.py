@@ -114,3 +114,21 @@ def test_cholesky_multi(P, Q):
     if ngpus() < P * Q:
         pytest.skip(f"needs {P * Q} GPUs")
     spawn(P, Q, next_cases.F3_CASES + F3_GPU)
+
+
+# ---- row 4: PDGETRI ----
+F4_GPU = [
+    dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=3000, nb=512),
+    dict(kind="getri", n=1200, nb=128, off=2, rsrc=1, csrc=1), dict(kind="getri", n=1000, nb=128, singular=900),
+]
+
+
+def test_inverse_1x1():
+    spawn(1, 1, next_cases.F4_CASES + F4_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 1), (2, 2)])
+def test_inverse_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.F4_CASES + F4_GPU)
