@@ -147,6 +147,16 @@ void pdposv_(const char *uplo, const int *n, const int *nrhs, double *a, const i
 void pdgetri_(const int *n, double *a, const int *ia, const int *ja, const int *desca, const int *ipiv, double *work,
               const int *lwork, int *iwork, const int *liwork, int *info);                                         /* SRC/pdgetri.f:1-2 */
 
+/* ---- standalone PBLAS entry points over the LU's kernels: any alignment / blocking / transposition ---- */
+void pdgemm_(const char *transa, const char *transb, const int *m, const int *n, const int *k, const double *alpha,
+             const double *a, const int *ia, const int *ja, const int *desca, const double *b, const int *ib, const int *jb,
+             const int *descb, const double *beta, double *c, const int *ic, const int *jc, const int *descc);      /* PBLAS/SRC/pdgemm_.c:21-33 */
+void pdtrsm_(const char *side, const char *uplo, const char *transa, const char *diag, const int *m, const int *n,
+             const double *alpha, const double *a, const int *ia, const int *ja, const int *desca, double *b,
+             const int *ib, const int *jb, const int *descb);                                                       /* PBLAS/SRC/pdtrsm_.c:21-31 */
+void pdtran_(const int *m, const int *n, const double *alpha, const double *a, const int *ia, const int *ja,
+             const int *desca, const double *beta, double *c, const int *ic, const int *jc, const int *descc);      /* PBLAS/SRC/pdtran_.c:21-29 */
+
 /* ---- test-driver helpers (TESTING/traditional/LIN, run on the device) ---- */
 /* PDMATGEN 'N','N' closed form into a local block-cyclic array (pdmatgen.f:448-510);
  * a may be host or device. */

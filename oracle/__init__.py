@@ -311,3 +311,23 @@ def dgetri(lu, ipiv, nb):
     n = lu.shape[0]
     ip = np.ascontiguousarray(ipiv, dtype=np.int32)
     return int(lib().orcn_dgetri(n, _f(lu), C.c_int64(lu.strides[1] // 8), _p(ip), nb))
+
+
+# ---------------------------------------------------------------- PBLAS definitions (numpy; the reference's Purpose blocks)
+def dgemm(transa, transb, alpha, a, b, beta, c):
+    """PBLAS/SRC/pdgemm_.c:36-50: C := alpha op(A) op(B) + beta C on the global sub-matrices."""
+    opa = a.T if transa.upper() in "TC" else a
+    opb = b.T if transb.upper() in "TC" else b
+    return alpha * (opa @ opb) + (beta * c if beta != 0.0 else 0.0)
+
+
+def dtrsm(side, uplo, transa, diag, alpha, a, b):
+    """PBLAS/SRC/pdtrsm_.c:34-52: X with op(A) X = alpha B (side L) or X op(A) = alpha B (side R); only the UPLO triangle of A
+    is referenced, DIAG = 'U' assumes a unit diagonal."""
+    t = np.tril(a) if uplo.upper() == "L" else np.triu(a)
+    if diag.upper() == "U":
+        t = t - np.diag(np.diag(t)) + np.eye(a.shape[0])
+    opt = t.T if transa.upper() in "TC" else t
+    if side.upper() == "L":
+        return np.linalg.solve(opt, alpha * b)
+    return np.linalg.solve(opt.T, alpha * b.T).T

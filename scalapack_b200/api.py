@@ -348,6 +348,21 @@ def pdgetri(n, a, ia, ja, desca, ipiv, lwork=None, liwork=None):
     return info.value
 
 
+# ------------------------------------------------------------------ PBLAS entry points
+def pdgemm(transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc):
+    lib().pdgemm_(transa.encode(), transb.encode(), _i(m), _i(n), _i(k), _d(alpha), _ptr(a), _i(ia), _i(ja), _desc(desca), _ptr(b), _i(ib),
+                  _i(jb), _desc(descb), _d(beta), _ptr(c), _i(ic), _i(jc), _desc(descc))
+
+
+def pdtrsm(side, uplo, transa, diag, m, n, alpha, a, ia, ja, desca, b, ib, jb, descb):
+    lib().pdtrsm_(side.encode(), uplo.encode(), transa.encode(), diag.encode(), _i(m), _i(n), _d(alpha), _ptr(a), _i(ia), _i(ja),
+                  _desc(desca), _ptr(b), _i(ib), _i(jb), _desc(descb))
+
+
+def pdtran(m, n, alpha, a, ia, ja, desca, beta, c, ic, jc, descc):
+    lib().pdtran_(_i(m), _i(n), _d(alpha), _ptr(a), _i(ia), _i(ja), _desc(desca), _d(beta), _ptr(c), _i(ic), _i(jc), _desc(descc))
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

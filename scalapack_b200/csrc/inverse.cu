@@ -21,16 +21,30 @@ namespace slb {
 
 namespace {
 
-// Lt(i, j) = Uf(i, j) / Uf(j, j) for i > j (0 elsewhere), dinv[i] = 1 / Uf(i, i), with Uf = J U J: Uf(i, j) = U(jb-1-i, jb-1-j)
+// The jb x jb triangular block Tk as a UNIT lower triangle times a diagonal: F = Tk (flip == 0, lower) or F = J Tk J (flip == 1,
+// upper; J reverses the index order: F(i, j) = Tk(jb-1-i, jb-1-j) is lower triangular).  d_j = 1 if unitdiag else F(j, j);
+// Lt(i, j) = F(i, j) / d_j for i > j (0 elsewhere); dinv[i] = 1 / d_i.  Then F^-1 = diag(dinv) Lt^-1.
 __global__ void __launch_bounds__(256)
-unit_lower_flip_kernel(int jb, const double *__restrict__ U, int64_t ldu, double *__restrict__ Lt, double *__restrict__ dinv)
+unit_tri_kernel(int jb, const double *__restrict__ Tk, int64_t ldt, int flip, int unitdiag, double *__restrict__ Lt, double *__restrict__ dinv)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= jb * jb) return;
     const int i = e % jb, j = e / jb;
-    const double djj = U[(jb - 1 - j) + (int64_t)(jb - 1 - j) * ldu];
-    Lt[i + (int64_t)j * jb] = i > j ? U[(jb - 1 - i) + (int64_t)(jb - 1 - j) * ldu] / djj : 0.0;
+    const int si = flip ? jb - 1 - i : i, sj = flip ? jb - 1 - j : j;
+    const double djj = unitdiag ? 1.0 : Tk[sj + (int64_t)sj * ldt];
+    Lt[i + (int64_t)j * jb] = i > j ? Tk[si + (int64_t)sj * ldt] / djj : 0.0;
     if (i == j) dinv[i] = 1.0 / djj;
+}
+
+// M(k, j) *= scale[k] for the jb x n block at M (ld)
+__global__ void __launch_bounds__(256)
+scale_block_rows_kernel(int jb, int64_t n, double *__restrict__ M, int64_t ld, const double *__restrict__ scale)
+{
+    const int64_t total = (int64_t)jb * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = e % jb, j = e / jb;
+        M[k + j * ld] *= scale[k];
+    }
 }
 
 // dst(jb-1-i, j) = src(i, j) * (scale ? scale[i] : 1): reverse the row order of a jb x n block (optionally scaling source row i)
@@ -68,9 +82,11 @@ __global__ void zero_diag_kernel(int jb, const double *__restrict__ Akk, int64_t
 
 }  // namespace
 
-// X <- U^-1 L^-1 X, level 3.  A: the factors (local window, first block on (rsrc, csrc)); X: local array whose ROWS are
-// distributed like the rows of A (same nb, rsrc) and which holds nlocx local columns on this process (any column distribution).
-void getrs_l3_device(Grid *g, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx, int64_t nlocx)
+// X <- T^-1 X, level 3, T = the lower / upper triangle (unit: implicit unit diagonal) of the distributed N x N matrix at A (local
+// window, first block on (rsrc, csrc)).  X: local array whose ROWS are distributed like the rows of A (same nb, rsrc) and which
+// holds nlocx local columns on this process (any column distribution).  The other triangle of A is never read.
+void tri_l3_sweep(Grid *g, bool upper, bool unit, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx,
+                  int64_t nlocx)
 {
     Runtime &r = rt();
     cudaStream_t s = r.s_main;
@@ -78,7 +94,7 @@ void getrs_l3_device(Grid *g, int N, const double *A, int64_t lld, int nb, int r
     if (P * Q > 1 && !g->nccl) g->nccl = nccl_create(g);
     NcclComms *nc = g->nccl;
     const int64_t mloc = numroc(N, nb, myrow, rsrc, P);
-    // every process column may hold a different number of X's columns: a column communicator moves jb x nlocx blocks, fine;
+    // a column communicator moves jb x nlocx blocks of X (nlocx may differ between process columns, not inside one);
     // a row communicator only ever moves pieces of A
     double *Dk = (double *)workspace("l3_D", ((size_t)nb * nb * 2 + nb) * sizeof(double));
     double *Lt = Dk + (size_t)nb * nb, *dinv = Lt + (size_t)nb * nb;
@@ -86,57 +102,67 @@ void getrs_l3_device(Grid *g, int N, const double *A, int64_t lld, int nb, int r
     double *Xk = (double *)workspace("l3_xk", (size_t)nb * (nlocx > 0 ? nlocx : 1) * 2 * sizeof(double));       // block row k of X (+ a flipped copy)
     double *Yk = Xk + (size_t)nb * (nlocx > 0 ? nlocx : 1);
     const int nblk = (N + nb - 1) / nb;
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool fwd = pass == 0;                              // pass 0: L forward, pass 1: U backward
-        for (int q = 0; q < nblk; ++q) {
-            const int k = fwd ? q : nblk - 1 - q;
-            const int j0 = k * nb, jb = N - j0 < nb ? N - j0 : nb;
-            const int pr = (rsrc + k) % P, pc = (csrc + k) % Q;
-            const int64_t lr0 = numroc(j0, nb, myrow, rsrc, P), lc0 = numroc(j0, nb, mycol, csrc, Q);
-            // ---- block row k of X on process row pr: X_k <- T_kk^-1 X_k ----
-            if (myrow == pr) {
-                const double *Tkk = A + lr0 + lc0 * lld; int64_t ldt = lld;
-                if (Q > 1) {
-                    if (mycol == pc) launch_copy2d<double>(jb, jb, Tkk, lld, Dk, jb, s);
-                    nccl_bcast(nc->row, Dk, (size_t)jb * jb, NT_F64, pc, s);
-                    Tkk = Dk; ldt = jb;
-                }
-                if (nlocx > 0) {
-                    double *Xrow = X + lr0;
-                    if (fwd) launch_dtrsm_llnu(jb, nlocx, Tkk, ldt, Xrow, ldx, s);
-                    else {
-                        SLB_LAUNCH(unit_lower_flip_kernel, (unsigned)((jb * jb + 255) / 256), 256, s, jb, Tkk, ldt, Lt, dinv);
+    const bool fwd = !upper;                                     // lower: top-down, upper: bottom-up
+    for (int q = 0; q < nblk; ++q) {
+        const int k = fwd ? q : nblk - 1 - q;
+        const int j0 = k * nb, jb = N - j0 < nb ? N - j0 : nb;
+        const int pr = (rsrc + k) % P, pc = (csrc + k) % Q;
+        const int64_t lr0 = numroc(j0, nb, myrow, rsrc, P), lc0 = numroc(j0, nb, mycol, csrc, Q);
+        // ---- block row k of X on process row pr: X_k <- T_kk^-1 X_k ----
+        if (myrow == pr) {
+            const double *Tkk = A + lr0 + lc0 * lld; int64_t ldt = lld;
+            if (Q > 1) {
+                if (mycol == pc) launch_copy2d<double>(jb, jb, Tkk, lld, Dk, jb, s);
+                nccl_bcast(nc->row, Dk, (size_t)jb * jb, NT_F64, pc, s);
+                Tkk = Dk; ldt = jb;
+            }
+            if (nlocx > 0) {
+                double *Xrow = X + lr0;
+                if (!upper && unit) launch_dtrsm_llnu(jb, nlocx, Tkk, ldt, Xrow, ldx, s);
+                else {
+                    SLB_LAUNCH(unit_tri_kernel, (unsigned)((jb * jb + 255) / 256), 256, s, jb, Tkk, ldt, upper ? 1 : 0, unit ? 1 : 0, Lt, dinv);
+                    if (!upper) {
+                        launch_dtrsm_llnu(jb, nlocx, Lt, jb, Xrow, ldx, s);
+                        SLB_LAUNCH(scale_block_rows_kernel, grid1d((int64_t)jb * nlocx), 256, s, jb, nlocx, Xrow, ldx, (const double *)dinv);
+                    } else {
                         SLB_LAUNCH(flip_rows_kernel, grid1d((int64_t)jb * nlocx), 256, s, jb, nlocx, (const double *)Xrow, ldx, Yk, (int64_t)jb, (const double *)nullptr);
                         launch_dtrsm_llnu(jb, nlocx, Lt, jb, Yk, jb, s);
                         SLB_LAUNCH(flip_rows_kernel, grid1d((int64_t)jb * nlocx), 256, s, jb, nlocx, (const double *)Yk, (int64_t)jb, Xrow, ldx, (const double *)dinv);
                     }
                 }
             }
-            // ---- the rows still to be solved: below block k (L) / above it (U) ----
-            const int64_t rbeg = fwd ? numroc(j0 + jb, nb, myrow, rsrc, P) : 0, rend = fwd ? mloc : lr0;
-            const int64_t mr = rend - rbeg;
-            // solved block row to every process row (each process column moves its own jb x nlocx block)
-            const double *Bop = X + lr0; int64_t ldb = ldx;
-            if (P > 1) {
-                if (nlocx > 0) {
-                    if (myrow == pr) launch_copy2d<double>(jb, nlocx, X + lr0, ldx, Xk, jb, s);
-                    nccl_bcast(nc->col, Xk, (size_t)jb * nlocx, NT_F64, pr, s);
-                }
-                Bop = Xk; ldb = jb;
-            }
-            // my rows of the panel of block column k along my process row (mr depends on the process row only)
-            const double *Aop = A + rbeg + lc0 * lld; int64_t lda = lld;
-            if (Q > 1) {
-                if (mr > 0) {
-                    if (mycol == pc) launch_copy2d<double>(mr, jb, A + rbeg + lc0 * lld, lld, Pan, mr, s);
-                    nccl_bcast(nc->row, Pan, (size_t)mr * jb, NT_F64, pc, s);
-                }
-                Aop = Pan; lda = mr;
-            }
-            if (mr > 0 && nlocx > 0) launch_dgemm_minus(mr, nlocx, jb, Aop, lda, Bop, ldb, X + rbeg, ldx, s);
         }
+        // ---- the rows still to be solved: below block k (lower) / above it (upper) ----
+        const int64_t rbeg = fwd ? numroc(j0 + jb, nb, myrow, rsrc, P) : 0, rend = fwd ? mloc : lr0;
+        const int64_t mr = rend - rbeg;
+        // solved block row to every process row (each process column moves its own jb x nlocx block)
+        const double *Bop = X + lr0; int64_t ldb = ldx;
+        if (P > 1) {
+            if (nlocx > 0) {
+                if (myrow == pr) launch_copy2d<double>(jb, nlocx, X + lr0, ldx, Xk, jb, s);
+                nccl_bcast(nc->col, Xk, (size_t)jb * nlocx, NT_F64, pr, s);
+            }
+            Bop = Xk; ldb = jb;
+        }
+        // my rows of the panel of block column k along my process row (mr depends on the process row only)
+        const double *Aop = A + rbeg + lc0 * lld; int64_t lda = lld;
+        if (Q > 1) {
+            if (mr > 0) {
+                if (mycol == pc) launch_copy2d<double>(mr, jb, A + rbeg + lc0 * lld, lld, Pan, mr, s);
+                nccl_bcast(nc->row, Pan, (size_t)mr * jb, NT_F64, pc, s);
+            }
+            Aop = Pan; lda = mr;
+        }
+        if (mr > 0 && nlocx > 0) launch_dgemm_minus(mr, nlocx, jb, Aop, lda, Bop, ldb, X + rbeg, ldx, s);
     }
     SLB_CUDA(cudaStreamSynchronize(s));
+}
+
+// X <- U^-1 L^-1 X with the factors of PDGETRF at A
+void getrs_l3_device(Grid *g, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx, int64_t nlocx)
+{
+    tri_l3_sweep(g, false, true, N, A, lld, nb, rsrc, csrc, X, ldx, nlocx);
+    tri_l3_sweep(g, true, false, N, A, lld, nb, rsrc, csrc, X, ldx, nlocx);
 }
 
 }  // namespace slb

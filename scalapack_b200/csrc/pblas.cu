@@ -1,0 +1,231 @@
+// pblas.cu -- SURVEY 8(f) row 4, second half: the standalone PBLAS entry points behind which the LU's kernels sit.
+//   PDGEMM (PBLAS/SRC/pdgemm_.c): sub(C) <- alpha op(sub(A)) op(sub(B)) + beta sub(C)
+//   PDTRSM (PBLAS/SRC/pdtrsm_.c): op(sub(A)) X = alpha sub(B)  or  X op(sub(A)) = alpha sub(B), sub(B) overwritten by X
+//   PDTRAN (PBLAS/SRC/pdtran_.c): sub(C) <- beta sub(C) + alpha sub(A)'
+//
+// The PBLAS accept operands with any alignment, any blocking and any transposition; the kernels want one layout.  So every
+// operand is first brought into a WORKING LAYOUT on the caller's grid -- square nb x nb blocks, first block on process (0, 0),
+// transposition already applied -- by the redistribution engine of redist.cu (gemr2d_core: index lists on the host, one packed
+// NCCL exchange), the arithmetic runs there on the FP64 tensor cores, and the result goes back the same way:
+//   PDGEMM = SUMMA over the K blocks: the block column of op(A) along the process rows, the block row of op(B) down the process
+//            columns, C -= (-alpha A_k) B_k with the LU's update kernel;
+//   PDTRSM = one level-3 triangular sweep (tri_l3_sweep, inverse.cu); a right-hand side solve is the left-hand side solve of
+//            the transposed system.
+#include "common.h"
+#include "dist.h"
+#include "kernels.cuh"
+#include "launch.h"
+#include "lu.h"
+#include "ncclw.h"
+
+namespace slb {
+
+template <typename T>
+void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr);   // redist.cu
+void tri_l3_sweep(Grid *g, bool upper, bool unit, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx,
+                  int64_t nlocx);                                                                                                            // inverse.cu
+
+namespace {
+
+// M <- f M on a rows x cols block (f == 0 stores zeros, so NaNs in an overwritten operand do not propagate, like the BLAS)
+__global__ void __launch_bounds__(256)
+scale_block_kernel(int64_t rows, int64_t cols, double *__restrict__ M, int64_t ld, double f)
+{
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % rows, j = e / rows;
+        M[i + j * ld] = f == 0.0 ? 0.0 : f * M[i + j * ld];
+    }
+}
+
+// M <- M + f S (same shape)
+__global__ void __launch_bounds__(256)
+axpy_block_kernel(int64_t rows, int64_t cols, double *__restrict__ M, int64_t ld, const double *__restrict__ S, int64_t lds, double f)
+{
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % rows, j = e / rows;
+        M[i + j * ld] += f * S[i + j * lds];
+    }
+}
+
+// An m x n matrix in the working layout on grid g: nb x nb blocks from process (0, 0), local array in a named device workspace
+struct Work {
+    double *dev = nullptr; int64_t ld = 2, mloc = 0, nloc = 0; int desc[9]; int m = 0, n = 0;
+    Work(const char *name, Grid *g, int m_, int n_, int nb)
+    {
+        m = m_; n = n_;
+        mloc = numroc(m, nb, g->myrow, 0, g->nprow); nloc = numroc(n, nb, g->mycol, 0, g->npcol);
+        ld = ((mloc > 0 ? mloc : 1) + 1) & ~(int64_t)1;
+        dev = (double *)workspace(name, (size_t)ld * (size_t)(nloc > 0 ? nloc : 1) * sizeof(double));
+        const int d[9] = { 1, g->ctxt, m, n, nb, nb, 0, 0, (int)ld };
+        memcpy(desc, d, sizeof(d));
+    }
+    // this <- op(sub(S)) with sub(S) = S(is:, js:) of shape (tr ? n x m : m x n)
+    void load(const double *S, int is, int js, const int *descs, bool tr)
+    { gemr2d_core<double>(tr ? n : m, tr ? m : n, S, is, js, descs, dev, 1, 1, desc, desc[CTXT_], tr); }
+    // sub(D) (shape tr ? n x m : m x n) <- op(this)
+    void store(double *D, int id, int jd, const int *descd, bool tr) const
+    { gemr2d_core<double>(m, n, dev, 1, 1, desc, D, id, jd, descd, desc[CTXT_], tr); }
+    void scale(double f) const
+    {
+        if (mloc > 0 && nloc > 0 && f != 1.0) SLB_LAUNCH(scale_block_kernel, grid1d(mloc * nloc), 256, rt().s_main, mloc, nloc, dev, ld, f);
+    }
+};
+
+bool is_trans(char t) { return t == 'T' || t == 'C'; }
+char upc(const char *c) { return (char)(c[0] & ~0x20); }
+
+// C <- C - A B in the working layout (A: m x k, B: k x n, C: m x n, same nb): SUMMA over the block columns of A / block rows of B
+void summa_minus(Grid *g, int nb, const Work &A, const Work &B, Work &C)
+{
+    cudaStream_t s = rt().s_main;
+    const int P = g->nprow, Q = g->npcol, K = A.n;
+    if (P * Q > 1 && !g->nccl) g->nccl = nccl_create(g);
+    NcclComms *nc = g->nccl;
+    double *Apan = (double *)workspace("pb_apan", (size_t)nb * (A.mloc > 0 ? A.mloc : 1) * sizeof(double));
+    double *Bpan = (double *)workspace("pb_bpan", (size_t)nb * (B.nloc > 0 ? B.nloc : 1) * sizeof(double));
+    for (int k0 = 0, kk = 0; k0 < K; k0 += nb, ++kk) {
+        const int kw = K - k0 < nb ? K - k0 : nb;
+        const int pc = kk % Q, pr = kk % P;
+        const int64_t lc = numroc(k0, nb, g->mycol, 0, Q), lr = numroc(k0, nb, g->myrow, 0, P);
+        const double *Aop = A.dev + lc * A.ld; int64_t lda = A.ld;
+        if (Q > 1) {
+            if (A.mloc > 0) {
+                if (g->mycol == pc) launch_copy2d<double>(A.mloc, kw, A.dev + lc * A.ld, A.ld, Apan, A.mloc, s);
+                nccl_bcast(nc->row, Apan, (size_t)A.mloc * kw, NT_F64, pc, s);
+            }
+            Aop = Apan; lda = A.mloc;
+        }
+        const double *Bop = B.dev + lr; int64_t ldb = B.ld;
+        if (P > 1) {
+            if (B.nloc > 0) {
+                if (g->myrow == pr) launch_copy2d<double>(kw, B.nloc, B.dev + lr, B.ld, Bpan, kw, s);
+                nccl_bcast(nc->col, Bpan, (size_t)kw * B.nloc, NT_F64, pr, s);
+            }
+            Bop = Bpan; ldb = kw;
+        }
+        if (C.mloc > 0 && C.nloc > 0) launch_dgemm_minus(C.mloc, C.nloc, kw, Aop, lda, Bop, ldb, C.dev, C.ld, s);
+    }
+    SLB_CUDA(cudaStreamSynchronize(s));
+}
+
+int working_nb(const int *desc) { const int nb = desc[MB_] < desc[NB_] ? desc[MB_] : desc[NB_]; return nb < 1 ? 1 : (nb > 512 ? 512 : nb); }
+
+bool bad_sub(int m, int n, int i, int j, const int *desc) { return i < 1 || j < 1 || i + m - 1 > desc[M_] || j + n - 1 > desc[N_]; }
+
+}  // namespace
+
+}  // namespace slb
+
+using namespace slb;
+
+extern "C" {
+
+void pdgemm_(const char *transa, const char *transb, const int *m_, const int *n_, const int *k_, const double *alpha_, const double *a,
+             const int *ia, const int *ja, const int *desca, const double *b, const int *ib, const int *jb, const int *descb,
+             const double *beta_, double *c, const int *ic, const int *jc, const int *descc)
+{
+    const int m = *m_, n = *n_, k = *k_, ictxt = descc[CTXT_];
+    const double alpha = *alpha_, beta = *beta_;
+    const char ta = upc(transa), tb = upc(transb);
+    int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
+    // argument checks in the order of pdgemm_.c:254-287 (PB_Cchkmat); an error is reported through PXERBLA and the call returns
+    int info = 0;
+    if (P == -1) info = -(1900 + CTXT_ + 1);
+    else if (ta != 'N' && !is_trans(ta)) info = -1;
+    else if (tb != 'N' && !is_trans(tb)) info = -2;
+    else if (m < 0) info = -3;
+    else if (n < 0) info = -4;
+    else if (k < 0) info = -5;
+    else if (desca[CTXT_] != ictxt) info = -(1000 + CTXT_ + 1);
+    else if (descb[CTXT_] != ictxt) info = -(1400 + CTXT_ + 1);
+    else if (m && k && (is_trans(ta) ? bad_sub(k, m, *ia, *ja, desca) : bad_sub(m, k, *ia, *ja, desca))) info = -8;
+    else if (k && n && (is_trans(tb) ? bad_sub(n, k, *ib, *jb, descb) : bad_sub(k, n, *ib, *jb, descb))) info = -12;
+    else if (m && n && bad_sub(m, n, *ic, *jc, descc)) info = -17;
+    if (info != 0) { xerbla(ictxt, "PDGEMM", info); return; }
+    if (m == 0 || n == 0 || ((alpha == 0.0 || k == 0) && beta == 1.0)) return;         // pdgemm_.c:295-297
+    Grid *g = grid_of(ictxt);
+    const int nb = working_nb(descc);
+    Work C("pb_C", g, m, n, nb);
+    C.load(c, *ic, *jc, descc, false);
+    C.scale(beta);
+    if (alpha != 0.0 && k > 0) {
+        Work A("pb_A", g, m, k, nb), B("pb_B", g, k, n, nb);
+        A.load(a, *ia, *ja, desca, is_trans(ta));
+        B.load(b, *ib, *jb, descb, is_trans(tb));
+        A.scale(-alpha);                                                                // C -= (-alpha A) B
+        summa_minus(g, nb, A, B, C);
+    }
+    SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+    C.store(c, *ic, *jc, descc, false);
+}
+
+void pdtrsm_(const char *side, const char *uplo, const char *transa, const char *diag, const int *m_, const int *n_, const double *alpha_,
+             const double *a, const int *ia, const int *ja, const int *desca, double *b, const int *ib, const int *jb, const int *descb)
+{
+    const int m = *m_, n = *n_, ictxt = descb[CTXT_];
+    const double alpha = *alpha_;
+    const char sd = upc(side), ul = upc(uplo), ta = upc(transa), dg = upc(diag);
+    int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
+    const int na = sd == 'L' ? m : n;                                                   // order of the triangular matrix
+    int info = 0;                                                                       // pdtrsm_.c:251-289
+    if (P == -1) info = -(1500 + CTXT_ + 1);
+    else if (sd != 'L' && sd != 'R') info = -1;
+    else if (ul != 'U' && ul != 'L') info = -2;
+    else if (ta != 'N' && !is_trans(ta)) info = -3;
+    else if (dg != 'U' && dg != 'N') info = -4;
+    else if (m < 0) info = -5;
+    else if (n < 0) info = -6;
+    else if (desca[CTXT_] != ictxt) info = -(1100 + CTXT_ + 1);
+    else if (na && bad_sub(na, na, *ia, *ja, desca)) info = -9;
+    else if (m && n && bad_sub(m, n, *ib, *jb, descb)) info = -13;
+    if (info != 0) { xerbla(ictxt, "PDTRSM", info); return; }
+    if (m == 0 || n == 0) return;
+    Grid *g = grid_of(ictxt);
+    const int nb = working_nb(descb);
+    const bool right = sd == 'R';
+    // X op(A) = alpha B  <=>  op(A)' X' = alpha B': work on X' (n x m) with the triangle op(A)'
+    Work X("pb_C", g, right ? n : m, right ? m : n, nb);
+    X.load(b, *ib, *jb, descb, right);
+    if (alpha == 0.0) { X.scale(0.0); SLB_CUDA(cudaStreamSynchronize(rt().s_main)); X.store(b, *ib, *jb, descb, right); return; }   // pdtrsm_.c:300-305
+    X.scale(alpha);
+    const bool tr_copy = is_trans(ta) != right;                                         // the working triangle is op(A) (left) or op(A)' (right)
+    const bool upper = (ul == 'U') != tr_copy;
+    Work T("pb_A", g, na, na, nb);
+    T.load(a, *ia, *ja, desca, tr_copy);
+    SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+    tri_l3_sweep(g, upper, dg == 'U', na, T.dev, T.ld, nb, 0, 0, X.dev, X.ld, X.nloc);
+    X.store(b, *ib, *jb, descb, right);
+}
+
+void pdtran_(const int *m_, const int *n_, const double *alpha_, const double *a, const int *ia, const int *ja, const int *desca,
+             const double *beta_, double *c, const int *ic, const int *jc, const int *descc)
+{
+    const int m = *m_, n = *n_, ictxt = descc[CTXT_];                                   // sub(C) is m x n, sub(A) is n x m
+    const double alpha = *alpha_, beta = *beta_;
+    int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
+    int info = 0;                                                                       // pdtran_.c:228-245
+    if (P == -1) info = -(1200 + CTXT_ + 1);
+    else if (m < 0) info = -1;
+    else if (n < 0) info = -2;
+    else if (desca[CTXT_] != ictxt) info = -(700 + CTXT_ + 1);
+    else if (m && n && bad_sub(n, m, *ia, *ja, desca)) info = -5;
+    else if (m && n && bad_sub(m, n, *ic, *jc, descc)) info = -10;
+    if (info != 0) { xerbla(ictxt, "PDTRAN", info); return; }
+    if (m == 0 || n == 0 || (alpha == 0.0 && beta == 1.0)) return;
+    Grid *g = grid_of(ictxt);
+    const int nb = working_nb(descc);
+    Work C("pb_C", g, m, n, nb);
+    C.load(c, *ic, *jc, descc, false);
+    C.scale(beta);
+    if (alpha != 0.0) {
+        Work At("pb_A", g, m, n, nb);
+        At.load(a, *ia, *ja, desca, true);
+        if (C.mloc > 0 && C.nloc > 0) SLB_LAUNCH(axpy_block_kernel, grid1d(C.mloc * C.nloc), 256, rt().s_main, C.mloc, C.nloc, C.dev, C.ld, (const double *)At.dev, At.ld, alpha);
+    }
+    SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+    C.store(c, *ic, *jc, descc, false);
+}
+
+}  // extern "C"

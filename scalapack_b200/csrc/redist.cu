@@ -18,8 +18,10 @@ namespace slb {
 
 namespace {
 
-// buf[kr + kc * nr] = A[ridx[kr] + cidx[kc] * lda]  (PACK)  or the reverse (!PACK); indices are local to the window at A
-template <typename T, bool PACK>
+// buf[kr + kc * nr] = A[ridx[kr] + cidx[kc] * lda]  (PACK)  or the reverse (!PACK); indices are local to the window at A.
+// TRANS (unpacking a transposed copy): the block arrives in the SOURCE's order, so its row kr is a column of the destination:
+// A[ridx[kc] + cidx[kr] * lda] = buf[kr + kc * nr], ridx / cidx being the destination's row / column lists.
+template <typename T, bool PACK, bool TRANS>
 __global__ void __launch_bounds__(256)
 block_move_kernel(int64_t nr, int64_t nc, const int *__restrict__ ridx, const int *__restrict__ cidx, T *__restrict__ A, int64_t lda,
                   T *__restrict__ buf)
@@ -27,7 +29,7 @@ block_move_kernel(int64_t nr, int64_t nc, const int *__restrict__ ridx, const in
     const int64_t total = nr * nc;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t kr = e % nr, kc = e / nr;
-        const int64_t a = (int64_t)ridx[kr] + (int64_t)cidx[kc] * lda;
+        const int64_t a = TRANS ? (int64_t)ridx[kc] + (int64_t)cidx[kr] * lda : (int64_t)ridx[kr] + (int64_t)cidx[kc] * lda;
         if (PACK) buf[e] = A[a]; else A[a] = buf[e];
     }
 }
@@ -69,18 +71,23 @@ Side resolve(const char *which, const std::vector<SideInfo> &all, int off, int m
     return s;
 }
 
-// lists[q] = the indices k in [0, len) (row or column numbers of the sub-matrix) that `mine` owns on side X and q owns on side Y
-void split_by_peer(int len, int mine, bool rows, const Side &X, const Side &Y, std::vector<std::vector<int>> &lists)
+// lists[q] = the indices k in [0, len) that `mine` owns on side X (as a row index if xrows, else as a column index) and that
+// process row / column q owns on side Y (as a row index if yrows, else as a column index)
+void split_by_peer(int len, int mine, bool xrows, bool yrows, const Side &X, const Side &Y, std::vector<std::vector<int>> &lists)
 {
-    lists.assign((size_t)(rows ? Y.P : Y.Q), std::vector<int>());
+    lists.assign((size_t)(yrows ? Y.P : Y.Q), std::vector<int>());
     for (int k = 0; k < len; ++k) {
-        if ((rows ? X.owner_row(k) : X.owner_col(k)) != mine) continue;
-        lists[(size_t)(rows ? Y.owner_row(k) : Y.owner_col(k))].push_back(k);
+        if ((xrows ? X.owner_row(k) : X.owner_col(k)) != mine) continue;
+        lists[(size_t)(yrows ? Y.owner_row(k) : Y.owner_col(k))].push_back(k);
     }
 }
 
+}  // namespace
+
+// sub(B) <- sub(A) (tr = false; sub(A), sub(B) m x n) or sub(B) <- sub(A)^T (tr = true; sub(A) m x n, sub(B) n x m: PDTRAN's data
+// movement, used by the PBLAS entry points of pblas.cu to bring op(A) into their working layout)
 template <typename T>
-void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt)
+void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr)
 {
     if (m == 0 || n == 0) return;                               // pdgemr.c:303-304
     Grid *gg = grid_of(gctxt);
@@ -101,17 +108,22 @@ void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     }
     std::vector<SideInfo> all((size_t)2 * np);
     if (np > 1) grid_allgather(gg, 'A', mine, all.data(), sizeof(mine)); else { all[0] = mine[0]; all[1] = mine[1]; }
-    const Side SA = resolve("A", all, 0, m, n), SB = resolve("B", all, 1, m, n);
+    const Side SA = resolve("A", all, 0, m, n), SB = resolve("B", all, 1, tr ? n : m, tr ? m : n);
 
     // ---- what I send (as a process of A's grid) and what I receive (as a process of B's grid), peer by peer ----
     std::vector<size_t> scount((size_t)np, 0), sdispl((size_t)np, 0), rcount((size_t)np, 0), rdispl((size_t)np, 0);
     std::vector<std::vector<int>> srow, scol, rrow, rcol;
-    if (gs[0]) { split_by_peer(m, gs[0]->myrow, true, SA, SB, srow); split_by_peer(n, gs[0]->mycol, false, SA, SB, scol); }
-    if (gs[1]) { split_by_peer(m, gs[1]->myrow, true, SB, SA, rrow); split_by_peer(n, gs[1]->mycol, false, SB, SA, rcol); }
+    // srow / rrow: lists over the ROW indices [0, m) of sub(A); scol / rcol: over its COLUMN indices [0, n).  Under tr a row
+    // index of sub(A) is a column index of sub(B) and vice versa.
+    if (gs[0]) { split_by_peer(m, gs[0]->myrow, true, !tr, SA, SB, srow); split_by_peer(n, gs[0]->mycol, false, tr, SA, SB, scol); }
+    if (gs[1]) {
+        split_by_peer(m, tr ? gs[1]->mycol : gs[1]->myrow, !tr, true, SB, SA, rrow);
+        split_by_peer(n, tr ? gs[1]->myrow : gs[1]->mycol, tr, false, SB, SA, rcol);
+    }
     size_t stot = 0, rtot = 0;
     for (int p = 0; p < np; ++p) {                              // buffers are laid out in the order of the global context
         const SideInfo &pa = all[(size_t)2 * p], &pb = all[(size_t)2 * p + 1];
-        if (gs[0] && pb.in) scount[(size_t)p] = srow[(size_t)pb.r].size() * scol[(size_t)pb.c].size() * sizeof(T);
+        if (gs[0] && pb.in) scount[(size_t)p] = srow[(size_t)(tr ? pb.c : pb.r)].size() * scol[(size_t)(tr ? pb.r : pb.c)].size() * sizeof(T);
         if (gs[1] && pa.in) rcount[(size_t)p] = rrow[(size_t)pa.r].size() * rcol[(size_t)pa.c].size() * sizeof(T);
         sdispl[(size_t)p] = stot; rdispl[(size_t)p] = rtot;
         stot += scount[(size_t)p]; rtot += rcount[(size_t)p];
@@ -120,7 +132,7 @@ void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     // ---- index lists on the device: local positions inside the windows of sub(A) / sub(B) ----
     AnyWindow wa, wb; memset(&wa, 0, sizeof(wa)); memset(&wb, 0, sizeof(wb));
     if (gs[0]) wa = any_window(m, n, ia, ja, desca, SA.P, SA.Q, gs[0]->myrow, gs[0]->mycol);
-    if (gs[1]) wb = any_window(m, n, ib, jb, descb, SB.P, SB.Q, gs[1]->myrow, gs[1]->mycol);
+    if (gs[1]) wb = any_window(tr ? n : m, tr ? m : n, ib, jb, descb, SB.P, SB.Q, gs[1]->myrow, gs[1]->mycol);
     std::vector<int> idx;                                       // [send rows by r1 | send cols by c1 | recv rows by r0 | recv cols by c0]
     std::vector<size_t> o_srow, o_scol, o_rrow, o_rcol;
     auto append = [&](const std::vector<std::vector<int>> &lists, std::vector<size_t> &offs, const Side &S, bool rows, int64_t loff) {
@@ -130,7 +142,7 @@ void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *
         }
     };
     append(srow, o_srow, SA, true, wa.loff_r); append(scol, o_scol, SA, false, wa.loff_c);
-    append(rrow, o_rrow, SB, true, wb.loff_r); append(rcol, o_rcol, SB, false, wb.loff_c);
+    append(rrow, o_rrow, SB, !tr, tr ? wb.loff_c : wb.loff_r); append(rcol, o_rcol, SB, tr, tr ? wb.loff_r : wb.loff_c);
     int *idx_dev = (int *)workspace("rd_idx", (idx.size() + 1) * sizeof(int));
     if (!idx.empty()) SLB_CUDA(cudaMemcpyAsync(idx_dev, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     char *sbuf = (char *)workspace("rd_send", stot + 16), *rbuf = (char *)workspace("rd_recv", rtot + 16);
@@ -141,9 +153,10 @@ void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     for (int p = 0; p < np && gs[0]; ++p) {
         if (!scount[(size_t)p]) continue;
         const SideInfo &pb = all[(size_t)2 * p + 1];
-        const int64_t nr = (int64_t)srow[(size_t)pb.r].size(), nc = (int64_t)scol[(size_t)pb.c].size();
+        const int qr = tr ? pb.c : pb.r, qc = tr ? pb.r : pb.c;
+        const int64_t nr = (int64_t)srow[(size_t)qr].size(), nc = (int64_t)scol[(size_t)qc].size();
         const unsigned grid = grid1d(nr * nc);
-        SLB_LAUNCH((block_move_kernel<T, true>), grid, 256, s, nr, nc, idx_dev + o_srow[(size_t)pb.r], idx_dev + o_scol[(size_t)pb.c], A.dev, A.ld,
+        SLB_LAUNCH((block_move_kernel<T, true, false>), grid, 256, s, nr, nc, idx_dev + o_srow[(size_t)qr], idx_dev + o_scol[(size_t)qc], A.dev, A.ld,
                    reinterpret_cast<T *>(sbuf + sdispl[(size_t)p]));
     }
     if (np > 1 && !gg->nccl) gg->nccl = nccl_create(gg);
@@ -153,14 +166,21 @@ void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *
         const SideInfo &pa = all[(size_t)2 * p];
         const int64_t nr = (int64_t)rrow[(size_t)pa.r].size(), nc = (int64_t)rcol[(size_t)pa.c].size();
         const unsigned grid = grid1d(nr * nc);
-        SLB_LAUNCH((block_move_kernel<T, false>), grid, 256, s, nr, nc, idx_dev + o_rrow[(size_t)pa.r], idx_dev + o_rcol[(size_t)pa.c], B.dev, B.ld,
-                   reinterpret_cast<T *>(rbuf + rdispl[(size_t)p]));
+        // tr: the destination's ROW list is the one over sub(A)'s column indices (rcol), its COLUMN list the one over row indices (rrow)
+        if (tr) SLB_LAUNCH((block_move_kernel<T, false, true>), grid, 256, s, nr, nc, idx_dev + o_rcol[(size_t)pa.c], idx_dev + o_rrow[(size_t)pa.r], B.dev, B.ld,
+                           reinterpret_cast<T *>(rbuf + rdispl[(size_t)p]));
+        else SLB_LAUNCH((block_move_kernel<T, false, false>), grid, 256, s, nr, nc, idx_dev + o_rrow[(size_t)pa.r], idx_dev + o_rcol[(size_t)pa.c], B.dev, B.ld,
+                        reinterpret_cast<T *>(rbuf + rdispl[(size_t)p]));
     }
     SLB_CUDA(cudaStreamSynchronize(s));
     B.download();
 }
+template void gemr2d_core<double>(int, int, const double *, int, int, const int *, double *, int, int, const int *, int, bool);
+template void gemr2d_core<zcomplex>(int, int, const zcomplex *, int, int, const int *, zcomplex *, int, int, const int *, int, bool);
 
-}  // namespace
+template <typename T>
+static void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt)
+{ gemr2d_core<T>(m, n, a, ia, ja, desca, b, ib, jb, descb, gctxt, false); }
 
 }  // namespace slb
 

@@ -375,7 +375,99 @@ def case_getri(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri}
+def _place(G, S, glob, blk, src=(0, 0), guard=-9923.0):
+    """local array (+ one guard row) and descriptor of a global matrix with mb x nb blocks from process src"""
+    mb, nb = blk
+    rs, cs_ = src[0] % G.P, src[1] % G.Q
+    mloc = S.numroc(glob.shape[0], mb, G.r, rs, G.P)
+    lld = max(1, mloc) + 1
+    al = O.scatter(np.asfortranarray(glob), mb, nb, G.P, G.Q, G.r, G.c, rsrc=rs, csrc=cs_, lld=lld)
+    al[mloc:, :] = guard
+    desc, info = S.descinit(glob.shape[0], glob.shape[1], mb, nb, rs, cs_, G.ctx, lld)
+    assert info == 0
+    return al, desc, (mb, nb, rs, cs_, mloc)
+
+
+def _expect(G, glob, lay, lld, guard=-9923.0):
+    mb, nb, rs, cs_, mloc = lay
+    e = O.scatter(np.asfortranarray(glob), mb, nb, G.P, G.Q, G.r, G.c, rsrc=rs, csrc=cs_, lld=lld)
+    e[mloc:, :] = guard
+    return e
+
+
+def case_pdgemm(G, cs):
+    """PDGEMM on sub-matrices with unrelated alignments and blockings, all four transposition pairs"""
+    S, msgs = G.S, []
+    m, n, k = cs["m"], cs["n"], cs["k"]
+    ta, tb, alpha, beta = cs.get("ta", "N"), cs.get("tb", "N"), cs.get("alpha", 1.0), cs.get("beta", 1.0)
+    (ia, ja), (ib, jb), (ic, jc) = cs.get("ija", (1, 1)), cs.get("ijb", (1, 1)), cs.get("ijc", (1, 1))
+    sa = (k, m) if ta in "TC" else (m, k); sb = (n, k) if tb in "TC" else (k, n)
+    ag = matrix(ia - 1 + sa[0] + 2, ja - 1 + sa[1] + 1, seed=11); bg = matrix(ib - 1 + sb[0] + 1, jb - 1 + sb[1] + 3, seed=12)
+    cg = matrix(ic - 1 + m + 2, jc - 1 + n + 2, seed=13)
+    al, desca, _ = _place(G, S, ag, cs.get("blk_a", (4, 4)), cs.get("src_a", (0, 0)))
+    bl, descb, _ = _place(G, S, bg, cs.get("blk_b", (4, 4)), cs.get("src_b", (0, 0)))
+    cl, descc, layc = _place(G, S, cg, cs.get("blk_c", (4, 4)), cs.get("src_c", (0, 0)))
+    a_before, b_before = al.copy(), bl.copy()
+    S.pdgemm(ta, tb, m, n, k, alpha, al, ia, ja, desca, bl, ib, jb, descb, beta, cl, ic, jc, descc)
+    want = cg.copy(order="F")
+    want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = O.dgemm(ta, tb, alpha, ag[ia - 1:ia - 1 + sa[0], ja - 1:ja - 1 + sa[1]],
+                                                         bg[ib - 1:ib - 1 + sb[0], jb - 1:jb - 1 + sb[1]], beta, cg[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n])
+    exp = _expect(G, want, layc, cl.shape[0])
+    scale = max(1.0, np.abs(want).max())
+    if not np.allclose(cl, exp, rtol=0, atol=1e-13 * scale * max(1, k)):
+        msgs.append(f"C differs by {np.abs(cl - exp).max()}")
+    outside = np.ones_like(want, dtype=bool); outside[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = False
+    mask = _expect(G, outside.astype(float), layc, cl.shape[0], guard=1.0) == 1.0
+    if not np.array_equal(cl[mask], exp[mask]):
+        msgs.append("elements outside sub(C) were modified")
+    if not (np.array_equal(al, a_before) and np.array_equal(bl, b_before)):
+        msgs.append("an input operand was modified")
+    return msgs
+
+
+def case_pdtrsm(G, cs):
+    """PDTRSM: every SIDE / UPLO / TRANS / DIAG combination on non-aligned sub-matrices; the other triangle holds NaNs"""
+    S, msgs = G.S, []
+    m, n, alpha = cs["m"], cs["n"], cs.get("alpha", 1.0)
+    side, uplo, ta, diag = cs.get("side", "L"), cs.get("uplo", "L"), cs.get("ta", "N"), cs.get("diag", "N")
+    (ia, ja), (ib, jb) = cs.get("ija", (1, 1)), cs.get("ijb", (1, 1))
+    na = m if side == "L" else n
+    tri = matrix(na, seed=21) + 2.0 * na ** 0.5 * np.eye(na)       # well conditioned triangles
+    tri = np.tril(tri) if uplo == "L" else np.triu(tri)
+    stored = tri.copy()
+    stored[np.triu_indices(na, 1) if uplo == "L" else np.tril_indices(na, -1)] = np.nan     # must never be read
+    if diag == "U":
+        stored[np.diag_indices(na)] = np.nan
+    ag = matrix(ia - 1 + na + 1, ja - 1 + na + 2, seed=22); ag[ia - 1:ia - 1 + na, ja - 1:ja - 1 + na] = stored
+    bg = matrix(ib - 1 + m + 2, jb - 1 + n + 1, seed=23)
+    al, desca, _ = _place(G, S, ag, cs.get("blk_a", (4, 4)), cs.get("src_a", (0, 0)))
+    bl, descb, layb = _place(G, S, bg, cs.get("blk_b", (4, 4)), cs.get("src_b", (0, 0)))
+    S.pdtrsm(side, uplo, ta, diag, m, n, alpha, al, ia, ja, desca, bl, ib, jb, descb)
+    want = bg.copy(order="F")
+    want[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n] = O.dtrsm(side, uplo, ta, diag, alpha, tri, bg[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n])
+    exp = _expect(G, want, layb, bl.shape[0])
+    if not np.allclose(bl, exp, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(want).max())):
+        msgs.append(f"X differs by {np.nanmax(np.abs(bl - exp))}")
+    return msgs
+
+
+def case_pdtran(G, cs):
+    S, msgs = G.S, []
+    m, n, alpha, beta = cs["m"], cs["n"], cs.get("alpha", 1.0), cs.get("beta", 0.0)
+    (ia, ja), (ic, jc) = cs.get("ija", (1, 1)), cs.get("ijc", (1, 1))
+    ag = matrix(ia - 1 + n + 1, ja - 1 + m + 2, seed=31); cg = matrix(ic - 1 + m + 2, jc - 1 + n + 1, seed=32)
+    al, desca, _ = _place(G, S, ag, cs.get("blk_a", (4, 4)), cs.get("src_a", (0, 0)))
+    cl, descc, layc = _place(G, S, cg, cs.get("blk_c", (4, 4)), cs.get("src_c", (0, 0)))
+    S.pdtran(m, n, alpha, al, ia, ja, desca, beta, cl, ic, jc, descc)
+    want = cg.copy(order="F")
+    want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = beta * cg[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] + alpha * ag[ia - 1:ia - 1 + n, ja - 1:ja - 1 + m].T
+    exp = _expect(G, want, layc, cl.shape[0])
+    if not np.allclose(cl, exp, rtol=1e-14, atol=1e-14):
+        msgs.append(f"C differs by {np.abs(cl - exp).max()}")
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri, "pdgemm": case_pdgemm, "pdtrsm": case_pdtrsm, "pdtran": case_pdtran}
 
 
 def run(S, ctx, cases):
@@ -436,3 +528,15 @@ F4_CASES = [
     dict(kind="getri", n=64, nb=8), dict(kind="getri", n=45, nb=4, cond=2), dict(kind="getri", n=150, nb=40), dict(kind="getri", n=7, nb=16),
     dict(kind="getri", n=100, nb=100), dict(kind="getri", n=40, nb=8, off=2, rsrc=1, csrc=1), dict(kind="getri", n=64, nb=8, singular=37),
 ]
+
+F4B_CASES = (
+    [dict(kind="pdgemm", m=30, n=25, k=20, ta=ta, tb=tb, alpha=1.5, beta=-0.5, ija=(3, 2), ijb=(2, 6), ijc=(4, 3), blk_a=(4, 3), blk_b=(5, 5), blk_c=(6, 6),
+          src_a=(1, 0), src_b=(0, 1), src_c=(1, 1)) for ta in "NT" for tb in "NT"]
+    + [dict(kind="pdgemm", m=32, n=32, k=32, blk_a=(8, 8), blk_b=(8, 8), blk_c=(8, 8)), dict(kind="pdgemm", m=17, n=9, k=0, beta=2.0),
+       dict(kind="pdgemm", m=17, n=9, k=5, alpha=0.0, beta=0.0), dict(kind="pdgemm", m=40, n=33, k=45, beta=0.0, blk_c=(16, 16), tb="T")]
+    + [dict(kind="pdtrsm", m=26, n=19, side=sd, uplo=ul, ta=ta, diag=dg, alpha=0.75, ija=(2, 3), ijb=(3, 2), blk_a=(4, 4), blk_b=(5, 5), src_a=(0, 1), src_b=(1, 0))
+       for sd in "LR" for ul in "LU" for ta in "NT" for dg in "NU"]
+    + [dict(kind="pdtrsm", m=64, n=8, blk_a=(8, 8), blk_b=(8, 8)), dict(kind="pdtrsm", m=12, n=50, side="R", uplo="U", alpha=0.0),
+       dict(kind="pdtrsm", m=45, n=45, side="R", uplo="L", ta="T", blk_b=(16, 16), blk_a=(16, 16))]
+    + [dict(kind="pdtran", m=23, n=31, alpha=2.0, beta=0.5, ija=(2, 2), ijc=(3, 1), blk_a=(4, 4), blk_c=(7, 3), src_a=(1, 1)), dict(kind="pdtran", m=16, n=16, blk_a=(8, 8), blk_c=(8, 8))]
+)

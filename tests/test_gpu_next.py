@@ -132,3 +132,27 @@ def test_inverse_multi(P, Q):
     if ngpus() < P * Q:
         pytest.skip(f"needs {P * Q} GPUs")
     spawn(P, Q, next_cases.F4_CASES + F4_GPU)
+
+
+# ---- row 4, second half: PDGEMM / PDTRSM / PDTRAN entry points ----
+F4B_GPU = [
+    dict(kind="pdgemm", m=2000, n=1500, k=1800, ta="N", tb="N", alpha=1.5, beta=-0.5, ija=(3, 2), ijb=(2, 6), ijc=(4, 3), blk_a=(64, 48), blk_b=(128, 128), blk_c=(256, 256)),
+    dict(kind="pdgemm", m=1024, n=1024, k=1024, ta="T", tb="N", blk_a=(128, 128), blk_b=(128, 128), blk_c=(128, 128)),
+    dict(kind="pdgemm", m=1000, n=1100, k=900, ta="N", tb="T", beta=0.0, blk_a=(100, 100), blk_b=(64, 64), blk_c=(512, 512)),
+    dict(kind="pdtrsm", m=2048, n=512, side="L", uplo="L", ta="N", diag="U", blk_a=(256, 256), blk_b=(256, 256)),
+    dict(kind="pdtrsm", m=1500, n=700, side="L", uplo="U", ta="N", diag="N", alpha=0.5, ija=(2, 3), ijb=(3, 2), blk_a=(128, 128), blk_b=(64, 64)),
+    dict(kind="pdtrsm", m=600, n=1500, side="R", uplo="L", ta="T", diag="N", blk_a=(128, 128), blk_b=(128, 128)),
+    dict(kind="pdtrsm", m=900, n=1000, side="R", uplo="U", ta="N", diag="U", blk_a=(200, 200), blk_b=(512, 512)),
+    dict(kind="pdtran", m=1500, n=2000, alpha=2.0, beta=0.5, blk_a=(64, 64), blk_c=(256, 128)),
+]
+
+
+def test_pblas_entry_points_1x1():
+    spawn(1, 1, next_cases.F4B_CASES + F4B_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 2)])
+def test_pblas_entry_points_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.F4B_CASES + F4B_GPU)
