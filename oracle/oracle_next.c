@@ -296,15 +296,18 @@ int orcn_dpotrf(char uplo, int n, double *a, int64_t lda, int nb)
         if (info != 0) return info + j0;
         if (t0 >= n) break;
         if (upper) {
-            /* A12 <- U11^-T A12 (pdpotrf.f:261), then A22 -= A12^T A12 on the upper triangle (:264) */
+            /* A12 <- U11^-T A12 (pdpotrf.f:261), then A22 -= A12^T A12 on the upper triangle (:264); loops ordered for contiguous access */
             for (int c = t0; c < n; ++c)
                 for (int k = 0; k < jb; ++k) { double s = A_(j0 + k, c); for (int q = 0; q < k; ++q) s -= A_(j0 + q, j0 + k) * A_(j0 + q, c); A_(j0 + k, c) = s / A_(j0 + k, j0 + k); }
             for (int c = t0; c < n; ++c) for (int i = t0; i <= c; ++i) { double s = A_(i, c); for (int k = 0; k < jb; ++k) s -= A_(j0 + k, i) * A_(j0 + k, c); A_(i, c) = s; }
         } else {
             /* A21 <- A21 L11^-T (pdpotrf.f:318), then A22 -= A21 A21^T on the lower triangle (:321) */
-            for (int i = t0; i < n; ++i)
-                for (int k = 0; k < jb; ++k) { double s = A_(i, j0 + k); for (int q = 0; q < k; ++q) s -= A_(i, j0 + q) * A_(j0 + k, j0 + q); A_(i, j0 + k) = s / A_(j0 + k, j0 + k); }
-            for (int c = t0; c < n; ++c) for (int i = c; i < n; ++i) { double s = A_(i, c); for (int k = 0; k < jb; ++k) s -= A_(i, j0 + k) * A_(c, j0 + k); A_(i, c) = s; }
+            for (int k = 0; k < jb; ++k) {
+                for (int q = 0; q < k; ++q) { const double lkq = A_(j0 + k, j0 + q); for (int i = t0; i < n; ++i) A_(i, j0 + k) -= A_(i, j0 + q) * lkq; }
+                const double d = A_(j0 + k, j0 + k);
+                for (int i = t0; i < n; ++i) A_(i, j0 + k) /= d;
+            }
+            for (int c = t0; c < n; ++c) for (int k = 0; k < jb; ++k) { const double wv = A_(c, j0 + k); for (int i = c; i < n; ++i) A_(i, c) -= A_(i, j0 + k) * wv; }
         }
     }
     return 0;

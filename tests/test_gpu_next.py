@@ -100,7 +100,7 @@ def test_redistribution_multi(P, Q):
 # ---- row 3: PDPOTRF / PDPOTRS / PDPOSV ----
 F3_GPU = [
     dict(kind="potrf", n=2048, nb=256, uplo="L"), dict(kind="potrf", n=2048, nb=256, uplo="U"),
-    dict(kind="potrf", n=3000, nb=512, uplo="L", nrhs=1), dict(kind="potrf", n=1500, nb=64, uplo="U", nrhs=3),
+    dict(kind="potrf", n=2500, nb=512, uplo="L", nrhs=1), dict(kind="potrf", n=1500, nb=64, uplo="U", nrhs=3),
     dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
 ]
 
@@ -118,7 +118,7 @@ def test_cholesky_multi(P, Q):
 
 # ---- row 4: PDGETRI ----
 F4_GPU = [
-    dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=3000, nb=512),
+    dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=2200, nb=512),
     dict(kind="getri", n=1200, nb=128, off=2, rsrc=1, csrc=1), dict(kind="getri", n=1000, nb=128, singular=900),
 ]
 

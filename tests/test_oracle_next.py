@@ -118,3 +118,54 @@ def test_dgesvx_singular(O):
     ipiv, r, c = np.zeros(n, np.int32), np.zeros(n), np.zeros(n)
     eq, rcond, ferr, berr, info = O.dgesvx("N", "N", a.copy(order="F"), af, ipiv, "N", r, c, b.copy(order="F"), x)
     assert info > 0 and (rcond == 0.0 or info == n + 1)
+
+
+@pytest.mark.parametrize("uplo", ["L", "U"])
+@pytest.mark.parametrize("n,nb", [(1, 4), (7, 3), (64, 8), (150, 40), (100, 100)])
+def test_dpotrf_dpotrs(O, uplo, n, nb):
+    m = rnd(n, seed=n)
+    a = np.asfortranarray(m @ m.T + n * np.eye(n))
+    f = a.copy(order="F")
+    assert O.dpotrf(uplo, f, nb) == 0
+    c, info = lapack.dpotrf(a, lower=(uplo == "L"))
+    tri = np.tril if uplo == "L" else np.triu
+    np.testing.assert_allclose(tri(f), tri(c), rtol=1e-12, atol=1e-13 * np.abs(c).max())
+    other = (np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1))
+    assert np.array_equal(f[other], a[other])                   # the other triangle is not referenced
+    b = rnd(n, 3, seed=5); x = b.copy(order="F")
+    O.dpotrs(uplo, f, x)
+    np.testing.assert_allclose(x, lapack.dpotrs(c, b, lower=(uplo == "L"))[0], rtol=1e-10, atol=1e-13)
+    bad = a.copy(order="F"); k = n // 2; bad[k, k] = -1.0
+    assert lapack.dpotrf(bad, lower=(uplo == "L"))[1] == k + 1 == O.dpotrf(uplo, bad, nb)
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (7, 3), (64, 8), (150, 40), (33, 64)])
+def test_dgetri(O, n, nb):
+    a = rnd(n, seed=3 * n)
+    lu = a.copy(order="F"); ip, info = O.getrf(lu, nb)
+    inv = lu.copy(order="F")
+    assert O.dgetri(inv, ip, nb) == 0
+    inv2, info2 = lapack.dgetri(lu, ip - 1)
+    assert info2 == 0
+    np.testing.assert_allclose(inv, inv2, rtol=1e-9, atol=1e-12 * np.abs(inv2).max())
+    if n > 2:
+        lu[2, 2] = 0.0
+        assert O.dgetri(lu.copy(order="F"), ip, nb) == 3 == lapack.dgetri(lu, ip - 1)[1]
+
+
+def test_pblas_definitions(O):
+    a, b, c = rnd(5, 4, seed=1), rnd(4, 6, seed=2), rnd(5, 6, seed=3)
+    np.testing.assert_allclose(O.dgemm("N", "N", 2.0, a, b, 0.5, c), 2.0 * a @ b + 0.5 * c)
+    np.testing.assert_allclose(O.dgemm("T", "T", 1.0, a.T.copy(), b.T.copy(), 0.0, np.full_like(c, np.nan)), a @ b)
+    t = rnd(5, seed=4) + 3 * np.eye(5); bb = rnd(5, 3, seed=5)
+    for side in "LR":
+        for uplo in "LU":
+            for ta in "NT":
+                for dg in "NU":
+                    tri = np.tril(t) if uplo == "L" else np.triu(t)
+                    if dg == "U":
+                        tri = tri - np.diag(np.diag(tri)) + np.eye(5)
+                    op = tri.T if ta == "T" else tri
+                    rhs = bb if side == "L" else bb.T.copy()
+                    x = O.dtrsm(side, uplo, ta, dg, 0.5, t, rhs)
+                    np.testing.assert_allclose(op @ x if side == "L" else x @ op, 0.5 * rhs, atol=1e-12)
