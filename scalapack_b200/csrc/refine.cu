@@ -50,16 +50,28 @@ matvec_reduce_kernel(int64_t mloc, int64_t nloc, const double *__restrict__ A, i
     const int64_t k0 = sl * chunk, k1 = (k0 + chunk < red) ? k0 + chunk : red;
     const double *ap = ROWS ? A + idx : A + idx * lda;
     const int64_t step = ROWS ? lda : 1;
-    double acc = 0.0, acc2 = 0.0;
-    for (int64_t k = k0; k < k1; ++k) {
-        const double a = ap[k * step];
-        const double xv = x ? x[k] : 1.0;
-        if (MODE == RM_DOTABS) { acc = fma(a, xv, acc); acc2 = fma(fabs(a), fabs(xv), acc2); }
-        else if (MODE == RM_MAX) { const double t = fabs(a) * fabs(xv); if (t > acc || t != t) acc = t; }
-        else { const double t = fabs(a) * xv; acc = fma(t, t, acc); }
+    // four independent chains (k, k+1, k+2, k+3 modulo 4): four loads in flight per thread, a fixed summation order
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 }, acc2[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int64_t kb = k0; kb < k1; kb += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = kb + u;
+            if (k >= k1) break;
+            const double a = ap[k * step];
+            const double xv = x ? x[k] : 1.0;
+            if (MODE == RM_DOTABS) { acc[u] = fma(a, xv, acc[u]); acc2[u] = fma(fabs(a), fabs(xv), acc2[u]); }
+            else if (MODE == RM_MAX) { const double t = fabs(a) * fabs(xv); if (t > acc[u] || t != t) acc[u] = t; }
+            else { const double t = fabs(a) * xv; acc[u] = fma(t, t, acc[u]); }
+        }
     }
-    part[sl * len + idx] = acc;
-    if (MODE == RM_DOTABS) part[(nsl + sl) * len + idx] = acc2;
+    double r0, r1;
+    if (MODE == RM_MAX) {
+        r0 = acc[0];
+        for (int u = 1; u < 4; ++u) if (acc[u] > r0 || acc[u] != acc[u]) r0 = acc[u];
+        r1 = 0.0;
+    } else { r0 = (acc[0] + acc[1]) + (acc[2] + acc[3]); r1 = (acc2[0] + acc2[1]) + (acc2[2] + acc2[3]); }
+    part[sl * len + idx] = r0;
+    if (MODE == RM_DOTABS) part[(nsl + sl) * len + idx] = r1;
 }
 
 // A[il, c] *= (r ? r[il] : 1) * (c ? cs[c] : 1): the three branches of PDLAQGE (pdlaqge.f:223-262; CJ*R(I) first, then * A)
