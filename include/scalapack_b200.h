@@ -172,6 +172,11 @@ void slb200_zmatgen64(const int *ictxt, const int64_t *m, const int64_t *n, cons
 double slb200_pdlaschk(const int *ictxt, const int *n, const int *nrhs, const double *x, const int *descx,
                        const int *desca, const uint64_t *aseed, const uint64_t *bseed, const int *gen);
 
+/* PDGETRS through the level-3 distributed path (block-cyclic copy of sub(B), tensor-core sweeps) whatever NRHS is; pdgetrs_ itself
+ * switches to it when NRHS exceeds the option "solve_l3_min_nrhs" (default 64).  Real; TRANS = 'N' / 'T'. */
+void slb200_pdgetrs_l3(const char *trans, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja,
+                       const int *desca, const int *ipiv, double *b, const int *ib, const int *jb, const int *descb, int *info);
+
 /* ---- runtime controls / introspection (not in the reference) ------------- */
 int  slb200_device(void);                  /* CUDA device this process drives, -1 if none */
 int  slb200_has_cuda(void);                /* 1 when a usable sm_100 device is present     */

@@ -13,7 +13,7 @@ from .api import (  # noqa: F401
     numroc, indxg2p, indxg2l, indxl2g, infog2l, descinit, iceil, ilcm, chk1mat,
     pdgetrf, pdgetrs, pdgesv, pzgetrf, pzgetrs, pzgesv,
     pdlange, pdgeequ, pdlaqge, pdgecon, pdgerfs, pdgesvx, pdgemr2d, pzgemr2d,
-    pdpotrf, pdpotrs, pdposv, pdgetri, pdgemm, pdtrsm, pdtran,
+    pdpotrf, pdpotrs, pdposv, pdgetri, pdgemm, pdtrsm, pdtran, pdgetrs_l3,
     pdmatgen, matgen64, zmatgen64, pdlaschk,
     set_option, get_counter, reset_counters, last_factor_ms, last_solve_ms, last_update,
     DTYPE_, CTXT_, M_, N_, MB_, NB_, RSRC_, CSRC_, LLD_,

@@ -363,6 +363,14 @@ def pdtran(m, n, alpha, a, ia, ja, desca, beta, c, ic, jc, descc):
     lib().pdtran_(_i(m), _i(n), _d(alpha), _ptr(a), _i(ia), _i(ja), _desc(desca), _d(beta), _ptr(c), _i(ic), _i(jc), _desc(descc))
 
 
+def pdgetrs_l3(trans, n, nrhs, a, ia, ja, desca, ipiv, b, ib, jb, descb):
+    """PDGETRS forced through the level-3 (many right-hand sides) path."""
+    info = C.c_int()
+    lib().slb200_pdgetrs_l3(trans.encode(), _i(n), _i(nrhs), _ptr(a), _i(ia), _i(ja), _desc(desca), _ipiv_ptr(ipiv), _ptr(b), _i(ib), _i(jb),
+                            _desc(descb), C.byref(info))
+    return info.value
+
+
 # ------------------------------------------------------------------ test-driver helpers
 def pdmatgen(ictxt, m, n, mb, nb, a, lda, iarow=0, iacol=0, iseed=100):
     lib().slb200_pdmatgen(_i(ictxt), _i(m), _i(n), _i(mb), _i(nb), _ptr(a), _i(lda), _i(iarow), _i(iacol), _i(iseed))

@@ -8,6 +8,11 @@
 #include "stage.h"
 #include "entry.h"
 
+namespace slb {
+void getrs_l3_entry(Grid *g, char trans, int n, int nrhs, const double *Adev, int64_t lda, int nb, int rsrc, int csrc, const int *ipg,
+                    double *b, int ib, int jb, const int *descb);   // pblas.cu
+}
+
 #include <cmath>
 
 namespace slb {
@@ -153,6 +158,16 @@ static void getrs_entry(const char *name, const char *trans, const int *n, const
     std::vector<int> ipg;
     gather_global_ipiv(g, *n, nb, w.rsrc, ipiv + w.loff_r, *ia - 1, ipg);
     DevWindow<T> A("stage_A", const_cast<T *>(a), desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
+    if constexpr (sizeof(T) == sizeof(double)) {
+        // many right-hand sides (the PB_CptrsmAB case): block-cyclic copy of sub(B), level-3 sweeps on the tensor cores (pblas.cu)
+        const int64_t l3min = opt("solve_l3_min_nrhs", 64);
+        if (l3min > 0 && *nrhs > l3min) {
+            A.upload_all();
+            getrs_l3_entry(g, t == 'N' ? 'N' : 'T', *n, *nrhs, reinterpret_cast<const double *>(A.dev), A.ld, nb, w.rsrc, w.csrc, ipg.data(),
+                           reinterpret_cast<double *>(b), *ib, *jb, descb);
+            return;
+        }
+    }
     DevWindow<T> B("stage_B", b, descb[LLD_], wb.loff_r, 0, w.mloc, wb.nloc_all);
     A.upload_all(); B.upload_all();
     getrs_device<T>(g, t, *n, *nrhs, A.dev, A.ld, nb, w.rsrc, w.csrc, ipg.data(), B.dev, B.ld, descb[NB_], descb[CSRC_], *jb - 1, wb.nloc_all);

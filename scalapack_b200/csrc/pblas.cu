@@ -21,9 +21,11 @@
 namespace slb {
 
 template <typename T>
-void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr);   // redist.cu
+void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr,
+                 const int *rowmap);                                                                                                        // redist.cu
 void tri_l3_sweep(Grid *g, bool upper, bool unit, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx,
                   int64_t nlocx);                                                                                                            // inverse.cu
+void getrs_l3_device(Grid *g, int N, const double *A, int64_t lld, int nb, int rsrc, int csrc, double *X, int64_t ldx, int64_t nlocx);      // inverse.cu
 
 namespace {
 
@@ -52,21 +54,22 @@ axpy_block_kernel(int64_t rows, int64_t cols, double *__restrict__ M, int64_t ld
 // An m x n matrix in the working layout on grid g: nb x nb blocks from process (0, 0), local array in a named device workspace
 struct Work {
     double *dev = nullptr; int64_t ld = 2, mloc = 0, nloc = 0; int desc[9]; int m = 0, n = 0;
-    Work(const char *name, Grid *g, int m_, int n_, int nb)
+    // rs: the process row that holds the first row block (0 for the PBLAS entry points; the factors' own for PDGETRS)
+    Work(const char *name, Grid *g, int m_, int n_, int nb, int rs = 0)
     {
         m = m_; n = n_;
-        mloc = numroc(m, nb, g->myrow, 0, g->nprow); nloc = numroc(n, nb, g->mycol, 0, g->npcol);
+        mloc = numroc(m, nb, g->myrow, rs, g->nprow); nloc = numroc(n, nb, g->mycol, 0, g->npcol);
         ld = ((mloc > 0 ? mloc : 1) + 1) & ~(int64_t)1;
         dev = (double *)workspace(name, (size_t)ld * (size_t)(nloc > 0 ? nloc : 1) * sizeof(double));
-        const int d[9] = { 1, g->ctxt, m, n, nb, nb, 0, 0, (int)ld };
+        const int d[9] = { 1, g->ctxt, m, n, nb, nb, rs, 0, (int)ld };
         memcpy(desc, d, sizeof(d));
     }
-    // this <- op(sub(S)) with sub(S) = S(is:, js:) of shape (tr ? n x m : m x n)
-    void load(const double *S, int is, int js, const int *descs, bool tr)
-    { gemr2d_core<double>(tr ? n : m, tr ? m : n, S, is, js, descs, dev, 1, 1, desc, desc[CTXT_], tr); }
-    // sub(D) (shape tr ? n x m : m x n) <- op(this)
-    void store(double *D, int id, int jd, const int *descd, bool tr) const
-    { gemr2d_core<double>(m, n, dev, 1, 1, desc, D, id, jd, descd, desc[CTXT_], tr); }
+    // this <- op(sub(S)) with sub(S) = S(is:, js:) of shape (tr ? n x m : m x n); rowmap: my row k <- row rowmap[k] of sub(S)
+    void load(const double *S, int is, int js, const int *descs, bool tr, const int *rowmap = nullptr)
+    { gemr2d_core<double>(tr ? n : m, tr ? m : n, S, is, js, descs, dev, 1, 1, desc, desc[CTXT_], tr, rowmap); }
+    // sub(D) (shape tr ? n x m : m x n) <- op(this); rowmap: row k of sub(D) <- my row rowmap[k]
+    void store(double *D, int id, int jd, const int *descd, bool tr, const int *rowmap = nullptr) const
+    { gemr2d_core<double>(m, n, dev, 1, 1, desc, D, id, jd, descd, desc[CTXT_], tr, rowmap); }
     void scale(double f) const
     {
         if (mloc > 0 && nloc > 0 && f != 1.0) SLB_LAUNCH(scale_block_kernel, grid1d(mloc * nloc), 256, rt().s_main, mloc, nloc, dev, ld, f);
@@ -116,9 +119,58 @@ bool bad_sub(int m, int n, int i, int j, const int *desc) { return i < 1 || j < 
 
 }  // namespace
 
+// PDGETRS for MANY right-hand sides (the PB_CptrsmAB case of the reference's PDTRSM): instead of replicating sub(B) on every GPU,
+// sub(B) is redistributed -- with the row interchanges applied on the way -- into a block-cyclic copy whose rows are aligned with the
+// factors, both sweeps run at level 3 on the tensor cores (tri_l3_sweep), and the solution is redistributed back.
+//   'N': X = P B;  X <- U^-1 L^-1 X.       'T': X = B;  X <- L^-T U^-T X on a transposed copy of the factors;  B = P' X.
+// Adev: device window of the factors (ld, first block on (rsrc, csrc)); ipg: N pivots, 1-based, relative to sub(A).
+void getrs_l3_entry(Grid *g, char trans, int n, int nrhs, const double *Adev, int64_t lda, int nb, int rsrc, int csrc, const int *ipg,
+                    double *b, int ib, int jb, const int *descb)
+{
+    std::vector<int> perm((size_t)n), inv((size_t)n);
+    for (int i = 0; i < n; ++i) perm[(size_t)i] = i;
+    for (int i = 0; i < n; ++i) { const int p = ipg[i] - 1; if (p != i) { const int t = perm[(size_t)i]; perm[(size_t)i] = perm[(size_t)p]; perm[(size_t)p] = t; } }
+    for (int i = 0; i < n; ++i) inv[(size_t)perm[(size_t)i]] = i;
+    if (trans == 'N') {
+        Work X("pb_C", g, n, nrhs, nb, rsrc);
+        X.load(b, ib, jb, descb, false, perm.data());             // row i of P b is row perm[i] of b
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        getrs_l3_device(g, n, Adev, lda, nb, rsrc, csrc, X.dev, X.ld, X.nloc);
+        X.store(b, ib, jb, descb, false);
+    } else {
+        const int descf[9] = { 1, g->ctxt, n, n, nb, nb, rsrc, csrc, (int)lda };
+        Work F("pb_A", g, n, n, nb), X("pb_C", g, n, nrhs, nb);
+        F.load(Adev, 1, 1, descf, true);                           // F = (L \ U)': lower triangle U' (general diagonal), upper L' (unit)
+        X.load(b, ib, jb, descb, false);
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        tri_l3_sweep(g, false, false, n, F.dev, F.ld, nb, 0, 0, X.dev, X.ld, X.nloc);
+        tri_l3_sweep(g, true, true, n, F.dev, F.ld, nb, 0, 0, X.dev, X.ld, X.nloc);
+        X.store(b, ib, jb, descb, false, inv.data());             // x = P' z: row perm[i] of x is row i of z
+    }
+}
+
 }  // namespace slb
 
 using namespace slb;
+
+// PDGETRS through the level-3 path whatever NRHS is (pdgetrs_ itself switches to it above the option solve_l3_min_nrhs); real, TRANS = N / T
+extern "C" void slb200_pdgetrs_l3(const char *trans, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja, const int *desca,
+                                  const int *ipiv, double *b, const int *ib, const int *jb, const int *descb, int *info)
+{
+    const int ictxt = desca[CTXT_];
+    int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
+    *info = 0;
+    if (P == -1) { *info = -(700 + CTXT_ + 1); return; }
+    if (*n == 0 || *nrhs == 0) return;
+    const char t = (char)(trans[0] & ~0x20);
+    if ((*ia - 1) % desca[MB_] || (*ja - 1) % desca[NB_] || desca[MB_] != desca[NB_] || (t != 'N' && t != 'T' && t != 'C')) { *info = -1; return; }
+    Grid *g = grid_of(ictxt);
+    const Window w = window(*n, *n, *ia, *ja, desca, P, Q, myrow, mycol);
+    std::vector<int> ipg;
+    gather_global_ipiv(g, *n, desca[NB_], w.rsrc, ipiv + w.loff_r, *ia - 1, ipg);
+    StageMat<double> A("stage_A", a, desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
+    getrs_l3_entry(g, t == 'N' ? 'N' : 'T', *n, *nrhs, A.dev, A.ld, desca[NB_], w.rsrc, w.csrc, ipg.data(), b, *ib, *jb, descb);
+}
 
 extern "C" {
 

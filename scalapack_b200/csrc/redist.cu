@@ -14,6 +14,8 @@
 #include "launch.h"
 #include "ncclw.h"
 
+#include <algorithm>
+
 namespace slb {
 
 namespace {
@@ -72,23 +74,34 @@ Side resolve(const char *which, const std::vector<SideInfo> &all, int off, int m
 }
 
 // lists[q] = the indices k in [0, len) that `mine` owns on side X (as a row index if xrows, else as a column index) and that
-// process row / column q owns on side Y (as a row index if yrows, else as a column index)
-void split_by_peer(int len, int mine, bool xrows, bool yrows, const Side &X, const Side &Y, std::vector<std::vector<int>> &lists)
+// process row / column q owns on side Y (as a row index if yrows, else as a column index).  ymap (optional): index k of side X
+// corresponds to index ymap[k] of side Y (a row permutation between source and destination); the lists are then ordered by
+// `order[k]` (the index on the SOURCE side), so that sender and receiver enumerate a block in the same order.
+void split_by_peer(int len, int mine, bool xrows, bool yrows, const Side &X, const Side &Y, std::vector<std::vector<int>> &lists,
+                   const int *ymap = nullptr, bool order_by_y = false)
 {
     lists.assign((size_t)(yrows ? Y.P : Y.Q), std::vector<int>());
     for (int k = 0; k < len; ++k) {
         if ((xrows ? X.owner_row(k) : X.owner_col(k)) != mine) continue;
-        lists[(size_t)(yrows ? Y.owner_row(k) : Y.owner_col(k))].push_back(k);
+        const int ky = ymap ? ymap[k] : k;
+        lists[(size_t)(yrows ? Y.owner_row(ky) : Y.owner_col(ky))].push_back(k);
     }
+    if (ymap && order_by_y)
+        for (auto &l : lists) std::sort(l.begin(), l.end(), [&](int a_, int b_) { return ymap[a_] < ymap[b_]; });
 }
 
 }  // namespace
 
 // sub(B) <- sub(A) (tr = false; sub(A), sub(B) m x n) or sub(B) <- sub(A)^T (tr = true; sub(A) m x n, sub(B) n x m: PDTRAN's data
 // movement, used by the PBLAS entry points of pblas.cu to bring op(A) into their working layout)
+// rowmap (optional, tr = false only): row k of sub(B) <- row rowmap[k] of sub(A) (a row permutation on the way: PDLAPIV's movement)
 template <typename T>
-void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr)
+void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt, bool tr,
+                 const int *rowmap)
 {
+    if (rowmap && tr) fatal("gemr2d_core: a row map cannot be combined with a transposition");
+    std::vector<int> invmap;                                    // source row i goes to destination row invmap[i]
+    if (rowmap) { invmap.resize((size_t)m); for (int k = 0; k < m; ++k) invmap[(size_t)rowmap[k]] = k; }
     if (m == 0 || n == 0) return;                               // pdgemr.c:303-304
     Grid *gg = grid_of(gctxt);
     if (!gg || !gg->in_grid()) return;                          // not a member of the global context: nothing to do, nothing to wait for
@@ -115,9 +128,11 @@ void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     std::vector<std::vector<int>> srow, scol, rrow, rcol;
     // srow / rrow: lists over the ROW indices [0, m) of sub(A); scol / rcol: over its COLUMN indices [0, n).  Under tr a row
     // index of sub(A) is a column index of sub(B) and vice versa.
-    if (gs[0]) { split_by_peer(m, gs[0]->myrow, true, !tr, SA, SB, srow); split_by_peer(n, gs[0]->mycol, false, tr, SA, SB, scol); }
+    // with a row map both sides order a block's rows by their SOURCE index: the sender's lists are over source rows anyway,
+    // the receiver's lists are over destination rows k and are sorted by rowmap[k]
+    if (gs[0]) { split_by_peer(m, gs[0]->myrow, true, !tr, SA, SB, srow, rowmap ? invmap.data() : nullptr, false); split_by_peer(n, gs[0]->mycol, false, tr, SA, SB, scol); }
     if (gs[1]) {
-        split_by_peer(m, tr ? gs[1]->mycol : gs[1]->myrow, !tr, true, SB, SA, rrow);
+        split_by_peer(m, tr ? gs[1]->mycol : gs[1]->myrow, !tr, true, SB, SA, rrow, rowmap, true);
         split_by_peer(n, tr ? gs[1]->myrow : gs[1]->mycol, tr, false, SB, SA, rcol);
     }
     size_t stot = 0, rtot = 0;
@@ -148,8 +163,8 @@ void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     char *sbuf = (char *)workspace("rd_send", stot + 16), *rbuf = (char *)workspace("rd_recv", rtot + 16);
 
     // ---- pack, exchange, unpack ----
-    StageMat<T> A("stage_A", gs[0] ? a : nullptr, gs[0] ? desca[LLD_] : 1, wa.loff_r, wa.loff_c, gs[0] ? wa.mloc : 0, gs[0] ? wa.nloc : 0);
-    StageMat<T> B("stage_A2", gs[1] ? b : nullptr, gs[1] ? descb[LLD_] : 1, wb.loff_r, wb.loff_c, gs[1] ? wb.mloc : 0, gs[1] ? wb.nloc : 0, false);
+    StageMat<T> A("rd_stage_src", gs[0] ? a : nullptr, gs[0] ? desca[LLD_] : 1, wa.loff_r, wa.loff_c, gs[0] ? wa.mloc : 0, gs[0] ? wa.nloc : 0);
+    StageMat<T> B("rd_stage_dst", gs[1] ? b : nullptr, gs[1] ? descb[LLD_] : 1, wb.loff_r, wb.loff_c, gs[1] ? wb.mloc : 0, gs[1] ? wb.nloc : 0, false);
     for (int p = 0; p < np && gs[0]; ++p) {
         if (!scount[(size_t)p]) continue;
         const SideInfo &pb = all[(size_t)2 * p + 1];
@@ -175,12 +190,12 @@ void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *
     SLB_CUDA(cudaStreamSynchronize(s));
     B.download();
 }
-template void gemr2d_core<double>(int, int, const double *, int, int, const int *, double *, int, int, const int *, int, bool);
-template void gemr2d_core<zcomplex>(int, int, const zcomplex *, int, int, const int *, zcomplex *, int, int, const int *, int, bool);
+template void gemr2d_core<double>(int, int, const double *, int, int, const int *, double *, int, int, const int *, int, bool, const int *);
+template void gemr2d_core<zcomplex>(int, int, const zcomplex *, int, int, const int *, zcomplex *, int, int, const int *, int, bool, const int *);
 
 template <typename T>
 static void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt)
-{ gemr2d_core<T>(m, n, a, ia, ja, desca, b, ib, jb, descb, gctxt, false); }
+{ gemr2d_core<T>(m, n, a, ia, ja, desca, b, ib, jb, descb, gctxt, false, nullptr); }
 
 }  // namespace slb
 

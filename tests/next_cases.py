@@ -467,7 +467,35 @@ def case_pdtran(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri, "pdgemm": case_pdgemm, "pdtrsm": case_pdtrsm, "pdtran": case_pdtran}
+def case_getrs_l3(G, cs):
+    """PDGETRS through the level-3 (many right-hand sides) path: TRANS = N / T, sub-matrix factors, B with its own column blocking"""
+    S, msgs = G.S, []
+    n, nb, nrhs, trans, off = cs["n"], cs["nb"], cs["nrhs"], cs.get("trans", "N"), cs.get("off", 0)
+    rsrc, csrc = cs.get("rsrc", 0) % G.P, cs.get("csrc", 0) % G.Q
+    nbb = cs.get("nbb", nb)
+    ng = n + off * nb
+    a0 = matrix(n, cond=cs.get("cond")); lu = a0.copy(order="F"); ipg, info = O.getrf(lu, nb)
+    big = O.pdmatgen(ng, ng, 55); big[off * nb:, off * nb:] = lu; big = np.asfortranarray(big)
+    al, desca = G.dist(big, nb, rsrc, csrc)
+    mloc = S.numroc(ng, nb, G.r, rsrc, G.P)
+    ipfull = np.concatenate([np.arange(1, off * nb + 1, dtype=np.int32), ipg + off * nb]).astype(np.int32)
+    ipl = O.ipiv_local(ng, ng, nb, G.P, G.r, ipfull, mloc + nb, rsrc=rsrc, fill=-77)
+    bg = matrix(ng, nrhs + 3, seed=200)                          # sub(B) = B(off*nb+1 :, 3 : 3+nrhs)
+    bl, descb, layb = _place(G, S, bg, (nb, nbb), (rsrc, 1))
+    ia = off * nb + 1
+    f = S.pdgetrs if cs.get("entry") else S.pdgetrs_l3
+    info = f(trans, n, nrhs, al, ia, ia, desca, ipl, bl, ia, 3, descb)
+    x = np.asfortranarray(bg[off * nb:, 2:2 + nrhs].copy()); O.getrs(lu, ipg, x, trans)
+    want = bg.copy(order="F"); want[off * nb:, 2:2 + nrhs] = x
+    exp = _expect(G, want, layb, bl.shape[0])
+    if info != 0:
+        msgs.append(f"info {info}")
+    if not np.allclose(bl, exp, rtol=1e-9, atol=1e-12 * np.abs(x).max()):
+        msgs.append(f"X differs by {np.abs(bl - exp).max()} (|x| max {np.abs(x).max()})")
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri, "pdgemm": case_pdgemm, "pdtrsm": case_pdtrsm, "pdtran": case_pdtran, "getrs_l3": case_getrs_l3}
 
 
 def run(S, ctx, cases):
@@ -540,3 +568,10 @@ F4B_CASES = (
        dict(kind="pdtrsm", m=45, n=45, side="R", uplo="L", ta="T", blk_b=(16, 16), blk_a=(16, 16))]
     + [dict(kind="pdtran", m=23, n=31, alpha=2.0, beta=0.5, ija=(2, 2), ijc=(3, 1), blk_a=(4, 4), blk_c=(7, 3), src_a=(1, 1)), dict(kind="pdtran", m=16, n=16, blk_a=(8, 8), blk_c=(8, 8))]
 )
+
+F5_CASES = [
+    dict(kind="getrs_l3", n=64, nb=8, nrhs=20), dict(kind="getrs_l3", n=64, nb=8, nrhs=20, trans="T"),
+    dict(kind="getrs_l3", n=45, nb=4, nrhs=7, nbb=3, cond=1), dict(kind="getrs_l3", n=45, nb=4, nrhs=7, nbb=3, trans="T"),
+    dict(kind="getrs_l3", n=40, nb=8, nrhs=50, off=2, rsrc=1, csrc=1), dict(kind="getrs_l3", n=40, nb=8, nrhs=50, off=2, rsrc=1, csrc=1, trans="T"),
+    dict(kind="getrs_l3", n=100, nb=40, nrhs=1),
+]

@@ -66,3 +66,8 @@ def test_inverse(emul_lib, P, Q):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
 def test_pblas_entry_points(emul_lib, P, Q):
     spawn(P, Q, "F4B_CASES")
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
+def test_level3_solve(emul_lib, P, Q):
+    spawn(P, Q, "F5_CASES")

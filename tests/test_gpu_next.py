@@ -166,3 +166,22 @@ def test_pblas_entry_points_multi(P, Q):
     if ngpus() < P * Q:
         pytest.skip(f"needs {P * Q} GPUs")
     spawn(P, Q, next_cases.F4B_CASES + F4B_GPU)
+
+
+# ---- PDGETRS with many right-hand sides (level-3 path; `entry`: through pdgetrs_ itself, which switches above 64) ----
+F5_GPU = [
+    dict(kind="getrs_l3", n=2048, nb=256, nrhs=300), dict(kind="getrs_l3", n=2048, nb=256, nrhs=300, trans="T"),
+    dict(kind="getrs_l3", n=1500, nb=128, nrhs=100, nbb=32, entry=True), dict(kind="getrs_l3", n=1500, nb=128, nrhs=100, nbb=32, entry=True, trans="T"),
+    dict(kind="getrs_l3", n=1024, nb=128, nrhs=65, off=2, rsrc=1, csrc=1, entry=True),
+]
+
+
+def test_level3_solve_1x1():
+    spawn(1, 1, next_cases.F5_CASES + F5_GPU)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 2), (2, 2)])
+def test_level3_solve_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.F5_CASES + F5_GPU)
