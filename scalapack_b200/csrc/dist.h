@@ -40,7 +40,11 @@ struct StageMat {
     {
         T *win = const_cast<T *>(base) + loff_r + loff_c * lld;
         rows = rows_; cols = cols_;
-        if (rows <= 0 || cols <= 0 || is_device_ptr(base)) { dev = win; ld = lld; return; }
+        if (rows > 0 && cols > 0 && is_device_ptr(base)) { dev = win; ld = lld; return; }
+        if (rows <= 0 || cols <= 0) {                          // nothing of sub(A) lives here: a valid device address that is never read
+            dev = (T *)workspace("stage_empty", 256); ld = lld > 0 ? lld : 1; rows = cols = 0;
+            return;
+        }
         staged = true; host = win; hld = lld;
         ld = (rows + 1) & ~(int64_t)1;                        // even: 16-byte alignment of every column for the update's epilogue
         dev = (T *)workspace(name, (size_t)ld * (size_t)cols * sizeof(T));

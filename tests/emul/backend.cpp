@@ -27,14 +27,17 @@ void *workspace(const char *name, size_t bytes, bool zero_on_alloc)
 {
     WsEntry &e = g_ws[name];
     if (e.bytes < bytes) {
-        free(e.p);
+        cudaFree(e.p);                                       // like the product: a grown workspace moves, stale pointers die
         e.bytes = bytes + 64;
-        e.p = malloc(e.bytes);
-        memset(e.p, zero_on_alloc ? 0 : 0xA5, e.bytes);      // poison: a read of never-written workspace shows up as garbage
+        cudaMalloc(&e.p, e.bytes);                           // registered as device memory and poisoned (cuda_runtime.h)
+        if (zero_on_alloc) memset(e.p, 0, e.bytes);
     }
     return e.p;
 }
-void workspace_release_all() { for (auto &kv : g_ws) free(kv.second.p); g_ws.clear(); }
+void workspace_release_all() { for (auto &kv : g_ws) cudaFree(kv.second.p); g_ws.clear(); }
+
+// the pointer arguments of the contract functions below are device pointers on a GPU
+#define DEV(p) emul_need_dev((const void *)(p), "a device routine was given a pointer that is not device memory (" #p ")")
 
 LuStats g_last_lu;
 
@@ -63,10 +66,10 @@ static void gemm_minus(int64_t M, int64_t N, int K, const T *A, int64_t lda, con
 }
 void launch_dgemm_minus(int64_t M, int64_t N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
                         cudaStream_t, int, int)
-{ gemm_minus<double>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
+{ DEV(A); DEV(B); DEV(C); gemm_minus<double>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
 void launch_zgemm_minus(int64_t M, int64_t N, int K, const zcomplex *A, int64_t lda, const zcomplex *B, int64_t ldb, zcomplex *C, int64_t ldc,
                         cudaStream_t, int, int)
-{ gemm_minus<zcomplex>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
+{ DEV(A); DEV(B); DEV(C); gemm_minus<zcomplex>(M, N, K, A, lda, B, ldb, C, ldc); counter_add("kernel_launches", 1); }
 
 template <typename T>
 static void trsm_llnu(int jb, int64_t n, const T *L, int64_t ldl, T *B, int64_t ldb)
@@ -78,13 +81,15 @@ static void trsm_llnu(int jb, int64_t n, const T *L, int64_t ldl, T *B, int64_t 
         }
 }
 void launch_dtrsm_llnu(int jb, int64_t n, const double *L, int64_t ldl, double *B, int64_t ldb, cudaStream_t)
-{ trsm_llnu<double>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
+{ DEV(L); DEV(B); trsm_llnu<double>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
 void launch_ztrsm_llnu(int jb, int64_t n, const zcomplex *L, int64_t ldl, zcomplex *B, int64_t ldb, cudaStream_t)
-{ trsm_llnu<zcomplex>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
+{ DEV(L); DEV(B); trsm_llnu<zcomplex>(jb, n, L, ldl, B, ldb); counter_add("kernel_launches", 1); }
 
 template <typename T>
 void launch_copy2d(int64_t rows, int64_t cols, const T *src, int64_t lds, T *dst, int64_t ldd, cudaStream_t)
 {
+    if (rows <= 0 || cols <= 0) return;
+    DEV(src); DEV(dst);
     for (int64_t c = 0; c < cols; ++c) for (int64_t i = 0; i < rows; ++i) dst[i + c * ldd] = src[i + c * lds];
     counter_add("kernel_launches", 1);
 }
@@ -95,6 +100,7 @@ template void launch_copy2d<zcomplex>(int64_t, int64_t, const zcomplex *, int64_
 template <typename T>
 void launch_trsv_block(int kb, const T *A, int64_t lda, T *X, int64_t ldx, int nrhs, int mode, cudaStream_t)
 {
+    DEV(A); DEV(X);
     const bool upper = mode & TRSV_UPPER, trans = mode & TRSV_TRANS, cj = (mode & TRSV_CONJ) != 0;
     const bool unit = !upper && !(mode & TRSV_NONUNIT_L);
     auto op = [&](int i, int k) { T v = trans ? A[k + (int64_t)i * lda] : A[i + (int64_t)k * lda]; return cj ? cconj(v) : v; };   // element (i, k) of op(A)
@@ -114,6 +120,8 @@ void launch_trsv_block(int kb, const T *A, int64_t lda, T *X, int64_t ldx, int n
 template <typename T>
 void launch_gemv_minus(int64_t rows, int kb, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs, cudaStream_t)
 {
+    if (rows <= 0 || kb <= 0 || nrhs <= 0) return;
+    DEV(A); DEV(X); DEV(Y);
     for (int c = 0; c < nrhs; ++c) for (int k = 0; k < kb; ++k) for (int64_t i = 0; i < rows; ++i)
         Y[i + (int64_t)c * ldy] = cmul_sub(Y[i + (int64_t)c * ldy], A[i + (int64_t)k * lda], X[k + (int64_t)c * ldx]);
     counter_add("kernel_launches", 1);
@@ -121,6 +129,8 @@ void launch_gemv_minus(int64_t rows, int kb, const T *A, int64_t lda, const T *X
 template <typename T>
 void launch_gemvt_minus(int kb, int64_t ncols, const T *A, int64_t lda, const T *X, int64_t ldx, T *Y, int64_t ldy, int nrhs, bool conj, cudaStream_t)
 {
+    if (ncols <= 0 || kb <= 0 || nrhs <= 0) return;
+    DEV(A); DEV(X); DEV(Y);
     for (int c = 0; c < nrhs; ++c) for (int64_t j = 0; j < ncols; ++j) for (int i = 0; i < kb; ++i)
         Y[j + (int64_t)c * ldy] = cmul_sub(Y[j + (int64_t)c * ldy], conj ? cconj(A[i + j * lda]) : A[i + j * lda], X[i + (int64_t)c * ldx]);
     counter_add("kernel_launches", 1);
@@ -172,6 +182,7 @@ static void scatter_bc(Grid *g, int M, int N, const std::vector<T> &G, T *A, int
 template <typename T>
 int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int csrc, int *ipiv_glob_host, int *info_host, HostLink *)
 {
+    DEV(A);
     std::vector<T> G = gather_bc<T>(g, M, N, A, lld, nb, rsrc, csrc);
     const int mn = M < N ? M : N;
     int info = 0;
@@ -202,6 +213,7 @@ template <typename T>
 int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv,
                  T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all, const T *Xin, T *Xout)
 {
+    DEV(A); DEV(B); DEV(Xin); DEV(Xout);
     std::vector<T> G = gather_bc<T>(g, N, N, A, lld, nb, rsrc, csrc);
     const int P = g->nprow, Q = g->npcol;
     std::vector<T> X((size_t)N * nrhs);
@@ -265,6 +277,7 @@ void nccl_group_start() {}
 void nccl_group_end() {}
 void nccl_bcast(ncclComm_t_ comm, void *buf, size_t count, NcclType t, int root, cudaStream_t)
 {
+    DEV(buf);
     const int np = grid_scope_size(comm->g, comm->scope);
     const size_t len = count * tsize(t);
     if (np <= 1 || len == 0) return;
@@ -276,6 +289,7 @@ void nccl_send(ncclComm_t_, const void *, size_t, NcclType, int, cudaStream_t) {
 void nccl_recv(ncclComm_t_, void *, size_t, NcclType, int, cudaStream_t) { fatal("emulation: nccl_recv is not modelled"); }
 void nccl_allgather(ncclComm_t_ comm, const void *send, void *recv, size_t sendcount, NcclType t, cudaStream_t)
 {
+    DEV(send); DEV(recv);
     const size_t len = sendcount * tsize(t);
     if (grid_scope_size(comm->g, comm->scope) <= 1) { if (recv != send) memmove(recv, send, len); return; }
     std::vector<char> tmp((const char *)send, (const char *)send + len);
@@ -284,6 +298,7 @@ void nccl_allgather(ncclComm_t_ comm, const void *send, void *recv, size_t sendc
 template <typename T, typename F>
 static void allreduce(ncclComm_t_ comm, const void *send, void *recv, size_t count, F f)
 {
+    DEV(send); DEV(recv);
     const int np = grid_scope_size(comm->g, comm->scope);
     std::vector<T> mine((const T *)send, (const T *)send + count);
     if (np > 1) {
@@ -299,6 +314,7 @@ void nccl_allreduce_max_f64(ncclComm_t_ c, const void *s, void *r, size_t n, cud
 void nccl_alltoallv(ncclComm_t_ comm, int np, int me, const void *send, const size_t *scount, const size_t *sdispl, void *recv,
                     const size_t *rcount, const size_t *rdispl, cudaStream_t)
 {
+    DEV(send); DEV(recv);
     // every rank publishes its counts / displacements and its whole send buffer (padded to the largest); each picks its parts
     size_t mytot = 0; for (int p = 0; p < np; ++p) if (sdispl[p] + scount[p] > mytot) mytot = sdispl[p] + scount[p];
     std::vector<size_t> meta((size_t)2 * np + 1), allmeta(((size_t)2 * np + 1) * np);

@@ -71,3 +71,15 @@ def test_pblas_entry_points(emul_lib, P, Q):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
 def test_level3_solve(emul_lib, P, Q):
     spawn(P, Q, "F5_CASES")
+
+
+def test_compiled_c_caller_on_the_emulation(emul_lib, tmp_path):
+    """examples/expert_example.c (PDGESVX -> PDGECON -> PDGEMR2D -> PDGETRI -> PDGEMM -> PDPOSV from plain C) linked against the
+    emulation library runs its whole flow on the CPU and checks its own residuals."""
+    exe = str(tmp_path / "expert_emul")
+    cc = subprocess.run(["gcc", "-O1", "-Wall", os.path.join(ROOT, "examples", "expert_example.c"), "-I" + os.path.join(ROOT, "include"), "-L" + EMUL,
+                         "-lslb_emul", "-Wl,-rpath," + EMUL, "-lm", "-lstdc++", "-o", exe], capture_output=True, text=True, timeout=120)
+    assert cc.returncode == 0, cc.stderr
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    assert run.returncode == 0 and "expert example ok" in run.stdout, (run.stdout, run.stderr)

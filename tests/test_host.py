@@ -267,6 +267,22 @@ def test_compiled_c_caller_links_against_the_boundary(S, tmp_path):
         assert run.returncode != 0 and "no CPU fallback" in run.stderr
 
 
+def test_compiled_expert_caller_links_against_the_boundary(S, tmp_path):
+    """examples/expert_example.c: PDGESVX / PDLANGE / PDGECON / PDGEMR2D / PDGETRI / PDGEMM / PDPOSV called from plain C with the
+    header's prototypes; without a GPU it must stop loudly, with one every step checks its own residual."""
+    exe = str(tmp_path / "expert_example")
+    libdir = os.path.join(ROOT, "scalapack_b200", "lib")
+    cc = subprocess.run(["gcc", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "examples", "expert_example.c"), "-I" + os.path.join(ROOT, "include"),
+                         "-L" + libdir, "-lscalapack_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True, timeout=120)
+    assert cc.returncode == 0, cc.stderr
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    if S.has_cuda():
+        assert run.returncode == 0 and "expert example ok" in run.stdout, (run.stdout, run.stderr)
+    else:
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr
+
+
 def test_submatrix_window_against_infog2l_and_enumeration(S):
     """The local window of a block-aligned sub(A) = A(IA:IA+M-1, JA:JA+N-1) that PDGETRF / PDGETRS work on (api.cu `window`): offsets
     equal INFOG2L's local indices (TOOLS/infog2l.f, which pdgetrf.f:202 uses), the window's source process is the owner of (IA, JA),
