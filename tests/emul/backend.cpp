@@ -58,8 +58,9 @@ static inline zcomplex cconj(zcomplex a) { return make_double2(a.x, -a.y); }
 template <typename T>
 static void gemm_minus(int64_t M, int64_t N, int K, const T *A, int64_t lda, const T *B, int64_t ldb, T *C, int64_t ldc)
 {
+    // k runs DOWNWARDS: another summation order than the oracle's, like the tensor-core kernel's (tolerances must not depend on it)
     for (int64_t j = 0; j < N; ++j)
-        for (int k = 0; k < K; ++k) {
+        for (int k = K - 1; k >= 0; --k) {
             const T b = B[k + j * ldb];
             for (int64_t i = 0; i < M; ++i) C[i + j * ldc] = cmul_sub(C[i + j * ldc], A[i + (int64_t)k * lda], b);
         }
@@ -240,8 +241,10 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
         T *x = X.data() + (size_t)c * N;
         if (trans == 'N') {
             for (int i = 0; i < N; ++i) { const int p = ipiv[i] - 1; if (p != i) { T t = x[i]; x[i] = x[p]; x[p] = t; } }
-            for (int k = 0; k < N; ++k) for (int i = k + 1; i < N; ++i) x[i] = cmul_sub(x[i], el(i, k), x[k]);
-            for (int k = N - 1; k >= 0; --k) { x[k] = cdiv(x[k], el(k, k)); for (int i = 0; i < k; ++i) x[i] = cmul_sub(x[i], el(i, k), x[k]); }
+            // row-oriented substitution with the inner products accumulated from the far end: a rounding pattern unlike the
+            // oracle's column sweeps, as different from it as the GPU's blocked sweeps are
+            for (int i = 0; i < N; ++i) for (int k = i - 1; k >= 0; --k) x[i] = cmul_sub(x[i], el(i, k), x[k]);
+            for (int i = N - 1; i >= 0; --i) { for (int k = N - 1; k > i; --k) x[i] = cmul_sub(x[i], el(i, k), x[k]); x[i] = cdiv(x[i], el(i, i)); }
         } else {
             for (int k = 0; k < N; ++k) {                      // U^T (U^H) forward
                 for (int i = 0; i < k; ++i) x[k] = cmul_sub(x[k], cj ? cconj(el(i, k)) : el(i, k), x[i]);
