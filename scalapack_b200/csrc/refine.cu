@@ -17,6 +17,7 @@
 #include "lacon.h"
 #include "launch.h"
 #include "lu.h"
+#include "worklayout.h"
 
 #include <cfloat>
 #include <cmath>
@@ -285,9 +286,6 @@ struct Factors {
     }
 };
 
-[[noreturn]] void unaligned(const char *name)
-{ fatal("%s: sub(A) must start on a block boundary (IA-1, JA-1 multiples of the block size) in this implementation", name); }
-
 // ---- PDGECON -----------------------------------------------------------------------------------------------------------
 int gecon_lwmin(int n, int ia, int ja, const int *desca, int P, int Q, int myrow, int mycol, int *liwmin)
 {
@@ -338,8 +336,18 @@ void gecon_impl(const char *norm, int n, const double *a, int ia, int ja, const 
     if (n == 0) { *rcond = 1.0; return; }
     if (anorm == 0.0) return;
     if (n == 1) { *rcond = 1.0; return; }
-    if ((ia - 1) % desca[MB_] || (ja - 1) % desca[NB_] || desca[MB_] != desca[NB_]) unaligned("PDGECON");
     Grid *g = grid_of(ictxt);
+    if ((ia - 1) % desca[MB_] || (ja - 1) % desca[NB_] || desca[MB_] != desca[NB_]) {
+        // the reference's PDTRSV takes the factors at any alignment; the solves here want block-aligned square blocks: work on an
+        // aligned copy of sub(A) (one redistribution)
+        const int nbw = desca[NB_] < desca[MB_] ? desca[NB_] : desca[MB_];
+        Work F("pb_A", g, n, n, nbw);
+        F.load(a, ia, ja, desca, false);
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        Window wf; wf.loff_r = wf.loff_c = 0; wf.mloc = F.mloc; wf.nloc = F.nloc; wf.rsrc = wf.csrc = 0;
+        gecon_core(g, onenrm, n, nbw, wf, F.dev, F.ld, anorm, rcond);
+        return;
+    }
     const Window w = window(n, n, ia, ja, desca, P, Q, myrow, mycol);
     StageMat<double> AF("stage_A", a, desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
     gecon_core(g, onenrm, n, desca[NB_], w, AF.dev, AF.ld, anorm, rcond);
@@ -573,8 +581,10 @@ void gesvx_impl(const char *fact_, const char *trans_, int n, int nrhs, double *
     }
     if (*info != 0) { xerbla(ictxt, "PDGESVX", *info); return; }
     if (lquery) return;
-    if ((jaf - 1) % descaf[NB_] || descaf[MB_] != descaf[NB_] || descaf[NB_] != desca[NB_]) unaligned("PDGESVX (AF)");
-    if ((ib - 1) % descb[MB_] || (ix - 1) % descx[MB_]) unaligned("PDGESVX (B, X)");
+    // what the reference's inner calls would report (PDGETRF on AF: pdgetrf.f:180-185; PDGETRS on X: pdgetrs.f:211-222)
+    if ((jaf - 1) % descaf[NB_]) { *info = -5; xerbla(ictxt, "PDGETRF", *info); return; }
+    if (descaf[MB_] != descaf[NB_] || descaf[NB_] != desca[NB_]) { *info = -(600 + NB_ + 1); xerbla(ictxt, "PDGETRF", *info); return; }
+    if ((ix - 1) % descx[MB_] || (ib - 1) % descb[MB_]) { *info = -10; xerbla(ictxt, "PDGETRS", *info); return; }
 
     Grid *g = grid_of(ictxt);
     const int nb = desca[NB_];

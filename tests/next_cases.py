@@ -125,6 +125,16 @@ def case_gecon(G, cs):
         # the solves inside the estimator round differently on the GPU (blocked order): the estimate moves by ~cond * eps
         if info != 0 or not abs(rc - want) <= 1e-6 * want:
             msgs.append(f"pdgecon {nm}: rcond {rc} info {info}, oracle {want}")
+    if cs.get("unaligned"):
+        # the factors as a sub-matrix that starts inside a block (the reference's PDTRSV accepts that): same estimate
+        oi, oj = cs["unaligned"]
+        big = matrix(n + oi + 2, n + oj + 1, seed=9); big[oi:oi + n, oj:oj + n] = lu
+        bl_, descb_ = G.dist(np.asfortranarray(big), nb, 1 % G.P, 1 % G.Q)
+        anorm = O.dlange("1", ag)
+        rc, info = S.pdgecon("1", n, bl_, oi + 1, oj + 1, descb_, anorm)
+        want = O.dgecon("1", lu, anorm)
+        if info != 0 or not abs(rc - want) <= 1e-6 * want:
+            msgs.append(f"pdgecon on an unaligned sub-matrix: rcond {rc} info {info}, oracle {want}")
     rc, info = S.pdgecon("X", n, ll, 1, 1, desc, 1.0)
     if info != -1:
         msgs.append(f"pdgecon bad NORM: info {info}")
@@ -526,7 +536,7 @@ F1_CASES = [
     dict(kind="lange", mg=64, ng=64, nb=8, ia=1, ja=1, m=64, n=64),
     dict(kind="lange", mg=20, ng=20, nb=32, ia=2, ja=2, m=1, n=7),
     dict(kind="equ", n=37, m=45, nb=4, cond=6), dict(kind="equ", n=64, nb=8), dict(kind="equ", n=30, nb=4, cond=1, zero_row=7),
-    dict(kind="gecon", n=64, nb=8), dict(kind="gecon", n=45, nb=4, cond=2), dict(kind="gecon", n=2, nb=2),
+    dict(kind="gecon", n=64, nb=8), dict(kind="gecon", n=45, nb=4, cond=2), dict(kind="gecon", n=2, nb=2), dict(kind="gecon", n=37, nb=8, unaligned=(3, 5)),
     dict(kind="gerfs", n=64, nb=8, nrhs=3), dict(kind="gerfs", n=45, nb=4, nrhs=2, trans="T", cond=2), dict(kind="gerfs", n=30, nb=4, nrhs=5, nbr=2),
     dict(kind="gesvx", n=64, nb=8, fact="N"), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5, trans="T"),
     dict(kind="gesvx", n=40, nb=8, fact="E"), dict(kind="gesvx", n=24, nb=4, fact="N", singular=True),
