@@ -36,6 +36,27 @@ class Grid:
         return self.local_of(np.asfortranarray(v.reshape(-1, 1)), nb, rsrc=rsrc, nbc=1)[:, 0] if self.c == 0 or True else None
 
 
+class OnDevice:
+    """Device-resident operands (GPU runs only, case key dev=True): the local arrays go to the process's GPU as torch tensors with the
+    same column-major memory, the routine works on them in place, back() copies them into the numpy arrays the checks look at."""
+
+    def __init__(self, S, enabled):
+        self.S, self.enabled, self.pairs = S, bool(enabled), []
+
+    def __call__(self, al):
+        if not self.enabled or al is None:
+            return al
+        import torch
+        torch.cuda.set_device(self.S.device())
+        t = torch.from_numpy(np.ascontiguousarray(al.T)).cuda()
+        self.pairs.append((al, t))
+        return t
+
+    def back(self):
+        for al, t in self.pairs:
+            al[...] = np.asfortranarray(t.cpu().numpy().T)
+
+
 def matrix(n, m=None, seed=100, cond=None):
     a = O.pdmatgen(n, m or n, seed)
     if cond:
@@ -118,6 +139,7 @@ def case_gecon(G, cs):
     n, nb = cs["n"], cs["nb"]
     ag = matrix(n, cond=cs.get("cond"))
     ll, desc, ipl, lu, ipg = _factored(G, ag, nb)
+    dev = OnDevice(S, cs.get("dev")); ll_host = ll; ll = dev(ll)
     for nm in ("1", "I"):
         anorm = O.dlange(nm, ag)
         rc, info = S.pdgecon(nm, n, ll, 1, 1, desc, anorm)
@@ -271,8 +293,10 @@ def case_gemr2d(G, cs):
     bl, descb, rc = local(cb, Pb, Qb, bg, mbb, nbb, rsb, csb)
     a_before = None if al is None else al.copy()
     f = S.pzgemr2d if z else S.pdgemr2d
-    f(m, n, al if al is not None else np.zeros(1, dtype=ag.dtype), ia, ja, desca, bl if bl is not None else np.zeros(1, dtype=ag.dtype), ib, jb,
+    dev = OnDevice(S, cs.get("dev") and not z)
+    f(m, n, dev(al) if al is not None else np.zeros(1, dtype=ag.dtype), ia, ja, desca, dev(bl) if bl is not None else np.zeros(1, dtype=ag.dtype), ib, jb,
       descb, G.ctx)
+    dev.back()
     if al is not None and not np.array_equal(al, a_before):
         msgs.append("A was modified")
     if bl is not None:
@@ -304,7 +328,9 @@ def case_potrf(G, cs):
     ag = np.asfortranarray(ag)
     al, desca = G.dist(ag, nb, rsrc, csrc, extra=1)
     ia = off * nb + 1
-    info = S.pdpotrf(uplo, n, al, ia, ia, desca)
+    dev = OnDevice(S, cs.get("dev"))
+    info = S.pdpotrf(uplo, n, dev(al), ia, ia, desca)
+    dev.back()
     ref = a0.copy(order="F"); info0 = O.dpotrf(uplo, ref, nb)
     if info != info0:
         msgs.append(f"pdpotrf info {info} != {info0}")
@@ -365,7 +391,9 @@ def case_getri(G, cs):
     ipfull = np.concatenate([np.arange(1, off * nb + 1, dtype=np.int32), ipg + off * nb]).astype(np.int32)
     ipl = O.ipiv_local(ng, ng, nb, G.P, G.r, ipfull, mloc + nb, rsrc=rsrc, fill=-77)
     ia = off * nb + 1
-    info = S.pdgetri(n, al, ia, ia, desca, ipl)
+    dev = OnDevice(S, cs.get("dev"))
+    info = S.pdgetri(n, dev(al), ia, ia, desca, ipl)
+    dev.back()
     inv = lu.copy(order="F"); info0 = O.dgetri(inv, ipg, nb)
     if info != info0:
         msgs.append(f"pdgetri info {info} != {info0}")
@@ -420,7 +448,9 @@ def case_pdgemm(G, cs):
     bl, descb, _ = _place(G, S, bg, cs.get("blk_b", (4, 4)), cs.get("src_b", (0, 0)))
     cl, descc, layc = _place(G, S, cg, cs.get("blk_c", (4, 4)), cs.get("src_c", (0, 0)))
     a_before, b_before = al.copy(), bl.copy()
-    S.pdgemm(ta, tb, m, n, k, alpha, al, ia, ja, desca, bl, ib, jb, descb, beta, cl, ic, jc, descc)
+    dev = OnDevice(S, cs.get("dev"))
+    S.pdgemm(ta, tb, m, n, k, alpha, dev(al), ia, ja, desca, dev(bl), ib, jb, descb, beta, dev(cl), ic, jc, descc)
+    dev.back()
     want = cg.copy(order="F")
     want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = O.dgemm(ta, tb, alpha, ag[ia - 1:ia - 1 + sa[0], ja - 1:ja - 1 + sa[1]],
                                                          bg[ib - 1:ib - 1 + sb[0], jb - 1:jb - 1 + sb[1]], beta, cg[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n])

@@ -61,7 +61,7 @@ def spawn(P, Q, cases, timeout=240):
 F1_GPU = [
     dict(kind="lange", mg=3000, ng=2500, nb=128, ia=130, ja=7, m=2000, n=2200),
     dict(kind="equ", n=2000, m=2300, nb=128, cond=6),
-    dict(kind="gecon", n=2048, nb=256), dict(kind="gecon", n=1500, nb=64, cond=2), dict(kind="gecon", n=1000, nb=1024),
+    dict(kind="gecon", n=2048, nb=256), dict(kind="gecon", n=1500, nb=64, cond=2), dict(kind="gecon", n=1000, nb=1024), dict(kind="gecon", n=1536, nb=128, dev=True),
     dict(kind="gerfs", n=2048, nb=256, nrhs=2), dict(kind="gerfs", n=1500, nb=64, nrhs=2, trans="T", cond=1),
     dict(kind="gesvx", n=2048, nb=256, fact="N"), dict(kind="gesvx", n=1500, nb=128, fact="E", cond=4),
     dict(kind="gesvx", n=1000, nb=64, fact="E", cond=4, trans="T"),
@@ -91,6 +91,7 @@ F2_GPU = [
     dict(kind="gemr2d", m=3000, n=2000, ia=65, ja=130, ib=7, jb=3, shape_a=(3100, 2200), shape_b=(3010, 2005), blk_a=(64, 32), blk_b=(100, 256),
          src_a=(1, 1), src_b=(0, 1)),
     dict(kind="gemr2d", m=1500, n=1500, shape_a=(1500, 1500), shape_b=(1500, 1500), blk_a=(128, 128), blk_b=(32, 32), z=True),
+    dict(kind="gemr2d", m=2000, n=1800, ia=3, ja=2, shape_a=(2100, 1900), shape_b=(2000, 1800), blk_a=(64, 64), blk_b=(256, 256), dev=True),
     dict(kind="gemr2d", m=2048, n=2048, shape_a=(2048, 2048), shape_b=(2048, 2048), blk_a=(64, 64), blk_b=(512, 512), ga=(1, 2), gb=(2, 1)),
     dict(kind="gemr2d", m=2048, n=2048, shape_a=(2048, 2048), shape_b=(2048, 2048), blk_a=(64, 64), blk_b=(512, 512), ga=(2, 2), gb=(1, 1)),
 ]
@@ -111,7 +112,7 @@ def test_redistribution_multi(P, Q):
 F3_GPU = [
     dict(kind="potrf", n=2048, nb=256, uplo="L"), dict(kind="potrf", n=2048, nb=256, uplo="U"),
     dict(kind="potrf", n=2500, nb=512, uplo="L", nrhs=1), dict(kind="potrf", n=1500, nb=64, uplo="U", nrhs=3),
-    dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
+    dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1536, nb=256, uplo="L", dev=True), dict(kind="potrf", n=1100, nb=128, uplo="U", dev=True), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
 ]
 
 
@@ -129,7 +130,7 @@ def test_cholesky_multi(P, Q):
 # ---- row 4: PDGETRI ----
 F4_GPU = [
     dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=2200, nb=512),
-    dict(kind="getri", n=1200, nb=128, off=2, rsrc=1, csrc=1), dict(kind="getri", n=1000, nb=128, singular=900),
+    dict(kind="getri", n=1200, nb=128, off=2, rsrc=1, csrc=1), dict(kind="getri", n=1000, nb=128, singular=900), dict(kind="getri", n=1536, nb=256, dev=True),
 ]
 
 
@@ -154,6 +155,7 @@ F4B_GPU = [
     dict(kind="pdtrsm", m=600, n=1500, side="R", uplo="L", ta="T", diag="N", blk_a=(128, 128), blk_b=(128, 128)),
     dict(kind="pdtrsm", m=900, n=1000, side="R", uplo="U", ta="N", diag="U", blk_a=(200, 200), blk_b=(512, 512)),
     dict(kind="pdtran", m=1500, n=2000, alpha=2.0, beta=0.5, blk_a=(64, 64), blk_c=(256, 128)),
+    dict(kind="pdgemm", m=1024, n=768, k=512, ta="N", tb="N", alpha=-1.0, beta=1.0, blk_a=(128, 128), blk_b=(128, 128), blk_c=(128, 128), dev=True),
 ]
 
 
