@@ -111,6 +111,42 @@ void getrs_l3_entry(Grid *g, char trans, int n, int nrhs, const double *Adev, in
     }
 }
 
+// PDPOTRS for many right-hand sides, the same way: A = L L' ('L') or U' U ('U'); the sweep with the stored triangle runs on the
+// factor in place, the one with its transpose on a transposed copy.
+void potrs_l3_entry(Grid *g, bool upper, int n, int nrhs, const double *Adev, int64_t lda, int nb, int rsrc, int csrc, double *b, int ib, int jb,
+                    const int *descb)
+{
+    const int descf[9] = { 1, g->ctxt, n, n, nb, nb, rsrc, csrc, (int)lda };
+    Work F("pb_A", g, n, n, nb);
+    F.load(Adev, 1, 1, descf, true);                               // F = A': the other triangle of the factor
+    if (!upper) {                                                  // L y = b on A (rows aligned with A), then L' x = y on F (rows from process 0)
+        Work X("pb_C", g, n, nrhs, nb, rsrc);
+        X.load(b, ib, jb, descb, false);
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        tri_l3_sweep(g, false, false, n, Adev, lda, nb, rsrc, csrc, X.dev, X.ld, X.nloc);
+        if (rsrc == 0) tri_l3_sweep(g, true, false, n, F.dev, F.ld, nb, 0, 0, X.dev, X.ld, X.nloc);
+        else {                                                     // F's rows start on process row 0: move X there for the second sweep
+            Work Y("pb_B", g, n, nrhs, nb, 0);
+            Y.load(X.dev, 1, 1, X.desc, false);
+            SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+            tri_l3_sweep(g, true, false, n, F.dev, F.ld, nb, 0, 0, Y.dev, Y.ld, Y.nloc);
+            Y.store(b, ib, jb, descb, false);
+            return;
+        }
+        X.store(b, ib, jb, descb, false);
+    } else {                                                       // U' y = b on F, then U x = y on A
+        Work Y("pb_B", g, n, nrhs, nb, 0);
+        Y.load(b, ib, jb, descb, false);
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        tri_l3_sweep(g, false, false, n, F.dev, F.ld, nb, 0, 0, Y.dev, Y.ld, Y.nloc);
+        Work X("pb_C", g, n, nrhs, nb, rsrc);
+        X.load(Y.dev, 1, 1, Y.desc, false);
+        SLB_CUDA(cudaStreamSynchronize(rt().s_main));
+        tri_l3_sweep(g, true, false, n, Adev, lda, nb, rsrc, csrc, X.dev, X.ld, X.nloc);
+        X.store(b, ib, jb, descb, false);
+    }
+}
+
 }  // namespace slb
 
 using namespace slb;

@@ -105,6 +105,8 @@ void potrs_device(Grid *g, bool upper, int N, int nrhs, const double *A, int64_t
 }
 
 void potrf_device(Grid *g, bool upper, int N, double *A, int64_t lld, int nb, int rsrc, int csrc, int *info_host);   // chol.cu
+void potrs_l3_entry(Grid *g, bool upper, int n, int nrhs, const double *Adev, int64_t lda, int nb, int rsrc, int csrc, double *b, int ib, int jb,
+                    const int *descb);                                                                               // pblas.cu
 
 namespace {
 
@@ -140,6 +142,9 @@ void potrs_run(Grid *g, bool upper, int n, int nrhs, const double *Adev, int64_t
                const int *descb)
 {
     cudaStream_t s = rt().s_main;
+    // many right-hand sides: block-cyclic copy of sub(B), level-3 sweeps on the tensor cores (option potrs_l3_min_nrhs, 0 = never)
+    const int64_t l3min = opt("potrs_l3_min_nrhs", 64);
+    if (l3min > 0 && nrhs > l3min) { potrs_l3_entry(g, upper, n, nrhs, Adev, lda, nb, w.rsrc, w.csrc, b, ib, jb, descb); return; }
     std::vector<double> xg;
     gather_small(g, n, nrhs, b, ib, jb, descb, xg);
     double *Xw = (double *)workspace("ts_X", xg.size() * sizeof(double));

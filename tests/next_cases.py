@@ -356,18 +356,19 @@ def case_potrf(G, cs):
             msgs.append("elements outside the triangle were modified")
     if not np.all(al[mloc:, :] == -9923.0):
         msgs.append("guard row overwritten")
-    if off or rsrc or csrc:
+    if off:
         return msgs
-    # PDPOTRS on the factor, PDPOSV from scratch
+    # PDPOTRS on the factor, PDPOSV from scratch (l3: force the many-right-hand-sides path whatever NRHS is)
+    S.set_option("potrs_l3_min_nrhs", 1 if cs.get("l3") else 64)
     bg = matrix(n, nrhs, seed=200)
-    bl, descb = G.dist(bg, nb, nbc=1); nlocb = S.numroc(nrhs, 1, G.c, 0, G.Q)
+    bl, descb = G.dist(bg, nb, rsrc, 0, nbc=1); nlocb = S.numroc(nrhs, 1, G.c, 0, G.Q)
     info = S.pdpotrs(uplo, n, nrhs, al, 1, 1, desca, bl, 1, 1, descb)
     xg = bg.copy(order="F"); O.dpotrs(uplo, ref, xg)
-    xe = G.local_of(xg, nb, nbc=1)
+    xe = G.local_of(xg, nb, rsrc, 0, nbc=1)
     if info != 0:
         msgs.append(f"pdpotrs info {info}")
     _close(msgs, "X (PDPOTRS)", bl[:mloc, :nlocb], xe[:mloc, :nlocb], 1e-10, atol=1e-14 * np.abs(xg).max())
-    al2, _ = G.dist(np.asfortranarray(a0), nb); bl2, _ = G.dist(bg, nb, nbc=1)
+    al2, _ = G.dist(np.asfortranarray(a0), nb, rsrc, csrc); bl2, _ = G.dist(bg, nb, rsrc, 0, nbc=1)
     info = S.pdposv(uplo, n, nrhs, al2, 1, 1, desca[:8] + [al2.shape[0]], bl2, 1, 1, descb)
     if info != 0:
         msgs.append(f"pdposv info {info}")
@@ -594,6 +595,8 @@ F2_CASES = [
 F3_CASES = [
     dict(kind="potrf", n=64, nb=8, uplo="L"), dict(kind="potrf", n=64, nb=8, uplo="U"),
     dict(kind="potrf", n=45, nb=4, uplo="L", nrhs=3), dict(kind="potrf", n=45, nb=4, uplo="U", nrhs=3),
+    dict(kind="potrf", n=45, nb=4, uplo="L", nrhs=9, l3=True), dict(kind="potrf", n=45, nb=4, uplo="U", nrhs=9, l3=True), dict(kind="potrf", n=64, nb=16, uplo="L", nrhs=2, l3=True), dict(kind="potrf", n=50, nb=8, uplo="L", nrhs=5, l3=True, rsrc=1, csrc=1),
+    dict(kind="potrf", n=50, nb=8, uplo="U", nrhs=5, l3=True, rsrc=1, csrc=1), dict(kind="potrf", n=50, nb=8, uplo="L", nrhs=2, rsrc=1, csrc=1),
     dict(kind="potrf", n=150, nb=40, uplo="L"), dict(kind="potrf", n=150, nb=40, uplo="U"),
     dict(kind="potrf", n=100, nb=100, uplo="L"), dict(kind="potrf", n=7, nb=16, uplo="U"), dict(kind="potrf", n=1, nb=4, uplo="L", nrhs=1), dict(kind="potrf", n=2, nb=1, uplo="U", nrhs=1),
     dict(kind="potrf", n=40, nb=8, uplo="L", off=2, rsrc=1, csrc=1), dict(kind="potrf", n=40, nb=8, uplo="U", off=1, csrc=1),

@@ -112,7 +112,7 @@ def test_redistribution_multi(P, Q):
 F3_GPU = [
     dict(kind="potrf", n=2048, nb=256, uplo="L"), dict(kind="potrf", n=2048, nb=256, uplo="U"),
     dict(kind="potrf", n=2500, nb=512, uplo="L", nrhs=1), dict(kind="potrf", n=1500, nb=64, uplo="U", nrhs=3),
-    dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1536, nb=256, uplo="L", dev=True), dict(kind="potrf", n=1100, nb=128, uplo="U", dev=True), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
+    dict(kind="potrf", n=1000, nb=128, uplo="L", notpd=700), dict(kind="potrf", n=1536, nb=256, uplo="L", nrhs=200), dict(kind="potrf", n=1024, nb=128, uplo="U", nrhs=100), dict(kind="potrf", n=1536, nb=256, uplo="L", dev=True), dict(kind="potrf", n=1100, nb=128, uplo="U", dev=True), dict(kind="potrf", n=1200, nb=128, uplo="U", off=2, rsrc=1, csrc=1),
 ]
 
 
