@@ -71,17 +71,21 @@ inline void grid_combine(Grid *g, char scope, double *v, size_t len, char op)
 {
     const int np = grid_scope_size(g, scope);
     if (np <= 1 || len == 0) return;
-    std::vector<double> all(len * (size_t)np);
-    grid_allgather(g, scope, v, all.data(), len * sizeof(double));
-    for (size_t e = 0; e < len; ++e) {
-        double a = all[e];
-        for (int p = 1; p < np; ++p) {
-            const double b = all[(size_t)p * len + e];
-            if (op == '+') a += b;
-            else if (op == 'M') { if (b > a || b != b) a = b; }
-            else { if (b < a || b != b) a = b; }
+    const size_t CHUNK = (size_t)1 << 21;                       // 16 MiB per process and exchange: the control plane bounds a message
+    std::vector<double> all((len < CHUNK ? len : CHUNK) * (size_t)np);
+    for (size_t c0 = 0; c0 < len; c0 += CHUNK) {
+        const size_t cl = len - c0 < CHUNK ? len - c0 : CHUNK;
+        grid_allgather(g, scope, v + c0, all.data(), cl * sizeof(double));
+        for (size_t e = 0; e < cl; ++e) {
+            double a = all[e];
+            for (int p = 1; p < np; ++p) {
+                const double b = all[(size_t)p * cl + e];
+                if (op == '+') a += b;
+                else if (op == 'M') { if (b > a || b != b) a = b; }
+                else { if (b < a || b != b) a = b; }
+            }
+            v[c0 + e] = a;
         }
-        v[e] = a;
     }
 }
 
