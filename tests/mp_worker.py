@@ -10,6 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import oracle as O  # noqa: E402
+if os.environ.get("SLB200_EMUL") == "1":      # host-logic emulation (tests/emul, CPU): the real lu.cu / api.cu over contract kernels
+    import scalapack_b200.api as _api  # noqa: E402
+    _api._SO = os.path.join(ROOT, "tests", "emul", "libslb_emul.so")
 import scalapack_b200 as S  # noqa: E402
 
 EPS = 2.0 ** -53
