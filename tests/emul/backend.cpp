@@ -370,27 +370,49 @@ double bench_dmma_peak_tflops(int) { return 0; }
 double bench_dfma_peak_tflops(int) { return 0; }
 double bench_copy_gbs(size_t) { return 0; }
 
-// HostLink (stage.cu) by contract: the transfers of a host-resident caller happen at once, every ticket is complete
-struct HostLink::Impl {};
+// HostLink (stage.cu) by contract.  Downloads happen at once (everything recorded before them has completed: the emulation runs in
+// program order).  Uploads can ARRIVE LATE: with SLB200_EMUL_SLAB_DELAY = d > 0 ticket t only lands in "device" memory after
+// (7 t + 3) mod (d + 1) polls of done(t), or when something waits for it -- until then the staging copy holds poison, so a sweep that
+// touches a slab before it has joined (lu.cu's replay logic) produces garbage instead of passing by luck.
+struct HostLink::Impl {
+    struct Up { int64_t r0, r1, c0, c1; int polls_left; bool landed; };
+    std::vector<Up> ups;
+};
 bool host_ptr_is_pinned(const void *) { return false; }
-HostLink::HostLink(const HostMat &h, void *dev, int64_t ldd) : h_(h), dev_(dev), ldd_(ldd) {}
+HostLink::HostLink(const HostMat &h, void *dev, int64_t ldd) : im_(new Impl()), h_(h), dev_(dev), ldd_(ldd) {}
 HostLink::~HostLink() {}
 int HostLink::upload(int64_t r0, int64_t r1, int64_t c0, int64_t c1)
 {
-    for (int64_t c = c0; c < c1; ++c) memcpy((char *)dev_ + (size_t)(r0 + c * ldd_) * h_.elem, (const char *)h_.p + (size_t)(r0 + c * h_.ld) * h_.elem, (size_t)(r1 - r0) * h_.elem);
+    static const int delay = getenv("SLB200_EMUL_SLAB_DELAY") ? atoi(getenv("SLB200_EMUL_SLAB_DELAY")) : 0;
+    const int t = (int)im_->ups.size();
+    im_->ups.push_back(Impl::Up{ r0, r1, c0, c1, delay > 0 ? (7 * t + 3) % (delay + 1) : 0, false });
     up_bytes_ += (r1 - r0) * (c1 - c0) * (int64_t)h_.elem;
-    return 0;
+    if (im_->ups.back().polls_left == 0) wait(t);
+    return t;
 }
 int HostLink::download(int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaEvent_t)
 {
     for (int64_t c = c0; c < c1; ++c) memcpy((char *)h_.p + (size_t)(r0 + c * h_.ld) * h_.elem, (const char *)dev_ + (size_t)(r0 + c * ldd_) * h_.elem, (size_t)(r1 - r0) * h_.elem);
     down_bytes_ += (r1 - r0) * (c1 - c0) * (int64_t)h_.elem;
-    return 0;
+    return -1;
 }
-bool HostLink::done(int) { return true; }
-void HostLink::wait(int) {}
-void HostLink::stream_wait(int, cudaStream_t) {}
-void HostLink::finish() {}
+void HostLink::wait(int t)
+{
+    if (t < 0 || t >= (int)im_->ups.size()) return;
+    Impl::Up &u = im_->ups[(size_t)t];
+    if (u.landed) return;
+    for (int64_t c = u.c0; c < u.c1; ++c) memcpy((char *)dev_ + (size_t)(u.r0 + c * ldd_) * h_.elem, (const char *)h_.p + (size_t)(u.r0 + c * h_.ld) * h_.elem, (size_t)(u.r1 - u.r0) * h_.elem);
+    u.landed = true;
+}
+bool HostLink::done(int t)
+{
+    if (t < 0 || t >= (int)im_->ups.size()) return true;
+    Impl::Up &u = im_->ups[(size_t)t];
+    if (!u.landed && --u.polls_left <= 0) { wait(t); if (getenv("SLB200_EMUL_TRACE")) fprintf(stderr, "emulated HostLink: slab %d (columns %lld..%lld) arrived late\n", t, (long long)u.c0, (long long)u.c1); }
+    return u.landed;
+}
+void HostLink::stream_wait(int t, cudaStream_t) { wait(t); }
+void HostLink::finish() { for (int t = 0; t < (int)im_->ups.size(); ++t) wait(t); }
 
 // ---- NCCL wrappers over the TCP control plane ------------------------------------------------------------------------------
 static size_t tsize(NcclType t) { return t == NT_F64 ? 8 : (t == NT_I32 ? 4 : 1); }

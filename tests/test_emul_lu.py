@@ -23,12 +23,12 @@ def emul_lib():
     return os.path.join(EMUL, "libslb_emul.so")
 
 
-def spawn(world, cases, timeout=240):
+def spawn(world, cases, timeout=240, extra_env=None):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   SLB200_PORT_OFFSET="0", SLB200_EMUL="1", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+                   SLB200_PORT_OFFSET="0", SLB200_EMUL="1", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", **(extra_env or {}))
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py"), json.dumps(cases)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
@@ -64,3 +64,14 @@ def cases_for(P, Q):
 @pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (1, 4), (4, 1), (2, 3), (2, 4), (4, 2)])
 def test_lu_orchestration_on_the_cpu(emul_lib, P, Q):
     spawn(P * Q, cases_for(P, Q))
+
+
+@pytest.mark.parametrize("delay", [0, 1, 2, 5, 11])
+@pytest.mark.parametrize("save_mb", [16384, 0])
+def test_host_streaming_with_late_slabs(emul_lib, delay, save_mb):
+    """1 x 1 grid, host-resident caller: the column slabs of A land in the staging copy after a varying number of polls (the emulated
+    HostLink poisons what has not arrived), so they join the sweep at different block steps and are replayed through the steps they
+    missed; with no panel-keep budget (save_mb = 0) every slab is forced in at once.  The factors must not depend on any of that."""
+    cases = [dict(P=1, Q=1, m=384, n=384, nb=32, nrhs=1, split=64, hoststream=True), dict(P=1, Q=1, m=300, n=420, nb=32, nrhs=0, split=64, hoststream=True),
+             dict(P=1, Q=1, m=420, n=300, nb=32, nrhs=0, hoststream=True), dict(P=1, Q=1, m=256, n=256, nb=16, nrhs=2, z=True, split=32, hoststream=True)]
+    spawn(1, cases, extra_env={"SLB200_EMUL_SLAB_DELAY": str(delay), "SLB200_E2E_SAVE_MB": str(save_mb), "SLB200_E2E_SLAB_MB": "0"})
