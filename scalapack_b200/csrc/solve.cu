@@ -12,6 +12,7 @@
 #include "ncclw.h"
 #include "lu.h"
 #include "devmath.cuh"
+#include "launch.h"
 
 namespace slb {
 
@@ -90,8 +91,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
     SLB_CUDA(cudaMemsetAsync(X0, 0, (size_t)N * nrhs * sizeof(T), s));
     if (mloc > 0 && nlocB_all > 0) {
         dim3 grid((unsigned)((mloc + 255) / 256), gyb);
-        rhs_scatter_kernel<T><<<grid, 256, 0, s>>>(mloc, nlocB_all, nb, nbb, P, Q, myr_rel, myc_relb, B, lldb, X0, N, jb0, nrhs, 1);
-        SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
+        SLB_LAUNCH((rhs_scatter_kernel<T>), grid, 256, s, mloc, nlocB_all, nb, nbb, P, Q, myr_rel, myc_relb, (const T *)B, lldb, X0, (int64_t)N, jb0, nrhs, 1);
     }
     if (multi) nccl_allreduce_sum_f64(nc->all, X0, X0, (size_t)N * nrhs * nelem, s);
     }
@@ -133,8 +133,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
                 }
                 if (myrow == pr && mycol == pc) {
                     dim3 grid((unsigned)((jb + 127) / 128), gy);
-                    add_block_kernel<T><<<grid, 128, 0, s>>>(jb, nrhs, xk, N, part, ldp, tmp, jb);
-                    SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
+                    SLB_LAUNCH((add_block_kernel<T>), grid, 128, s, jb, nrhs, (const T *)xk, (int64_t)N, part, ldp, tmp, (int64_t)jb);
                     launch_trsv_block<T>(jb, A + lr0 + lc0 * lld, lld, tmp, jb, nrhs,
                                          (use_u ? TRSV_UPPER : 0) | (tr ? TRSV_TRANS : 0) | (cj ? TRSV_CONJ : 0), s);
                 }
@@ -168,8 +167,7 @@ int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, 
     if (Xrep_out) SLB_CUDA(cudaMemcpyAsync(Xrep_out, Xg, (size_t)N * nrhs * sizeof(T), cudaMemcpyDeviceToDevice, s));
     else if (mloc > 0 && nlocB_all > 0) {
         dim3 grid((unsigned)((mloc + 255) / 256), gyb);
-        rhs_scatter_kernel<T><<<grid, 256, 0, s>>>(mloc, nlocB_all, nb, nbb, P, Q, myr_rel, myc_relb, B, lldb, Xg, N, jb0, nrhs, 0);
-        SLB_CUDA(cudaGetLastError()); counter_add("kernel_launches", 1);
+        SLB_LAUNCH((rhs_scatter_kernel<T>), grid, 256, s, mloc, nlocB_all, nb, nbb, P, Q, myr_rel, myc_relb, (const T *)B, lldb, Xg, (int64_t)N, jb0, nrhs, 0);
     }
     SLB_CUDA(cudaEventRecord(ev1, s));
     SLB_CUDA(cudaStreamSynchronize(s));

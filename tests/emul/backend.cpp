@@ -179,66 +179,25 @@ static void scatter_bc(Grid *g, int M, int N, const std::vector<T> &G, T *A, int
     }
 }
 
-// PDGETRS by contract, replicated or block-cyclic right-hand sides
+// solve.cu (the PDGETRS orchestration) is compiled for real; what it calls from solve_kernels.cu / solve_fast.cu by contract:
+bool getrs_fast_applies(int, int, char, int, int) { return false; }      // the 1x1 two-stream fast path is GPU-only
+void getrs_fast_device(int, int, const double *, int64_t, int, double *) { fatal("emulation: the solve fast path is not modelled"); }
+double solve_fast_probe(int, int, int64_t, const double *, int64_t, int, int) { return 0; }
 template <typename T>
-int getrs_device(Grid *g, char trans, int N, int nrhs, const T *A, int64_t lld, int nb, int rsrc, int csrc, const int *ipiv,
-                 T *B, int64_t lldb, int nbb, int csrcb, int jb0, int64_t nlocB_all, const T *Xin, T *Xout)
+void launch_gather_rows(int64_t n, const int *perm, const T *src, int64_t lds, T *dst, int64_t ldd, int nrhs, cudaStream_t, bool scatter)
 {
-    // a process that holds nothing of the factors (or of B) may pass any address: it is never read
-    if (numroc(N, nb, g->myrow, rsrc, g->nprow) > 0 && numroc(N, nb, g->mycol, csrc, g->npcol) > 0) DEV(A);
-    if (numroc(N, nb, g->myrow, rsrc, g->nprow) > 0 && nlocB_all > 0) DEV(B);
-    DEV(Xin); DEV(Xout);
-    std::vector<T> G = gather_bc<T>(g, N, N, A, lld, nb, rsrc, csrc);
-    const int P = g->nprow, Q = g->npcol;
-    std::vector<T> X((size_t)N * nrhs);
-    memset(X.data(), 0, X.size() * sizeof(T));
-    const int64_t mloc = numroc(N, nb, g->myrow, rsrc, P);
-    auto bcol = [&](int64_t jl) { return (int64_t)indxl2g((int)jl + 1, nbb, g->mycol, csrcb, Q) - 1 - jb0; };
-    if (Xin) memcpy(X.data(), Xin, X.size() * sizeof(T));
-    else {
-        for (int64_t jl = 0; jl < nlocB_all; ++jl) {
-            const int64_t jg = bcol(jl); if (jg < 0 || jg >= nrhs) continue;
-            for (int64_t il = 0; il < mloc; ++il) X[(size_t)(indxl2g((int)il + 1, nb, g->myrow, rsrc, P) - 1 + jg * N)] = B[il + jl * lldb];
+    if (n <= 0 || nrhs <= 0) return;
+    DEV(perm); DEV(src); DEV(dst);
+    for (int c = 0; c < nrhs; ++c)
+        for (int64_t i = 0; i < n; ++i) {
+            const int p = perm[i];
+            if (p < 0) continue;
+            if (scatter) dst[p + (int64_t)c * ldd] = src[i + (int64_t)c * lds]; else dst[i + (int64_t)c * ldd] = src[p + (int64_t)c * lds];
         }
-        if (P * Q > 1) {
-            std::vector<T> all(X.size() * (size_t)(P * Q));
-            grid_allgather(g, 'A', X.data(), all.data(), X.size() * sizeof(T));
-            const size_t nd = X.size() * sizeof(T) / sizeof(double);
-            double *x = reinterpret_cast<double *>(X.data()); const double *a = reinterpret_cast<const double *>(all.data());
-            for (size_t e = 0; e < nd; ++e) { double v = 0; for (int p = 0; p < P * Q; ++p) v += a[(size_t)p * nd + e]; x[e] = v; }
-        }
-    }
-    const bool cj = trans == 'C';
-    auto el = [&](int i, int k) { return G[(size_t)(i + (int64_t)k * N)]; };
-    for (int c = 0; c < nrhs; ++c) {
-        T *x = X.data() + (size_t)c * N;
-        if (trans == 'N') {
-            for (int i = 0; i < N; ++i) { const int p = ipiv[i] - 1; if (p != i) { T t = x[i]; x[i] = x[p]; x[p] = t; } }
-            // row-oriented substitution with the inner products accumulated from the far end: a rounding pattern unlike the
-            // oracle's column sweeps, as different from it as the GPU's blocked sweeps are
-            for (int i = 0; i < N; ++i) for (int k = i - 1; k >= 0; --k) x[i] = cmul_sub(x[i], el(i, k), x[k]);
-            for (int i = N - 1; i >= 0; --i) { for (int k = N - 1; k > i; --k) x[i] = cmul_sub(x[i], el(i, k), x[k]); x[i] = cdiv(x[i], el(i, i)); }
-        } else {
-            for (int k = 0; k < N; ++k) {                      // U^T (U^H) forward
-                for (int i = 0; i < k; ++i) x[k] = cmul_sub(x[k], cj ? cconj(el(i, k)) : el(i, k), x[i]);
-                x[k] = cdiv(x[k], cj ? cconj(el(k, k)) : el(k, k));
-            }
-            for (int k = N - 1; k >= 0; --k)                   // L^T (L^H) backward, unit diagonal
-                for (int i = k + 1; i < N; ++i) x[k] = cmul_sub(x[k], cj ? cconj(el(i, k)) : el(i, k), x[i]);
-            for (int i = N - 1; i >= 0; --i) { const int p = ipiv[i] - 1; if (p != i) { T t = x[i]; x[i] = x[p]; x[p] = t; } }
-        }
-    }
-    if (Xout) memcpy(Xout, X.data(), X.size() * sizeof(T));
-    else
-        for (int64_t jl = 0; jl < nlocB_all; ++jl) {
-            const int64_t jg = bcol(jl); if (jg < 0 || jg >= nrhs) continue;
-            for (int64_t il = 0; il < mloc; ++il) B[il + jl * lldb] = X[(size_t)(indxl2g((int)il + 1, nb, g->myrow, rsrc, P) - 1 + jg * N)];
-        }
-    g_last_lu.solve_ms = 0;
-    return 0;
+    counter_add("kernel_launches", 1);
 }
-template int getrs_device<double>(Grid *, char, int, int, const double *, int64_t, int, int, int, const int *, double *, int64_t, int, int, int, int64_t, const double *, double *);
-template int getrs_device<zcomplex>(Grid *, char, int, int, const zcomplex *, int64_t, int, int, int, const int *, zcomplex *, int64_t, int, int, int, int64_t, const zcomplex *, zcomplex *);
+template void launch_gather_rows<double>(int64_t, const int *, const double *, int64_t, double *, int64_t, int, cudaStream_t, bool);
+template void launch_gather_rows<zcomplex>(int64_t, const int *, const zcomplex *, int64_t, zcomplex *, int64_t, int, cudaStream_t, bool);
 
 // ---- the LU's own kernels by contract (kernels.cuh; panel.cu, swap.cu) so that lu.cu / api.cu run their REAL orchestration --------
 static inline double crecip(double x) { return 1.0 / x; }

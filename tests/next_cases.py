@@ -625,4 +625,7 @@ F5_CASES = [
     dict(kind="getrs_l3", n=45, nb=4, nrhs=7, nbb=3, cond=1), dict(kind="getrs_l3", n=45, nb=4, nrhs=7, nbb=3, trans="T"),
     dict(kind="getrs_l3", n=40, nb=8, nrhs=50, off=2, rsrc=1, csrc=1), dict(kind="getrs_l3", n=40, nb=8, nrhs=50, off=2, rsrc=1, csrc=1, trans="T"),
     dict(kind="getrs_l3", n=100, nb=40, nrhs=1),
+    # through pdgetrs_ itself, which takes this path above 64 right-hand sides (and the replicated path below)
+    dict(kind="getrs_l3", n=64, nb=8, nrhs=70, entry=True), dict(kind="getrs_l3", n=64, nb=8, nrhs=70, entry=True, trans="T"),
+    dict(kind="getrs_l3", n=40, nb=8, nrhs=66, off=1, rsrc=1, csrc=1, entry=True), dict(kind="getrs_l3", n=64, nb=8, nrhs=5, entry=True),
 ]
