@@ -15,6 +15,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def S():
     """The product's Python mirror (ctypes over the C-ABI library); builds the library if missing."""
+    if os.environ.get("SLB200_EMUL") == "1":
+        # host-logic emulation (tests/emul, CPU only): the GPU test files can be pointed at it to check the entry points' host side
+        import scalapack_b200.api as api_
+        api_._SO = os.path.join(ROOT, "tests", "emul", "libslb_emul.so")
     import scalapack_b200 as S_
     if not S_.have_library():
         import __graft_entry__ as g

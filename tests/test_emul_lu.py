@@ -75,3 +75,20 @@ def test_host_streaming_with_late_slabs(emul_lib, delay, save_mb):
     cases = [dict(P=1, Q=1, m=384, n=384, nb=32, nrhs=1, split=64, hoststream=True), dict(P=1, Q=1, m=300, n=420, nb=32, nrhs=0, split=64, hoststream=True),
              dict(P=1, Q=1, m=420, n=300, nb=32, nrhs=0, hoststream=True), dict(P=1, Q=1, m=256, n=256, nb=16, nrhs=2, z=True, split=32, hoststream=True)]
     spawn(1, cases, extra_env={"SLB200_EMUL_SLAB_DELAY": str(delay), "SLB200_E2E_SAVE_MB": str(save_mb), "SLB200_E2E_SLAB_MB": "0"})
+
+
+def test_gpu_interface_tests_against_the_emulation(emul_lib):
+    """The host-resident cases of tests/test_gpu_iface.py and tests/test_gpu_lu.py (argument checks and INFO codes, sub-matrix operands,
+    RSRC / CSRC, TRANS = N / T / C, the reference's 6 x 6 example and LU.dat grid, zero pivots, guard rows, complex) run UNCHANGED
+    against the emulation library: the entry points' host side is checked on every CPU run, not only when a GPU is at hand.
+    Deselected: device-resident operands, kernel-vs-kernel bit-identity tests, the on-device generators, the full-size runs."""
+    env = dict(os.environ, SLB200_EMUL="1", OPENBLAS_NUM_THREADS="2", OMP_NUM_THREADS="2")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    run = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_iface.py"), os.path.join(ROOT, "tests", "test_gpu_lu.py"),
+                          "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                          "-k", "not True and not bit_identical and not device_generators and not full_size and not large_properties"],
+                         env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    tail = run.stdout[-1500:]
+    assert run.returncode == 0, tail + run.stderr[-1500:]
+    assert " passed" in tail and "failed" not in tail, tail
