@@ -193,9 +193,24 @@ void gemr2d_core(int m, int n, const T *a, int ia, int ja, const int *desca, T *
 template void gemr2d_core<double>(int, int, const double *, int, int, const int *, double *, int, int, const int *, int, bool, const int *);
 template void gemr2d_core<zcomplex>(int, int, const zcomplex *, int, int, const int *, zcomplex *, int, int, const int *, int, bool, const int *);
 
+// The public entry walks the columns in chunks so that the pack / receive buffers stay bounded (option redist_chunk_mb per process,
+// default 1024): a 64 GiB local array is redistributed with 2 GiB of scratch, not 128.  Every process of the global context computes
+// the same chunking from the global sizes.
 template <typename T>
 static void gemr2d_impl(int m, int n, const T *a, int ia, int ja, const int *desca, T *b, int ib, int jb, const int *descb, int gctxt)
-{ gemr2d_core<T>(m, n, a, ia, ja, desca, b, ib, jb, descb, gctxt, false, nullptr); }
+{
+    if (m <= 0 || n <= 0) return;
+    Grid *gg = grid_of(gctxt);
+    const int64_t np = gg && gg->in_grid() ? (int64_t)gg->nprow * gg->npcol : 1;
+    const int64_t budget = opt("redist_chunk_mb", 1024) << 20;
+    int64_t nc = budget * np / ((int64_t)m * (int64_t)sizeof(T));
+    if (nc < 1) nc = 1;
+    if (nc >= n) { gemr2d_core<T>(m, n, a, ia, ja, desca, b, ib, jb, descb, gctxt, false, nullptr); return; }
+    for (int64_t j0 = 0; j0 < n; j0 += nc) {
+        const int w = (int)(n - j0 < nc ? n - j0 : nc);
+        gemr2d_core<T>(m, w, a, ia, ja + (int)j0, desca, b, ib, jb + (int)j0, descb, gctxt, false, nullptr);
+    }
+}
 
 }  // namespace slb
 

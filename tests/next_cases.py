@@ -293,6 +293,7 @@ def case_gemr2d(G, cs):
     bl, descb, rc = local(cb, Pb, Qb, bg, mbb, nbb, rsb, csb)
     a_before = None if al is None else al.copy()
     f = S.pzgemr2d if z else S.pdgemr2d
+    S.set_option("redist_chunk_mb", cs.get("chunk_mb", 1024))      # 0: one column per exchange (the chunked walk of the public entry)
     dev = OnDevice(S, cs.get("dev") and not z)
     f(m, n, dev(al) if al is not None else np.zeros(1, dtype=ag.dtype), ia, ja, desca, dev(bl) if bl is not None else np.zeros(1, dtype=ag.dtype), ib, jb,
       descb, G.ctx)
@@ -588,6 +589,7 @@ F2_CASES = [
     dict(kind="gemr2d", m=37, n=41, shape_a=(37, 41), shape_b=(37, 41), blk_a=(4, 4), blk_b=(6, 2), ga=(1, 3), gb=(3, 2)),
     dict(kind="gemr2d", m=20, n=25, ja=3, shape_a=(20, 30), shape_b=(25, 25), ib=6, blk_a=(2, 2), blk_b=(4, 4), z=True),
     dict(kind="gemr2d", m=1, n=1, ia=7, ja=9, ib=3, jb=2, shape_a=(10, 10), shape_b=(5, 5), blk_a=(2, 2), blk_b=(3, 3)),
+    dict(kind="gemr2d", m=33, n=29, ia=5, ja=8, ib=2, jb=11, shape_a=(45, 41), shape_b=(37, 50), blk_a=(4, 3), blk_b=(7, 5), src_a=(1, 0), src_b=(0, 1), chunk_mb=0),
 ]
 
 # Cholesky: both triangles, partial last blocks, blocks wider than 32 (the diagonal block's inner loop), sub-matrices, shifted sources,
