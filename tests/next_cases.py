@@ -543,7 +543,64 @@ def case_getrs_l3(G, cs):
     return msgs
 
 
-CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri, "pdgemm": case_pdgemm, "pdtrsm": case_pdtrsm, "pdtran": case_pdtran, "getrs_l3": case_getrs_l3}
+def case_ludriver(G, cs):
+    """The reference's own LU test driver with EST = T (TESTING/traditional/LIN/pdludriver.f:380-900 on the LU.dat grid): PDLANGE ->
+    PDGETRF -> PDGECON -> PDGETRS -> solve residual (pdlaschk.f, threshold 1.0) -> PDGERFS -> solve residual again, with the driver's
+    guard zones (PADVAL) around A0, A, IPIV, B0, B, FERR, BERR checked after every call (PDCHEKPAD)."""
+    S, msgs = G.S, []
+    n, nb, nrhs, nbrhs = cs["n"], cs["nb"], cs["nrhs"], cs["nbrhs"]
+    PAD = -9923.0
+    a0g = O.pdmatgen(n, n, 100); b0g = O.pdmatgen(n, nrhs, 200)
+    mloc, nloc, nlocb = S.numroc(n, nb, G.r, 0, G.P), S.numroc(n, nb, G.c, 0, G.Q), S.numroc(nrhs, nbrhs, G.c, 0, G.Q)
+    lld = max(1, mloc) + 2
+    def padded(glob, nbc):
+        al = O.scatter(np.asfortranarray(glob), nb, nbc, G.P, G.Q, G.r, G.c, lld=lld)
+        al[mloc:, :] = PAD
+        return al
+    a0l, al = padded(a0g, nb), padded(a0g, nb)
+    b0l, bl = padded(b0g, nbrhs), padded(b0g, nbrhs)
+    desca, _ = S.descinit(n, n, nb, nb, 0, 0, G.ctx, lld); descb, _ = S.descinit(n, nrhs, nb, nbrhs, 0, 0, G.ctx, lld)
+    ipiv = np.full(mloc + nb + 2, -77, np.int32)             # LIPIV + a guard zone
+    ferr, berr = np.full(max(1, nlocb) + 2, PAD), np.full(max(1, nlocb) + 2, PAD)
+    def pads(where):
+        ok = (np.all(a0l[mloc:, :] == PAD) and np.all(al[mloc:, :] == PAD) and np.all(b0l[mloc:, :] == PAD) and np.all(bl[mloc:, :] == PAD)
+              and np.all(ipiv[mloc + nb:] == -77) and np.all(ferr[max(1, nlocb):] == PAD) and np.all(berr[max(1, nlocb):] == PAD)
+              and np.array_equal(a0l[:mloc, :nloc], G.local_of(a0g, nb, lld=lld)[:mloc, :nloc]))
+        if not ok:
+            msgs.append(f"a guard zone (or A0) was overwritten by {where}")
+    anorm1 = S.pdlange("1", n, n, al, 1, 1, desca)
+    info = S.pdgetrf(n, n, al, 1, 1, desca, ipiv[:mloc + nb]); pads("PDGETRF")
+    if info != 0:
+        msgs.append(f"PDGETRF info {info}")
+        return msgs
+    rcond, info = S.pdgecon("1", n, al, 1, 1, desca, anorm1); pads("PDGECON")
+    true_rc = 1.0 / (np.abs(a0g).sum(axis=0).max() * np.abs(np.linalg.inv(a0g)).sum(axis=0).max())
+    if info != 0 or not (true_rc * (1 - 1e-8) <= rcond <= 10 * true_rc):
+        msgs.append(f"PDGECON rcond {rcond} (true {true_rc}) info {info}")
+    info = S.pdgetrs("N", n, nrhs, al, 1, 1, desca, ipiv[:mloc + nb], bl, 1, 1, descb); pads("PDGETRS")
+    # the residual check needs the global X: collect the pieces over the control plane (tiny) via PDGEMR2D onto one process
+    xall = np.zeros((n + 1, nrhs), order="F") if (G.r, G.c) == (0, 0) else None
+    one = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1) if cs.get("_ctx1") is None else cs["_ctx1"]
+    cs["_ctx1"] = one
+    descx = S.descinit(n, nrhs, n, nrhs, 0, 0, one, n + 1)[0] if xall is not None else [1, -1, n, nrhs, n, nrhs, 0, 0, 1]
+    def check(tag):
+        S.pdgemr2d(n, nrhs, bl, 1, 1, descb, xall if xall is not None else np.zeros(1), 1, 1, descx, G.ctx)
+        if xall is not None:
+            res = O.sresid(a0g, np.asfortranarray(xall[:n, :]), b0g)
+            if not res < 1.0:
+                msgs.append(f"solve residual after {tag}: {res}")
+    check("PDGETRS")
+    info = S.pdgerfs("N", n, nrhs, a0l, 1, 1, desca, al, 1, 1, desca, ipiv[:mloc + nb], b0l, 1, 1, descb, bl, 1, 1, descb, ferr[:max(1, nlocb)], berr[:max(1, nlocb)])
+    pads("PDGERFS")
+    if info != 0:
+        msgs.append(f"PDGERFS info {info}")
+    check("PDGERFS")
+    if nlocb and n > 1 and not (np.all(berr[:nlocb] >= 0) and np.all(berr[:nlocb] < 1e-13) and np.all(ferr[:nlocb] >= 0)):
+        msgs.append(f"FERR {ferr[:nlocb]} BERR {berr[:nlocb]}")
+    return msgs
+
+
+CASES = {"lange": case_lange, "equ": case_equ, "gecon": case_gecon, "gerfs": case_gerfs, "gesvx": case_gesvx, "gemr2d": case_gemr2d, "potrf": case_potrf, "getri": case_getri, "pdgemm": case_pdgemm, "pdtrsm": case_pdtrsm, "pdtran": case_pdtran, "getrs_l3": case_getrs_l3, "ludriver": case_ludriver}
 
 
 def run(S, ctx, cases):
@@ -631,3 +688,6 @@ F5_CASES = [
     dict(kind="getrs_l3", n=64, nb=8, nrhs=70, entry=True), dict(kind="getrs_l3", n=64, nb=8, nrhs=70, entry=True, trans="T"),
     dict(kind="getrs_l3", n=40, nb=8, nrhs=66, off=1, rsrc=1, csrc=1, entry=True), dict(kind="getrs_l3", n=64, nb=8, nrhs=5, entry=True),
 ]
+
+# TESTING/traditional/LU.dat with EST = T: the square problem sizes x NB x NRHS x NBRHS of the reference's own input file
+LUDAT_CASES = [dict(kind="ludriver", n=n, nb=nb, nrhs=nrhs, nbrhs=nbrhs) for n in (4, 13) for nb in (2, 3, 4) for nrhs in (1, 3, 9) for nbrhs in (1, 3, 5)]

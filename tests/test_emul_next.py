@@ -83,3 +83,9 @@ def test_compiled_c_caller_on_the_emulation(emul_lib, tmp_path):
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
     assert run.returncode == 0 and "expert example ok" in run.stdout, (run.stdout, run.stderr)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (2, 2), (1, 4), (4, 1)])
+def test_reference_lu_driver_with_est(emul_lib, P, Q):
+    """TESTING/traditional/LU.dat (EST = T) on its own process grids: the flow of pdludriver.f through the real entry points."""
+    spawn(P, Q, "LUDAT_CASES")

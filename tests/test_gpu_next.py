@@ -187,3 +187,15 @@ def test_level3_solve_multi(P, Q):
     if ngpus() < P * Q:
         pytest.skip(f"needs {P * Q} GPUs")
     spawn(P, Q, next_cases.F5_CASES + F5_GPU)
+
+
+# ---- the reference's own LU test driver with EST = T on the LU.dat grid (PDGETRF -> PDGECON -> PDGETRS -> PDGERFS, guard zones) ----
+def test_reference_lu_driver_with_est_1x1():
+    spawn(1, 1, next_cases.LUDAT_CASES + [dict(kind="ludriver", n=1000, nb=64, nrhs=3, nbrhs=2), dict(kind="ludriver", n=2048, nb=256, nrhs=1, nbrhs=1)])
+
+
+@pytest.mark.parametrize("P,Q", [(2, 2), (1, 4), (4, 1)])
+def test_reference_lu_driver_with_est_multi(P, Q):
+    if ngpus() < P * Q:
+        pytest.skip(f"needs {P * Q} GPUs")
+    spawn(P, Q, next_cases.LUDAT_CASES)
