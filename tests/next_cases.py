@@ -357,6 +357,14 @@ def case_potrf(G, cs):
             msgs.append("elements outside the triangle were modified")
     if not np.all(al[mloc:, :] == -9923.0):
         msgs.append("guard row overwritten")
+    # the reference's own check (pdlltdriver.f: PDPOTRRV + PDLAFCHK): || L L' - A || / (||A|| N eps) <= 3.0 (LLT.dat)
+    fac = _to_root(G, n, n, al, ia, ia, desca)
+    if fac is not None:
+        t = np.tril(fac) if uplo == "L" else np.triu(fac)
+        rec = t @ t.T if uplo == "L" else t.T @ t
+        fres = np.abs(rec - a0).sum(axis=1).max() / (np.abs(a0).sum(axis=1).max() * n * EPS)
+        if not fres <= 3.0:
+            msgs.append(f"Cholesky factor residual {fres} > 3.0")
     if off:
         return msgs
     # PDPOTRS on the factor, PDPOSV from scratch (l3: force the many-right-hand-sides path whatever NRHS is)
@@ -377,6 +385,19 @@ def case_potrf(G, cs):
     return msgs
 
 
+def _to_root(G, m, n, al, ia, ja, desc, cache={}):
+    """sub(A) gathered on process (0, 0) through PDGEMR2D onto a 1 x 1 grid (None elsewhere); every process of the grid calls"""
+    S = G.S
+    key = (id(S), G.ctx)
+    if key not in cache:
+        cache[key] = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1)
+    root = (G.r, G.c) == (0, 0)
+    full = np.zeros((m + 1, n), order="F") if root else np.zeros(1)
+    descf = S.descinit(m, n, m, n, 0, 0, cache[key], m + 1)[0] if root else [1, -1, m, n, m, n, 0, 0, 1]
+    S.pdgemr2d(m, n, al, ia, ja, desc, full, 1, 1, descf, G.ctx)
+    return np.asfortranarray(full[:m, :]) if root else None
+
+
 def case_getri(G, cs):
     """PDGETRI on the oracle's factors (optionally of a sub-matrix with shifted source processes)"""
     S, msgs = G.S, []
@@ -384,6 +405,8 @@ def case_getri(G, cs):
     rsrc, csrc = cs.get("rsrc", 0) % G.P, cs.get("csrc", 0) % G.Q
     ng = n + off * nb
     a0 = matrix(n, cond=cs.get("cond"))
+    if cs.get("dominant"):
+        a0 = np.asfortranarray(a0 + n * np.eye(n))               # PDMATGEN( ..., 'N', 'D', ... ): the matrices of pdinvdriver.f
     lu = a0.copy(order="F"); ipg, info = O.getrf(lu, nb)
     if cs.get("singular") is not None:
         lu[cs["singular"], cs["singular"]] = 0.0
@@ -412,6 +435,13 @@ def case_getri(G, cs):
             msgs.append(f"inverse differs: {err} (cond {cond:.3g})")
     if not np.all(al[mloc:, :] == -9923.0):
         msgs.append("guard row overwritten")
+    if cs.get("dominant") and info0 == 0:
+        # the reference's own check (TESTING/traditional/LIN/pdinvchk.f:378): || inv(A) A - I ||_1 / (N eps ||A||_1) <= 1.0 (INV.dat)
+        inv_root = _to_root(G, n, n, al, ia, ia, desca)
+        if inv_root is not None:
+            fres = np.abs(inv_root @ a0 - np.eye(n)).sum(axis=0).max() / (n * EPS * np.abs(a0).sum(axis=0).max())
+            if not fres <= 1.0:
+                msgs.append(f"pdinvchk residual {fres} > 1.0")
     if S.pdgetri(n, al, ia, ia, desca, ipl, lwork=0) != -8:
         msgs.append("short LWORK not reported")
     return msgs
@@ -663,7 +693,8 @@ F3_CASES = [
 ]
 
 F4_CASES = [
-    dict(kind="getri", n=64, nb=8), dict(kind="getri", n=1, nb=3), dict(kind="getri", n=2, nb=1), dict(kind="getri", n=45, nb=4, cond=2), dict(kind="getri", n=150, nb=40), dict(kind="getri", n=7, nb=16),
+    dict(kind="getri", n=64, nb=8), dict(kind="getri", n=1, nb=3),
+    dict(kind="getri", n=50, nb=6, dominant=True), dict(kind="getri", n=15, nb=4, dominant=True), dict(kind="getri", n=30, nb=20, dominant=True), dict(kind="getri", n=2, nb=1), dict(kind="getri", n=45, nb=4, cond=2), dict(kind="getri", n=150, nb=40), dict(kind="getri", n=7, nb=16),
     dict(kind="getri", n=100, nb=100), dict(kind="getri", n=40, nb=8, off=2, rsrc=1, csrc=1), dict(kind="getri", n=64, nb=8, singular=37),
 ]
 

@@ -129,7 +129,7 @@ def test_cholesky_multi(P, Q):
 
 # ---- row 4: PDGETRI ----
 F4_GPU = [
-    dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=2200, nb=512),
+    dict(kind="getri", n=2048, nb=256), dict(kind="getri", n=2048, nb=128, dominant=True), dict(kind="getri", n=1500, nb=64, cond=1), dict(kind="getri", n=2200, nb=512),
     dict(kind="getri", n=1200, nb=128, off=2, rsrc=1, csrc=1), dict(kind="getri", n=1000, nb=128, singular=900), dict(kind="getri", n=1536, nb=256, dev=True),
 ]
 
