@@ -89,3 +89,36 @@ def test_compiled_c_caller_on_the_emulation(emul_lib, tmp_path):
 def test_reference_lu_driver_with_est(emul_lib, P, Q):
     """TESTING/traditional/LU.dat (EST = T) on its own process grids: the flow of pdludriver.f through the real entry points."""
     spawn(P, Q, "LUDAT_CASES")
+
+
+def test_argument_errors_of_the_8f_entry_points(emul_lib):
+    """INFO codes of the reference for illegal arguments (SRC/pdgesvx.f:499-573, pdgerfs.f:340-400, pdgecon.f:241-254, pdpotrf.f:181-190,
+    pdpotrs.f:193-206, pdgetri.f:231-240): the checks run before any device work, so the emulation exercises exactly the product's code."""
+    code = r'''
+import sys
+sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(root)s/tests")
+import numpy as np
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import scalapack_b200 as S, oracle as O
+ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1)
+n, nb, nrhs = 12, 4, 2
+a = np.asfortranarray(O.pdmatgen(n, n, 100)); b = np.asfortranarray(O.pdmatgen(n, nrhs, 200))
+da, _ = S.descinit(n, n, nb, nb, 0, 0, ctx, n); db, _ = S.descinit(n, nrhs, nb, 1, 0, 0, ctx, n)
+af = np.zeros_like(a); x = np.zeros_like(b); ipiv = np.zeros(n + nb, np.int32); r = np.ones(n); c = np.ones(n); fe = np.zeros(nrhs); be = np.zeros(nrhs)
+def svx(fact, trans, equed, r=r, c=c):
+    return S.pdgesvx(fact, trans, n, nrhs, a.copy(order="F"), 1, 1, da, af, 1, 1, da, ipiv, equed, r, c, b.copy(order="F"), 1, 1, db, x, 1, 1, db, fe, be)[2]
+rb = r.copy(); rb[3] = 0.0
+cb = c.copy(); cb[5] = -1.0
+out = [svx("X", "N", "N"), svx("N", "X", "N"), svx("N", "N", "N"), svx("F", "N", "Q"), svx("F", "N", "R", r=rb), svx("F", "N", "C", c=cb), svx("F", "N", "B"), svx("F", "T", "B"),
+       S.pdgerfs("X", n, nrhs, a, 1, 1, da, af, 1, 1, da, ipiv, b, 1, 1, db, x, 1, 1, db, fe, be), S.pdgecon("1", n, af, 1, 1, da, -1.0)[1],
+       S.pdpotrf("X", n, a.copy(order="F"), 1, 1, da), S.pdpotrf("L", 4, a.copy(order="F"), 2, 1, da), S.pdpotrs("Q", n, nrhs, a, 1, 1, da, b.copy(order="F"), 1, 1, db),
+       S.pdgetri(4, a.copy(order="F"), 2, 2, da, ipiv), S.pdgetri(n, a.copy(order="F"), 1, 1, da, ipiv, lwork=1), S.pdgetri(n, a.copy(order="F"), 1, 1, da, ipiv, liwork=0)]
+print("CODES", out)
+''' % dict(root=ROOT)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+    assert run.returncode == 0, run.stderr[-2000:]
+    line = [ln for ln in run.stdout.splitlines() if ln.startswith("CODES")][0]
+    assert line == "CODES [-1, -2, 0, -13, -14, -15, 0, 0, -1, -7, -1, -4, -1, -4, -8, -10]", line
+    assert "On entry to PDGESVX parameter number  13 had an illegal value" in run.stderr       # PXERBLA's text
