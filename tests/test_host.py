@@ -328,3 +328,50 @@ def test_worker_pool_2d_copy(S, threads):
         for j in range(n):
             want[j * dpitch:j * dpitch + width] = src[j * spitch:j * spitch + width]
         assert np.array_equal(dst, want), (width, n, spitch, dpitch)
+
+
+def test_fortran_interface_module_matches_the_c_header(S):
+    """No Fortran compiler exists in the build image or on the GPU boxes, so fortran/scalapack_b200_iface.f90 cannot be compiled.  It is
+    parsed with a real Fortran parser instead (numpy.f2py's crackfortran): every interface must bind a symbol the library exports, with
+    as many arguments as the C prototype in include/scalapack_b200.h, each argument declared with a C-interoperable type of the right
+    class (integer -> int*, real(c_double) -> double*, complex -> slb200_z*, character -> char*)."""
+    import ctypes as C
+    import re
+    import numpy.f2py.crackfortran as cf
+    cf.verbose = 0
+    cf.quiet = 1
+    blocks = cf.crackfortran([os.path.join(ROOT, "fortran", "scalapack_b200_iface.f90")])
+    procs = []
+
+    def walk(bs):
+        for b in bs:
+            if b.get("block") in ("subroutine", "function"):
+                procs.append(b)
+            walk(b.get("body", []))
+    walk(blocks)
+    assert len(procs) >= 24
+    header = open(os.path.join(ROOT, "include", "scalapack_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    L = S.lib()
+    for p in procs:
+        name = p["name"]
+        cname = p["bindlang"][name]["name"]
+        assert p["bindlang"][name]["lang"] == "c"
+        assert hasattr(L, cname), f"{cname} is not exported"
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % re.escape(cname), header, flags=re.S)
+        assert m, f"{cname} is not declared in the header"
+        cargs = [a.strip() for a in m.group(1).split(",")] if m.group(1).strip() not in ("", "void") else []
+        assert len(cargs) == len(p["args"]), f"{cname}: {len(p['args'])} Fortran arguments, {len(cargs)} in the C prototype"
+        for fa, ca in zip(p["args"], cargs):
+            spec = p["vars"][fa]
+            ts = spec["typespec"]
+            if ts == "integer":
+                assert re.search(r"\b(int|int64_t|uint64_t)\b", ca) and "*" in ca, (cname, fa, ca)
+            elif ts == "real":
+                assert "double" in ca and "*" in ca, (cname, fa, ca)
+            elif ts == "complex":
+                assert "slb200_z" in ca and "*" in ca, (cname, fa, ca)
+            elif ts == "character":
+                assert "char" in ca and "*" in ca, (cname, fa, ca)
+            else:
+                raise AssertionError((cname, fa, ts))
