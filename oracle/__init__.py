@@ -331,3 +331,50 @@ def dtrsm(side, uplo, transa, diag, alpha, a, b):
     if side.upper() == "L":
         return np.linalg.solve(opt, alpha * b)
     return np.linalg.solve(opt.T, alpha * b.T).T
+
+
+# ---------------------------------------------------------------- oracle/_ref: the reference's own PDGEMR2D (REDIST/SRC/pdgemr.c)
+_REF = None
+
+
+def ref_redist_lib():
+    """oracle/_ref/libref_redist.so = the reference's REDIST sources compiled in place + oracle/ref_redist.c (thread-based mini-BLACS);
+    None when it has not been built (no /root/reference at build time)."""
+    global _REF
+    if _REF is None:
+        so = os.path.join(_HERE, "_ref", "libref_redist.so")
+        if not os.path.exists(so):
+            try:
+                subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+            except Exception:
+                pass
+        _REF = C.CDLL(so) if os.path.exists(so) else False
+    return _REF or None
+
+
+def ref_pdgemr2d(ag, m, n, ia, ja, ib, jb, grid_a, blk_a, src_a, shape_b, grid_b, blk_b, src_b, fill=-9923.0):
+    """The REFERENCE redistributes sub(A) of the global matrix ag (distributed on grid_a with blk_a blocks from process src_a) into
+    sub(B) of a `fill`-initialised B (shape_b on grid_b, blk_b, src_b).  Returns the list of local B arrays (LOCr x LOCc, Fortran order;
+    None for processes outside B's grid), indexed by the process number in the global 1 x np context (= row-major position in a grid)."""
+    L = ref_redist_lib()
+    assert L is not None
+    (pa, qa), (pb, qb) = grid_a, grid_b
+    np_ = max(pa * qa, pb * qb)
+    ag = np.asfortranarray(ag, dtype=np.float64)
+    ma, na = ag.shape
+    mb, nb = shape_b
+    stride = (mb + 1) * (nb + 1)
+    bout = np.zeros(np_ * stride)
+    dims = np.zeros(2 * np_, np.int32)
+    rc = L.ref_pdgemr2d_run(np_, m, n, ia, ja, ib, jb, pa, qa, ma, na, blk_a[0], blk_a[1], src_a[0], src_a[1], pb, qb, mb, nb, blk_b[0], blk_b[1],
+                            src_b[0], src_b[1], _f(ag), C.c_double(fill), _f(bout), C.c_int64(stride), _p(dims))
+    assert rc == 0
+    out = []
+    for r in range(np_):
+        ml, nl = int(dims[2 * r]), int(dims[2 * r + 1])
+        if r >= pb * qb:
+            out.append(None)
+        else:
+            lld = max(1, ml)
+            out.append(np.asfortranarray(bout[r * stride:r * stride + lld * max(1, nl)].reshape((lld, max(1, nl)), order="F")[:ml, :nl]))
+    return out

@@ -1,5 +1,7 @@
 """The oracle's restatement of the SURVEY 8(f) routines (oracle/oracle_next.c) against an independent LAPACK (scipy):
 every routine restated there has a LAPACK twin with the same algorithm, so agreement is to rounding."""
+import os
+
 import numpy as np
 import pytest
 from scipy.linalg import lapack
@@ -169,3 +171,35 @@ def test_pblas_definitions(O):
                     rhs = bb if side == "L" else bb.T.copy()
                     x = O.dtrsm(side, uplo, ta, dg, 0.5, t, rhs)
                     np.testing.assert_allclose(op @ x if side == "L" else x @ op, 0.5 * rhs, atol=1e-12)
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 2), (2, 3), (3, 2)])
+def test_redistribution_expectation_against_the_reference_itself(O, P, Q):
+    """oracle/_ref: the reference's own PDGEMR2D (REDIST/SRC/pdgemr.c + pgemraux.c + pdgemr2.c compiled in place, run with one thread
+    per BLACS process over oracle/ref_redist.c's mini-BLACS) must produce, bit for bit, what the parity cases of tests/next_cases.py
+    expect of the product: sub(B) = sub(A), everything else of B untouched, for every layout / grid / offset case."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import next_cases
+    if O.ref_redist_lib() is None:
+        pytest.skip("oracle/_ref not built (no reference sources on this machine)")
+    ran = 0
+    for cs in next_cases.F2_CASES:
+        if cs.get("z"):
+            continue
+        (Pa, Qa), (Pb, Qb) = cs.get("ga", (P, Q)), cs.get("gb", (P, Q))
+        if Pa * Qa > P * Q or Pb * Qb > P * Q:
+            continue
+        m, n, ia, ja, ib, jb = cs["m"], cs["n"], cs.get("ia", 1), cs.get("ja", 1), cs.get("ib", 1), cs.get("jb", 1)
+        (rsa, csa), (rsb, csb) = cs.get("src_a", (0, 0)), cs.get("src_b", (0, 0))
+        rsa, csa, rsb, csb = rsa % Pa, csa % Qa, rsb % Pb, csb % Qb
+        ag = np.asfortranarray(O.pdmatgen(*cs["shape_a"], 100))
+        out = O.ref_pdgemr2d(ag, m, n, ia, ja, ib, jb, (Pa, Qa), cs["blk_a"], (rsa, csa), cs["shape_b"], (Pb, Qb), cs["blk_b"], (rsb, csb))
+        want = np.full(cs["shape_b"], -9923.0, order="F"); want[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n] = ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]
+        for r in range(Pb * Qb):
+            pr, pc = divmod(r, Qb)
+            exp = O.scatter(want, cs["blk_b"][0], cs["blk_b"][1], Pb, Qb, pr, pc, rsrc=rsb, csrc=csb)
+            ml, nl = out[r].shape
+            assert np.array_equal(out[r], exp[:ml, :nl]), (cs, r)
+        ran += 1
+    assert ran >= 5
