@@ -360,14 +360,17 @@ def ref_pdgemr2d(ag, m, n, ia, ja, ib, jb, grid_a, blk_a, src_a, shape_b, grid_b
     assert L is not None
     (pa, qa), (pb, qb) = grid_a, grid_b
     np_ = max(pa * qa, pb * qb)
-    ag = np.asfortranarray(ag, dtype=np.float64)
+    z = np.iscomplexobj(ag)                                   # complex: the reference's PZGEMR2D (REDIST/SRC/pzgemr.c)
+    dt = np.complex128 if z else np.float64
+    ag = np.asfortranarray(ag, dtype=dt)
     ma, na = ag.shape
     mb, nb = shape_b
-    stride = (mb + 1) * (nb + 1)
+    w = 2 if z else 1
+    stride = w * (mb + 1) * (nb + 1)
     bout = np.zeros(np_ * stride)
     dims = np.zeros(2 * np_, np.int32)
     rc = L.ref_pdgemr2d_run(np_, m, n, ia, ja, ib, jb, pa, qa, ma, na, blk_a[0], blk_a[1], src_a[0], src_a[1], pb, qb, mb, nb, blk_b[0], blk_b[1],
-                            src_b[0], src_b[1], _f(ag), C.c_double(fill), _f(bout), C.c_int64(stride), _p(dims))
+                            src_b[0], src_b[1], ag.ctypes.data_as(C.c_void_p), C.c_double(fill), _f(bout), C.c_int64(stride), _p(dims), 8 * w)
     assert rc == 0
     out = []
     for r in range(np_):
@@ -376,5 +379,6 @@ def ref_pdgemr2d(ag, m, n, ia, ja, ib, jb, grid_a, blk_a, src_a, shape_b, grid_b
             out.append(None)
         else:
             lld = max(1, ml)
-            out.append(np.asfortranarray(bout[r * stride:r * stride + lld * max(1, nl)].reshape((lld, max(1, nl)), order="F")[:ml, :nl]))
+            loc = bout[r * stride:r * stride + w * lld * max(1, nl)].view(dt)
+            out.append(np.asfortranarray(loc.reshape((lld, max(1, nl)), order="F")[:ml, :nl]))
     return out

@@ -20,6 +20,7 @@
 
 typedef struct { int desctype, ctxt, m, n, nbrow, nbcol, sprow, spcol, lda; } MDESC;       /* REDIST/SRC/pdgemr.c:160-170 */
 void Cpdgemr2d(int m, int n, double *a, int ia, int ja, MDESC *ma, double *b, int ib, int jb, MDESC *mb, int gctxt);   /* the reference */
+void Cpzgemr2d(int m, int n, void *a, int ia, int ja, MDESC *ma, void *b, int ib, int jb, MDESC *mb, int gctxt);       /* REDIST/SRC/pzgemr.c */
 
 /* ---- mini-BLACS ------------------------------------------------------------------------------------------------------------- */
 #define MAXCTX 16
@@ -118,6 +119,8 @@ static void gerv(int ctxt, int m, int n, char *a, int lda, int rsrc, int csrc, s
 }
 void Cdgesd2d(int ctxt, int m, int n, double *a, int lda, int rdest, int cdest) { gesd(ctxt, m, n, (const char *)a, lda, rdest, cdest, 8); }
 void Cdgerv2d(int ctxt, int m, int n, double *a, int lda, int rsrc, int csrc) { gerv(ctxt, m, n, (char *)a, lda, rsrc, csrc, 8); }
+void Czgesd2d(int ctxt, int m, int n, void *a, int lda, int rdest, int cdest) { gesd(ctxt, m, n, (const char *)a, lda, rdest, cdest, 16); }
+void Czgerv2d(int ctxt, int m, int n, void *a, int lda, int rsrc, int csrc) { gerv(ctxt, m, n, (char *)a, lda, rsrc, csrc, 16); }
 void Cigesd2d(int ctxt, int m, int n, int *a, int lda, int rdest, int cdest) { gesd(ctxt, m, n, (const char *)a, lda, rdest, cdest, 4); }
 void Cigerv2d(int ctxt, int m, int n, int *a, int lda, int rsrc, int csrc) { gerv(ctxt, m, n, (char *)a, lda, rsrc, csrc, 4); }
 /* element-wise minimum over ALL processes of the context, result everywhere (BLACS/SRC/igamn2d_.c with rdest = -1) */
@@ -149,10 +152,11 @@ typedef struct {
     int rank, np, m, n, ia, ja, ib, jb;
     int pa, qa, ma, na, mba, nba, rsa, csa;
     int pb, qb, mb, nb, mbb, nbb, rsb, csb;
-    const double *aglob;            /* ma x na, column-major */
-    double fill;                    /* what B holds outside sub(B) */
-    double *bout; int64_t bstride;  /* rank r returns its local B (lld = max(1, LOCr) x LOCc, packed) at bout + r * bstride */
+    const double *aglob;            /* ma x na, column-major (es / 8 doubles per element) */
+    double fill;                    /* what B holds outside sub(B) (every double of an element) */
+    double *bout; int64_t bstride;  /* rank r returns its local B (lld = max(1, LOCr) x LOCc, packed) at bout + r * bstride (in doubles) */
     int *bdims;                     /* 2 ints per rank: LOCr, LOCc of B (0, 0 when not in B's grid) */
+    int es;                         /* element size: 8 (PDGEMR2D) or 16 (PZGEMR2D) */
 } Job;
 
 static int numroc(int n, int nb, int iproc, int isrc, int nprocs)
@@ -173,16 +177,17 @@ static void *worker(void *arg)
     Cblacs_get(0, 0, &ctxb); Cblacs_gridinit(&ctxb, "R", j->pb, j->qb);
     MDESC da = { 1, -1, j->ma, j->na, j->mba, j->nba, j->rsa, j->csa, 1 }, db = { 1, -1, j->mb, j->nb, j->mbb, j->nbb, j->rsb, j->csb, 1 };
     double *al = NULL, *bl = NULL;
+    const int w = j->es / 8;                                      /* doubles per element */
     Cblacs_gridinfo(ctxa, &p, &q, &r, &c);
     if (r >= 0) {
         const int ml = numroc(j->ma, j->mba, r, j->rsa, p), nl = numroc(j->na, j->nba, c, j->csa, q), lld = ml > 0 ? ml : 1;
-        al = malloc(sizeof(double) * (size_t)lld * (size_t)(nl > 0 ? nl : 1));
+        al = malloc(sizeof(double) * w * (size_t)lld * (size_t)(nl > 0 ? nl : 1));
         for (int gj = 0; gj < j->na; ++gj) {
             if ((j->csa + gj / j->nba) % q != c) continue;
             const int lj = (gj / (j->nba * q)) * j->nba + gj % j->nba;
             for (int gi = 0; gi < j->ma; ++gi) {
                 if ((j->rsa + gi / j->mba) % p != r) continue;
-                al[(gi / (j->mba * p)) * j->mba + gi % j->mba + (size_t)lj * lld] = j->aglob[gi + (size_t)gj * j->ma];
+                for (int d = 0; d < w; ++d) al[w * ((gi / (j->mba * p)) * j->mba + gi % j->mba + (size_t)lj * lld) + d] = j->aglob[w * (gi + (size_t)gj * j->ma) + d];
             }
         }
         da.ctxt = ctxa; da.lda = lld;
@@ -191,14 +196,15 @@ static void *worker(void *arg)
     int mlb = 0, nlb = 0, lldb = 1;
     if (r >= 0) {
         mlb = numroc(j->mb, j->mbb, r, j->rsb, p); nlb = numroc(j->nb, j->nbb, c, j->csb, q); lldb = mlb > 0 ? mlb : 1;
-        bl = malloc(sizeof(double) * (size_t)lldb * (size_t)(nlb > 0 ? nlb : 1));
-        for (size_t e = 0; e < (size_t)lldb * (size_t)(nlb > 0 ? nlb : 1); ++e) bl[e] = j->fill;
+        bl = malloc(sizeof(double) * w * (size_t)lldb * (size_t)(nlb > 0 ? nlb : 1));
+        for (size_t e = 0; e < (size_t)w * lldb * (size_t)(nlb > 0 ? nlb : 1); ++e) bl[e] = j->fill;
         db.ctxt = ctxb; db.lda = lldb;
     }
-    double dummy = 0.0;
-    Cpdgemr2d(j->m, j->n, al ? al : &dummy, j->ia, j->ja, &da, bl ? bl : &dummy, j->ib, j->jb, &db, gctxt);
+    double dummy[2] = { 0.0, 0.0 };
+    if (j->es == 8) Cpdgemr2d(j->m, j->n, al ? al : dummy, j->ia, j->ja, &da, bl ? bl : dummy, j->ib, j->jb, &db, gctxt);
+    else Cpzgemr2d(j->m, j->n, al ? (void *)al : (void *)dummy, j->ia, j->ja, &da, bl ? (void *)bl : (void *)dummy, j->ib, j->jb, &db, gctxt);
     j->bdims[2 * j->rank] = mlb; j->bdims[2 * j->rank + 1] = nlb;
-    if (bl) memcpy(j->bout + (size_t)j->rank * j->bstride, bl, sizeof(double) * (size_t)lldb * (size_t)(nlb > 0 ? nlb : 1));
+    if (bl) memcpy(j->bout + (size_t)j->rank * j->bstride, bl, sizeof(double) * w * (size_t)lldb * (size_t)(nlb > 0 ? nlb : 1));
     free(al); free(bl);
     return NULL;
 }
@@ -209,14 +215,14 @@ static void *worker(void *arg)
 int ref_pdgemr2d_run(int np, int m, int n, int ia, int ja, int ib, int jb,
                      int pa, int qa, int ma, int na, int mba, int nba, int rsa, int csa,
                      int pb, int qb, int mb, int nb, int mbb, int nbb, int rsb, int csb,
-                     const double *aglob, double fill, double *bout, int64_t bstride, int *bdims)
+                     const double *aglob, double fill, double *bout, int64_t bstride, int *bdims, int es)
 {
     if (np > MAXP) return -1;
     memset(g_ctx, 0, sizeof(g_ctx)); memset(g_box, 0, sizeof(g_box)); memset(g_boxtail, 0, sizeof(g_boxtail));
     g_np = np;
     pthread_t th[MAXP]; Job jobs[MAXP];
     for (int r = 0; r < np; ++r) {
-        jobs[r] = (Job){ r, np, m, n, ia, ja, ib, jb, pa, qa, ma, na, mba, nba, rsa, csa, pb, qb, mb, nb, mbb, nbb, rsb, csb, aglob, fill, bout, bstride, bdims };
+        jobs[r] = (Job){ r, np, m, n, ia, ja, ib, jb, pa, qa, ma, na, mba, nba, rsa, csa, pb, qb, mb, nb, mbb, nbb, rsb, csb, aglob, fill, bout, bstride, bdims, es };
         pthread_create(&th[r], NULL, worker, &jobs[r]);
     }
     for (int r = 0; r < np; ++r) pthread_join(th[r], NULL);

@@ -185,17 +185,15 @@ def test_redistribution_expectation_against_the_reference_itself(O, P, Q):
         pytest.skip("oracle/_ref not built (no reference sources on this machine)")
     ran = 0
     for cs in next_cases.F2_CASES:
-        if cs.get("z"):
-            continue
         (Pa, Qa), (Pb, Qb) = cs.get("ga", (P, Q)), cs.get("gb", (P, Q))
         if Pa * Qa > P * Q or Pb * Qb > P * Q:
             continue
         m, n, ia, ja, ib, jb = cs["m"], cs["n"], cs.get("ia", 1), cs.get("ja", 1), cs.get("ib", 1), cs.get("jb", 1)
         (rsa, csa), (rsb, csb) = cs.get("src_a", (0, 0)), cs.get("src_b", (0, 0))
         rsa, csa, rsb, csb = rsa % Pa, csa % Qa, rsb % Pb, csb % Qb
-        ag = np.asfortranarray(O.pdmatgen(*cs["shape_a"], 100))
+        ag = np.asfortranarray((O.pzmatgen if cs.get("z") else O.pdmatgen)(*cs["shape_a"], 100))
         out = O.ref_pdgemr2d(ag, m, n, ia, ja, ib, jb, (Pa, Qa), cs["blk_a"], (rsa, csa), cs["shape_b"], (Pb, Qb), cs["blk_b"], (rsb, csb))
-        want = np.full(cs["shape_b"], -9923.0, order="F"); want[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n] = ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]
+        want = np.full(cs["shape_b"], -9923.0 * (1 + 1j) if cs.get("z") else -9923.0, dtype=ag.dtype, order="F"); want[ib - 1:ib - 1 + m, jb - 1:jb - 1 + n] = ag[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]
         for r in range(Pb * Qb):
             pr, pc = divmod(r, Qb)
             exp = O.scatter(want, cs["blk_b"][0], cs["blk_b"][1], Pb, Qb, pr, pc, rsrc=rsb, csrc=csb)
