@@ -1,0 +1,313 @@
+"""A tiny interpreter for the INTEGER subset of Fortran 77 the reference's index / descriptor tools are written in
+(TOOLS/numroc.f, indxg2p.f, indxg2l.f, indxl2g.f, iceil.f, ilcm.f, infog2l.f, descinit.f, chk1mat.f): fixed form, INTEGER scalars and
+1-based arrays, PARAMETER, assignments, block IF / ELSE IF / ELSE / END IF, logical IF, GO TO, labelled CONTINUE, CALL, RETURN, the
+intrinsics MOD / MAX / MIN / ABS, and calls to other units or to Python callbacks.
+
+TEST INFRASTRUCTURE.  There is no Fortran compiler in this image, so this is how the tests execute the reference's OWN source text of
+those routines (read from /root/reference at test time, never copied) and pin the product's and the oracle's restatements against it
+instead of against each other.  tests/golden/make_tools_golden.py stores the values it produces so the check also travels."""
+import re
+
+_TOKEN = re.compile(r"\s*(?:(\d+)|('(?:[^']|'')*')|(\.[A-Z]+\.)|([A-Z_][A-Z0-9_]*)|(\*\*|[-+*/(),=]))")
+
+
+def _idiv(a, b):
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q          # Fortran integer division truncates toward zero
+
+
+def _imod(a, b):
+    return a - _idiv(a, b) * b                          # MOD has the sign of the first argument
+
+
+class Unit:
+    def __init__(self, kind, name, args, stmts):
+        self.kind, self.name, self.args, self.stmts = kind, name, args, stmts
+        self.labels = {lab: i for i, (lab, _) in enumerate(stmts) if lab}
+
+
+def parse(text):
+    """-> Unit.  One program unit per file (the reference's TOOLS files)."""
+    lines = []
+    for raw in text.splitlines():
+        if not raw.strip() or raw[0] in "*Cc!":
+            continue
+        raw = raw.rstrip("\n").upper().split("!")[0] if "'" not in raw else raw.rstrip("\n")
+        body = raw[6:72] if len(raw) > 6 else ""
+        if len(raw) > 5 and raw[5] not in " 0":          # continuation line
+            lines[-1][1] += " " + body.strip()
+        else:
+            lines.append([raw[:5].strip(), body.strip()])
+    up = lambda s: re.sub(r"'[^']*'|[^']+", lambda m: m.group(0) if m.group(0).startswith("'") else m.group(0).upper(), s)
+    lines = [(lab, up(st)) for lab, st in lines]
+    head = lines[0][1]
+    m = re.match(r"(?:(INTEGER)\s+)?(FUNCTION|SUBROUTINE)\s+([A-Z0-9_]+)\s*\((.*)\)\s*$", head)
+    assert m, head
+    args = [a.strip() for a in m.group(4).split(",") if a.strip()]
+    return Unit(m.group(2), m.group(3), args, lines[1:])
+
+
+class Interp:
+    def __init__(self, units=(), callbacks=None):
+        self.units = {u.name: u for u in units}
+        self.callbacks = dict(callbacks or {})          # NAME -> f(interp, env, arg_exprs) for CALLs; NAME -> f(*values) for functions
+
+    # ---- expressions --------------------------------------------------------------------------------------------------------
+    def eval(self, text, env):
+        toks = []
+        pos = 0
+        while pos < len(text):
+            m = _TOKEN.match(text, pos)
+            if not m:
+                if text[pos:].strip() == "":
+                    break
+                raise SyntaxError(text[pos:])
+            toks.append(m.group(m.lastindex))
+            pos = m.end()
+        self._t, self._i, self._env = toks, 0, env
+        v = self._or()
+        assert self._i == len(toks), (text, toks[self._i:])
+        return v
+
+    def _peek(self):
+        return self._t[self._i] if self._i < len(self._t) else None
+
+    def _next(self):
+        self._i += 1
+        return self._t[self._i - 1]
+
+    def _or(self):
+        v = self._and()
+        while self._peek() == ".OR.":
+            self._next(); w = self._and(); v = bool(v) or bool(w)
+        return v
+
+    def _and(self):
+        v = self._not()
+        while self._peek() == ".AND.":
+            self._next(); w = self._not(); v = bool(v) and bool(w)
+        return v
+
+    def _not(self):
+        if self._peek() == ".NOT.":
+            self._next()
+            return not self._not()
+        return self._rel()
+
+    def _rel(self):
+        v = self._add()
+        ops = {".LT.": lambda a, b: a < b, ".LE.": lambda a, b: a <= b, ".EQ.": lambda a, b: a == b, ".NE.": lambda a, b: a != b,
+               ".GT.": lambda a, b: a > b, ".GE.": lambda a, b: a >= b}
+        if self._peek() in ops:
+            f = ops[self._next()]
+            v = f(v, self._add())
+        return v
+
+    def _add(self):
+        if self._peek() == "-":
+            self._next(); v = -self._mul()
+        elif self._peek() == "+":
+            self._next(); v = self._mul()
+        else:
+            v = self._mul()
+        while self._peek() in ("+", "-"):
+            op = self._next(); w = self._mul()
+            v = v + w if op == "+" else v - w
+        return v
+
+    def _mul(self):
+        v = self._pow()
+        while self._peek() in ("*", "/"):
+            op = self._next(); w = self._pow()
+            v = v * w if op == "*" else _idiv(v, w)
+        return v
+
+    def _pow(self):
+        v = self._prim()
+        if self._peek() == "**":
+            self._next(); v = v ** self._pow()
+        return v
+
+    def _prim(self):
+        t = self._next()
+        if t == "(":
+            v = self._or(); assert self._next() == ")"
+            return v
+        if t == "-":
+            return -self._prim()
+        if t.isdigit():
+            return int(t)
+        if t.startswith("'"):
+            return t[1:-1]
+        name = t
+        if self._peek() == "(":
+            self._next()
+            args = []
+            if self._peek() != ")":
+                args.append(self._or())
+                while self._peek() == ",":
+                    self._next(); args.append(self._or())
+            assert self._next() == ")"
+            env = self._env
+            if name in env and isinstance(env[name], list):
+                return env[name][args[0] - 1]
+            if name == "MOD":
+                return _imod(*args)
+            if name == "MAX":
+                return max(args)
+            if name == "MIN":
+                return min(args)
+            if name == "ABS":
+                return abs(args[0])
+            if name in self.units:
+                saved = (self._t, self._i, self._env)
+                out = self.call(name, *args)
+                self._t, self._i, self._env = saved
+                return out["__result__"]
+            return self.callbacks[name](*args)
+        return self._env[name]
+
+    # ---- statements ---------------------------------------------------------------------------------------------------------
+    def call(self, name, *args):
+        """Runs unit `name`; scalars by value (their final values come back in the result dict), arrays as Python lists (in place)."""
+        u = self.units[name]
+        env = dict(zip(u.args, args))
+        if u.kind == "FUNCTION":
+            env[u.name] = 0
+        st = u.stmts
+        pc = 0
+
+        def skip_to_branch(i):
+            """from a false IF / ELSE IF at i: index of the next ELSE IF / ELSE / END IF of the same block"""
+            depth = 0
+            j = i + 1
+            while True:
+                s = st[j][1]
+                if re.match(r"IF\s*\(.*\)\s*THEN$", s):
+                    depth += 1
+                elif re.match(r"END\s*IF$", s):
+                    if depth == 0:
+                        return j
+                    depth -= 1
+                elif depth == 0 and (re.match(r"ELSE\s*IF\s*\(.*\)\s*THEN$", s) or s == "ELSE"):
+                    return j
+                j += 1
+
+        def skip_to_end(i):
+            depth = 0
+            j = i + 1
+            while True:
+                s = st[j][1]
+                if re.match(r"IF\s*\(.*\)\s*THEN$", s):
+                    depth += 1
+                elif re.match(r"END\s*IF$", s):
+                    if depth == 0:
+                        return j
+                    depth -= 1
+                j += 1
+
+        def split_cond(s):
+            """'IF ( cond ) rest' -> (cond, rest)"""
+            i = s.index("(")
+            depth, j = 0, i
+            while True:
+                if s[j] == "(":
+                    depth += 1
+                elif s[j] == ")":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j += 1
+            return s[i + 1:j], s[j + 1:].strip()
+
+        def simple(s):
+            """executes a non-block statement; returns 'RETURN', ('GOTO', label) or None"""
+            if s in ("CONTINUE",):
+                return None
+            if s in ("RETURN", "END"):
+                return "RETURN"
+            m = re.match(r"GO\s*TO\s*(\d+)$", s)
+            if m:
+                return ("GOTO", m.group(1))
+            m = re.match(r"CALL\s+([A-Z0-9_]+)\s*\((.*)\)$", s)
+            if m:
+                cname, inner = m.group(1), m.group(2)
+                parts, depth, cur = [], 0, ""
+                for ch in inner:
+                    if ch == "," and depth == 0:
+                        parts.append(cur.strip()); cur = ""
+                    else:
+                        depth += ch == "("; depth -= ch == ")"; cur += ch
+                parts.append(cur.strip())
+                self.callbacks[cname](self, env, parts)
+                return None
+            m = re.match(r"([A-Z_][A-Z0-9_]*)\s*(\(.*?\))?\s*=\s*(.*)$", s)
+            assert m, s
+            val = self.eval(m.group(3), env)
+            if m.group(2):
+                env[m.group(1)][self.eval(m.group(2)[1:-1], env) - 1] = val
+            else:
+                env[m.group(1)] = val
+            return None
+
+        while pc < len(st):
+            s = st[pc][1]
+            if re.match(r"(IMPLICIT|INTEGER|EXTERNAL|INTRINSIC|LOGICAL|CHARACTER|DOUBLE)\b", s) and "=" not in s.split("(")[0]:
+                pc += 1; continue
+            if s.startswith("PARAMETER"):
+                for part in re.findall(r"([A-Z_][A-Z0-9_]*)\s*=\s*([^,()]+(?:\([^()]*\))?[^,()]*)", s[s.index("(") + 1:s.rindex(")")]):
+                    env[part[0]] = self.eval(part[1].strip(), env)
+                pc += 1; continue
+            m = re.match(r"(ELSE\s*)?IF\s*\(", s)
+            if m and s.endswith("THEN"):
+                if m.group(1):                           # ELSE IF reached by falling out of a taken branch
+                    pc = skip_to_end(pc); continue
+                cond, _ = split_cond(s)
+                while True:
+                    if self.eval(cond, env):
+                        pc += 1; break
+                    pc = skip_to_branch(pc)
+                    s2 = st[pc][1]
+                    if s2 == "ELSE":
+                        pc += 1; break
+                    if re.match(r"END\s*IF$", s2):
+                        pc += 1; break
+                    cond, _ = split_cond(s2[s2.index("IF"):])
+                continue
+            if s == "ELSE":
+                pc = skip_to_end(pc); continue
+            if re.match(r"END\s*IF$", s):
+                pc += 1; continue
+            if re.match(r"IF\s*\(", s):                  # logical IF
+                cond, rest = split_cond(s)
+                r = simple(rest) if self.eval(cond, env) else None
+            else:
+                r = simple(s)
+            if r == "RETURN":
+                break
+            if isinstance(r, tuple):
+                pc = u.labels[r[1]]; continue
+            pc += 1
+        out = {k: env[k] for k in u.args}
+        if u.kind == "FUNCTION":
+            out["__result__"] = env[u.name]
+        return out
+
+
+def load_tools(ref_root, grid=None, errors=None):
+    """The reference's TOOLS units with BLACS_GRIDINFO answering from `grid` = (nprow, npcol, myrow, mycol) and PXERBLA recorded."""
+    import os
+    units = [parse(open(os.path.join(ref_root, "TOOLS", f + ".f")).read())
+             for f in ("numroc", "indxg2p", "indxg2l", "indxl2g", "iceil", "ilcm", "infog2l", "descinit", "chk1mat")]
+    state = {"grid": grid or (1, 1, 0, 0)}
+
+    def gridinfo(interp, env, parts):
+        for name, v in zip(parts[1:], state["grid"]):
+            env[name] = v
+
+    def pxerbla(interp, env, parts):
+        if errors is not None:
+            errors.append((interp.eval(parts[1], env), interp.eval(parts[2], env)))
+    it = Interp(units, {"BLACS_GRIDINFO": gridinfo, "PXERBLA": pxerbla})
+    it.state = state
+    return it

@@ -375,3 +375,62 @@ def test_fortran_interface_module_matches_the_c_header(S):
                 assert "char" in ca and "*" in ca, (cname, fa, ca)
             else:
                 raise AssertionError((cname, fa, ts))
+
+
+def _tools_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "tools_reference.npz"))
+
+
+def test_index_tools_against_the_reference_source(S, O):
+    """NUMROC / INDXG2P / INDXG2L / INDXL2G / ICEIL / ILCM / INFOG2L of the product (tools.cpp) and of the oracle against values
+    produced by EXECUTING the reference's own Fortran (tests/golden/tools_reference.npz, made by tests/golden/make_tools_golden.py with
+    the Fortran-77 mini interpreter of tests/fortran77_mini.py): neither restatement is checked against the other any more."""
+    g = _tools_golden()
+    for n, nb, ip, isrc, np_, ig, il, a, b, r_numroc, r_g2p, r_g2l, r_l2g, r_ceil, r_lcm in g["index"].tolist():
+        assert S.numroc(n, nb, ip, isrc, np_) == r_numroc == O.numroc(n, nb, ip, isrc, np_)
+        assert S.indxg2p(ig, nb, ip, isrc, np_) == r_g2p == O.indxg2p(ig, nb, ip, isrc, np_)
+        assert S.indxg2l(ig, nb, ip, isrc, np_) == r_g2l == O.indxg2l(ig, nb, ip, isrc, np_)
+        assert S.indxl2g(il, nb, ip, isrc, np_) == r_l2g == O.indxl2g(il, nb, ip, isrc, np_)
+        assert S.iceil(a, b) == r_ceil and S.ilcm(a, b) == r_lcm
+    for row in g["infog2l"].tolist():
+        P, Q, r, c = row[:4]; d = row[4:13]; gi, gj = row[13:15]; want = tuple(row[15:19])
+        assert S.infog2l(gi, gj, d, P, Q, r, c) == want == O.infog2l(gi, gj, d, P, Q, r, c)
+
+
+def test_descinit_chk1mat_against_the_reference_source(S, O, ctx11):
+    """DESCINIT / CHK1MAT (INFO codes and the descriptor DESCINIT leaves behind on illegal input) against the executed reference source:
+    the oracle on every P x Q grid of the golden set, the product on the cases whose grid is the 1 x 1 grid a single process can make."""
+    g = _tools_golden()
+    n11 = 0
+    for row in g["descinit"].tolist():
+        P, Q, r, c, m, n, mb, nb, rs, cs, ictxt, lld = row[:12]; want_desc = row[12:21]; want_info = row[21]
+        d, info = O.descinit(m, n, mb, nb, rs, cs, ictxt, lld, P, Q, r)
+        assert (d, info) == (want_desc, want_info), row
+        if (P, Q) == (1, 1):
+            d, info = S.descinit(m, n, mb, nb, rs, cs, ctx11, lld)
+            assert info == want_info and d[:1] + d[2:] == want_desc[:1] + want_desc[2:], row      # all but the context handle
+            n11 += 1
+    for row in g["chk1mat"].tolist():
+        P, Q, r, c = row[:4]; d = row[4:13]; ma, na, ia, ja, info_in, want = row[13:19]
+        assert O.chk1mat(ma, 1, na, 2, ia, ja, d, 6, P, Q, r, c, info=info_in) == want, row
+        if (P, Q) == (1, 1):
+            d1 = list(d); d1[1] = ctx11
+            assert S.chk1mat(ma, 1, na, 2, ia, ja, d1, 6, info=info_in) == want, row
+            n11 += 1
+    assert n11 >= 20
+
+
+def test_reference_fortran_executed_live(O):
+    """When the reference tree is on this machine: fresh random inputs through the interpreted Fortran (the golden file is not stale)."""
+    if not os.path.exists("/root/reference/TOOLS/numroc.f"):
+        pytest.skip("no reference tree here")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fortran77_mini as F
+    it = F.load_tools("/root/reference")
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        np_ = int(rng.integers(1, 9)); nb = int(rng.integers(1, 33)); n = int(rng.integers(0, 5000)); ip = int(rng.integers(0, np_)); isrc = int(rng.integers(0, np_))
+        assert it.call("NUMROC", n, nb, ip, isrc, np_)["__result__"] == O.numroc(n, nb, ip, isrc, np_)
+        ig = int(rng.integers(1, 5000))
+        assert it.call("INDXG2P", ig, nb, ip, isrc, np_)["__result__"] == O.indxg2p(ig, nb, ip, isrc, np_)
+        assert it.call("INDXL2G", ig, nb, ip, isrc, np_)["__result__"] == O.indxl2g(ig, nb, ip, isrc, np_)
