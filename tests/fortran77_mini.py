@@ -1,14 +1,15 @@
 """A tiny interpreter for the INTEGER subset of Fortran 77 the reference's index / descriptor tools are written in
 (TOOLS/numroc.f, indxg2p.f, indxg2l.f, indxl2g.f, iceil.f, ilcm.f, infog2l.f, descinit.f, chk1mat.f): fixed form, INTEGER scalars and
 1-based arrays, PARAMETER, assignments, block IF / ELSE IF / ELSE / END IF, logical IF, GO TO, labelled CONTINUE, CALL, RETURN, the
-intrinsics MOD / MAX / MIN / ABS, and calls to other units or to Python callbacks.
+intrinsics MOD / MAX / MIN / ABS, DO loops, DOUBLE PRECISION scalars, LSAME, and calls to other units or to Python callbacks
+(the latter is how SRC/pdgetrf.f, pdgetf2.f, pdlaswp.f and pdgetrs.f are run with numpy standing in for the PBLAS leaves).
 
 TEST INFRASTRUCTURE.  There is no Fortran compiler in this image, so this is how the tests execute the reference's OWN source text of
 those routines (read from /root/reference at test time, never copied) and pin the product's and the oracle's restatements against it
 instead of against each other.  tests/golden/make_tools_golden.py stores the values it produces so the check also travels."""
 import re
 
-_TOKEN = re.compile(r"\s*(?:(\d+)|('(?:[^']|'')*')|(\.[A-Z]+\.)|([A-Z_][A-Z0-9_]*)|(\*\*|[-+*/(),=]))")
+_TOKEN = re.compile(r"\s*(?:(\d+\.(?![A-Z]+\.)\d*(?:[DE][-+]?\d+)?|\d+[DE][-+]?\d+|\d+)|('(?:[^']|'')*')|(\.[A-Z]+\.)|([A-Z_][A-Z0-9_]*)|(\*\*|[-+*/(),=]))")
 
 
 def _idiv(a, b):
@@ -119,7 +120,7 @@ class Interp:
         v = self._pow()
         while self._peek() in ("*", "/"):
             op = self._next(); w = self._pow()
-            v = v * w if op == "*" else _idiv(v, w)
+            v = v * w if op == "*" else (_idiv(v, w) if isinstance(v, int) and isinstance(w, int) else v / w)
         return v
 
     def _pow(self):
@@ -137,6 +138,12 @@ class Interp:
             return -self._prim()
         if t.isdigit():
             return int(t)
+        if t[0].isdigit():
+            return float(t.replace("D", "E"))
+        if t == ".TRUE.":
+            return True
+        if t == ".FALSE.":
+            return False
         if t.startswith("'"):
             return t[1:-1]
         name = t
@@ -149,8 +156,14 @@ class Interp:
                     self._next(); args.append(self._or())
             assert self._next() == ")"
             env = self._env
-            if name in env and isinstance(env[name], list):
+            if name in env and hasattr(env[name], "__getitem__") and not isinstance(env[name], str):
                 return env[name][args[0] - 1]
+            if name == "LSAME":
+                return str(args[0])[:1].upper() == str(args[1])[:1].upper()
+            if name == "DBLE":
+                return float(args[0])
+            if name == "ICHAR":
+                return ord(str(args[0])[:1])
             if name == "MOD":
                 return _imod(*args)
             if name == "MAX":
@@ -166,6 +179,15 @@ class Interp:
                 return out["__result__"]
             return self.callbacks[name](*args)
         return self._env[name]
+
+    def assign(self, target, env, value):
+        """target: a variable name or an array element as written in the source, e.g. 'IPIV( IIA+J-JA )'"""
+        m = re.match(r"\s*([A-Z_][A-Z0-9_]*)\s*(\((.*)\))?\s*$", target)
+        assert m, target
+        if m.group(2):
+            env[m.group(1)][self.eval(m.group(3), env) - 1] = value
+        else:
+            env[m.group(1)] = value
 
     # ---- statements ---------------------------------------------------------------------------------------------------------
     def call(self, name, *args):
@@ -239,21 +261,64 @@ class Interp:
                     else:
                         depth += ch == "("; depth -= ch == ")"; cur += ch
                 parts.append(cur.strip())
+                if cname in self.units:                  # another interpreted unit: by reference = copy in, copy back
+                    callee = self.units[cname]
+                    # an actual argument that is a not-yet-defined variable is an output of the callee: pass a placeholder
+                    vals = [env[p_] if p_ in env else (0 if re.fullmatch(r"[A-Z_][A-Z0-9_]*", p_) else self.eval(p_, env)) for p_ in parts]
+                    out = self.call(cname, *vals)
+                    for p_, d_ in zip(parts, callee.args):
+                        v_ = out[d_]
+                        if isinstance(v_, (int, float, bool, str)):
+                            m_ = re.fullmatch(r"([A-Z_][A-Z0-9_]*)\s*(\(.*\))?", p_)
+                            if m_ and m_.group(2):               # an array element only if ITS parenthesis closes at the very end
+                                depth_ = 0
+                                for k_, ch_ in enumerate(m_.group(2)):
+                                    depth_ += ch_ == "("; depth_ -= ch_ == ")"
+                                    if depth_ == 0 and k_ < len(m_.group(2)) - 1:
+                                        m_ = None
+                                        break
+                            if m_ and (m_.group(2) is None or (m_.group(1) in env and hasattr(env[m_.group(1)], "__setitem__"))):
+                                self.assign(p_, env, v_)
+                    return None
                 self.callbacks[cname](self, env, parts)
                 return None
             m = re.match(r"([A-Z_][A-Z0-9_]*)\s*(\(.*?\))?\s*=\s*(.*)$", s)
             assert m, s
             val = self.eval(m.group(3), env)
             if m.group(2):
+                if m.group(1) not in env:
+                    env[m.group(1)] = [0] * 64             # a small local work array (e.g. IDUM1( 1 ), DESCIP( DLEN_ ))
                 env[m.group(1)][self.eval(m.group(2)[1:-1], env) - 1] = val
             else:
                 env[m.group(1)] = val
             return None
 
+        loops = []                                       # active DO loops: [label, var, last, step, body_start]
         while pc < len(st):
             s = st[pc][1]
             if re.match(r"(IMPLICIT|INTEGER|EXTERNAL|INTRINSIC|LOGICAL|CHARACTER|DOUBLE)\b", s) and "=" not in s.split("(")[0]:
+                if re.match(r"(INTEGER|DOUBLE)\b", s):       # local arrays such as IDUM1( 1 ), DESCIP( DLEN_ ): small work arrays
+                    for nm in re.findall(r"([A-Z_][A-Z0-9_]*)\s*\(", s):
+                        if nm not in env and nm not in ("PRECISION",):
+                            env[nm] = [0] * 64
                 pc += 1; continue
+            m = re.match(r"DO\s+(\d+)\s+([A-Z_][A-Z0-9_]*)\s*=\s*(.*)$", s)
+            if m:
+                bounds, depth, cur = [], 0, ""
+                for ch in m.group(3):
+                    if ch == "," and depth == 0:
+                        bounds.append(cur); cur = ""
+                    else:
+                        depth += ch == "("; depth -= ch == ")"; cur += ch
+                bounds.append(cur)
+                first, last = self.eval(bounds[0], env), self.eval(bounds[1], env)
+                step = self.eval(bounds[2], env) if len(bounds) > 2 else 1
+                env[m.group(2)] = first
+                if (step > 0 and first > last) or (step < 0 and first < last):
+                    pc = u.labels[m.group(1)] + 1         # zero-trip loop
+                else:
+                    loops.append([m.group(1), m.group(2), last, step, pc + 1]); pc += 1
+                continue
             if s.startswith("PARAMETER"):
                 for part in re.findall(r"([A-Z_][A-Z0-9_]*)\s*=\s*([^,()]+(?:\([^()]*\))?[^,()]*)", s[s.index("(") + 1:s.rindex(")")]):
                     env[part[0]] = self.eval(part[1].strip(), env)
@@ -287,6 +352,12 @@ class Interp:
                 break
             if isinstance(r, tuple):
                 pc = u.labels[r[1]]; continue
+            if loops and st[pc][0] == loops[-1][0]:      # the terminal statement of the innermost DO loop
+                lab, var, last, step, start = loops[-1]
+                env[var] += step
+                if (step > 0 and env[var] <= last) or (step < 0 and env[var] >= last):
+                    pc = start; continue
+                loops.pop()
             pc += 1
         out = {k: env[k] for k in u.args}
         if u.kind == "FUNCTION":

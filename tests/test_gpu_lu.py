@@ -327,3 +327,40 @@ def test_host_resident_small_matrix_takes_the_one_copy_path(S, O, ctx11):
     lu, ipiv, info, _ = run_getrf(S, O, ctx11, a0, nb, pad=2)
     assert S.get_counter("e2e_upload_overlapped") == 0
     check_against_oracle(O, a0, lu, ipiv, info, nb)
+
+
+def test_product_against_the_executed_reference_fortran(S, ctx11):
+    """PDGETRF / PDGETRS through the C-ABI against tests/golden/lu_reference.npz = what the reference's OWN Fortran (pdgetrf.f, pdgetf2.f,
+    pdlaswp.f, pdgetrs.f, executed by tests/fortran77_mini.py with numpy PBLAS leaves; tests/golden/make_lu_golden.py) produces on a
+    1 x 1 grid: INFO and IPIV exactly (sub-matrix operands, partial blocks, M != N, NB > N, zero pivot columns), factors and solutions to
+    rounding, nothing outside sub(A) touched.  No oracle in between."""
+    import oracle as O                                        # only for the PDMATGEN input matrices (closed-form generator)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "lu_reference.npz"))
+    ncases = sum(1 for k in g.files if k.startswith("case"))
+    for i in range(ncases):
+        m, n, nb, mg, ng, ia, ja, zero_col, info_ref = [int(v) for v in g[f"case{i}"]]
+        a0 = O.pdmatgen(mg, ng, 100).copy(order="F")
+        if zero_col >= 0:
+            a0[:, zero_col] = 0.0
+        lld = mg + 1
+        al = np.full((lld, ng), PADVAL, order="F"); al[:mg, :] = a0
+        desc, info = S.descinit(mg, ng, nb, nb, 0, 0, ctx11, lld)
+        ipiv = np.full(mg + nb, -77, np.int32)
+        info = S.pdgetrf(m, n, al, ia, ja, desc, ipiv)
+        lu_ref, ipiv_ref = g[f"lu{i}"], g[f"ipiv{i}"]
+        mn = min(m, n)
+        assert info == info_ref, (i, info, info_ref)
+        assert np.array_equal(ipiv[ia - 1:ia - 1 + mn], ipiv_ref[ia - 1:ia - 1 + mn]), i
+        anorm = max(np.abs(a0[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]).sum(axis=1).max(), 1e-300)
+        assert np.abs(al[:mg, :] - lu_ref).max() / (anorm * max(m, n) * 2.0 ** -53) < 1.0, i
+        outside = np.ones((mg, ng), bool); outside[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n] = False
+        assert np.array_equal(al[:mg, :][outside], a0[outside]) and np.all(al[mg:, :] == PADVAL), i
+        for trans in "NT":
+            if f"x{trans}{i}" not in g.files:
+                continue
+            b = np.asfortranarray(O.pdmatgen(n, 3, 200).copy(order="F"))
+            descb, _ = S.descinit(n, 3, nb, 1, 0, 0, ctx11, n)
+            assert S.pdgetrs(trans, n, 3, al, 1, 1, desc, ipiv, b, 1, 1, descb) == 0
+            xref = g[f"x{trans}{i}"]
+            assert np.abs(b - xref).max() <= 1e-9 * np.abs(xref).max(), (i, trans)

@@ -1,0 +1,65 @@
+"""The oracle's restatement of the LU algorithm against the reference's OWN Fortran control flow, executed.
+
+tests/golden/lu_reference.npz holds what SRC/pdgetrf.f + pdgetf2.f + pdlaswp.f + pdgetrs.f produce on a 1 x 1 grid when their source
+text is run by the mini interpreter of tests/fortran77_mini.py (numpy standing in for the PBLAS leaves, tests/fortran_lu_runner.py;
+generator: tests/golden/make_lu_golden.py).  The oracle (oracle/oracle.c) must agree: INFO and IPIV exactly -- including the peeled
+first block of sub-matrix operands (pdgetrf.f:219-250), partial last blocks, M != N, NB > N and exactly-zero pivot columns -- and the
+factors / solutions to rounding.  Where the reference tree is present the same is done live on fresh matrices."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS = 2.0 ** -53
+
+
+def _check(O, hdr, lu_ref, ipiv_ref, xs):
+    m, n, nb, mg, ng, ia, ja, zero_col, info_ref = [int(v) for v in hdr]
+    a0 = O.pdmatgen(mg, ng, 100).copy(order="F")
+    if zero_col >= 0:
+        a0[:, zero_col] = 0.0
+    sub = np.asfortranarray(a0[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n])
+    lu = sub.copy(order="F")
+    ipiv, info = O.getrf(lu, nb)
+    assert info == info_ref
+    mn = min(m, n)
+    # the reference's IPIV entries are row indices of A, stored at the rows' positions (1 x 1 grid: position = global row)
+    assert np.array_equal(ipiv[:mn] + (ia - 1), ipiv_ref[ia - 1:ia - 1 + mn])
+    anorm = max(np.abs(sub).sum(axis=1).max(), 1e-300)
+    assert np.abs(lu - lu_ref[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]).max() / (anorm * max(m, n) * EPS) < 1.0
+    outside = np.ones((mg, ng), bool); outside[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n] = False
+    assert np.array_equal(lu_ref[outside], a0[outside])          # the reference touched nothing outside sub(A)
+    for trans, xref in xs.items():
+        x = O.pdmatgen(n, 3, 200).copy(order="F")
+        O.getrs(lu, ipiv, x, trans)
+        assert np.abs(x - xref).max() <= 1e-9 * np.abs(xref).max()
+
+
+def test_oracle_against_the_executed_reference_fortran(O):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lu_reference.npz"))
+    ncases = sum(1 for k in g.files if k.startswith("case"))
+    assert ncases >= 20
+    for i in range(ncases):
+        xs = {t: g[f"x{t}{i}"] for t in "NT" if f"x{t}{i}" in g.files}
+        _check(O, g[f"case{i}"], g[f"lu{i}"], g[f"ipiv{i}"], xs)
+
+
+def test_reference_fortran_lu_executed_live(O):
+    if not os.path.exists("/root/reference/SRC/pdgetrf.f"):
+        pytest.skip("no reference tree here")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fortran_lu_runner as R
+    it = R.make()
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        m, n, nb = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(1, 9))
+        a0 = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+        a = a0.copy(order="F")
+        ipiv_ref, info_ref = R.pdgetrf(it, a, nb)
+        lu = a0.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+        mn = min(m, n)
+        assert info == info_ref and np.array_equal(ipiv[:mn], ipiv_ref[:mn])
+        assert np.abs(lu - a).max() <= 1e-12 * max(1.0, np.abs(a).max())
+    assert it.log == []
