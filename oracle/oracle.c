@@ -17,9 +17,15 @@
  * EXAMPLE/DSCAEXMAT.dat + DSCAEXRHS.dat (accept resid < 10,
  * EXAMPLE/pdscaex.f:181-192), (2) the LU.dat grid of cases with threshold 1.0
  * (TESTING/traditional/LU.dat:17), (3) an independent LAPACK dgetrf
- * (scipy) giving the same pivots.  Bit-level parity with a reference *build*
- * is unpinned (the reference's local flops are delegated to an external,
- * unversioned BLAS: CMakeLists.txt:160-190).
+ * (scipy) giving the same pivots, and -- since round 2 -- (4) the reference's
+ * OWN Fortran, executed: tests/fortran77_mini.py interprets SRC/pdgetrf.f,
+ * pdgetf2.f, pdlaswp.f, pdgetrs.f and the TOOLS index routines on a 1 x 1
+ * grid (numpy for the PBLAS leaves); tests/test_reference_fortran.py holds
+ * this file to their INFO / IPIV exactly and to their factors and solutions
+ * to rounding (golden vectors in tests/golden/lu_reference.npz).  What stays
+ * unpinned is the floating-point order inside the reference's external,
+ * unversioned BLAS (CMakeLists.txt:160-190), which the reference itself does
+ * not define.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference root).
