@@ -147,6 +147,27 @@ class Interp:
         if t.startswith("'"):
             return t[1:-1]
         name = t
+        if self._peek() == "(" and name in getattr(self, "raw_functions", {}):
+            # a function that needs its arguments BY ADDRESS (e.g. DDOT( N, A( IOFFA ), 1, ... )): hand over the argument texts
+            self._next()
+            parts, depth, cur = [], 0, []
+            while True:
+                tk = self._next()
+                if tk == "(":
+                    depth += 1
+                elif tk == ")":
+                    if depth == 0:
+                        break
+                    depth -= 1
+                if tk == "," and depth == 0:
+                    parts.append(" ".join(cur)); cur = []
+                else:
+                    cur.append(tk)
+            parts.append(" ".join(cur))
+            saved = (self._t, self._i, self._env)
+            v = self.raw_functions[name](self, self._env, parts)
+            self._t, self._i, self._env = saved
+            return v
         if self._peek() == "(":
             self._next()
             args = []
@@ -164,6 +185,12 @@ class Interp:
                 return float(args[0])
             if name == "ICHAR":
                 return ord(str(args[0])[:1])
+            if name == "SQRT":
+                return float(args[0]) ** 0.5
+            if name == "SIGN":
+                return abs(args[0]) if str(args[1])[0] != "-" and args[1] >= 0 else -abs(args[0])
+            if name == "NINT":
+                return int(round(args[0]))
             if name == "MOD":
                 return _imod(*args)
             if name == "MAX":
@@ -179,6 +206,12 @@ class Interp:
                 return out["__result__"]
             return self.callbacks[name](*args)
         return self._env[name]
+
+    def address(self, part, env):
+        """('NAME( expr )' or 'NAME') -> (array object, 0-based offset): Fortran's pass-by-address of an array element"""
+        m = re.match(r"\s*([A-Z_][A-Z0-9_]*)\s*(?:\((.*)\))?\s*$", part)
+        assert m, part
+        return env[m.group(1)], (self.eval(m.group(2), env) - 1 if m.group(2) else 0)
 
     def assign(self, target, env, value):
         """target: a variable name or an array element as written in the source, e.g. 'IPIV( IIA+J-JA )'"""

@@ -63,3 +63,30 @@ def test_reference_fortran_lu_executed_live(O):
         assert info == info_ref and np.array_equal(ipiv[:mn], ipiv_ref[:mn])
         assert np.abs(lu - a).max() <= 1e-12 * max(1.0, np.abs(a).max())
     assert it.log == []
+
+
+def test_cholesky_oracle_against_the_executed_reference_fortran(O):
+    """oracle/oracle_next.c's PDPOTRF / PDPOTRS against tests/golden/chol_reference.npz = SRC/pdpotrf.f + pdpotf2.f + pdpotrs.f executed
+    (tests/fortran_chol_runner.py): INFO exactly (including matrices that are not positive definite), the factored triangle and the
+    solutions to rounding, the other triangle untouched."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_chol_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "chol_reference.npz"))
+    ncases = sum(1 for k in g.files if k.startswith("case"))
+    assert ncases >= 30
+    for i in range(ncases):
+        n, nb, u, notpd, info_ref = [int(v) for v in g[f"case{i}"]]
+        uplo = chr(u)
+        a0 = G.matrix(n, None if notpd < 0 else notpd)
+        a = a0.copy(order="F")
+        assert O.dpotrf(uplo, a, nb) == info_ref
+        if info_ref != 0:
+            continue
+        f = g[f"f{i}"]
+        tri = np.tril if uplo == "L" else np.triu
+        assert np.abs(tri(a) - tri(f)).max() <= 1e-13 * np.abs(f).max()
+        other = np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)
+        assert np.array_equal(f[other], a0[other]) and np.array_equal(a[other], a0[other])
+        x = O.pdmatgen(n, 3, 200).copy(order="F")
+        O.dpotrs(uplo, a, x)
+        assert np.abs(x - g[f"x{i}"]).max() <= 1e-12 * np.abs(g[f"x{i}"]).max()
