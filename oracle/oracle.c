@@ -22,7 +22,10 @@
  * pdgetf2.f, pdlaswp.f, pdgetrs.f and the TOOLS index routines on a 1 x 1
  * grid (numpy for the PBLAS leaves); tests/test_reference_fortran.py holds
  * this file to their INFO / IPIV exactly and to their factors and solutions
- * to rounding (golden vectors in tests/golden/lu_reference.npz).  What stays
+ * to rounding (golden vectors in tests/golden/lu_reference.npz); the matrix
+ * generator below is held BIT FOR BIT to TESTING/traditional/LIN/pdmatgen.f,
+ * pzmatgen.f + pmatgeninc.f executed per process of P x Q grids
+ * (tests/golden/matgen_reference.npz).  What stays
  * unpinned is the floating-point order inside the reference's external,
  * unversioned BLAS (CMakeLists.txt:160-190), which the reference itself does
  * not define.

@@ -42,16 +42,35 @@ def parse(text):
     up = lambda s: re.sub(r"'[^']*'|[^']+", lambda m: m.group(0) if m.group(0).startswith("'") else m.group(0).upper(), s)
     lines = [(lab, up(st)) for lab, st in lines]
     head = lines[0][1]
-    m = re.match(r"(?:(INTEGER)\s+)?(FUNCTION|SUBROUTINE)\s+([A-Z0-9_]+)\s*\((.*)\)\s*$", head)
+    m = re.match(r"(?:(INTEGER|REAL|DOUBLE\s+PRECISION|LOGICAL)\s+)?(FUNCTION|SUBROUTINE)\s+([A-Z0-9_]+)\s*\((.*)\)\s*$", head)
     assert m, head
     args = [a.strip() for a in m.group(4).split(",") if a.strip()]
     return Unit(m.group(2), m.group(3), args, lines[1:])
+
+
+def parse_file(text):
+    """-> [Unit, ...] for a file that holds several program units (each ends with a line END)"""
+    units, cur = [], []
+    for raw in text.splitlines():
+        cur.append(raw)
+        if raw[:1] not in "*Cc!" and raw[6:72].strip().upper() == "END":
+            if any(l.strip() and l[:1] not in "*Cc!" for l in cur[:-1]):
+                units.append(parse("\n".join(cur)))
+            cur = []
+    return units
+
+
+def _wrap32(v):
+    """INTEGER arithmetic of the reference is 32-bit two's complement (the generator's LMUL overflows and corrects for it, pmatgeninc.f)"""
+    return ((v + 2 ** 31) % 2 ** 32) - 2 ** 31
 
 
 class Interp:
     def __init__(self, units=(), callbacks=None):
         self.units = {u.name: u for u in units}
         self.callbacks = dict(callbacks or {})          # NAME -> f(interp, env, arg_exprs) for CALLs; NAME -> f(*values) for functions
+        self.common = {}                                 # COMMON block name -> {variable name: storage}
+        self.wrap32 = False                              # wrap INTEGER + - * to 32 bits
 
     # ---- expressions --------------------------------------------------------------------------------------------------------
     def eval(self, text, env):
@@ -114,6 +133,8 @@ class Interp:
         while self._peek() in ("+", "-"):
             op = self._next(); w = self._mul()
             v = v + w if op == "+" else v - w
+            if self.wrap32 and isinstance(v, int) and not isinstance(v, bool):
+                v = _wrap32(v)
         return v
 
     def _mul(self):
@@ -121,6 +142,8 @@ class Interp:
         while self._peek() in ("*", "/"):
             op = self._next(); w = self._pow()
             v = v * w if op == "*" else (_idiv(v, w) if isinstance(v, int) and isinstance(w, int) else v / w)
+            if self.wrap32 and isinstance(v, int) and not isinstance(v, bool):
+                v = _wrap32(v)
         return v
 
     def _pow(self):
@@ -178,11 +201,20 @@ class Interp:
             assert self._next() == ")"
             env = self._env
             if name in env and hasattr(env[name], "__getitem__") and not isinstance(env[name], str):
+                if len(args) == 2:
+                    v2 = env[name][args[0] - 1, args[1] - 1]
+                    return complex(v2) if isinstance(v2, complex) or getattr(v2, "dtype", None) == "complex128" else float(v2)
                 return env[name][args[0] - 1]
             if name == "LSAME":
                 return str(args[0])[:1].upper() == str(args[1])[:1].upper()
-            if name == "DBLE":
-                return float(args[0])
+            if name in ("DBLE", "REAL"):
+                return float(args[0].real) if isinstance(args[0], complex) else float(args[0])
+            if name == "DCMPLX":
+                return complex(args[0], args[1] if len(args) > 1 else 0.0)
+            if name == "DCONJG":
+                return complex(args[0]).conjugate()
+            if name == "DIMAG":
+                return float(complex(args[0]).imag)
             if name == "ICHAR":
                 return ord(str(args[0])[:1])
             if name == "SQRT":
@@ -218,9 +250,23 @@ class Interp:
         m = re.match(r"\s*([A-Z_][A-Z0-9_]*)\s*(\((.*)\))?\s*$", target)
         assert m, target
         if m.group(2):
-            env[m.group(1)][self.eval(m.group(3), env) - 1] = value
+            self._store(env, m.group(1), m.group(3), value)
         else:
             env[m.group(1)] = value
+
+    def _store(self, env, name, index_text, value):
+        parts, depth, cur = [], 0, ""
+        for ch in index_text:
+            if ch == "," and depth == 0:
+                parts.append(cur); cur = ""
+            else:
+                depth += ch == "("; depth -= ch == ")"; cur += ch
+        parts.append(cur)
+        idx = [self.eval(p_, env) - 1 for p_ in parts]
+        if len(idx) == 2:
+            env[name][idx[0], idx[1]] = value
+        else:
+            env[name][idx[0]] = value
 
     # ---- statements ---------------------------------------------------------------------------------------------------------
     def call(self, name, *args):
@@ -315,13 +361,20 @@ class Interp:
                     return None
                 self.callbacks[cname](self, env, parts)
                 return None
-            m = re.match(r"([A-Z_][A-Z0-9_]*)\s*(\(.*?\))?\s*=\s*(.*)$", s)
+            depth, eq = 0, -1
+            for k_, ch_ in enumerate(s):
+                depth += ch_ == "("; depth -= ch_ == ")"
+                if ch_ == "=" and depth == 0:
+                    eq = k_; break
+            assert eq > 0, s
+            m = re.match(r"([A-Z_][A-Z0-9_]*)\s*(\(.*\))?\s*$", s[:eq])
             assert m, s
+            m = type("M", (), {"group": lambda self_, i_, m_=m, rhs_=s[eq + 1:].strip(): rhs_ if i_ == 3 else m_.group(i_)})()
             val = self.eval(m.group(3), env)
             if m.group(2):
                 if m.group(1) not in env:
                     env[m.group(1)] = [0] * 64             # a small local work array (e.g. IDUM1( 1 ), DESCIP( DLEN_ ))
-                env[m.group(1)][self.eval(m.group(2)[1:-1], env) - 1] = val
+                self._store(env, m.group(1), m.group(2)[1:-1], val)
             else:
                 env[m.group(1)] = val
             return None
@@ -329,11 +382,19 @@ class Interp:
         loops = []                                       # active DO loops: [label, var, last, step, body_start]
         while pc < len(st):
             s = st[pc][1]
-            if re.match(r"(IMPLICIT|INTEGER|EXTERNAL|INTRINSIC|LOGICAL|CHARACTER|DOUBLE)\b", s) and "=" not in s.split("(")[0]:
+            if re.match(r"(IMPLICIT|INTEGER|EXTERNAL|INTRINSIC|LOGICAL|CHARACTER|DOUBLE|REAL|COMPLEX)\b", s) and "=" not in s.split("(")[0]:
                 if re.match(r"(INTEGER|DOUBLE)\b", s):       # local arrays such as IDUM1( 1 ), DESCIP( DLEN_ ): small work arrays
                     for nm in re.findall(r"([A-Z_][A-Z0-9_]*)\s*\(", s):
                         if nm not in env and nm not in ("PRECISION",):
                             env[nm] = [0] * 64
+                pc += 1; continue
+            if s.startswith("SAVE"):
+                pc += 1; continue
+            m = re.match(r"COMMON\s*/\s*([A-Z0-9_]+)\s*/\s*(.*)$", s)
+            if m:
+                blk = self.common.setdefault(m.group(1), {})
+                for nm in [x.strip() for x in m.group(2).split(",")]:
+                    env[nm] = blk.setdefault(nm, [0] * 8)  # the common blocks met here hold small integer arrays
                 pc += 1; continue
             m = re.match(r"DO\s+(\d+)\s+([A-Z_][A-Z0-9_]*)\s*=\s*(.*)$", s)
             if m:
@@ -384,7 +445,10 @@ class Interp:
             if r == "RETURN":
                 break
             if isinstance(r, tuple):
-                pc = u.labels[r[1]]; continue
+                pc = u.labels[r[1]]
+                while loops and not (loops[-1][4] <= pc <= u.labels[loops[-1][0]]):
+                    loops.pop()                          # a jump out of (nested) DO loops ends them (pdmatgen.f: GO TO 270 / 300)
+                continue
             if loops and st[pc][0] == loops[-1][0]:      # the terminal statement of the innermost DO loop
                 lab, var, last, step, start = loops[-1]
                 env[var] += step

@@ -90,3 +90,42 @@ def test_cholesky_oracle_against_the_executed_reference_fortran(O):
         x = O.pdmatgen(n, 3, 200).copy(order="F")
         O.dpotrs(uplo, a, x)
         assert np.abs(x - g[f"x{i}"]).max() <= 1e-12 * np.abs(g[f"x{i}"]).max()
+
+
+def test_matrix_generator_against_the_executed_reference_fortran(O):
+    """Every parity test's input comes from the oracle's closed-form (jump-ahead) PDMATGEN / PZMATGEN.  tests/golden/matgen_reference.npz
+    holds what TESTING/traditional/LIN/pdmatgen.f + pzmatgen.f + pmatgeninc.f produce when their source text is executed once per process
+    of P x Q grids (tests/fortran_matgen_runner.py): the oracle must reproduce every local piece and the assembled global matrix BIT FOR
+    BIT, for any block size, grid shape, source process and seed -- which is also the reference's own claim that the matrix does not
+    depend on the distribution."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "matgen_reference.npz"))
+    ncases = sum(1 for k in g.files if k.startswith("case"))
+    assert ncases >= 16
+    for i in range(ncases):
+        m, n, mb, nb, p, q, seed, ir, ic, z = [int(v) for v in g[f"case{i}"]]
+        if z:
+            assert np.array_equal(O.pzmatgen(m, n, seed), g[f"g{i}"])
+            continue
+        assert np.array_equal(O.pdmatgen(m, n, seed), g[f"g{i}"])
+        for pr in range(p):
+            for pc in range(q):
+                assert np.array_equal(O.pdmatgen_local(m, n, mb, nb, pr, pc, p, q, seed, ir, ic), g[f"l{i}_{pr}_{pc}"])
+
+
+def test_reference_matrix_generator_executed_live(O):
+    if not os.path.exists("/root/reference/TESTING/traditional/LIN/pdmatgen.f"):
+        pytest.skip("no reference tree here")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fortran_matgen_runner as R
+    it = R.make()
+    rng = np.random.default_rng(11)
+    for _ in range(3):
+        m, n, mb, nb = (int(rng.integers(1, 14)) for _ in range(4))
+        p, q = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        seed = int(rng.integers(0, 2 ** 31))
+        ir, ic = int(rng.integers(0, p)), int(rng.integers(0, q))
+        assert np.array_equal(R.global_(it, m, n, mb, nb, p, q, seed, ir, ic), O.pdmatgen(m, n, seed))
+        pr, pc = int(rng.integers(0, p)), int(rng.integers(0, q))
+        assert np.array_equal(R.local(it, m, n, mb, nb, pr, pc, p, q, seed, ir, ic), O.pdmatgen_local(m, n, mb, nb, pr, pc, p, q, seed, ir, ic))
+    assert np.array_equal(R.global_(it, 7, 6, 3, 2, 2, 2, 100, complex_=True), O.pzmatgen(7, 6, 100))
+    assert it.log == []
