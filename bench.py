@@ -494,6 +494,29 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_sample(min(nb, 512))
+    # ---- supplementary: first hardware numbers of the SURVEY 8(f) rows (bench_next.py), one process per row, hard time limits; never
+    # part of `value` / `e2e`, and unable to delay or break this line: the leg is abandoned when it does not return in time ----
+    next_rows, next_thread = None, None
+    if not args.no_next:
+        # every rank takes the same decision (max over the ranks): each one starts its own rank of every row's process group.  The
+        # driver allows 870 s per run; a multi-GPU run leaves less room, and at 8 GPUs this leg normally does not fit at all.
+        elapsed = maxr(time.time() - t_start)
+        limit = min(240.0, 780.0 - elapsed) if world == 1 else min(150.0, 600.0 - elapsed)
+        if limit < 40.0:
+            next_rows = {"error": f"skipped: {elapsed:.0f} s of the run's time were used before this leg"}
+        else:
+            import threading
+            box = {}
+
+            def _work():
+                try:
+                    import bench_next
+                    box["r"] = bench_next.run_all(per_row_timeout=60.0, total_timeout=limit)
+                except Exception as ex:  # noqa: BLE001
+                    box["r"] = {"error": repr(ex)[:300]}
+            next_thread = threading.Thread(target=_work, daemon=True)
+            next_thread.start(); next_thread.join(limit + 20.0)
+            next_rows = box.get("r", {"error": "abandoned: the supplementary rows did not return within their limit"})
     if rank == 0:
         line = {"metric": METRIC[routine], "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
@@ -509,12 +532,17 @@ def run_ours(args):
                            "hbm_gbs_measured": peaks.get("hbm_gbs")},
                 "parity_preflight": pre, "roofline": roof, "roofline_solve": roof_solve, "cpu_baseline": cpu, "e2e": e2e,
                 "e2e_pageable": e2e_pageable, "gpu_launches": launches, "clocks": clocks}
+        if next_rows is not None:
+            line["next_rows"] = next_rows
         if prof:
             line["phase_profile_us"] = prof
         print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
     assert sresid < 1.0, f"solve residual {sresid} of the timed workload exceeds the reference threshold"
+    if next_thread is not None and next_thread.is_alive():      # a child that cannot be reaped must not keep this process from exiting
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -530,6 +558,7 @@ def main():
     ap.add_argument("--no-pageable", action="store_true", help="e2e with a pinned host array only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--no-next", action="store_true", help="skip the supplementary SURVEY 8(f) measurements (bench_next.py, 1 GPU only)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--time-budget", type=int, default=640, help="seconds after which the optional pageable e2e leg is skipped")
     ap.add_argument("--profile", action="store_true")

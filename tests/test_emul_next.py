@@ -122,3 +122,78 @@ print("CODES", out)
     line = [ln for ln in run.stdout.splitlines() if ln.startswith("CODES")][0]
     assert line == "CODES [-1, -2, 0, -13, -14, -15, 0, 0, -1, -7, -1, -4, -1, -4, -8, -10]", line
     assert "On entry to PDGESVX parameter number  13 had an illegal value" in run.stderr       # PXERBLA's text
+
+
+def test_supplementary_bench_rows_on_the_emulation(emul_lib):
+    """bench_next.py (the 8(f) measurements bench.py embeds as `next_rows`) checks every result it times with a size-independent property.
+    Its own logic -- layouts, calls, checks -- is exercised here at a small size with host operands on the emulation; on a B200 the same
+    functions run on device-resident operands."""
+    code = r'''
+import sys, json
+sys.path.insert(0, "%(root)s")
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import bench_next as BN
+out = {}
+for row in BN.ROWS:
+    out[row] = BN.run_row(row, n=72, nb=32, device="cpu")
+print("ROWS" + json.dumps(out))
+''' % dict(root=ROOT)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert run.returncode == 0, run.stderr[-2000:]
+    out = json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("ROWS")][0][4:])
+    entries = {f"{row}.{k}": v for row, r in out.items() for k, v in r.items() if isinstance(v, dict)}
+    assert len(entries) >= 23, sorted(entries)
+    bad = {k: v for k, v in entries.items() if not v["ok"]}
+    assert not bad, bad
+    assert all(r["_kernel_launches"] > 0 for r in out.values())
+
+
+def test_supplementary_bench_reports_a_failing_row_without_raising(monkeypatch):
+    """bench.py must get a result object even when a row's process dies or hangs: run_all reports the error per row."""
+    sys.path.insert(0, ROOT)
+    import bench_next as BN
+    monkeypatch.setattr(BN, "ROWS", ["potrf", "getri"])
+    monkeypatch.setattr(BN.sys, "executable", "/bin/false")
+    out = BN.run_all(per_row_timeout=5.0, total_timeout=20.0)
+    assert out["summary"]["rows_failed"] == ["potrf", "getri"] and out["summary"]["entries"] == 0
+    assert all("error" in out[r] for r in ("potrf", "getri"))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_supplementary_bench_rows_on_emulated_grids(emul_lib, world):
+    """The same rows on 1 x 2 and 2 x 2 grids (gloo for the checker's own collectives, the emulation for the library): block-cyclic
+    operands, results assembled on every rank, every size-independent check green, identical reports on all ranks."""
+    code = r'''
+import sys, json
+sys.path.insert(0, "%(root)s")
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import bench_next as BN
+print("ROWS" + json.dumps(BN.run_row(sys.argv[1], n=70, nb=16, device="cpu")))
+''' % dict(root=ROOT)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    for k, row in enumerate(["potrf", "gemr2d", "refine", "getrs_l3"] if world == 4 else ["getri", "pblas", "refine"]):
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port + 50 * k),
+                       OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")       # torch's store on MASTER_PORT, the library's control plane on + 23
+            env.pop("SLB200_PORT_OFFSET", None)
+            procs.append(subprocess.Popen([sys.executable, "-c", code, row], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = []
+        try:
+            for p in procs:
+                o, e = p.communicate(timeout=300)
+                assert p.returncode == 0, e[-2000:]
+                outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("ROWS")][0][4:]))
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+        entries = {k_: v for k_, v in outs[0].items() if isinstance(v, dict)}
+        bad = {k_: v for k_, v in entries.items() if not v["ok"]}
+        assert entries and not bad, (row, bad)
+        assert outs[0]["_grid"] == ("1x2" if world == 2 else "2x2")
+        for o in outs[1:]:                                       # every rank assembled the same results and drew the same conclusions
+            assert {k_: v["ok"] for k_, v in o.items() if isinstance(v, dict)} == {k_: v["ok"] for k_, v in entries.items()}
