@@ -344,6 +344,17 @@ def run_row(row, n=None, nb=512, device="cuda", backend=None):
     return res
 
 
+def _finite(o):
+    """non-finite numbers as strings: the report is embedded in bench.py's JSON line, which must stay strict JSON"""
+    if isinstance(o, float) and (o != o or o in (float("inf"), float("-inf"))):
+        return repr(o)
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, list):
+        return [_finite(v) for v in o]
+    return o
+
+
 def run_all(per_row_timeout=60.0, total_timeout=240.0, n=None, nb=512, port_shift=300):
     """Every row in its own process (a fault in one cannot poison the CUDA context of the next, nor of the caller).  Under torchrun
     every rank calls this: rank r starts rank r of each row's process group, which meets on MASTER_PORT + port_shift."""
@@ -375,7 +386,7 @@ def run_all(per_row_timeout=60.0, total_timeout=240.0, n=None, nb=512, port_shif
     out["summary"] = {"entries": len(flat), "ok": sum(1 for v in flat if v.get("ok")), "rows_failed": [r for r in ROWS if "error" in out[r]],
                       "timing": "wall clock (max over ranks) of one synchronous call, operands resident in HBM, after one warm-up call",
                       "grid": "%dx%d" % GRIDS.get(world, (0, 0))}
-    return out
+    return _finite(out)
 
 
 def main():
