@@ -210,14 +210,19 @@ def row_refine(E, n, nb):
     AF = E.mat(n, n, nb, nb, a0)
     ipiv = np.zeros(AF.mloc + nb, np.int32)
     assert S.pdgetrf(n, n, AF.flat, 1, 1, AF.desc, ipiv) == 0
-    # PDGECON against the true condition number (the estimate is a lower bound of ||inv(A)||: rcond_est >= rcond_true, usually within 3x)
-    S.pdgecon("1", n, AF.flat, 1, 1, AF.desc, anorm)
-    sec, (rcond, info) = E.timed(lambda: S.pdgecon("1", n, AF.flat, 1, 1, AF.desc, anorm))
+    # PDGECON against the true condition number.  Any estimate bounds ||inv(A)|| from below: rcond_est >= rcond_true.  The default
+    # returns what the reference's source returns -- the alternating-sign value only, pdlacon.f:188-189, one pair of solves, typically
+    # 5 - 30x above the true RCOND; option lacon_keep_estimate = 1 is LAPACK's full estimator (usually within 3x, ~5 pairs of solves)
     inv = torch.linalg.inv(a0)
     true = 1.0 / (anorm * _norm1(inv))
     del inv
-    out["pdgecon_1"] = {"n": n, "seconds": sec, "rcond": rcond, "rcond_true": true, "info": info,
-                        "ok": info == 0 and true <= rcond * (1 + 1e-6) and rcond <= 10.0 * true}
+    for key, keep, slack in (("pdgecon_1", 0, 200.0), ("pdgecon_1_lapack_estimator", 1, 10.0)):
+        S.set_option("lacon_keep_estimate", keep)
+        S.pdgecon("1", n, AF.flat, 1, 1, AF.desc, anorm)
+        sec, (rcond, info) = E.timed(lambda: S.pdgecon("1", n, AF.flat, 1, 1, AF.desc, anorm))
+        out[key] = {"n": n, "seconds": sec, "rcond": rcond, "rcond_true": true, "over_true": rcond / true, "info": info,
+                    "ok": info == 0 and true <= rcond * (1 + 1e-6) and rcond <= slack * true}
+    S.set_option("lacon_keep_estimate", 0)
     # PDGERFS: x from PDGETRS, perturbed, refined; BERR must reach rounding level and the true error must respect FERR
     nrhs = 2
     x_true = E.rand(n, nrhs, 6)
@@ -249,7 +254,7 @@ def row_refine(E, n, nb):
                                                         B2.flat, 1, 1, B2.desc, X2.flat, 1, 1, X2.desc, ferr, berr))
     err, fe_, be_ = errs(X2, ferr, berr)
     out["pdgesvx_E"] = {"n": n, "nrhs": nrhs, "seconds": sec, "info": info, "equed": equed, "rcond": rc2, "true_err": err, "ferr": fe_,
-                        "ok": info == 0 and all(e <= 4 * f + 1e-15 for e, f in zip(err, fe_)) and true <= rc2 * (1 + 1e-6) <= 10.0 * true * (1 + 1e-6)}
+                        "ok": info == 0 and all(e <= 4 * f + 1e-15 for e, f in zip(err, fe_)) and true <= rc2 * (1 + 1e-6) <= 200.0 * true * (1 + 1e-6)}
     return out
 
 

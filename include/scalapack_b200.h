@@ -181,7 +181,9 @@ void slb200_pdgetrs_l3(const char *trans, const int *n, const int *nrhs, const d
 int  slb200_device(void);                  /* CUDA device this process drives, -1 if none */
 int  slb200_has_cuda(void);                /* 1 when a usable sm_100 device is present     */
 const char *slb200_version(void);
-void slb200_set_option(const char *key, int64_t value);   /* "lookahead", "verbose", "panel_width", ... */
+void slb200_set_option(const char *key, int64_t value);   /* "lookahead", "verbose", "panel_width", ...;
+                                                             "lacon_keep_estimate" = 1: PDGECON / PDGERFS / PDGESVX use LAPACK's estimator instead of
+                                                             what SRC/pdlacon.f:188-189 makes the reference return */
 int64_t slb200_get_counter(const char *key);             /* "kernel_launches", "h2d_bytes", "d2h_bytes", ... */
 void slb200_reset_counters(void);
 /* Device-time (ms) of the last pdgetrf_/pdgetrs_ call on this rank, measured with CUDA events

@@ -265,6 +265,11 @@ def dlaqge(a, r, c, rowcnd, colcnd, amax):
                          C.c_double(amax)).decode()
 
 
+def lacon_keep_est(keep):
+    """False (default): PDLACON as the reference's source behaves (EST reset on every call, pdlacon.f:188-189); True: LAPACK's DLACON."""
+    lib().orcn_lacon_keep_est(1 if keep else 0)
+
+
 def dgecon(norm, lu, anorm):
     """SRC/pdgecon.f + pdlacon.f on the factors of getrf(); returns RCOND."""
     n = lu.shape[0]

@@ -99,8 +99,17 @@ typedef struct { int jump, iter, j, jlast; double estold; } lacon_state;
 static double sign1(double x) { return signbit(x) ? -1.0 : 1.0; }
 static double asum(int n, const double *x) { double s = 0.0; for (int i = 0; i < n; ++i) s += fabs(x[i]); return s; }
 static int iamax1(int n, const double *x) { int j = 0; for (int i = 1; i < n; ++i) if (fabs(x[i]) > fabs(x[j])) j = i; return j + 1; }
+/* pdlacon.f:188-189 begins EVERY call with  EST = ZERO ; ESTWORK( 1 ) = EST : the estimate of the iteration (labels 20, 70) never
+ * survives to the next call, ESTOLD is always zero, and at label 140 the alternating-sign value is compared with zero -- so the
+ * reference's PDLACON returns 2 ||B x_alt||_1 / (3 N) whatever the iteration found (a valid, weaker lower bound of ||B||_1; LAPACK's
+ * DLACON carries EST between calls and returns the larger of the two).  Executing the reference's source shows it
+ * (tests/fortran_refine_runner.py).  The default here is the reference's behaviour; orcn_lacon_keep_est(1) restates LAPACK's, which is
+ * what lets scipy's DGECON / DGESVX pin the machinery of the iteration itself. */
+static int g_lacon_keep_est = 0;
+void orcn_lacon_keep_est(int keep) { g_lacon_keep_est = keep; }
 static void lacon_rc(int n, double *v, double *x, int *isgn, double *est, int *kase, lacon_state *st)
 {
+    if (!g_lacon_keep_est) *est = 0.0;                               /* pdlacon.f:188-189 */
     if (*kase == 0) {                                                /* pdlacon.f:205-212 */
         for (int i = 0; i < n; ++i) x[i] = 1.0 / (double)n;
         *kase = 1; st->jump = 1; return;

@@ -2,7 +2,15 @@
 // final alternating-sign safeguard).  Host-only: PDGECON drives it on the replicated N-vector and the device does the solves.
 //
 //   est = || B ||_1 for a linear map B given only through  x <- B x  (kase 1)  and  x <- B^T x  (kase 2).
+//
+// What the reference's source actually returns: pdlacon.f:188-189 begins EVERY call with  EST = ZERO ; ESTWORK( 1 ) = EST , so the
+// estimate found by the iteration never survives to the next call and the value compared at label 140 is zero: PDLACON returns the
+// alternating-sign estimate 2 ||B x_alt||_1 / (3 N) whatever the iteration found (still a lower bound of ||B||_1, usually a few times
+// smaller than Higham's).  Executing the reference's text shows it (tests/fortran_refine_runner.py).  Default here = the reference's
+// result, obtained with the ONE application of B that determines it (the iteration's applications cannot change the value, so they are
+// not made); option lacon_keep_estimate = 1 runs the full estimator with EST carried between the stages, as LAPACK's DLACON does.
 #pragma once
+#include "common.h"
 #include <cmath>
 #include <functional>
 #include <vector>
@@ -22,6 +30,13 @@ inline double lacon_estimate(int n, const std::function<void(double *, int)> &ap
     auto B = [&](int kase) { apply(x.data(), kase); ++count; };
     double est = 0.0;
     if (n <= 0) return 0.0;
+    if (n > 1 && opt("lacon_keep_estimate", 0) == 0) {                    // the reference's result (see above): labels 120 - 150 only
+        for (int k = 1; k <= n; ++k) x[k - 1] = ((k % 2 == 0) ? -1.0 : 1.0) * (1.0 + (double)(k - 1) / (double)(n - 1));
+        B(1);
+        const double temp = 2.0 * (asum(x) / (double)(3 * n));
+        if (napplies) *napplies = count;
+        return temp > 0.0 ? temp : 0.0;                                   // IF( TEMP( 1 ).GT.ESTWORK( 1 ) ) with ESTWORK( 1 ) = 0
+    }
     for (int i = 0; i < n; ++i) x[i] = 1.0 / (double)n;                   // pdlacon.f:10 (KASE = 0 entry)
     B(1);
     if (n == 1) {                                                         // label 20, N = 1

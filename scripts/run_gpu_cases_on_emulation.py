@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import test_gpu_next as t
 lists = {"F1": t.F1_GPU, "F2": t.F2_GPU, "F3": t.F3_GPU, "F4": t.F4_GPU, "F4B": t.F4B_GPU, "F5": t.F5_GPU}
+if len(sys.argv) > 1:
+    lists = {k: v for k, v in lists.items() if k in sys.argv[1:]}
 for name, cases in lists.items():
     cases = [{k: v for k, v in c.items() if k not in ("dev", "entry")} for c in cases]
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()

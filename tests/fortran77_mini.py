@@ -25,6 +25,9 @@ class Unit:
     def __init__(self, kind, name, args, stmts):
         self.kind, self.name, self.args, self.stmts = kind, name, args, stmts
         self.labels = {lab: i for i, (lab, _) in enumerate(stmts) if lab}
+        decl = " ".join(st for _, st in stmts if re.match(r"(INTEGER|DOUBLE|REAL|COMPLEX|LOGICAL|CHARACTER)\b", st) and "=" not in st.split("(")[0])
+        self.array_args = {a for a in args if re.search(r"\b%s\s*\(" % re.escape(a), decl)}      # dummies declared with dimensions
+        self.saves_all = any(st == "SAVE" for _, st in stmts)                                    # a bare SAVE: every local persists
 
 
 def parse(text):
@@ -70,6 +73,7 @@ class Interp:
         self.units = {u.name: u for u in units}
         self.callbacks = dict(callbacks or {})          # NAME -> f(interp, env, arg_exprs) for CALLs; NAME -> f(*values) for functions
         self.common = {}                                 # COMMON block name -> {variable name: storage}
+        self.saved = {}                                  # unit name -> locals kept between calls (units with a bare SAVE)
         self.wrap32 = False                              # wrap INTEGER + - * to 32 bits
 
     # ---- expressions --------------------------------------------------------------------------------------------------------
@@ -330,6 +334,10 @@ class Interp:
             m = re.match(r"GO\s*TO\s*(\d+)$", s)
             if m:
                 return ("GOTO", m.group(1))
+            m = re.match(r"GO\s*TO\s*\(([\d,\s]+)\)\s*,?\s*(.+)$", s)
+            if m:                                         # computed GO TO: the k-th label, or fall through when k is out of range
+                labs, k_ = [x.strip() for x in m.group(1).split(",")], self.eval(m.group(2), env)
+                return ("GOTO", labs[k_ - 1]) if 1 <= k_ <= len(labs) else None
             m = re.match(r"CALL\s+([A-Z0-9_]+)\s*\((.*)\)$", s)
             if m:
                 cname, inner = m.group(1), m.group(2)
@@ -343,7 +351,13 @@ class Interp:
                 if cname in self.units:                  # another interpreted unit: by reference = copy in, copy back
                     callee = self.units[cname]
                     # an actual argument that is a not-yet-defined variable is an output of the callee: pass a placeholder
-                    vals = [env[p_] if p_ in env else (0 if re.fullmatch(r"[A-Z_][A-Z0-9_]*", p_) else self.eval(p_, env)) for p_ in parts]
+                    vals = []
+                    for p_, d_ in zip(parts, callee.args):
+                        m_ = re.fullmatch(r"([A-Z_][A-Z0-9_]*)\s*\((.*)\)", p_)
+                        if d_ in callee.array_args and m_ and m_.group(1) in env and hasattr(env[m_.group(1)], "shape"):
+                            vals.append(env[m_.group(1)][self.eval(m_.group(2), env) - 1:])      # numpy view: Fortran's pass-by-address
+                        else:
+                            vals.append(env[p_] if p_ in env else (0 if re.fullmatch(r"[A-Z_][A-Z0-9_]*", p_) else self.eval(p_, env)))
                     out = self.call(cname, *vals)
                     for p_, d_ in zip(parts, callee.args):
                         v_ = out[d_]
@@ -389,6 +403,8 @@ class Interp:
                             env[nm] = [0] * 64
                 pc += 1; continue
             if s.startswith("SAVE"):
+                if s == "SAVE":
+                    env.update(self.saved.get(u.name, {}))
                 pc += 1; continue
             m = re.match(r"COMMON\s*/\s*([A-Z0-9_]+)\s*/\s*(.*)$", s)
             if m:
@@ -456,6 +472,8 @@ class Interp:
                     pc = start; continue
                 loops.pop()
             pc += 1
+        if u.saves_all:
+            self.saved[u.name] = {k: v for k, v in env.items() if k not in u.args}
         out = {k: env[k] for k in u.args}
         if u.kind == "FUNCTION":
             out["__result__"] = env[u.name]

@@ -1,0 +1,197 @@
+"""Runs the reference's OWN Fortran of the condition estimate -- SRC/pdgecon.f, pdlacon.f (the reverse-communication estimator with its
+SAVEd state and computed GO TO), pdlatrs.f, pdrscl.f, read from /root/reference -- on a 1 x 1 process grid with the mini interpreter of
+tests/fortran77_mini.py.  The iteration (start vector, sign vectors, the ITMAX = 5 loop and its stopping tests, the alternating-sign
+safeguard, which of the two solves runs for KASE = 1 / 2 and ONENRM, RCOND = (1 / AINVNM) / ANORM) is the reference's source text,
+executed; the PBLAS leaves it calls (PDTRSV, PDASUM, PDAMAX, PDELGET, DCOPY, PDSCAL) are numpy / scipy stand-ins written from their
+Purpose blocks.  TEST INFRASTRUCTURE: pins oracle/oracle_next.c's restatement of PDGECON / PDLACON against the reference's own control flow
+(it was pinned to LAPACK's DGECON before, a different implementation of the same estimator)."""
+import os
+
+import numpy as np
+
+import fortran77_mini as F
+
+SAFMIN = float(np.finfo(np.float64).tiny)
+EPS = 2.0 ** -53
+
+
+def _pdlamch(ictxt, cmach):
+    c = str(cmach)[:1].upper()      # PDLAMCH = DLAMCH combined over the grid (TOOLS/pdlamch? -> LAPACK DLAMCH): 'S' safe minimum, 'E' eps, 'P' eps * base
+    return {"S": SAFMIN, "E": EPS, "P": 2.0 * EPS, "B": 2.0, "O": float(np.finfo(np.float64).max), "U": SAFMIN}[c]
+
+
+def make(ref_root="/root/reference", extra=()):
+    units = [F.parse(open(os.path.join(ref_root, d, f + ".f")).read())
+             for d, f in (("TOOLS", "numroc"), ("TOOLS", "indxg2p"), ("TOOLS", "indxg2l"), ("TOOLS", "indxl2g"), ("TOOLS", "iceil"), ("TOOLS", "infog2l"),
+                          ("TOOLS", "chk1mat"), ("TOOLS", "descset"), ("SRC", "pdgecon"), ("SRC", "pdlacon"), ("SRC", "pdlatrs"), ("SRC", "pdrscl")) + tuple(extra)]
+    log = []
+
+    def ev(it, env, parts, k):
+        return it.eval(parts[k], env)
+
+    def gridinfo(it, env, parts):
+        for name, v in zip(parts[1:], (1, 1, 0, 0)):
+            env[name] = v
+
+    def nop(it, env, parts):
+        pass
+
+    def topget(it, env, parts):
+        it.assign(parts[3], env, " ")
+
+    def pxerbla(it, env, parts):
+        log.append(("PXERBLA", it.eval(parts[1], env), it.eval(parts[2], env)))
+
+    def vec(it, env, parts, kx, n):
+        """the N entries of the distributed vector X(IX:IX+N-1, JX) given as (X, IX, JX, DESCX) from argument kx on: a numpy view"""
+        arr, off = it.address(parts[kx], env)
+        ix, jx, desc = ev(it, env, parts, kx + 1), ev(it, env, parts, kx + 2), env[parts[kx + 3]]
+        lld = desc[8]
+        o = off + (ix - 1) + (jx - 1) * lld
+        return arr[o:o + n], ix
+
+    # PBLAS/SRC/pdtrsv_.c: sub(X) := inv(op(sub(A))) sub(X), sub(A) = A(IA:IA+N-1, JA:JA+N-1) triangular
+    def pdtrsv(it, env, parts):
+        from scipy.linalg import solve_triangular
+        uplo, trans, diag = (ev(it, env, parts, k)[0].upper() for k in range(3))
+        n = ev(it, env, parts, 3)
+        a, aoff = it.address(parts[4], env)
+        ia, ja, desca = ev(it, env, parts, 5), ev(it, env, parts, 6), env[parts[7]]
+        lld = desca[8]
+        x, _ = vec(it, env, parts, 8, n)
+        if n <= 0:
+            return
+        ncols = ja - 1 + n
+        full = np.asarray(a[aoff:aoff + lld * ncols]).reshape((ncols, lld)).T       # column-major local array
+        t = full[ia - 1:ia - 1 + n, ja - 1:ja - 1 + n]
+        x[:] = solve_triangular(t, np.array(x), lower=(uplo == "L"), trans=(0 if trans == "N" else 1), unit_diagonal=(diag == "U"))
+
+    def pdasum(it, env, parts):                                                     # PBLAS/SRC/pdasum_.c: sum of |x_i|
+        x, _ = vec(it, env, parts, 2, ev(it, env, parts, 0))
+        it.assign(parts[1], env, float(np.abs(x).sum()))
+
+    def pdamax(it, env, parts):                                                     # PBLAS/SRC/pdamax_.c: first largest |x_i|, GLOBAL index
+        n = ev(it, env, parts, 0)
+        x, ix = vec(it, env, parts, 3, n)
+        k = int(np.argmax(np.abs(x))) if n > 0 else 0
+        it.assign(parts[1], env, float(x[k]) if n > 0 else 0.0); it.assign(parts[2], env, ix + k if n > 0 else 0)
+
+    def pdelget(it, env, parts):                                                    # TOOLS/pdelget.f: ALPHA = A(IA, JA)
+        arr, off = it.address(parts[3], env)
+        ia, ja, desc = ev(it, env, parts, 4), ev(it, env, parts, 5), env[parts[6]]
+        it.assign(parts[2], env, float(arr[off + (ia - 1) + (ja - 1) * desc[8]]))
+
+    def dcopy(it, env, parts):
+        n = ev(it, env, parts, 0)
+        x, xo = it.address(parts[1], env); y, yo = it.address(parts[3], env)
+        assert ev(it, env, parts, 2) == 1 and ev(it, env, parts, 4) == 1
+        if n > 0:
+            y[yo:yo + n] = np.array(x[xo:xo + n])
+
+    def pdscal(it, env, parts):
+        n, alpha = ev(it, env, parts, 0), ev(it, env, parts, 1)
+        x, _ = vec(it, env, parts, 2, n)
+        x[:] = alpha * np.array(x)
+
+    def window(it, env, parts, k, m, n):
+        """the m x n sub-matrix (A, IA, JA, DESCA) given from argument k on, as a numpy view of the flat column-major local array"""
+        a, aoff = it.address(parts[k], env)
+        ia, ja, desc = ev(it, env, parts, k + 1), ev(it, env, parts, k + 2), env[parts[k + 3]]
+        lld = desc[8]
+        ncols = ja - 1 + n
+        full = np.asarray(a[aoff:aoff + lld * ncols]).reshape((ncols, lld)).T
+        return full[ia - 1:ia - 1 + m, ja - 1:ja - 1 + n]
+
+    # PBLAS/SRC/pdgemv_.c: sub(Y) := alpha op(sub(A)) sub(X) + beta sub(Y);  pdagemv_.c: |alpha| |op(sub(A))| |sub(X)| + |beta sub(Y)|
+    def pdgemv(it, env, parts, absolute=False):
+        trans = ev(it, env, parts, 0)[0].upper()
+        m, n, alpha, beta = ev(it, env, parts, 1), ev(it, env, parts, 2), ev(it, env, parts, 3), ev(it, env, parts, 13)
+        a = window(it, env, parts, 4, m, n)
+        lx, ly = (n, m) if trans == "N" else (m, n)
+        x, _ = vec(it, env, parts, 8, lx)
+        y, _ = vec(it, env, parts, 14, ly)
+        assert ev(it, env, parts, 12) == 1 and ev(it, env, parts, 18) == 1
+        op = a if trans == "N" else a.T
+        if absolute:
+            y[:] = abs(alpha) * (np.abs(op) @ np.abs(np.array(x))) + np.abs(beta * np.array(y))
+        else:
+            y[:] = alpha * (op @ np.array(x)) + beta * np.array(y)
+
+    def pdagemv(it, env, parts):
+        pdgemv(it, env, parts, absolute=True)
+
+    def pdcopy(it, env, parts):
+        n = ev(it, env, parts, 0)
+        x, _ = vec(it, env, parts, 1, n); y, _ = vec(it, env, parts, 6, n)
+        y[:] = np.array(x)
+
+    def pdaxpy(it, env, parts):
+        n, alpha = ev(it, env, parts, 0), ev(it, env, parts, 1)
+        x, _ = vec(it, env, parts, 2, n); y, _ = vec(it, env, parts, 7, n)
+        y[:] = np.array(y) + alpha * np.array(x)
+
+    # SRC/pdgetrs.f (itself executed by tests/fortran_lu_runner.py): one right-hand side, the factors and IPIV of PDGETRF
+    def pdgetrs(it, env, parts):
+        from scipy.linalg import solve_triangular
+        trans, n, nrhs = ev(it, env, parts, 0)[0].upper(), ev(it, env, parts, 1), ev(it, env, parts, 2)
+        assert nrhs == 1
+        lu = window(it, env, parts, 3, n, n)
+        iaf = ev(it, env, parts, 4)
+        piv = [int(env[parts[7]][iaf - 1 + i]) - iaf for i in range(n)]                 # 0-based, relative to sub(A)
+        x, _ = vec(it, env, parts, 8, n)
+        v = np.array(x)
+        if trans == "N":
+            for i in range(n):
+                v[[i, piv[i]]] = v[[piv[i], i]]
+            v = solve_triangular(lu, solve_triangular(lu, v, lower=True, unit_diagonal=True))
+        else:
+            v = solve_triangular(lu, solve_triangular(lu, v, trans=1), lower=True, unit_diagonal=True, trans=1)
+            for i in range(n - 1, -1, -1):
+                v[[i, piv[i]]] = v[[piv[i], i]]
+        x[:] = v
+        it.assign(parts[12], env, 0)
+
+    cbs = {"PDGEMV": pdgemv, "PDAGEMV": pdagemv, "PDCOPY": pdcopy, "PDAXPY": pdaxpy, "PDGETRS": pdgetrs, "DGAMX2D": nop,
+           "BLACS_GRIDINFO": gridinfo, "PXERBLA": pxerbla, "PB_TOPGET": topget, "PB_TOPSET": nop, "PCHK1MAT": nop, "PCHK2MAT": nop, "DGEBS2D": nop,
+           "DGEBR2D": nop, "IGSUM2D": nop, "PDLABAD": nop, "PDTRSV": pdtrsv, "PDASUM": pdasum, "PDAMAX": pdamax, "PDELGET": pdelget, "DCOPY": dcopy,
+           "PDSCAL": pdscal, "PDLAMCH": _pdlamch}
+    it = F.Interp(units, cbs)
+    it.log = log
+    return it
+
+
+def pdgecon(it, norm, lu, anorm, nb, ia=1, ja=1, n=None):
+    """lu: the factors of PDGETRF as a global matrix (float64); the reference's PDGECON on a 1 x 1 grid with MB = NB = nb.
+    Returns (rcond, info)."""
+    M, N = lu.shape
+    n = M if n is None else n
+    a = np.asfortranarray(lu).reshape(-1, order="F").copy()
+    desc = [1, 0, M, N, nb, nb, 0, 0, max(1, M)]
+    work, iwork = np.zeros(1), np.zeros(1, np.int64)
+    q = it.call("PDGECON", norm, n, a, ia, ja, desc, float(anorm), 0.0, work, -1, iwork, -1, 0)
+    assert q["INFO"] == 0, q["INFO"]
+    lw, liw = int(work[0]), int(iwork[0])
+    work, iwork = np.zeros(lw + 8), np.zeros(liw + 8, np.int64)
+    out = it.call("PDGECON", norm, n, a, ia, ja, desc, float(anorm), 0.0, work, lw, iwork, liw, 0)
+    return out["RCOND"], out["INFO"]
+
+
+def pdgerfs(it, trans, a, lu, ipiv, b, x, nb):
+    """The reference's PDGERFS on a 1 x 1 grid (MB = NB = nb for A / AF, nb x nb blocks for B / X): refines x in place.
+    a, lu: n x n; ipiv: PDGETRF's pivots (1-based); b, x: n x nrhs.  Returns (ferr, berr, info)."""
+    n, nrhs = b.shape
+    desca = [1, 0, n, n, nb, nb, 0, 0, max(1, n)]
+    descb = [1, 0, n, nrhs, nb, nb, 0, 0, max(1, n)]
+    af_, a_, b_ = (np.asfortranarray(m_).reshape(-1, order="F").copy() for m_ in (lu, a, b))
+    x_ = np.asfortranarray(x).reshape(-1, order="F").copy()
+    ip = np.concatenate([np.asarray(ipiv, np.int64), np.zeros(nb, np.int64)])
+    ferr, berr = np.zeros(nrhs + 1), np.zeros(nrhs + 1)
+    args = lambda work, lw, iwork, liw: (trans, n, nrhs, a_, 1, 1, desca, af_, 1, 1, desca, ip, b_, 1, 1, descb, x_, 1, 1, descb, ferr, berr,  # noqa: E731
+                                         work, lw, iwork, liw, 0)
+    work, iwork = np.zeros(4), np.zeros(4, np.int64)
+    q = it.call("PDGERFS", *args(work, -1, iwork, -1))
+    assert q["INFO"] == 0, q["INFO"]
+    lw, liw = int(work[0]), int(iwork[0])
+    out = it.call("PDGERFS", *args(np.zeros(lw + 8), lw, np.zeros(liw + 8, np.int64), liw))
+    x[...] = x_.reshape((n, nrhs), order="F")
+    return ferr[:nrhs].copy(), berr[:nrhs].copy(), out["INFO"]

@@ -1,0 +1,81 @@
+"""Golden vectors of the condition estimate and of the iterative refinement produced by EXECUTING the reference's own Fortran
+(SRC/pdgecon.f, pdlacon.f, pdlatrs.f, pdgerfs.f under /root/reference) on a 1 x 1 grid with tests/fortran_refine_runner.py.  Inputs: the oracle's LU factors (block size NB) of
+A = PDMATGEN(seed 100), optionally badly scaled; sub-matrix cases factor A(IA:, JA:) in place inside a larger matrix.
+Writes tests/golden/refine_reference.npz.  python tests/golden/make_refine_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(HERE))
+import fortran_refine_runner as R  # noqa: E402
+import oracle as O  # noqa: E402
+
+CASES = [dict(n=n, nb=nb) for n, nb in ((2, 2), (3, 2), (6, 2), (10, 3), (17, 4), (30, 8), (40, 64), (64, 8), (90, 16))] + \
+        [dict(n=24, nb=4, scale=3), dict(n=45, nb=4, scale=6), dict(n=33, nb=8, off=8), dict(n=20, nb=4, off=12)]
+
+
+def matrix(cs):
+    n = cs["n"]
+    a = O.pdmatgen(n, n, 100).copy(order="F")
+    if cs.get("scale"):
+        k = np.arange(n)
+        a = np.asfortranarray((10.0 ** (cs["scale"] * np.sin(k))[:, None]) * a * (10.0 ** (cs["scale"] * np.cos(2 * k))[None, :]))
+    return a
+
+
+RFS_CASES = [dict(n=6, nb=2, nrhs=1, trans="N"), dict(n=17, nb=4, nrhs=3, trans="N"), dict(n=17, nb=4, nrhs=2, trans="T"), dict(n=30, nb=8, nrhs=9, trans="N"),
+             dict(n=24, nb=4, nrhs=2, trans="N", scale=2), dict(n=24, nb=4, nrhs=2, trans="T", scale=2), dict(n=2, nb=2, nrhs=1, trans="N"),
+             dict(n=40, nb=64, nrhs=2, trans="N", perturb=1e-3)]
+
+
+def rfs_inputs(cs):
+    """(a, lu, ipiv, b, x0): x0 = the PDGETRS solution, perturbed so that the refinement has something to do"""
+    a = matrix(cs)
+    n, nb, nrhs = cs["n"], cs["nb"], cs["nrhs"]
+    b = O.pdmatgen(n, nrhs, 200).copy(order="F")
+    lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+    assert info == 0
+    x0 = b.copy(order="F"); O.getrs(lu, ipiv, x0, cs["trans"])
+    x0 *= 1.0 + cs.get("perturb", 1e-7)
+    return a, lu, ipiv, b, x0
+
+
+if __name__ == "__main__":
+    it = R.make(extra=(("SRC", "pdgerfs"),))
+    store = {}
+    for i, cs in enumerate(CASES):
+        a = matrix(cs)
+        n, nb, off = cs["n"], cs["nb"], cs.get("off", 0)
+        lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+        assert info == 0
+        big = O.pdmatgen(n + off, n + off, 55).copy(order="F"); big[off:, off:] = lu
+        vals = []
+        for norm in "1I":
+            anorm = np.abs(a).sum(axis=0).max() if norm == "1" else np.abs(a).sum(axis=1).max()
+            rc, info = R.pdgecon(it, norm, big, anorm, nb, ia=off + 1, ja=off + 1, n=n)
+            assert info == 0
+            vals.append(rc)
+        store[f"case{i}"] = np.array([n, nb, cs.get("scale", 0), off], np.int64)
+        store[f"rcond{i}"] = np.array(vals)
+    for i, cs in enumerate(RFS_CASES):
+        a, lu, ipiv, b, x = rfs_inputs(cs)
+        ferr, berr, info = R.pdgerfs(it, cs["trans"], a, lu, ipiv, b, x, cs["nb"])
+        assert info == 0
+        store[f"rfs{i}"] = np.array([cs["n"], cs["nb"], cs["nrhs"], ord(cs["trans"]), cs.get("scale", 0)], np.int64)
+        store[f"rfs_pert{i}"] = np.array([cs.get("perturb", 1e-7)])
+        store[f"rfs_x{i}"], store[f"rfs_ferr{i}"], store[f"rfs_berr{i}"] = x, ferr, berr
+    # argument errors and quick returns as the executed source reports them: (NORM, N, ANORM, LWORK) -> (INFO, RCOND)
+    lu = O.pdmatgen(8, 8, 100).copy(order="F")
+    a = lu.reshape(-1, order="F").copy()
+    desc = [1, 0, 8, 8, 4, 4, 0, 0, 8]
+    quick = []
+    for norm, n, anorm, lwork in (("X", 8, 1.0, 100), ("1", 8, -1.0, 100), ("1", 8, 1.0, 1), ("1", 0, 1.0, 100), ("1", 8, 0.0, 100), ("I", 1, 2.0, 100)):
+        out = it.call("PDGECON", norm, n, a, 1, 1, desc, anorm, -7.0, np.zeros(128), lwork, np.zeros(128, np.int64), 100, 0)
+        quick.append([ord(norm), n, anorm, lwork, out["INFO"], out["RCOND"]])
+    store["quick"] = np.array(quick)
+    np.savez_compressed(os.path.join(HERE, "refine_reference.npz"), **store)
+    print("wrote", len(CASES), "+", len(RFS_CASES), "cases; PXERBLA log:", it.log)
+    print(store["quick"])

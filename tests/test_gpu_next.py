@@ -65,6 +65,8 @@ F1_GPU = [
     dict(kind="gerfs", n=2048, nb=256, nrhs=2), dict(kind="gerfs", n=1500, nb=64, nrhs=2, trans="T", cond=1),
     dict(kind="gesvx", n=2048, nb=256, fact="N"), dict(kind="gesvx", n=1500, nb=128, fact="E", cond=4),
     dict(kind="gesvx", n=1000, nb=64, fact="E", cond=4, trans="T"),
+    dict(kind="gecon", n=2048, nb=256, lapack_estimator=True), dict(kind="gerfs", n=1500, nb=64, nrhs=2, lapack_estimator=True),
+    dict(kind="gesvx", n=1500, nb=128, fact="E", cond=4, lapack_estimator=True),
 ]
 
 

@@ -7,6 +7,16 @@ import pytest
 from scipy.linalg import lapack
 
 
+@pytest.fixture(autouse=True)
+def lapack_estimator(O):
+    """LAPACK's DLACON carries EST between its stages; the reference's PDLACON resets it on every call (pdlacon.f:188-189) and so always
+    returns the alternating-sign value.  The oracle's default is the reference's behaviour (pinned by the executed source,
+    tests/test_reference_fortran.py); the LAPACK comparisons of this file run it in LAPACK's mode, which pins the iteration itself."""
+    O.lacon_keep_est(True)
+    yield
+    O.lacon_keep_est(False)
+
+
 def rnd(n, m=None, seed=0, cond=None):
     rng = np.random.default_rng(seed)
     a = rng.uniform(-1, 1, (n, m or n))
@@ -57,6 +67,26 @@ def test_dgecon(O, n):
             true = 1.0 / (anorm * np.linalg.norm(np.linalg.inv(a), 1 if nm == "1" else np.inf))
             assert true * (1 - 1e-8) <= rc <= 10 * true          # the estimate bounds ||inv(A)|| from below
     assert O.dgecon("1", np.asfortranarray(np.eye(1)), 1.0) == 1.0 and O.dgecon("1", lu, 0.0) == 0.0
+
+
+def test_dgecon_as_the_reference_source_behaves(O):
+    """default mode: RCOND = 1 / (ANORM * 2 ||inv(A) x_alt||_1 / (3 N)), x_alt the alternating-sign vector of pdlacon.f:360-371"""
+    O.lacon_keep_est(False)
+    for n in (2, 5, 40, 200):
+        a = rnd(n, seed=n)
+        lu = a.copy(order="F"); ip, info = O.getrf(lu, 16)
+        k = np.arange(1, n + 1)
+        xalt = np.where(k % 2 == 0, -1.0, 1.0) * (1.0 + (k - 1) / (n - 1))
+        for nm in "1I":
+            anorm = O.dlange(nm, a)
+            pa = (np.tril(lu, -1) + np.eye(n)) @ np.triu(lu)              # the solves use L and U without the interchanges: P A
+            y = np.linalg.solve(pa if nm == "1" else pa.T, xalt)
+            expect = 1.0 / (anorm * 2.0 * np.abs(y).sum() / (3 * n))
+            rc = O.dgecon(nm, lu, anorm)
+            assert rc == pytest.approx(expect, rel=1e-9)
+            O.lacon_keep_est(True)
+            assert O.dgecon(nm, lu, anorm) <= rc * (1 + 1e-12)        # LAPACK's estimate of ||inv(A)|| is never the smaller one
+            O.lacon_keep_est(False)
 
 
 @pytest.mark.parametrize("trans", ["N", "T"])

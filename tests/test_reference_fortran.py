@@ -6,6 +6,7 @@ generator: tests/golden/make_lu_golden.py).  The oracle (oracle/oracle.c) must a
 first block of sub-matrix operands (pdgetrf.f:219-250), partial last blocks, M != N, NB > N and exactly-zero pivot columns -- and the
 factors / solutions to rounding.  Where the reference tree is present the same is done live on fresh matrices."""
 import os
+import re
 import sys
 
 import numpy as np
@@ -129,3 +130,84 @@ def test_reference_matrix_generator_executed_live(O):
         assert np.array_equal(R.local(it, m, n, mb, nb, pr, pc, p, q, seed, ir, ic), O.pdmatgen_local(m, n, mb, nb, pr, pc, p, q, seed, ir, ic))
     assert np.array_equal(R.global_(it, 7, 6, 3, 2, 2, 2, 100, complex_=True), O.pzmatgen(7, 6, 100))
     assert it.log == []
+
+
+def test_condition_estimate_against_the_executed_reference_fortran(O):
+    """oracle/oracle_next.c's PDGECON (default mode) against tests/golden/refine_reference.npz = SRC/pdgecon.f + pdlacon.f + pdlatrs.f
+    executed (tests/fortran_refine_runner.py).  The executed source is what showed that the reference's PDLACON resets EST on every call
+    (pdlacon.f:188-189) and therefore returns the alternating-sign value, not the maximum the iteration found: LAPACK's DGECON -- the
+    oracle's previous pin -- returns a different (smaller) RCOND on the same factors."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_refine_golden as G
+    from scipy.linalg import lapack
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refine_reference.npz"))
+    ncases = sum(1 for k in g.files if k.startswith("case"))
+    assert ncases >= 13
+    O.lacon_keep_est(False)
+    differs = 0
+    for i in range(ncases):
+        n, nb, scale, off = [int(v) for v in g[f"case{i}"]]
+        a = G.matrix(dict(n=n, scale=scale))
+        lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+        for k, norm in enumerate("1I"):
+            anorm = np.abs(a).sum(axis=0).max() if norm == "1" else np.abs(a).sum(axis=1).max()
+            rc = O.dgecon(norm, lu, anorm)
+            assert rc == pytest.approx(float(g[f"rcond{i}"][k]), rel=1e-9), (n, nb, norm)
+            rc_lapack = lapack.dgecon(lu, anorm, norm=norm)[0]
+            assert rc_lapack <= rc * (1 + 1e-9)
+            differs += rc_lapack < 0.99 * rc
+    assert differs >= ncases                                     # the two estimators do not agree: the pin matters
+    # INFO codes / quick returns of the executed source (RCOND untouched = -7 when an argument is illegal)
+    for nm, n, anorm, lwork, info, rcond in g["quick"]:
+        if info == 0:
+            lu = O.pdmatgen(8, 8, 100)[:int(n), :int(n)].copy(order="F")
+            assert O.dgecon(chr(int(nm)), lu, float(anorm)) == rcond
+
+
+def test_reference_condition_estimate_executed_live(O):
+    if not os.path.exists("/root/reference/SRC/pdlacon.f"):
+        pytest.skip("no reference tree here")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fortran_refine_runner as R
+    it = R.make()
+    rng = np.random.default_rng(5)
+    O.lacon_keep_est(False)
+    for _ in range(4):
+        n, nb = int(rng.integers(2, 30)), int(rng.integers(1, 9))
+        a = np.asfortranarray(rng.uniform(-1, 1, (n, n)))
+        lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+        for norm in "1I":
+            anorm = O.dlange(norm, a)
+            rc, info = R.pdgecon(it, norm, lu, anorm, nb)
+            assert info == 0 and O.dgecon(norm, lu, anorm) == pytest.approx(rc, rel=1e-9)
+    assert it.log == []
+
+
+def test_refinement_against_the_executed_reference_fortran(O):
+    """oracle/oracle_next.c's PDGERFS against SRC/pdgerfs.f + pdlacon.f executed (tests/golden/refine_reference.npz): the refined solution
+    within its own error bound, BERR at rounding level on both sides, FERR -- built on the reference's PDLACON, i.e. on its
+    alternating-sign value -- to a few per cent (it is an estimate of a quantity that moves with the rounding of the residual)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_refine_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refine_reference.npz"))
+    ncases = sum(1 for k in g.files if re.fullmatch(r"rfs\d+", k))
+    assert ncases >= 8
+    O.lacon_keep_est(False)
+    for i in range(ncases):
+        n, nb, nrhs, tr, scale = [int(v) for v in g[f"rfs{i}"]]
+        cs = dict(n=n, nb=nb, nrhs=nrhs, trans=chr(tr), scale=scale, perturb=float(g[f"rfs_pert{i}"][0]))
+        a, lu, ipiv, b, x = G.rfs_inputs(cs)
+        ferr, berr = O.dgerfs(cs["trans"], a, lu, ipiv, b, x)
+        xr, fr, br = g[f"rfs_x{i}"], g[f"rfs_ferr{i}"], g[f"rfs_berr{i}"]
+        # LAPACK's estimator gives a different (larger) FERR on the same data: the pin distinguishes the two.  It is also the reliable
+        # bound: with the alternating-sign value alone FERR can fall an order of magnitude short of the true error (n = 17, TRANS = T
+        # below: two refinements that both reach BERR ~ eps differ by 12 x the reference's FERR), so X is compared within LAPACK's.
+        O.lacon_keep_est(True)
+        x2 = G.rfs_inputs(cs)[4]
+        f2, _ = O.dgerfs(cs["trans"], a, lu, ipiv, b, x2)
+        O.lacon_keep_est(False)
+        assert np.all(f2 >= ferr * (1 - 1e-9))
+        for k in range(nrhs):
+            assert np.abs(x[:, k] - xr[:, k]).max() <= 2.0 * f2[k] * np.abs(xr[:, k]).max(), (cs, k)
+            assert berr[k] <= 4 * EPS * (n + 1) and br[k] <= 4 * EPS * (n + 1)
+            assert ferr[k] == pytest.approx(fr[k], rel=0.1), (cs, k)
