@@ -48,6 +48,8 @@ def make(ref_root="/root/reference", extra=()):
         ix, jx, desc = ev(it, env, parts, kx + 1), ev(it, env, parts, kx + 2), env[parts[kx + 3]]
         lld = desc[8]
         o = off + (ix - 1) + (jx - 1) * lld
+        if len(parts) > kx + 4 and ev(it, env, parts, kx + 4) == desc[2]:             # INCX = M_X: a ROW vector X(IX, JX:JX+N-1)
+            return arr[o:o + (n - 1) * lld + 1:lld] if n > 0 else arr[o:o], jx
         return arr[o:o + n], ix
 
     # PBLAS/SRC/pdtrsv_.c: sub(X) := inv(op(sub(A))) sub(X), sub(A) = A(IA:IA+N-1, JA:JA+N-1) triangular
@@ -134,24 +136,70 @@ def make(ref_root="/root/reference", extra=()):
     def pdgetrs(it, env, parts):
         from scipy.linalg import solve_triangular
         trans, n, nrhs = ev(it, env, parts, 0)[0].upper(), ev(it, env, parts, 1), ev(it, env, parts, 2)
-        assert nrhs == 1
         lu = window(it, env, parts, 3, n, n)
         iaf = ev(it, env, parts, 4)
         piv = [int(env[parts[7]][iaf - 1 + i]) - iaf for i in range(n)]                 # 0-based, relative to sub(A)
-        x, _ = vec(it, env, parts, 8, n)
-        v = np.array(x)
-        if trans == "N":
-            for i in range(n):
-                v[[i, piv[i]]] = v[[piv[i], i]]
-            v = solve_triangular(lu, solve_triangular(lu, v, lower=True, unit_diagonal=True))
-        else:
-            v = solve_triangular(lu, solve_triangular(lu, v, trans=1), lower=True, unit_diagonal=True, trans=1)
-            for i in range(n - 1, -1, -1):
-                v[[i, piv[i]]] = v[[piv[i], i]]
-        x[:] = v
+        xs = window(it, env, parts, 8, n, nrhs)
+        for k in range(nrhs):
+            v = np.array(xs[:, k])
+            if trans == "N":
+                for i in range(n):
+                    v[[i, piv[i]]] = v[[piv[i], i]]
+                v = solve_triangular(lu, solve_triangular(lu, v, lower=True, unit_diagonal=True))
+            else:
+                v = solve_triangular(lu, solve_triangular(lu, v, trans=1), lower=True, unit_diagonal=True, trans=1)
+                for i in range(n - 1, -1, -1):
+                    v[[i, piv[i]]] = v[[piv[i], i]]
+            xs[:, k] = v
         it.assign(parts[12], env, 0)
 
-    cbs = {"PDGEMV": pdgemv, "PDAGEMV": pdagemv, "PDCOPY": pdcopy, "PDAXPY": pdaxpy, "PDGETRS": pdgetrs, "DGAMX2D": nop,
+    # SRC/pdgetrf.f (itself executed by tests/fortran_lu_runner.py, which pins oracle.getrf): the oracle's factorisation of the window
+    def pdgetrf(it, env, parts):
+        import oracle as O
+        m, n = ev(it, env, parts, 0), ev(it, env, parts, 1)
+        a = window(it, env, parts, 2, m, n)
+        ia, desc = ev(it, env, parts, 3), env[parts[5]]
+        lu = np.asfortranarray(np.array(a))
+        ipiv, info = O.getrf(lu, desc[5])
+        a[:, :] = lu
+        for i in range(min(m, n)):
+            env[parts[6]][ia - 1 + i] = int(ipiv[i]) + ia - 1
+        it.assign(parts[7], env, int(info))
+
+    def pdlacpy(it, env, parts):                                                        # SRC/pdlacpy.f, UPLO = 'Full'
+        assert ev(it, env, parts, 0)[0].upper() not in "UL"
+        m, n = ev(it, env, parts, 1), ev(it, env, parts, 2)
+        window(it, env, parts, 7, m, n)[:, :] = np.array(window(it, env, parts, 3, m, n))
+
+    def dlassq(it, env, parts):                                                         # LAPACK DLASSQ: (scale, sumsq) updated with x
+        n = ev(it, env, parts, 0)
+        x, xo = it.address(parts[1], env)
+        assert ev(it, env, parts, 2) == 1
+        scale, sumsq = ev(it, env, parts, 3), ev(it, env, parts, 4)
+        for v in np.abs(np.array(x[xo:xo + n])):
+            if v != 0.0:
+                if scale < v:
+                    sumsq = 1.0 + sumsq * (scale / v) ** 2; scale = float(v)
+                else:
+                    sumsq += (float(v) / scale) ** 2
+        it.assign(parts[3], env, float(scale)); it.assign(parts[4], env, float(sumsq))
+
+    def dcombssq(it, env, parts):                                                       # LAPACK DCOMBSSQ: V1 := V1 (+) V2 on (scale, sumsq) pairs
+        v1, o1 = it.address(parts[0], env); v2, o2 = it.address(parts[1], env)
+        if v1[o1] >= v2[o2]:
+            if v1[o1] != 0.0:
+                v1[o1 + 1] = v1[o1 + 1] + (v2[o2] / v1[o1]) ** 2 * v2[o2 + 1]
+        else:
+            v1[o1 + 1] = v2[o2 + 1] + (v1[o1] / v2[o2]) ** 2 * v1[o1 + 1]
+            v1[o1] = v2[o2]
+
+    def idamax(n, x, inc):
+        return int(np.argmax(np.abs(np.array(x[:n])))) + 1 if n > 0 else 0
+
+
+    cbs = {"PDGETRF": pdgetrf, "PDLACPY": pdlacpy, "DLASSQ": dlassq, "DCOMBSSQ": dcombssq, "IDAMAX": idamax, "PDTREECOMB": nop, "DGSUM2D": nop,
+           "DGAMN2D": nop, "IGAMX2D": nop,
+           "PDGEMV": pdgemv, "PDAGEMV": pdagemv, "PDCOPY": pdcopy, "PDAXPY": pdaxpy, "PDGETRS": pdgetrs, "DGAMX2D": nop,
            "BLACS_GRIDINFO": gridinfo, "PXERBLA": pxerbla, "PB_TOPGET": topget, "PB_TOPSET": nop, "PCHK1MAT": nop, "PCHK2MAT": nop, "DGEBS2D": nop,
            "DGEBR2D": nop, "IGSUM2D": nop, "PDLABAD": nop, "PDTRSV": pdtrsv, "PDASUM": pdasum, "PDAMAX": pdamax, "PDELGET": pdelget, "DCOPY": dcopy,
            "PDSCAL": pdscal, "PDLAMCH": _pdlamch}
@@ -195,3 +243,31 @@ def pdgerfs(it, trans, a, lu, ipiv, b, x, nb):
     out = it.call("PDGERFS", *args(np.zeros(lw + 8), lw, np.zeros(liw + 8, np.int64), liw))
     x[...] = x_.reshape((n, nrhs), order="F")
     return ferr[:nrhs].copy(), berr[:nrhs].copy(), out["INFO"]
+
+
+SVX_UNITS = (("SRC", "pdgerfs"), ("SRC", "pdgesvx"), ("SRC", "pdgeequ"), ("SRC", "pdlaqge"), ("SRC", "pdlange"), ("TOOLS", "ilcm"))
+
+
+def pdgesvx(it, fact, trans, a, af, ipiv, equed, r, c, b, nb):
+    """The reference's PDGESVX on a 1 x 1 grid.  a (n x n), b (n x nrhs) are overwritten as the routine overwrites them; af, ipiv, r, c are
+    inputs for FACT = 'F' and outputs otherwise.  Returns dict(equed, rcond, info, x, ferr, berr)."""
+    n, nrhs = b.shape
+    desca = [1, 0, n, n, nb, nb, 0, 0, max(1, n)]
+    descb = [1, 0, n, nrhs, nb, nb, 0, 0, max(1, n)]
+    flat = lambda m_: np.asfortranarray(m_).reshape(-1, order="F").copy()  # noqa: E731
+    a_, af_, b_, x_ = flat(a), flat(af), flat(b), np.zeros(n * nrhs)
+    ip = np.concatenate([np.asarray(ipiv, np.int64), np.zeros(nb, np.int64)])
+    r_, c_ = np.array(r, float), np.array(c, float)
+    ferr, berr = np.zeros(nrhs + 1), np.zeros(nrhs + 1)
+    args = lambda work, lw, iwork, liw: (fact, trans, n, nrhs, a_, 1, 1, desca, af_, 1, 1, desca, ip, equed, r_, c_, b_, 1, 1, descb, x_, 1, 1, descb,  # noqa: E731
+                                         0.0, ferr, berr, work, lw, iwork, liw, 0)
+    work, iwork = np.zeros(4), np.zeros(4, np.int64)
+    q = it.call("PDGESVX", *args(work, -1, iwork, -1))
+    if q["INFO"] != 0:
+        return dict(equed=q["EQUED"], rcond=q["RCOND"], info=q["INFO"])
+    lw, liw = int(work[0]), int(iwork[0])
+    out = it.call("PDGESVX", *args(np.zeros(lw + 8), lw, np.zeros(liw + 8, np.int64), liw))
+    a[...] = a_.reshape((n, n), order="F"); af[...] = af_.reshape((n, n), order="F"); b[...] = b_.reshape((n, nrhs), order="F")
+    ipiv[...] = ip[:n]; r[...] = r_; c[...] = c_
+    return dict(equed=out["EQUED"], rcond=out["RCOND"], info=out["INFO"], x=x_.reshape((n, nrhs), order="F"), ferr=ferr[:nrhs].copy(),
+                berr=berr[:nrhs].copy(), lwork=lw, liwork=liw)

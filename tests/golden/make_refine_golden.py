@@ -43,8 +43,32 @@ def rfs_inputs(cs):
     return a, lu, ipiv, b, x0
 
 
+SVX_CASES = [dict(n=6, nb=2, nrhs=1, fact="N", trans="N"), dict(n=17, nb=4, nrhs=2, fact="E", trans="N", scale=5), dict(n=17, nb=4, nrhs=2, fact="E", trans="T", scale=5),
+             dict(n=12, nb=4, nrhs=2, fact="E", trans="N"), dict(n=20, nb=8, nrhs=3, fact="N", trans="T"), dict(n=24, nb=4, nrhs=2, fact="E", trans="N", scale=2),
+             dict(n=24, nb=4, nrhs=2, fact="E", trans="N", rowscale=6), dict(n=24, nb=4, nrhs=2, fact="E", trans="T", colscale=6),
+             dict(n=16, nb=4, nrhs=1, fact="N", trans="N", twin=(2, 3)), dict(n=16, nb=4, nrhs=1, fact="E", trans="N", zero_row=5),
+             dict(n=16, nb=4, nrhs=1, fact="N", trans="N", zero_col=7), dict(n=2, nb=2, nrhs=1, fact="E", trans="N"), dict(n=1, nb=2, nrhs=2, fact="N", trans="N")]
+
+
+def svx_inputs(cs):
+    n, nrhs = cs["n"], cs["nrhs"]
+    a = matrix(cs)
+    k = np.arange(n)
+    if cs.get("rowscale"):
+        a = np.asfortranarray((10.0 ** (cs["rowscale"] * np.sin(k))[:, None]) * a)
+    if cs.get("colscale"):
+        a = np.asfortranarray(a * (10.0 ** (cs["colscale"] * np.cos(k))[None, :]))
+    if cs.get("twin"):
+        a[:, cs["twin"][1]] = a[:, cs["twin"][0]]                 # singular to working precision
+    if cs.get("zero_row") is not None:
+        a[cs["zero_row"], :] = 0.0
+    if cs.get("zero_col") is not None:
+        a[:, cs["zero_col"]] = 0.0                                # PDGETRF reports INFO > 0
+    return np.asfortranarray(a), O.pdmatgen(n, nrhs, 200).copy(order="F")
+
+
 if __name__ == "__main__":
-    it = R.make(extra=(("SRC", "pdgerfs"),))
+    it = R.make(extra=R.SVX_UNITS)
     store = {}
     for i, cs in enumerate(CASES):
         a = matrix(cs)
@@ -67,6 +91,30 @@ if __name__ == "__main__":
         store[f"rfs{i}"] = np.array([cs["n"], cs["nb"], cs["nrhs"], ord(cs["trans"]), cs.get("scale", 0)], np.int64)
         store[f"rfs_pert{i}"] = np.array([cs.get("perturb", 1e-7)])
         store[f"rfs_x{i}"], store[f"rfs_ferr{i}"], store[f"rfs_berr{i}"] = x, ferr, berr
+    for i, cs in enumerate(SVX_CASES):
+        a, b = svx_inputs(cs)
+        n = cs["n"]
+        af, ipiv, r, c = np.zeros((n, n), order="F"), np.zeros(n, np.int64), np.zeros(n), np.zeros(n)
+        res = R.pdgesvx(it, cs["fact"], cs["trans"], a, af, ipiv, "N", r, c, b, cs["nb"])
+        store[f"svx{i}"] = np.array([res["info"], ord(res["equed"][0])], np.int64)
+        store[f"svx_rcond{i}"] = np.array([res["rcond"]])
+        store[f"svx_work{i}"] = np.array([res.get("lwork", 0), res.get("liwork", 0)], np.int64)
+        for key, val in (("a", a), ("af", af), ("ipiv", ipiv), ("r", r), ("c", c), ("b", b)):
+            store[f"svx_{key}{i}"] = val
+        if "x" in res:
+            store[f"svx_x{i}"], store[f"svx_ferr{i}"], store[f"svx_berr{i}"] = res["x"], res["ferr"], res["berr"]
+        # FACT = 'F' on what the first call returned (only where it completed)
+        if res["info"] == 0:
+            a2, b2 = svx_inputs(cs)
+            eq = res["equed"][0]
+            if eq in "RB":
+                a2 = np.asfortranarray(r[:, None] * a2)
+            if eq in "CB":
+                a2 = np.asfortranarray(a2 * c[None, :])
+            resf = R.pdgesvx(it, "F", cs["trans"], a2, af.copy(order="F"), ipiv.copy(), eq, r.copy(), c.copy(), b2, cs["nb"])
+            store[f"svxF{i}"] = np.array([resf["info"], ord(resf["equed"][0])], np.int64)
+            store[f"svxF_rcond{i}"] = np.array([resf["rcond"]])
+            store[f"svxF_x{i}"] = resf["x"]
     # argument errors and quick returns as the executed source reports them: (NORM, N, ANORM, LWORK) -> (INFO, RCOND)
     lu = O.pdmatgen(8, 8, 100).copy(order="F")
     a = lu.reshape(-1, order="F").copy()
@@ -77,5 +125,6 @@ if __name__ == "__main__":
         quick.append([ord(norm), n, anorm, lwork, out["INFO"], out["RCOND"]])
     store["quick"] = np.array(quick)
     np.savez_compressed(os.path.join(HERE, "refine_reference.npz"), **store)
-    print("wrote", len(CASES), "+", len(RFS_CASES), "cases; PXERBLA log:", it.log)
+    print("wrote", len(CASES), "+", len(RFS_CASES), "+", len(SVX_CASES), "cases; PXERBLA log:", it.log)
+    print("PDGESVX (info, equed):", [(int(store[f"svx{i}"][0]), chr(int(store[f"svx{i}"][1]))) for i in range(len(SVX_CASES))])
     print(store["quick"])

@@ -211,3 +211,69 @@ def test_refinement_against_the_executed_reference_fortran(O):
             assert np.abs(x[:, k] - xr[:, k]).max() <= 2.0 * f2[k] * np.abs(xr[:, k]).max(), (cs, k)
             assert berr[k] <= 4 * EPS * (n + 1) and br[k] <= 4 * EPS * (n + 1)
             assert ferr[k] == pytest.approx(fr[k], rel=0.1), (cs, k)
+
+
+def test_expert_driver_against_the_executed_reference_fortran(O):
+    """oracle/oracle_next.c's PDGESVX against SRC/pdgesvx.f executed WITH its callees pdgeequ.f, pdlaqge.f, pdlange.f, pdgecon.f,
+    pdlacon.f, pdgerfs.f (PDGETRF / PDGETRS = the oracle's, themselves pinned by the executed pdgetrf.f / pdgetrs.f).  Discrete outputs
+    exactly: INFO (0, N + 1 for a matrix singular to working precision, k for a zero pivot), EQUED (N / R / C / B), IPIV; R, C and the
+    equilibrated A and B exactly (maxima and reciprocals); RCOND to 1e-9; FERR to 10 %; X within LAPACK's bound; FACT = 'F' on the
+    returned factors reproduces the solution."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_refine_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refine_reference.npz"))
+    assert len(G.SVX_CASES) >= 13
+    seen = set()
+    for i, cs in enumerate(G.SVX_CASES):
+        n, nrhs, nb = cs["n"], cs["nrhs"], cs["nb"]
+        info_ref, eq_ref = int(g[f"svx{i}"][0]), chr(int(g[f"svx{i}"][1]))
+        seen.add((min(info_ref, 1) if info_ref <= n else 2, eq_ref))
+
+        def run(fact, equed, a, af, ip, r, c, b, keep=False):
+            O.lacon_keep_est(keep)
+            x = np.zeros((n, nrhs), order="F")
+            out = O.dgesvx(fact, cs["trans"], a, af, ip, equed, r, c, b, x, nb=nb)
+            O.lacon_keep_est(False)
+            return out, x
+        a, b = G.svx_inputs(cs)
+        af, ip, r, c = np.zeros((n, n), order="F"), np.zeros(n, np.int32), np.zeros(n), np.zeros(n)
+        (eq, rcond, ferr, berr, info), x = run(cs["fact"], "N", a, af, ip, r, c, b)
+        assert (info, eq) == (info_ref, eq_ref), cs
+        assert rcond == pytest.approx(float(g[f"svx_rcond{i}"][0]), rel=1e-9, abs=1e-300), cs
+        assert np.array_equal(a, g[f"svx_a{i}"]) and np.array_equal(b, g[f"svx_b{i}"]), cs          # equilibrated in place (or untouched)
+        if eq_ref in "RB":
+            assert np.array_equal(r, g[f"svx_r{i}"])
+        if eq_ref in "CB":
+            assert np.array_equal(c, g[f"svx_c{i}"])
+        if info_ref == 0 or info_ref == n + 1:
+            assert np.array_equal(ip, g[f"svx_ipiv{i}"]), cs
+        if info_ref != 0:
+            continue
+        a2, b2 = G.svx_inputs(cs)
+        (_, _, fbound, _, _), _ = run(cs["fact"], "N", a2, np.zeros((n, n), order="F"), np.zeros(n, np.int32), np.zeros(n), np.zeros(n), b2, keep=True)
+        xr, fr = g[f"svx_x{i}"], g[f"svx_ferr{i}"]
+        for k in range(nrhs):
+            assert np.abs(x[:, k] - xr[:, k]).max() <= 2.0 * max(fbound[k], 1e-15) * np.abs(xr[:, k]).max(), (cs, k)
+            assert ferr[k] == pytest.approx(fr[k], rel=0.1, abs=1e-300), (cs, k)
+            assert berr[k] <= 4 * EPS * (n + 1) and g[f"svx_berr{i}"][k] <= 4 * EPS * (n + 1)
+        # FACT = 'F' with the factors, scalings and EQUED just returned
+        a3, b3 = G.svx_inputs(cs)
+        if eq in "RB":
+            a3 = np.asfortranarray(r[:, None] * a3)
+        if eq in "CB":
+            a3 = np.asfortranarray(a3 * c[None, :])
+        (eqf, rcf, _, _, inff), xf = run("F", eq, a3, af.copy(order="F"), ip.copy(), r.copy(), c.copy(), b3)
+        assert (inff, eqf) == (int(g[f"svxF{i}"][0]), chr(int(g[f"svxF{i}"][1])))
+        assert rcf == pytest.approx(float(g[f"svxF_rcond{i}"][0]), rel=1e-9)
+        stale_work = eq in "CB" and cs["trans"] == "N"
+        for k in range(nrhs):
+            tol = 2.0 * max(fbound[k], 1e-15) * np.abs(xr[:, k]).max()
+            assert np.abs(xf[:, k] - x[:, k]).max() <= tol                     # the oracle's FACT = 'F' reproduces its own solution
+            if not stale_work:
+                assert np.abs(xf[:, k] - g[f"svxF_x{i}"][:, k]).max() <= tol
+            else:
+                # A defect of the reference, shown by the execution and NOT reproduced: with FACT = 'F', column scaling and TRANS = 'N'
+                # ICOLEQU stays 0 (it is only set under FACT = 'E', pdgesvx.f:665-680), so C is never copied into WORK and X is
+                # multiplied by whatever PDGERFS left there (pdgesvx.f:796-822): the executed result is not the solution.
+                assert np.abs(g[f"svxF_x{i}"][:, k] - xr[:, k]).max() > 0.5 * np.abs(xr[:, k]).max()
+    assert {(0, "N"), (0, "B"), (0, "R"), (0, "C"), (2, "N"), (1, "N")} <= seen
