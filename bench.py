@@ -498,25 +498,8 @@ def run_ours(args):
     # part of `value` / `e2e`, and unable to delay or break this line: the leg is abandoned when it does not return in time ----
     next_rows, next_thread = None, None
     if not args.no_next:
-        # every rank takes the same decision (max over the ranks): each one starts its own rank of every row's process group.  The
-        # driver allows 870 s per run; a multi-GPU run leaves less room, and at 8 GPUs this leg normally does not fit at all.
-        elapsed = maxr(time.time() - t_start)
-        limit = min(240.0, 780.0 - elapsed) if world == 1 else min(150.0, 600.0 - elapsed)
-        if limit < 40.0:
-            next_rows = {"error": f"skipped: {elapsed:.0f} s of the run's time were used before this leg"}
-        else:
-            import threading
-            box = {}
-
-            def _work():
-                try:
-                    import bench_next
-                    box["r"] = bench_next.run_all(per_row_timeout=60.0, total_timeout=limit)
-                except Exception as ex:  # noqa: BLE001
-                    box["r"] = {"error": repr(ex)[:300]}
-            next_thread = threading.Thread(target=_work, daemon=True)
-            next_thread.start(); next_thread.join(limit + 20.0)
-            next_rows = box.get("r", {"error": "abandoned: the supplementary rows did not return within their limit"})
+        # every rank takes the same decision (max over the ranks): each one starts its own rank of every row's process group
+        next_rows, next_thread = next_rows_leg(world, maxr(time.time() - t_start))
     if rank == 0:
         line = {"metric": METRIC[routine], "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
@@ -543,6 +526,27 @@ def run_ours(args):
     if next_thread is not None and next_thread.is_alive():      # a child that cannot be reaped must not keep this process from exiting
         sys.stdout.flush(); sys.stderr.flush()
         os._exit(0)
+
+
+def next_rows_leg(world, elapsed, slack=20.0):
+    """Runs bench_next.run_all in a daemon thread and waits for it at most its time limit + slack: (report, thread).  The driver allows
+    870 s per run; a multi-GPU run leaves less room, and at 8 GPUs this leg normally does not fit at all.  A leg that does not come back
+    is abandoned (the caller prints its line and leaves with os._exit while the thread is still alive)."""
+    limit = min(240.0, 780.0 - elapsed) if world == 1 else min(150.0, 600.0 - elapsed)
+    if limit < 40.0:
+        return {"error": f"skipped: {elapsed:.0f} s of the run's time were used before this leg"}, None
+    import threading
+    box = {}
+
+    def _work():
+        try:
+            import bench_next
+            box["r"] = bench_next.run_all(per_row_timeout=60.0, total_timeout=limit)
+        except Exception as ex:  # noqa: BLE001
+            box["r"] = {"error": repr(ex)[:300]}
+    th = threading.Thread(target=_work, daemon=True)
+    th.start(); th.join(limit + slack)
+    return box.get("r", {"error": "abandoned: the supplementary rows did not return within their limit"}), th
 
 
 def main():

@@ -434,3 +434,30 @@ def test_reference_fortran_executed_live(O):
         ig = int(rng.integers(1, 5000))
         assert it.call("INDXG2P", ig, nb, ip, isrc, np_)["__result__"] == O.indxg2p(ig, nb, ip, isrc, np_)
         assert it.call("INDXL2G", ig, nb, ip, isrc, np_)["__result__"] == O.indxl2g(ig, nb, ip, isrc, np_)
+
+
+def test_bench_supplementary_leg_cannot_hold_the_bench_line(monkeypatch):
+    """bench.py's supplementary leg (the 8(f) measurements of bench_next.py): skipped when the run has used its time, reported when it
+    returns, ABANDONED when it does not come back within its limit -- the bench line is printed either way."""
+    import importlib
+    import time as _time
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    import bench_next
+    rep, th = bench.next_rows_leg(1, 760.0)
+    assert th is None and "skipped" in rep["error"]
+    rep, th = bench.next_rows_leg(4, 570.0)
+    assert th is None and "skipped" in rep["error"]
+    calls = {}
+    monkeypatch.setattr(bench_next, "run_all", lambda per_row_timeout, total_timeout: calls.update(t=total_timeout) or {"summary": {"ok": 3}})
+    rep, th = bench.next_rows_leg(1, 300.0)
+    assert rep == {"summary": {"ok": 3}} and calls["t"] == 240.0 and not th.is_alive()
+    rep, th = bench.next_rows_leg(2, 500.0)
+    assert calls["t"] == 100.0
+    monkeypatch.setattr(bench_next, "run_all", lambda per_row_timeout, total_timeout: (_ for _ in ()).throw(RuntimeError("boom")))
+    rep, th = bench.next_rows_leg(1, 0.0)
+    assert "boom" in rep["error"]
+    monkeypatch.setattr(bench_next, "run_all", lambda per_row_timeout, total_timeout: _time.sleep(3600))
+    t0 = _time.time()
+    rep, th = bench.next_rows_leg(1, 739.0, slack=-40.0)          # limit 41 s, waits 1 s
+    assert "abandoned" in rep["error"] and th.is_alive() and _time.time() - t0 < 10.0
