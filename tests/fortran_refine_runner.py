@@ -193,11 +193,96 @@ def make(ref_root="/root/reference", extra=()):
             v1[o1 + 1] = v2[o2 + 1] + (v1[o1] / v2[o2]) ** 2 * v1[o1 + 1]
             v1[o1] = v2[o2]
 
+    # ---- leaves of SRC/pdgetri.f / pdtrtri.f / pdtrti2.f ----
+    def tri_of(t, uplo, diag):
+        t = np.tril(np.array(t)) if uplo == "L" else np.triu(np.array(t))
+        if diag == "U":
+            np.fill_diagonal(t, 1.0)
+        return t
+
+    def pdtrmm(it, env, parts):                                                         # PBLAS/SRC/pdtrmm_.c, SIDE = 'L': B := alpha op(A) B
+        side, uplo, trans, diag = (ev(it, env, parts, k)[0].upper() for k in range(4))
+        m, n, alpha = ev(it, env, parts, 4), ev(it, env, parts, 5), ev(it, env, parts, 6)
+        assert side == "L" and trans == "N"
+        if m > 0 and n > 0:
+            t = tri_of(window(it, env, parts, 7, m, m), uplo, diag)
+            b = window(it, env, parts, 11, m, n)
+            b[:, :] = alpha * (t @ np.array(b))
+
+    def pdtrsm(it, env, parts):                                                         # PBLAS/SRC/pdtrsm_.c, SIDE = 'R': B := alpha B inv(A)
+        from scipy.linalg import solve_triangular
+        side, uplo, trans, diag = (ev(it, env, parts, k)[0].upper() for k in range(4))
+        m, n, alpha = ev(it, env, parts, 4), ev(it, env, parts, 5), ev(it, env, parts, 6)
+        assert side == "R" and trans == "N"
+        if m > 0 and n > 0:
+            t = window(it, env, parts, 7, n, n)
+            b = window(it, env, parts, 11, m, n)
+            # X A = alpha B  <=>  A' X' = alpha B'
+            b[:, :] = solve_triangular(np.array(t), alpha * np.array(b).T, lower=(uplo == "L"), trans=1, unit_diagonal=(diag == "U")).T
+
+    def pdgemm(it, env, parts):
+        ta, tb = ev(it, env, parts, 0)[0].upper(), ev(it, env, parts, 1)[0].upper()
+        m, n, k, alpha, beta = (ev(it, env, parts, q) for q in (2, 3, 4, 5, 14))
+        assert ta == "N" and tb == "N"
+        if m > 0 and n > 0:
+            c = window(it, env, parts, 15, m, n)
+            prod = np.array(window(it, env, parts, 6, m, k)) @ np.array(window(it, env, parts, 10, k, n)) if k > 0 else 0.0
+            c[:, :] = alpha * prod + beta * np.array(c)
+
+    def pdlacpy_any(it, env, parts):                                                    # SRC/pdlacpy.f: 'L' lower trapezoid, 'U' upper, else all
+        uplo = ev(it, env, parts, 0)[0].upper()
+        m, n = ev(it, env, parts, 1), ev(it, env, parts, 2)
+        if m <= 0 or n <= 0:
+            return
+        src, dst = window(it, env, parts, 3, m, n), window(it, env, parts, 7, m, n)
+        mask = np.tril(np.ones((m, n), bool)) if uplo == "L" else (np.triu(np.ones((m, n), bool)) if uplo == "U" else np.ones((m, n), bool))
+        dst[mask] = np.array(src)[mask]
+
+    def pdlaset(it, env, parts):                                                        # SRC/pdlaset.f: off-diagonal part := ALPHA, diagonal := BETA
+        uplo = ev(it, env, parts, 0)[0].upper()
+        m, n, alpha, beta = ev(it, env, parts, 1), ev(it, env, parts, 2), ev(it, env, parts, 3), ev(it, env, parts, 4)
+        if m <= 0 or n <= 0:
+            return
+        a = window(it, env, parts, 5, m, n)
+        i, j = np.indices((m, n))
+        a[(i > j) if uplo == "L" else ((i < j) if uplo == "U" else (i != j))] = alpha
+        a[i == j] = beta
+
+    def pdlapiv_cols(it, env, parts):                                                   # SRC/pdlapiv.f, ROWCOL = 'C', PIVROC = 'C'
+        direc, rowcol, pivroc = (ev(it, env, parts, k)[0].upper() for k in range(3))
+        m, n = ev(it, env, parts, 3), ev(it, env, parts, 4)
+        assert rowcol == "C" and pivroc == "C"
+        a = window(it, env, parts, 5, m, n)
+        ip = ev(it, env, parts, 10)                                                      # IPIV(IP:IP+N-1): global ROW indices of A (pdgetrf.f:118-121)
+        piv = env[parts[9]]
+        for j in (range(n) if direc == "F" else range(n - 1, -1, -1)):
+            p_ = int(piv[ip - 1 + j]) - ip
+            if p_ != j:
+                a[:, [j, p_]] = a[:, [p_, j]]
+
+    def dtrmv(it, env, parts):                                                          # BLAS DTRMV: x := A x
+        uplo, trans, diag = (ev(it, env, parts, k)[0].upper() for k in range(3))
+        n, lda = ev(it, env, parts, 3), ev(it, env, parts, 5)
+        a, ao = it.address(parts[4], env); x, xo = it.address(parts[6], env)
+        assert trans == "N" and ev(it, env, parts, 7) == 1
+        if n > 0:
+            t = tri_of(np.asarray(a[ao:ao + lda * (n - 1) + n]).copy() if False else np.array([[a[ao + i + j * lda] for j in range(n)] for i in range(n)]), uplo, diag)
+            x[xo:xo + n] = t @ np.array(x[xo:xo + n])
+
+    def dscal(it, env, parts):
+        n, alpha = ev(it, env, parts, 0), ev(it, env, parts, 1)
+        x, xo = it.address(parts[2], env)
+        assert ev(it, env, parts, 3) == 1
+        if n > 0:
+            x[xo:xo + n] = alpha * np.array(x[xo:xo + n])
+
     def idamax(n, x, inc):
         return int(np.argmax(np.abs(np.array(x[:n])))) + 1 if n > 0 else 0
 
 
-    cbs = {"PDGETRF": pdgetrf, "PDLACPY": pdlacpy, "DLASSQ": dlassq, "DCOMBSSQ": dcombssq, "IDAMAX": idamax, "PDTREECOMB": nop, "DGSUM2D": nop,
+    cbs = {"PDTRMM": pdtrmm, "PDTRSM": pdtrsm, "PDGEMM": pdgemm, "PDLASET": pdlaset, "PDLAPIV": pdlapiv_cols, "DTRMV": dtrmv, "DSCAL": dscal,
+           "BLACS_ABORT": nop,
+           "PDGETRF": pdgetrf, "PDLACPY": pdlacpy_any, "DLASSQ": dlassq, "DCOMBSSQ": dcombssq, "IDAMAX": idamax, "PDTREECOMB": nop, "DGSUM2D": nop,
            "DGAMN2D": nop, "IGAMX2D": nop,
            "PDGEMV": pdgemv, "PDAGEMV": pdagemv, "PDCOPY": pdcopy, "PDAXPY": pdaxpy, "PDGETRS": pdgetrs, "DGAMX2D": nop,
            "BLACS_GRIDINFO": gridinfo, "PXERBLA": pxerbla, "PB_TOPGET": topget, "PB_TOPSET": nop, "PCHK1MAT": nop, "PCHK2MAT": nop, "DGEBS2D": nop,
@@ -271,3 +356,23 @@ def pdgesvx(it, fact, trans, a, af, ipiv, equed, r, c, b, nb):
     ipiv[...] = ip[:n]; r[...] = r_; c[...] = c_
     return dict(equed=out["EQUED"], rcond=out["RCOND"], info=out["INFO"], x=x_.reshape((n, nrhs), order="F"), ferr=ferr[:nrhs].copy(),
                 berr=berr[:nrhs].copy(), lwork=lw, liwork=liw)
+
+
+TRI_UNITS = (("SRC", "pdgetri"), ("SRC", "pdtrtri"), ("SRC", "pdtrti2"), ("TOOLS", "ilcm"))
+
+
+def pdgetri(it, lu, ipiv, nb, ia=1, ja=1, n=None):
+    """The reference's PDGETRI (with PDTRTRI / PDTRTI2) on a 1 x 1 grid: lu (global matrix holding the factors of sub(A)) is overwritten by
+    the inverse; ipiv: PDGETRF's pivots for the rows of sub(A), as global row indices of A.  Returns INFO."""
+    M, N = lu.shape
+    n = M - ia + 1 if n is None else n
+    a = np.asfortranarray(lu).reshape(-1, order="F").copy()
+    desc = [1, 0, M, N, nb, nb, 0, 0, max(1, M)]
+    ip = np.zeros(M + nb, np.int64); ip[ia - 1:ia - 1 + n] = ipiv
+    work, iwork = np.zeros(4), np.zeros(4, np.int64)
+    q = it.call("PDGETRI", n, a, ia, ja, desc, ip, work, -1, iwork, -1, 0)
+    assert q["INFO"] == 0, q["INFO"]
+    lw, liw = int(work[0]), int(iwork[0])
+    out = it.call("PDGETRI", n, a, ia, ja, desc, ip, np.zeros(lw + 8), lw, np.zeros(liw + 8, np.int64), liw, 0)
+    lu[...] = a.reshape((M, N), order="F")
+    return out["INFO"], lw, liw

@@ -1,5 +1,6 @@
 """Golden vectors of the condition estimate and of the iterative refinement produced by EXECUTING the reference's own Fortran
-(SRC/pdgecon.f, pdlacon.f, pdlatrs.f, pdgerfs.f under /root/reference) on a 1 x 1 grid with tests/fortran_refine_runner.py.  Inputs: the oracle's LU factors (block size NB) of
+(SRC/pdgecon.f, pdlacon.f, pdlatrs.f, pdgerfs.f, pdgesvx.f, pdgeequ.f, pdlaqge.f, pdlange.f, pdgetri.f, pdtrtri.f, pdtrti2.f under
+/root/reference) on a 1 x 1 grid with tests/fortran_refine_runner.py.  Inputs: the oracle's LU factors (block size NB) of
 A = PDMATGEN(seed 100), optionally badly scaled; sub-matrix cases factor A(IA:, JA:) in place inside a larger matrix.
 Writes tests/golden/refine_reference.npz.  python tests/golden/make_refine_golden.py"""
 import os
@@ -67,8 +68,23 @@ def svx_inputs(cs):
     return np.asfortranarray(a), O.pdmatgen(n, nrhs, 200).copy(order="F")
 
 
+TRI_CASES = [dict(n=1, nb=2), dict(n=2, nb=1), dict(n=6, nb=2), dict(n=10, nb=3), dict(n=17, nb=4), dict(n=30, nb=8), dict(n=20, nb=64), dict(n=24, nb=4, scale=2),
+             dict(n=16, nb=4, zero=9), dict(n=16, nb=4, zero=0), dict(n=12, nb=4, off=8), dict(n=9, nb=3, off=3, zero=4)]
+
+
+def tri_inputs(cs):
+    """(big, ipiv, lu): the oracle's factors of A placed at (off, off) of a larger matrix; zero: U(zero, zero) set to 0 (singular)"""
+    n, nb, off = cs["n"], cs["nb"], cs.get("off", 0)
+    a = matrix(cs)
+    lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+    if cs.get("zero") is not None:
+        lu[cs["zero"], cs["zero"]] = 0.0
+    big = O.pdmatgen(n + off, n + off, 55).copy(order="F"); big[off:, off:] = lu
+    return big, np.asarray(ipiv, np.int64) + off, lu, a
+
+
 if __name__ == "__main__":
-    it = R.make(extra=R.SVX_UNITS)
+    it = R.make(extra=R.SVX_UNITS + R.TRI_UNITS)
     store = {}
     for i, cs in enumerate(CASES):
         a = matrix(cs)
@@ -115,6 +131,12 @@ if __name__ == "__main__":
             store[f"svxF{i}"] = np.array([resf["info"], ord(resf["equed"][0])], np.int64)
             store[f"svxF_rcond{i}"] = np.array([resf["rcond"]])
             store[f"svxF_x{i}"] = resf["x"]
+    for i, cs in enumerate(TRI_CASES):
+        big, ipiv, lu, a = tri_inputs(cs)
+        off = cs.get("off", 0)
+        info, lw, liw = R.pdgetri(it, big, ipiv, cs["nb"], ia=off + 1, ja=off + 1, n=cs["n"])
+        store[f"tri{i}"] = np.array([info, lw, liw], np.int64)
+        store[f"tri_inv{i}"] = big
     # argument errors and quick returns as the executed source reports them: (NORM, N, ANORM, LWORK) -> (INFO, RCOND)
     lu = O.pdmatgen(8, 8, 100).copy(order="F")
     a = lu.reshape(-1, order="F").copy()
@@ -125,6 +147,7 @@ if __name__ == "__main__":
         quick.append([ord(norm), n, anorm, lwork, out["INFO"], out["RCOND"]])
     store["quick"] = np.array(quick)
     np.savez_compressed(os.path.join(HERE, "refine_reference.npz"), **store)
-    print("wrote", len(CASES), "+", len(RFS_CASES), "+", len(SVX_CASES), "cases; PXERBLA log:", it.log)
+    print("wrote", len(CASES), "+", len(RFS_CASES), "+", len(SVX_CASES), "+", len(TRI_CASES), "cases; PXERBLA log:", it.log)
+    print("PDGETRI (info, lwmin, liwmin):", [tuple(int(v) for v in store[f"tri{i}"]) for i in range(len(TRI_CASES))])
     print("PDGESVX (info, equed):", [(int(store[f"svx{i}"][0]), chr(int(store[f"svx{i}"][1]))) for i in range(len(SVX_CASES))])
     print(store["quick"])

@@ -277,3 +277,30 @@ def test_expert_driver_against_the_executed_reference_fortran(O):
                 # multiplied by whatever PDGERFS left there (pdgesvx.f:796-822): the executed result is not the solution.
                 assert np.abs(g[f"svxF_x{i}"][:, k] - xr[:, k]).max() > 0.5 * np.abs(xr[:, k]).max()
     assert {(0, "N"), (0, "B"), (0, "R"), (0, "C"), (2, "N"), (1, "N")} <= seen
+
+
+def test_inverse_against_the_executed_reference_fortran(O):
+    """oracle/oracle_next.c's PDGETRI against SRC/pdgetri.f + pdtrtri.f + pdtrti2.f executed (tests/golden/refine_reference.npz): INFO
+    exactly (the first exactly-zero U(i,i); nothing is overwritten then), the inverse to rounding, everything outside sub(A) untouched,
+    and the workspace sizes the executed source reports against the formulas of pdgetri.f:202-229."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_refine_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refine_reference.npz"))
+    assert len(G.TRI_CASES) >= 12
+    for i, cs in enumerate(G.TRI_CASES):
+        n, nb, off = cs["n"], cs["nb"], cs.get("off", 0)
+        big, ipiv, lu, a = G.tri_inputs(cs)
+        info_ref, lw, liw = [int(v) for v in g[f"tri{i}"]]
+        ref = g[f"tri_inv{i}"]
+        inv = lu.copy(order="F")
+        info = O.dgetri(inv, (ipiv - off).astype(np.int32), nb)
+        assert info == info_ref, cs
+        assert (lw, liw) == (n * nb, (n + off) + nb)                     # LWMIN = LOCr(N + IROFF) NB, LIWMIN = LOCc(N_A) + NB on a square grid
+        outside = np.ones(big.shape, bool); outside[off:, off:] = False
+        assert np.array_equal(ref[outside], big[outside])
+        if info_ref > 0:
+            assert info_ref == cs["zero"] + 1 and np.array_equal(ref, big) and np.array_equal(inv, lu)
+            continue
+        scale = np.abs(ref[off:, off:]).max()
+        assert np.abs(inv - ref[off:, off:]).max() <= 1e-12 * scale * max(1.0, np.linalg.cond(a) * 1e-3), cs
+        assert np.abs(ref[off:, off:] @ a - np.eye(n)).max() <= 1e-10 * max(1.0, np.linalg.cond(a) * 1e-3)
