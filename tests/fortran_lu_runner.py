@@ -11,10 +11,12 @@ import numpy as np
 import fortran77_mini as F
 
 
-def make(ref_root="/root/reference"):
+def make(ref_root="/root/reference", real_lapiv=False):
+    """real_lapiv: SRC/pdlapiv.f + pdlapv2.f are executed too (their PDSWAP calls reach the numpy leaf) instead of the PDLAPIV stand-in"""
     units = [F.parse(open(os.path.join(ref_root, d, f + ".f")).read())
              for d, f in (("TOOLS", "numroc"), ("TOOLS", "indxg2p"), ("TOOLS", "indxg2l"), ("TOOLS", "indxl2g"), ("TOOLS", "iceil"), ("TOOLS", "infog2l"),
-                          ("TOOLS", "chk1mat"), ("TOOLS", "descset"), ("SRC", "pdgetrf"), ("SRC", "pdgetf2"), ("SRC", "pdlaswp"), ("SRC", "pdgetrs"))]
+                          ("TOOLS", "chk1mat"), ("TOOLS", "descset"), ("SRC", "pdgetrf"), ("SRC", "pdgetf2"), ("SRC", "pdlaswp"), ("SRC", "pdgetrs"))
+             + ((("SRC", "pdlapiv"), ("SRC", "pdlapv2")) if real_lapiv else ())]
     log = []
 
     def ev(it, env, parts, k):
@@ -114,6 +116,8 @@ def make(ref_root="/root/reference"):
     cbs = {"BLACS_GRIDINFO": gridinfo, "PXERBLA": pxerbla, "BLACS_ABORT": nop, "PB_TOPGET": topget, "PB_TOPSET": nop, "PCHK1MAT": nop, "PCHK2MAT": nop,
            "IGEBS2D": nop, "IGEBR2D": nop, "IGAMN2D": nop, "PDAMAX": pdamax, "PDSWAP": pdswap, "PDSCAL": pdscal, "PDGER": pdger, "PDTRSM": pdtrsm,
            "PDGEMM": pdgemm, "PDLAPIV": pdlapiv}
+    if real_lapiv:
+        del cbs["PDLAPIV"]
     it = F.Interp(units, cbs)
     it.log = log
     return it

@@ -304,3 +304,24 @@ def test_inverse_against_the_executed_reference_fortran(O):
         scale = np.abs(ref[off:, off:]).max()
         assert np.abs(inv - ref[off:, off:]).max() <= 1e-12 * scale * max(1.0, np.linalg.cond(a) * 1e-3), cs
         assert np.abs(ref[off:, off:] @ a - np.eye(n)).max() <= 1e-10 * max(1.0, np.linalg.cond(a) * 1e-3)
+
+
+def test_reference_row_interchanges_of_the_solve_executed_live(O):
+    """SRC/pdlapiv.f + pdlapv2.f (the PDLAPIV of PDGETRS, forward for TRANS = N and backward for T) executed as well: the solutions are
+    bit-identical to the ones the golden vectors were made with (where PDLAPIV was a numpy stand-in written from its Purpose block)."""
+    if not os.path.exists("/root/reference/SRC/pdlapv2.f"):
+        pytest.skip("no reference tree here")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fortran_lu_runner as R
+    it0, it1 = R.make(), R.make(real_lapiv=True)
+    for n, nb, nrhs in [(6, 2, 2), (17, 4, 3), (13, 5, 1), (9, 16, 2)]:
+        lu = O.pdmatgen(n, n, 100).copy(order="F")
+        ipiv, info = R.pdgetrf(it0, lu, nb)
+        for trans in "NT":
+            b0 = O.pdmatgen(n, nrhs, 200).copy(order="F"); b1 = b0.copy(order="F")
+            assert R.pdgetrs(it0, trans, lu, ipiv, b0, nb) == 0 and R.pdgetrs(it1, trans, lu, ipiv, b1, nb) == 0
+            assert np.array_equal(b0, b1)
+            x = O.pdmatgen(n, nrhs, 200).copy(order="F")
+            O.getrs(lu, ipiv[:n], x, trans)
+            assert np.abs(x - b1).max() <= 1e-9 * np.abs(b1).max()
+    assert it1.log == []
