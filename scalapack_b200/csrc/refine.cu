@@ -410,13 +410,13 @@ void store_err(int nrhs, int jb, const int *descb, int Q, int mycol, const std::
         if (indxg2p(jb + k, descb[NB_], descb[CSRC_], Q) == mycol) out[indxg2l(jb + k, descb[NB_], Q) - 1] = v[(size_t)k] / scale;
 }
 
-void gerfs_impl(const char *trans_, int n, int nrhs, const double *a, int ia, int ja, const int *desca, const double *af, int iaf,
-                int jaf, const int *descaf, const int *ipiv, const double *b, int ib, int jb, const int *descb, double *x, int ix,
-                int jx, const int *descx, double *ferr, double *berr, double *work, int lwork, int *iwork, int liwork, int *info)
+// the argument checks of PDGERFS (pdgerfs.f:304-452): INFO (0 = fine); *lquery: a workspace query.  Also what PDGESVX ends up
+// reporting for its B / X arguments: the expert driver checks little of them itself and returns the INFO of its last inner call.
+void gerfs_checks(char trans, int n, int nrhs, int ia, int ja, const int *desca, int iaf, int jaf, const int *descaf, int ib, int jb,
+                  const int *descb, int ix, int jx, const int *descx, double *work, int lwork, int *iwork, int liwork, bool *lquery_out, int *info)
 {
     const int ictxt = desca[CTXT_];
     int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
-    const char trans = up(trans_);
     const bool notran = trans == 'N';
     bool lquery = false;
     *info = 0;
@@ -466,6 +466,18 @@ void gerfs_impl(const char *trans_, int n, int nrhs, const double *a, int ia, in
         pchk2mat_(&n, &two, &n, &two, &ia, &ja, desca, &p7, &n, &two, &n, &two, &iaf, &jaf, descaf, &p11, &five, ex, expos, info);
         pchk2mat_(&n, &two, &nrhs, &three, &ib, &jb, descb, &p16, &n, &two, &nrhs, &three, &ix, &jx, descx, &p20, &five, ex, expos, info);
     }
+    *lquery_out = lquery;
+}
+
+void gerfs_impl(const char *trans_, int n, int nrhs, const double *a, int ia, int ja, const int *desca, const double *af, int iaf,
+                int jaf, const int *descaf, const int *ipiv, const double *b, int ib, int jb, const int *descb, double *x, int ix,
+                int jx, const int *descx, double *ferr, double *berr, double *work, int lwork, int *iwork, int liwork, int *info)
+{
+    const int ictxt = desca[CTXT_];
+    int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
+    const char trans = up(trans_);
+    bool lquery = false;
+    gerfs_checks(trans, n, nrhs, ia, ja, desca, iaf, jaf, descaf, ib, jb, descb, ix, jx, descx, work, lwork, iwork, liwork, &lquery, info);
     if (*info != 0) { xerbla(ictxt, "PDGERFS", *info); return; }
     if (lquery) return;
     if (n <= 1 || nrhs == 0) {                                                     // pdgerfs.f:457-463
@@ -515,9 +527,12 @@ void gesvx_impl(const char *fact_, const char *trans_, int n, int nrhs, double *
         int ibrow = 0, iarow = 0, ixrow = 0;
         if (*info == 0) {
             iarow = indxg2p(ia, desca[MB_], desca[RSRC_], P);
-            const int iafrow = indxg2p(iaf, descaf[MB_], descaf[RSRC_], P);
+            // AF's descriptor is only checked under FACT = 'F' (pdgesvx.f:453-455); a zero block size there is a division by zero in
+            // the reference (pdgesvx.f:468-470).  Here it falls through to the inner PDGETRF's own check below.
+            const int mbaf = descaf[MB_] > 0 ? descaf[MB_] : 1;
+            const int iafrow = descaf[MB_] > 0 ? indxg2p(iaf, mbaf, descaf[RSRC_], P) : iarow;
             ibrow = indxg2p(ib, descb[MB_], descb[RSRC_], P); ixrow = indxg2p(ix, descx[MB_], descx[RSRC_], P);
-            const int iroffa = (ia - 1) % desca[MB_], iroffaf = (iaf - 1) % descaf[MB_], icoffa = (ja - 1) % desca[NB_];
+            const int iroffa = (ia - 1) % desca[MB_], iroffaf = descaf[MB_] > 0 ? (iaf - 1) % mbaf : 0, icoffa = (ja - 1) % desca[NB_];
             const int iacol = indxg2p(ja, desca[NB_], desca[CSRC_], Q);
             int np = numroc(n + iroffa, desca[MB_], myrow, iarow, P); if (myrow == iarow) np -= iroffa;
             int nq = numroc(n + icoffa, desca[NB_], mycol, iacol, Q); if (mycol == iacol) nq -= icoffa;
@@ -582,9 +597,22 @@ void gesvx_impl(const char *fact_, const char *trans_, int n, int nrhs, double *
     if (*info != 0) { xerbla(ictxt, "PDGESVX", *info); return; }
     if (lquery) return;
     // what the reference's inner calls would report (PDGETRF on AF: pdgetrf.f:180-185; PDGETRS on X: pdgetrs.f:211-222)
-    if ((jaf - 1) % descaf[NB_]) { *info = -5; xerbla(ictxt, "PDGETRF", *info); return; }
-    if (descaf[MB_] != descaf[NB_] || descaf[NB_] != desca[NB_]) { *info = -(600 + NB_ + 1); xerbla(ictxt, "PDGETRF", *info); return; }
-    if ((ix - 1) % descx[MB_] || (ib - 1) % descb[MB_]) { *info = -10; xerbla(ictxt, "PDGETRS", *info); return; }
+    {
+        int i2 = 0;
+        if (nofact || equil) chk1mat(n, 1, n, 2, iaf, jaf, descaf, 6, &i2);              // pdgetrf.f:169
+        if (i2 == 0) {
+            if ((jaf - 1) % descaf[NB_]) i2 = -5;
+            else if (descaf[MB_] != descaf[NB_] || descaf[NB_] != desca[NB_]) i2 = -(600 + NB_ + 1);
+        }
+        if (i2 != 0) { *info = i2; xerbla(ictxt, "PDGETRF", *info); return; }
+    }
+    {
+        // PDGESVX does not look at INFO between PDGETRS and PDGERFS (pdgesvx.f:749-757): what the caller gets for a misplaced B or X is
+        // what PDGERFS, the last inner call, reports -- e.g. -14 for a B that starts inside a block, -19 for JB / JX inside one
+        std::vector<double> w1(1); std::vector<int> iw1(1); bool q = false; int i3 = 0;
+        gerfs_checks(trans, n, nrhs, ia, ja, desca, iaf, jaf, descaf, ib, jb, descb, ix, jx, descx, w1.data(), lwork, iw1.data(), liwork, &q, &i3);
+        if (i3 != 0) { *info = i3; xerbla(ictxt, "PDGERFS", *info); return; }
+    }
 
     Grid *g = grid_of(ictxt);
     const int nb = desca[NB_];

@@ -9,10 +9,10 @@ import numpy as np
 import fortran77_mini as F
 
 
-def make(ref_root="/root/reference"):
+def make(ref_root="/root/reference", extra=()):
     units = [F.parse(open(os.path.join(ref_root, d, f + ".f")).read())
              for d, f in (("TOOLS", "numroc"), ("TOOLS", "indxg2p"), ("TOOLS", "iceil"), ("TOOLS", "infog2l"), ("TOOLS", "chk1mat"),
-                          ("SRC", "pdpotrf"), ("SRC", "pdpotf2"), ("SRC", "pdpotrs"))]
+                          ("SRC", "pdpotrf"), ("SRC", "pdpotf2"), ("SRC", "pdpotrs")) + tuple(extra)]
     log = []
 
     def ev(it, env, parts, k):

@@ -11,12 +11,12 @@ import numpy as np
 import fortran77_mini as F
 
 
-def make(ref_root="/root/reference", real_lapiv=False):
+def make(ref_root="/root/reference", real_lapiv=False, extra=()):
     """real_lapiv: SRC/pdlapiv.f + pdlapv2.f are executed too (their PDSWAP calls reach the numpy leaf) instead of the PDLAPIV stand-in"""
     units = [F.parse(open(os.path.join(ref_root, d, f + ".f")).read())
              for d, f in (("TOOLS", "numroc"), ("TOOLS", "indxg2p"), ("TOOLS", "indxg2l"), ("TOOLS", "indxl2g"), ("TOOLS", "iceil"), ("TOOLS", "infog2l"),
                           ("TOOLS", "chk1mat"), ("TOOLS", "descset"), ("SRC", "pdgetrf"), ("SRC", "pdgetf2"), ("SRC", "pdlaswp"), ("SRC", "pdgetrs"))
-             + ((("SRC", "pdlapiv"), ("SRC", "pdlapv2")) if real_lapiv else ())]
+             + ((("SRC", "pdlapiv"), ("SRC", "pdlapv2")) if real_lapiv else ()) + tuple(extra)]
     log = []
 
     def ev(it, env, parts, k):

@@ -213,12 +213,44 @@ def make(ref_root="/root/reference", extra=()):
         from scipy.linalg import solve_triangular
         side, uplo, trans, diag = (ev(it, env, parts, k)[0].upper() for k in range(4))
         m, n, alpha = ev(it, env, parts, 4), ev(it, env, parts, 5), ev(it, env, parts, 6)
-        assert side == "R" and trans == "N"
-        if m > 0 and n > 0:
+        assert trans == "N"
+        if m > 0 and n > 0 and side == "R":
             t = window(it, env, parts, 7, n, n)
             b = window(it, env, parts, 11, m, n)
             # X A = alpha B  <=>  A' X' = alpha B'
             b[:, :] = solve_triangular(np.array(t), alpha * np.array(b).T, lower=(uplo == "L"), trans=1, unit_diagonal=(diag == "U")).T
+        elif m > 0 and n > 0:
+            t = window(it, env, parts, 7, m, m)
+            b = window(it, env, parts, 11, m, n)
+            b[:, :] = solve_triangular(np.array(t), alpha * np.array(b), lower=(uplo == "L"), unit_diagonal=(diag == "U"))
+
+    # callees of SRC/pdgetrf.f when that file is executed here (flat local arrays): the panel factorisation and the interchanges
+    def pdgetf2(it, env, parts):                                                        # SRC/pdgetf2.f (executed by tests/fortran_lu_runner.py)
+        import oracle as O
+        m, n = ev(it, env, parts, 0), ev(it, env, parts, 1)
+        a = window(it, env, parts, 2, m, n)
+        ia = ev(it, env, parts, 3)
+        lu = np.asfortranarray(np.array(a))
+        ipiv, info = O.getrf(lu, max(n, 1))                                              # one block = the unblocked algorithm
+        a[:, :] = lu
+        for i in range(min(m, n)):
+            env[parts[6]][ia - 1 + i] = int(ipiv[i]) + ia - 1
+        it.assign(parts[7], env, int(info))
+
+    def pdlaswp(it, env, parts):                                                        # SRC/pdlaswp.f: rows K1..K2 of the N columns from JA, forward
+        direc, rowcol = ev(it, env, parts, 0)[0].upper(), ev(it, env, parts, 1)[0].upper()
+        n, ja, k1, k2 = ev(it, env, parts, 2), ev(it, env, parts, 5), ev(it, env, parts, 7), ev(it, env, parts, 8)
+        assert direc == "F" and rowcol == "R"
+        if n <= 0:
+            return
+        a, aoff = it.address(parts[3], env)
+        desc = env[parts[6]]
+        lld = desc[8]
+        full = np.asarray(a[aoff:aoff + lld * (ja - 1 + n)]).reshape((ja - 1 + n, lld)).T
+        for i in range(k1, k2 + 1):
+            p_ = int(env[parts[9]][i - 1])
+            if p_ != i:
+                full[[i - 1, p_ - 1], ja - 1:ja - 1 + n] = full[[p_ - 1, i - 1], ja - 1:ja - 1 + n]
 
     def pdgemm(it, env, parts):
         ta, tb = ev(it, env, parts, 0)[0].upper(), ev(it, env, parts, 1)[0].upper()
@@ -280,7 +312,8 @@ def make(ref_root="/root/reference", extra=()):
         return int(np.argmax(np.abs(np.array(x[:n])))) + 1 if n > 0 else 0
 
 
-    cbs = {"PDTRMM": pdtrmm, "PDTRSM": pdtrsm, "PDGEMM": pdgemm, "PDLASET": pdlaset, "PDLAPIV": pdlapiv_cols, "DTRMV": dtrmv, "DSCAL": dscal,
+    cbs = {"PDGETF2": pdgetf2, "PDLASWP": pdlaswp, "IGAMN2D": nop,
+           "PDTRMM": pdtrmm, "PDTRSM": pdtrsm, "PDGEMM": pdgemm, "PDLASET": pdlaset, "PDLAPIV": pdlapiv_cols, "DTRMV": dtrmv, "DSCAL": dscal,
            "BLACS_ABORT": nop,
            "PDGETRF": pdgetrf, "PDLACPY": pdlacpy_any, "DLASSQ": dlassq, "DCOMBSSQ": dcombssq, "IDAMAX": idamax, "PDTREECOMB": nop, "DGSUM2D": nop,
            "DGAMN2D": nop, "IGAMX2D": nop,
@@ -331,6 +364,7 @@ def pdgerfs(it, trans, a, lu, ipiv, b, x, nb):
 
 
 SVX_UNITS = (("SRC", "pdgerfs"), ("SRC", "pdgesvx"), ("SRC", "pdgeequ"), ("SRC", "pdlaqge"), ("SRC", "pdlange"), ("TOOLS", "ilcm"))
+LU_UNITS = (("SRC", "pdgetrf"),)        # pdgetrf.f executed on flat arrays (its checks, its blocked loop); PDGETF2 / PDLASWP / PDTRSM / PDGEMM are leaves
 
 
 def pdgesvx(it, fact, trans, a, af, ipiv, equed, r, c, b, nb):

@@ -197,3 +197,35 @@ print("ROWS" + json.dumps(BN.run_row(sys.argv[1], n=70, nb=16, device="cpu")))
         assert outs[0]["_grid"] == ("1x2" if world == 2 else "2x2")
         for o in outs[1:]:                                       # every rank assembled the same results and drew the same conclusions
             assert {k_: v["ok"] for k_, v in o.items() if isinstance(v, dict)} == {k_: v["ok"] for k_, v in entries.items()}
+
+
+def test_info_codes_against_the_executed_reference_source(emul_lib):
+    """tests/golden/errors_reference.json: what the reference's OWN source returns as INFO (executed, tests/golden/make_errors_golden.py) for
+    515 illegal or unusual argument combinations of PDGETRF / PDGETRS / PDGESV / PDPOTRF / PDPOTRS / PDPOSV / PDGECON / PDGERFS / PDGESVX /
+    PDGETRI / PDGEEQU (tests/error_cases.py: bad scalars, characters, offsets, every descriptor field, workspace sizes, foreign contexts).
+    The product returns the same number for every one of them, and crashes on none."""
+    code = r'''
+import sys, json
+sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(root)s/tests")
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import scalapack_b200 as S
+import error_cases as E
+ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1)
+ctx2 = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1)
+g = json.load(open("%(root)s/tests/golden/errors_reference.json"))
+bad = []
+for i, c in enumerate(g["cases"]):
+    ch = {k: tuple(v) if isinstance(v, list) else v for k, v in c["changes"].items()}
+    print("AT", c["routine"], c["label"], flush=True)
+    info = E.product_info(S, ctx, c["routine"], E.apply(c["routine"], ch), ctx2)
+    if info != c["info"]:
+        bad.append([c["routine"], c["label"], c["info"], info])
+print("REPLAY" + json.dumps([len(g["cases"]), bad]))
+''' % dict(root=ROOT)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    last = [ln for ln in run.stdout.splitlines() if ln.startswith("AT")][-1:]
+    assert run.returncode == 0, (last, run.stderr[-1500:])                # a crash names the case it happened in
+    ncases, bad = json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("REPLAY")][0][6:])
+    assert ncases >= 500 and not bad, bad
