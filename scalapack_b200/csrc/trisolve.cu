@@ -161,6 +161,8 @@ void potrs_run(Grid *g, bool upper, int n, int nrhs, const double *Adev, int64_t
 
 using namespace slb;
 
+extern "C" void pdpotrf_(const char *uplo, const int *n, double *a, const int *ia, const int *ja, const int *desca, int *info);   // chol.cu
+
 extern "C" {
 
 void pdpotrs_(const char *uplo, const int *n, const int *nrhs, const double *a, const int *ia, const int *ja, const int *desca, double *b,
@@ -181,17 +183,30 @@ void pdposv_(const char *uplo, const int *n, const int *nrhs, double *a, const i
              const int *ib, const int *jb, const int *descb, int *info)
 {
     const int ictxt = desca[CTXT_];
-    potrs_checks("PDPOSV", 7, 11, 1000, uplo, *n, *nrhs, *ia, *ja, desca, *ib, *jb, descb, info);   // pdposv.f:197-228: -(1000+NB_) there
-    if (*info != 0) { xerbla(ictxt, "PDPOSV", *info); return; }
-    if (*n == 0) return;
     int P, Q, myrow, mycol; blacs_gridinfo_(&ictxt, &P, &Q, &myrow, &mycol);
-    Grid *g = grid_of(ictxt);
-    const bool upper = (uplo[0] & ~0x20) == 'U';
-    const Window w = window(*n, *n, *ia, *ja, desca, P, Q, myrow, mycol);
-    StageMat<double> A("stage_A", a, desca[LLD_], w.loff_r, w.loff_c, w.mloc, w.nloc);
-    potrf_device(g, upper, *n, A.dev, A.ld, desca[NB_], w.rsrc, w.csrc, info);
-    A.download();
-    if (*info == 0 && *nrhs > 0) potrs_run(g, upper, *n, *nrhs, A.dev, A.ld, desca[NB_], w, b, *ib, *jb, descb);   // pdposv.f:262-268
+    // pdposv.f:197-245 checks A and the ALIGNMENT of B only: B's descriptor, NRHS and JB are first looked at by the inner PDPOTRS,
+    // after the factorisation -- with PDPOTRS's argument numbers (executing the source shows it; tests/golden/errors_reference.json)
+    const char u = (char)(uplo[0] & ~0x20);
+    *info = 0;
+    if (P == -1) *info = -(700 + CTXT_ + 1);
+    else {
+        chk1mat(*n, 2, *n, 2, *ia, *ja, desca, 7, info);
+        if (*info == 0) {
+            const int mbb = descb[MB_] > 0 ? descb[MB_] : 1;                            // a zero MB_B is a division by zero in the reference
+            const int iarow = indxg2p(*ia, desca[MB_], desca[RSRC_], P), ibrow = indxg2p(*ib, mbb, descb[RSRC_], P);
+            if (u != 'U' && u != 'L') *info = -1;
+            else if ((*ia - 1) % desca[MB_]) *info = -5;
+            else if ((*ja - 1) % desca[NB_]) *info = -6;
+            else if (desca[MB_] != desca[NB_]) *info = -(700 + NB_ + 1);
+            else if ((*ib - 1) % mbb || ibrow != iarow) *info = -9;
+            else if (descb[MB_] != desca[NB_]) *info = -(1000 + NB_ + 1);               // sic: DESCB is argument 11
+        }
+        int ex[1] = { u == 'U' ? 'U' : 'L' }, expos[1] = { 1 }, one = 1, two = 2, three = 3, p7 = 7, p11 = 11;
+        pchk2mat_(n, &two, n, &two, ia, ja, desca, &p7, n, &two, nrhs, &three, ib, jb, descb, &p11, &one, ex, expos, info);
+    }
+    if (*info != 0) { xerbla(ictxt, "PDPOSV", *info); return; }
+    pdpotrf_(uplo, n, a, ia, ja, desca, info);                                          // pdposv.f:255
+    if (*info == 0) pdpotrs_(uplo, n, nrhs, a, ia, ja, desca, b, ib, jb, descb, info);  // pdposv.f:262-268
 }
 
 }  // extern "C"

@@ -46,6 +46,26 @@ def mutations():
     return out
 
 
+def pair_mutations(routine, count=40, seed=7):
+    """two mutations at once (which error is reported first is part of the behaviour): a seeded sample per routine"""
+    import random
+    rng = random.Random(seed + sum(map(ord, routine)))
+    singles = [(lab, ch) for lab, ch in mutations()[1:] if apply(routine, ch) is not None and len(ch) == 1]
+    out = []
+    while len(out) < count:
+        (l1, c1), (l2, c2) = rng.sample(singles, 2)
+        k1, k2 = next(iter(c1)), next(iter(c2))
+        if k1 == k2 and not k1.startswith("desc"):
+            continue
+        if k1 == k2:                                           # two fields of the same descriptor: a list of (index, value) pairs
+            if c1[k1][0] == c2[k2][0]:
+                continue
+            out.append((f"{l1} & {l2}", {k1: [c1[k1], c2[k2]]}))
+        else:
+            out.append((f"{l1} & {l2}", {**c1, **c2}))
+    return out
+
+
 def apply(routine, changes):
     """the argument set of one call, or None when the mutation does not concern this routine"""
     names = ROUTINES[routine]
@@ -54,7 +74,8 @@ def apply(routine, changes):
     a = base()
     for k, v in changes.items():
         if k.startswith("desc"):
-            a[k][v[0]] = v[1]
+            for idx, val in (v if isinstance(v, list) else [v]):
+                a[k][idx] = val
         else:
             a[k] = v
     return a

@@ -59,7 +59,7 @@ if __name__ == "__main__":
     its = (RL.make(extra=(("SRC", "pdgesv"),)), RC.make(extra=(("SRC", "pdposv"),)), RR.make(extra=RR.SVX_UNITS + RR.TRI_UNITS + RR.LU_UNITS))
     out, undefined = [], []
     for routine in E.ROUTINES:
-        for label, changes in E.mutations():
+        for label, changes in E.mutations() + E.pair_mutations(routine):
             a = E.apply(routine, changes)
             if a is None:
                 continue
@@ -71,7 +71,7 @@ if __name__ == "__main__":
                 signal.alarm(0)
                 undefined.append((routine, label, type(ex).__name__))     # the source divides by a zero block size, indexes out of range ...: no defined answer
                 continue
-            out.append(dict(routine=routine, label=label, changes={k: list(v) if isinstance(v, tuple) else v for k, v in changes.items()}, info=info))
+            out.append(dict(routine=routine, label=label, changes={k: ([list(x) for x in v] if isinstance(v, list) else list(v)) if isinstance(v, (tuple, list)) else v for k, v in changes.items()}, info=info))
     json.dump(dict(cases=out, undefined=undefined), open(os.path.join(HERE, "errors_reference.json"), "w"), indent=0)
     print(len(out), "cases;", len(undefined), "without a defined answer:", undefined[:12])
     for r in E.ROUTINES:
