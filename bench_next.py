@@ -360,17 +360,18 @@ def _finite(o):
     return o
 
 
-def run_all(per_row_timeout=60.0, total_timeout=240.0, n=None, nb=512, port_shift=300):
+def run_all(per_row_timeout=60.0, total_timeout=240.0, n=None, nb=512, port_shift=300, rows=None, extra_args=()):
     """Every row in its own process (a fault in one cannot poison the CUDA context of the next, nor of the caller).  Under torchrun
     every rank calls this: rank r starts rank r of each row's process group, which meets on MASTER_PORT + port_shift."""
     out, t_start = {}, time.time()
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    for k, row in enumerate(ROWS):
+    rows = list(rows or ROWS)
+    for k, row in enumerate(rows):
         left = total_timeout - (time.time() - t_start)
         if left < 10.0:
             out[row] = {"error": "skipped: the time limit of the supplementary rows was used up"}
             continue
-        cmd = [sys.executable, os.path.abspath(__file__), "--row", row, "--nb", str(nb)] + (["--n", str(n)] if n else [])
+        cmd = [sys.executable, os.path.abspath(__file__), "--row", row, "--nb", str(nb)] + (["--n", str(n)] if n else []) + list(extra_args)
         env = dict(os.environ)
         if world > 1:                                                                         # ports of its own, new ones for every row
             env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + port_shift + 40 * k)
@@ -388,7 +389,7 @@ def run_all(per_row_timeout=60.0, total_timeout=240.0, n=None, nb=512, port_shif
         except Exception as ex:  # noqa: BLE001
             out[row] = {"error": repr(ex)[:300]}
     flat = [v for r in out.values() if "error" not in r for k, v in r.items() if isinstance(v, dict)]
-    out["summary"] = {"entries": len(flat), "ok": sum(1 for v in flat if v.get("ok")), "rows_failed": [r for r in ROWS if "error" in out[r]],
+    out["summary"] = {"entries": len(flat), "ok": sum(1 for v in flat if v.get("ok")), "rows_failed": [r for r in rows if "error" in out[r]],
                       "timing": "wall clock (max over ranks) of one synchronous call, operands resident in HBM, after one warm-up call",
                       "grid": "%dx%d" % GRIDS.get(world, (0, 0))}
     return _finite(out)
@@ -399,9 +400,14 @@ def main():
     ap.add_argument("--row", default="", choices=[""] + ROWS)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--nb", type=int, default=512)
+    ap.add_argument("--device", default="cuda", help=argparse.SUPPRESS)       # 'cpu' + --lib: the CPU test of this script's own logic
+    ap.add_argument("--lib", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.lib:
+        import scalapack_b200.api as api
+        api._SO = args.lib
     if args.row:
-        print(json.dumps(run_row(args.row, args.n or None, args.nb)), flush=True)
+        print(json.dumps(run_row(args.row, args.n or None, args.nb, device=args.device)), flush=True)
     else:
         print(json.dumps(run_all(n=args.n or None, nb=args.nb)), flush=True)
 

@@ -229,3 +229,37 @@ print("REPLAY" + json.dumps([len(g["cases"]), bad]))
     assert run.returncode == 0, (last, run.stderr[-1500:])                # a crash names the case it happened in
     ncases, bad = json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("REPLAY")][0][6:])
     assert ncases >= 890 and not bad, bad
+
+
+def test_supplementary_bench_whole_leg_under_two_ranks(emul_lib):
+    """bench_next.run_all as bench.py calls it under torchrun: every rank starts its own rank of each row's process group on shifted
+    ports (the caller's control plane and store keep theirs), collects the row's report, and both ranks end with the same summary."""
+    code = r'''
+import sys, json
+sys.path.insert(0, "%(root)s")
+import bench_next as BN
+out = BN.run_all(per_row_timeout=200.0, total_timeout=400.0, n=48, nb=16, rows=["potrf", "gemr2d"],
+                 extra_args=["--device", "cpu", "--lib", "%(root)s/tests/emul/libslb_emul.so"])
+print("ALL" + json.dumps(out))
+''' % dict(root=ROOT)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   TORCHELASTIC_RUN_ID="x", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+        env.pop("SLB200_PORT_OFFSET", None)
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=500)
+            assert p.returncode == 0, e[-2000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("ALL")][0][3:]))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for o in outs:
+        assert o["summary"]["rows_failed"] == [] and o["summary"]["grid"] == "1x2", o
+        assert o["summary"]["entries"] == o["summary"]["ok"] == 8, o["summary"]
+        assert o["potrf"]["_grid"] == "1x2"
