@@ -325,3 +325,41 @@ def test_reference_row_interchanges_of_the_solve_executed_live(O):
             O.getrs(lu, ipiv[:n], x, trans)
             assert np.abs(x - b1).max() <= 1e-9 * np.abs(b1).max()
     assert it1.log == []
+
+
+def test_complex_lu_source_is_the_real_one_with_type_names_swapped():
+    """The complex path (PZGETRF / PZGETF2 / PZLASWP / PZGETRS) needs no separate execution: its source IS the real routines'
+    source with the type names swapped (COMPLEX*16, PZ*, PZGERU for PDGER, complex constants), statement for statement.  Checked on the
+    reference tree where it is present; with it, the executed-source pins of the real LU path carry over to the oracle's complex one."""
+    if not os.path.exists("/root/reference/SRC/pzgetrf.f"):
+        pytest.skip("no reference tree here")
+
+    def statements(path, swap):
+        out = []
+        for raw in open(path).read().splitlines():
+            if not raw.strip() or raw[0] in "*Cc!":
+                continue
+            body = raw[6:72]
+            if len(raw) > 5 and raw[5] not in " 0" and out:
+                out[-1] += " " + body.strip()
+            else:
+                out.append(body.strip())
+        norm = []
+        for st in out:
+            st = st.upper()
+            if swap:
+                st = st.replace("COMPLEX*16", "DOUBLE PRECISION").replace("PZGERU", "PDGER").replace("PZ", "PD")
+                st = re.sub(r"\(\s*([0-9.D+-]+)\s*,\s*0\.0D\+0\s*\)", r"\1", st)        # ( 1.0D+0, 0.0D+0 ) -> 1.0D+0
+            if st.startswith("EXTERNAL"):
+                st = "EXTERNAL " + ",".join(sorted(x.strip() for x in st[8:].split(",")))   # the lists are ordered alphabetically
+            norm.append(re.sub(r"\s+", "", st))
+        return norm
+    for name in ("getrf", "getf2", "laswp", "getrs"):
+        z = statements(f"/root/reference/SRC/pz{name}.f", True)
+        d = statements(f"/root/reference/SRC/pd{name}.f", False)
+        diff = [(a, b) for a, b in zip(z, d) if a != b]
+        if name == "getrs":
+            # the one real difference: the transposed solves pass TRANS ('T' or 'C') on where the real routine writes 'Transpose'
+            assert len(diff) == 2 and all(a.replace(",TRANS,", ",'TRANSPOSE',") == b and a.startswith("CALLPDTRSM(") for a, b in diff), diff
+            diff = []
+        assert len(z) == len(d) and not diff, (name, diff[:3])
