@@ -5,7 +5,7 @@ import json, os, subprocess, sys, time, socket
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import test_gpu_next as t
-lists = {"F1": t.F1_GPU, "F2": t.F2_GPU, "F3": t.F3_GPU, "F4": t.F4_GPU, "F4B": t.F4B_GPU, "F5": t.F5_GPU}
+lists = dict(t.ONE_GPU)                       # one list per entry point, exactly what tests/test_gpu_next.py::test_one_gpu runs
 if len(sys.argv) > 1:
     lists = {k: v for k, v in lists.items() if k in sys.argv[1:]}
 for name, cases in lists.items():

@@ -622,8 +622,15 @@ def case_ludriver(G, cs):
         return msgs
     rcond, info = S.pdgecon("1", n, al, 1, 1, desca, anorm1); pads("PDGECON")
     true_rc = 1.0 / (np.abs(a0g).sum(axis=0).max() * np.abs(np.linalg.inv(a0g)).sum(axis=0).max())
-    if info != 0 or not (true_rc * (1 - 1e-8) <= rcond <= 10 * true_rc):
+    # any estimate bounds ||inv(A)|| from below.  LAPACK's stays within ~10x of the truth; the reference's PDLACON returns its
+    # alternating-sign value only (pdlacon.f:188-189), which drifts away with N (1500x at N = 1000): only the bound is checked then
+    slack = 10.0 if cs.get("lapack_estimator") else float("inf")
+    if info != 0 or not (true_rc * (1 - 1e-8) <= rcond <= slack * true_rc):
         msgs.append(f"PDGECON rcond {rcond} (true {true_rc}) info {info}")
+    lu_o = a0g.copy(order="F"); O.getrf(lu_o, nb)
+    want = O.dgecon("1", lu_o, np.abs(a0g).sum(axis=0).max())
+    if not abs(rcond - want) <= 1e-6 * want:
+        msgs.append(f"PDGECON rcond {rcond}, oracle {want}")
     info = S.pdgetrs("N", n, nrhs, al, 1, 1, desca, ipiv[:mloc + nb], bl, 1, 1, descb); pads("PDGETRS")
     # the residual check needs the global X: collect the pieces over the control plane (tiny) via PDGEMR2D onto one process
     xall = np.zeros((n + 1, nrhs), order="F") if (G.r, G.c) == (0, 0) else None
