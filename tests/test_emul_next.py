@@ -144,7 +144,7 @@ print("ROWS" + json.dumps(out))
     assert run.returncode == 0, run.stderr[-2000:]
     out = json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("ROWS")][0][4:])
     entries = {f"{row}.{k}": v for row, r in out.items() for k, v in r.items() if isinstance(v, dict)}
-    assert len(entries) >= 23, sorted(entries)
+    assert len(entries) >= 25, sorted(entries)
     bad = {k: v for k, v in entries.items() if not v["ok"]}
     assert not bad, bad
     assert all(r["_kernel_launches"] > 0 for r in out.values())
