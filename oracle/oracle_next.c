@@ -101,7 +101,7 @@ static double asum(int n, const double *x) { double s = 0.0; for (int i = 0; i <
 static int iamax1(int n, const double *x) { int j = 0; for (int i = 1; i < n; ++i) if (fabs(x[i]) > fabs(x[j])) j = i; return j + 1; }
 /* pdlacon.f:188-189 begins EVERY call with  EST = ZERO ; ESTWORK( 1 ) = EST : the estimate of the iteration (labels 20, 70) never
  * survives to the next call, ESTOLD is always zero, and at label 140 the alternating-sign value is compared with zero -- so the
- * reference's PDLACON returns 2 ||B x_alt||_1 / (3 N) whatever the iteration found (a valid, weaker lower bound of ||B||_1; LAPACK's
+ * reference's PDLACON returns 2 ||B x_alt||_1 / (3 N) whatever the iteration found (a valid but much weaker lower bound of ||B||_1 -- 45x - 1500x on PDMATGEN matrices of order 50 - 3000; LAPACK's
  * DLACON carries EST between calls and returns the larger of the two).  Executing the reference's source shows it
  * (tests/fortran_refine_runner.py).  The default here is the reference's behaviour; orcn_lacon_keep_est(1) restates LAPACK's, which is
  * what lets scipy's DGECON / DGESVX pin the machinery of the iteration itself. */

@@ -5,8 +5,8 @@
 //
 // What the reference's source actually returns: pdlacon.f:188-189 begins EVERY call with  EST = ZERO ; ESTWORK( 1 ) = EST , so the
 // estimate found by the iteration never survives to the next call and the value compared at label 140 is zero: PDLACON returns the
-// alternating-sign estimate 2 ||B x_alt||_1 / (3 N) whatever the iteration found (still a lower bound of ||B||_1, usually a few times
-// smaller than Higham's).  Executing the reference's text shows it (tests/fortran_refine_runner.py).  Default here = the reference's
+// alternating-sign estimate 2 ||B x_alt||_1 / (3 N) whatever the iteration found (still a lower bound of ||B||_1, but 45x - 1500x
+// smaller than Higham's on PDMATGEN matrices of order 50 - 3000).  Executing the reference's text shows it (tests/fortran_refine_runner.py).  Default here = the reference's
 // result, obtained with the ONE application of B that determines it (the iteration's applications cannot change the value, so they are
 // not made); option lacon_keep_estimate = 1 runs the full estimator with EST carried between the stages, as LAPACK's DLACON does.
 #pragma once
