@@ -28,6 +28,8 @@ class Unit:
         decl = " ".join(st for _, st in stmts if re.match(r"(INTEGER|DOUBLE|REAL|COMPLEX|LOGICAL|CHARACTER)\b", st) and "=" not in st.split("(")[0])
         self.array_args = {a for a in args if re.search(r"\b%s\s*\(" % re.escape(a), decl)}      # dummies declared with dimensions
         self.saves_all = any(st == "SAVE" for _, st in stmts)                                    # a bare SAVE: every local persists
+        # leading dimension of the arrays declared with two dimensions, e.g. A( LDA, * ): needed when the actual is a flat 1-D view
+        self.lead = {m.group(1): m.group(2).strip() for m in re.finditer(r"\b([A-Z_][A-Z0-9_]*)\s*\(([^(),]+),[^()]*\)", decl)}
 
 
 def parse(text):
@@ -205,6 +207,9 @@ class Interp:
             assert self._next() == ")"
             env = self._env
             if name in env and hasattr(env[name], "__getitem__") and not isinstance(env[name], str):
+                if len(args) == 2 and getattr(env[name], "ndim", 2) == 1:
+                    v2 = env[name][args[0] - 1 + (args[1] - 1) * self._lead(name, env)]
+                    return complex(v2) if getattr(v2, "dtype", None) == "complex128" else float(v2)
                 if len(args) == 2:
                     v2 = env[name][args[0] - 1, args[1] - 1]
                     return complex(v2) if isinstance(v2, complex) or getattr(v2, "dtype", None) == "complex128" else float(v2)
@@ -267,14 +272,32 @@ class Interp:
                 depth += ch == "("; depth -= ch == ")"; cur += ch
         parts.append(cur)
         idx = [self.eval(p_, env) - 1 for p_ in parts]
-        if len(idx) == 2:
+        if len(idx) == 2 and getattr(env[name], "ndim", 2) == 1:
+            env[name][idx[0] + idx[1] * self._lead(name, env)] = value
+        elif len(idx) == 2:
             env[name][idx[0], idx[1]] = value
         else:
             env[name][idx[0]] = value
 
+    def _lead(self, name, env):
+        """value of the declared leading dimension of the two-dimensional array `name` in the unit being executed"""
+        saved = (self._t, self._i, self._env)
+        v = self.eval(self._unit_stack[-1].lead[name], env)
+        self._t, self._i, self._env = saved
+        return v
+
     # ---- statements ---------------------------------------------------------------------------------------------------------
     def call(self, name, *args):
         """Runs unit `name`; scalars by value (their final values come back in the result dict), arrays as Python lists (in place)."""
+        if not hasattr(self, "_unit_stack"):
+            self._unit_stack = []
+        self._unit_stack.append(self.units[name])
+        try:
+            return self._call(name, *args)
+        finally:
+            self._unit_stack.pop()
+
+    def _call(self, name, *args):
         u = self.units[name]
         env = dict(zip(u.args, args))
         if u.kind == "FUNCTION":

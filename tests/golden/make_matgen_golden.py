@@ -18,6 +18,17 @@ CASES = [(6, 6, 2, 2, 1, 1, 100, 0, 0, 0), (6, 6, 2, 2, 2, 3, 100, 0, 0, 0), (7,
          (6, 6, 2, 2, 2, 3, 100, 0, 0, 1), (9, 7, 3, 2, 3, 2, 200, 1, 0, 1), (12, 12, 4, 4, 1, 1, 100, 0, 0, 1), (17, 5, 4, 3, 2, 2, 31, 0, 1, 1)]
 
 
+#             n nrhs nb nbrhs perturbation of the solution
+CHK_CASES = [(6, 1, 2, 1, 1e-6), (13, 3, 4, 2, 1e-6), (20, 5, 8, 3, 1e-3), (9, 2, 16, 2, 1e-6), (16, 4, 4, 4, 0.0), (1, 1, 1, 1, 1e-6)]
+
+
+def chk_solution(O, n, nrhs, pert):
+    """the solution PDLASCHK is given: the exact one, perturbed (pert = 0: whatever rounding leaves)"""
+    a, b = O.pdmatgen(n, n, 100).copy(order="F"), O.pdmatgen(n, nrhs, 200).copy(order="F")
+    x = np.linalg.solve(a, b)
+    return a, b, np.asfortranarray(x * (1.0 + pert * np.cos(np.arange(n))[:, None]))
+
+
 if __name__ == "__main__":
     it = R.make()
     store = {}
@@ -27,5 +38,11 @@ if __name__ == "__main__":
         for pr in range(p):
             for pc in range(q):
                 store[f"l{i}_{pr}_{pc}"] = R.local(it, m, n, mb, nb, pr, pc, p, q, seed, ir, ic, complex_=bool(z))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import oracle as O
+    itc = R.make_checks()
+    for i, (n, nrhs, nb, nbr, pert) in enumerate(CHK_CASES):
+        a, b, x = chk_solution(O, n, nrhs, pert)
+        store[f"chk{i}"] = np.array([R.pdlaschk(itc, x, n, nrhs, nb, nbr, 100, 200, np.abs(a).sum(axis=1).max())])
     np.savez_compressed(os.path.join(HERE, "matgen_reference.npz"), **store)
     print("wrote", len(CASES), "cases; PXERBLA log:", it.log)

@@ -363,3 +363,20 @@ def test_complex_lu_source_is_the_real_one_with_type_names_swapped():
             assert len(diff) == 2 and all(a.replace(",TRANS,", ",'TRANSPOSE',") == b and a.startswith("CALLPDTRSM(") for a, b in diff), diff
             diff = []
         assert len(z) == len(d) and not diff, (name, diff[:3])
+
+
+def test_solve_residual_against_the_executed_reference_fortran(O):
+    """SRESID -- the number every bench line and parity test reports for a solve -- is TESTING/traditional/LIN/pdlaschk.f's:
+    max_j ||b_j - A x_j||_inf / (||x_j||_inf ANORM eps N) with A and b REGENERATED block by block by PDMATGEN.  The oracle's orc_sresid
+    against that file executed (with the executed generator underneath, tests/fortran_matgen_runner.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_matgen_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "matgen_reference.npz"))
+    for i, (n, nrhs, nb, nbr, pert) in enumerate(G.CHK_CASES):
+        a, b, x = G.chk_solution(O, n, nrhs, pert)
+        ref = float(g[f"chk{i}"][0])
+        mine = O.sresid(a, x, b)
+        if pert == 0.0:
+            assert ref < 10.0 and mine < 10.0                   # rounding level on both sides (the reference's threshold is 1 ... 3)
+        else:
+            assert mine == pytest.approx(ref, rel=1e-3), (n, nrhs, nb, nbr)
