@@ -26,7 +26,7 @@ def ngpus():
         return 0
 
 
-def spawn(P, Q, cases, timeout=240):
+def spawn(P, Q, cases, timeout=400):
     if _HUNG:
         pytest.fail(f"skipped after the hang of {_HUNG[0]}")
     world = P * Q
