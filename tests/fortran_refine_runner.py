@@ -20,10 +20,14 @@ def _pdlamch(ictxt, cmach):
     return {"S": SAFMIN, "E": EPS, "P": 2.0 * EPS, "B": 2.0, "O": float(np.finfo(np.float64).max), "U": SAFMIN}[c]
 
 
-def make(ref_root="/root/reference", extra=()):
+def make(ref_root="/root/reference", extra=(), matgen=False):
+    """matgen: also the test-matrix generator (TESTING/traditional/LIN/pdmatgen.f + pmatgeninc.f, 32-bit INTEGER wrap-around)"""
     units = [F.parse(open(os.path.join(ref_root, d, f + ".f")).read())
              for d, f in (("TOOLS", "numroc"), ("TOOLS", "indxg2p"), ("TOOLS", "indxg2l"), ("TOOLS", "indxl2g"), ("TOOLS", "iceil"), ("TOOLS", "infog2l"),
                           ("TOOLS", "chk1mat"), ("TOOLS", "descset"), ("SRC", "pdgecon"), ("SRC", "pdlacon"), ("SRC", "pdlatrs"), ("SRC", "pdrscl")) + tuple(extra)]
+    if matgen:
+        for f in ("pmatgeninc.f", "pdmatgen.f"):
+            units += F.parse_file(open(os.path.join(ref_root, "TESTING", "traditional", "LIN", f)).read())
     log = []
 
     def ev(it, env, parts, k):
@@ -41,6 +45,13 @@ def make(ref_root="/root/reference", extra=()):
 
     def pxerbla(it, env, parts):
         log.append(("PXERBLA", it.eval(parts[1], env), it.eval(parts[2], env)))
+
+    def dmatadd(it, env, parts):                                                        # TESTING/.../pdmatgen? dmatadd: C := alpha A + beta C (by address)
+        m, n, alpha, beta = ev(it, env, parts, 0), ev(it, env, parts, 1), ev(it, env, parts, 2), ev(it, env, parts, 5)
+        a, ao = it.address(parts[3], env); c, co = it.address(parts[6], env)
+        lda, ldc = ev(it, env, parts, 4), ev(it, env, parts, 7)
+        for j in range(n):
+            c[co + j * ldc:co + j * ldc + m] = alpha * np.array(a[ao + j * lda:ao + j * lda + m]) + beta * np.array(c[co + j * ldc:co + j * ldc + m])
 
     def vec(it, env, parts, kx, n):
         """the N entries of the distributed vector X(IX:IX+N-1, JX) given as (X, IX, JX, DESCX) from argument kx on: a numpy view"""
@@ -283,10 +294,19 @@ def make(ref_root="/root/reference", extra=()):
     def pdlapiv_cols(it, env, parts):                                                   # SRC/pdlapiv.f, ROWCOL = 'C', PIVROC = 'C'
         direc, rowcol, pivroc = (ev(it, env, parts, k)[0].upper() for k in range(3))
         m, n = ev(it, env, parts, 3), ev(it, env, parts, 4)
-        assert rowcol == "C" and pivroc == "C"
-        a = window(it, env, parts, 5, m, n)
+        assert pivroc == "C"                                                             # IPIV distributed like the rows of A
         ip = ev(it, env, parts, 10)                                                      # IPIV(IP:IP+N-1): global ROW indices of A (pdgetrf.f:118-121)
         piv = env[parts[9]]
+        if rowcol == "R":                                                               # rows of sub(A) = A(IA:IA+M-1, JA:JA+N-1) interchanged
+            arr, aoff = it.address(parts[5], env)
+            ia, ja, desc = ev(it, env, parts, 6), ev(it, env, parts, 7), env[parts[8]]
+            full = np.asarray(arr[aoff:aoff + desc[8] * (ja - 1 + n)]).reshape((ja - 1 + n, desc[8])).T
+            for i in (range(m) if direc == "F" else range(m - 1, -1, -1)):
+                r0, r1 = ia - 1 + i, int(piv[ip - 1 + i]) - 1
+                if r0 != r1:
+                    full[[r0, r1], ja - 1:ja - 1 + n] = full[[r1, r0], ja - 1:ja - 1 + n]
+            return
+        a = window(it, env, parts, 5, m, n)
         for j in (range(n) if direc == "F" else range(n - 1, -1, -1)):
             p_ = int(piv[ip - 1 + j]) - ip
             if p_ != j:
@@ -312,7 +332,8 @@ def make(ref_root="/root/reference", extra=()):
         return int(np.argmax(np.abs(np.array(x[:n])))) + 1 if n > 0 else 0
 
 
-    cbs = {"PDGETF2": pdgetf2, "PDLASWP": pdlaswp, "IGAMN2D": nop,
+    cbs = {"DMATADD": dmatadd,
+           "PDGETF2": pdgetf2, "PDLASWP": pdlaswp, "IGAMN2D": nop,
            "PDTRMM": pdtrmm, "PDTRSM": pdtrsm, "PDGEMM": pdgemm, "PDLASET": pdlaset, "PDLAPIV": pdlapiv_cols, "DTRMV": dtrmv, "DSCAL": dscal,
            "BLACS_ABORT": nop,
            "PDGETRF": pdgetrf, "PDLACPY": pdlacpy_any, "DLASSQ": dlassq, "DCOMBSSQ": dcombssq, "IDAMAX": idamax, "PDTREECOMB": nop, "DGSUM2D": nop,
@@ -322,6 +343,7 @@ def make(ref_root="/root/reference", extra=()):
            "DGEBR2D": nop, "IGSUM2D": nop, "PDLABAD": nop, "PDTRSV": pdtrsv, "PDASUM": pdasum, "PDAMAX": pdamax, "PDELGET": pdelget, "DCOPY": dcopy,
            "PDSCAL": pdscal, "PDLAMCH": _pdlamch}
     it = F.Interp(units, cbs)
+    it.wrap32 = bool(matgen)
     it.log = log
     return it
 
@@ -410,3 +432,22 @@ def pdgetri(it, lu, ipiv, nb, ia=1, ja=1, n=None):
     out = it.call("PDGETRI", n, a, ia, ja, desc, ip, np.zeros(lw + 8), lw, np.zeros(liw + 8, np.int64), liw, 0)
     lu[...] = a.reshape((M, N), order="F")
     return out["INFO"], lw, liw
+
+
+CHK_UNITS = (("TESTING/traditional/LIN", "pdgetrrv"), ("TESTING/traditional/LIN", "pdlafchk"), ("SRC", "pdlange"))
+
+
+def fresid(it, lu, ipiv, nb, aseed):
+    """FRESID as the reference's LU driver computes it (pdludriver.f:540-556) on a 1 x 1 grid: PDGETRRV rebuilds P L U from the factors
+    in place, PDLAFCHK subtracts the regenerated A = PDMATGEN(aseed) and scales the infinity norm of the difference."""
+    m, n = lu.shape
+    desc = [1, 0, m, n, nb, nb, 0, 0, max(1, m)]
+    a0 = np.zeros(m * n)
+    it.call("PDMATGEN", 0, "N", "N", m, n, nb, nb, a0, max(1, m), 0, 0, aseed, 0, m, 0, n, 0, 0, 1, 1)
+    work = np.zeros(m * nb + nb * n + m * n + 64)
+    anorm = it.call("PDLANGE", "I", m, n, a0, 1, 1, desc, work)["__result__"]
+    a = np.asfortranarray(lu).reshape(-1, order="F").copy()
+    ip = np.concatenate([np.asarray(ipiv, np.int64), np.zeros(nb, np.int64)])
+    it.call("PDGETRRV", m, n, a, 1, 1, desc, ip, work)
+    out = it.call("PDLAFCHK", "N", "N", m, n, a, 1, 1, desc, aseed, anorm, 0.0, work)
+    return out["FRESID"], anorm

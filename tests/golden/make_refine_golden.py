@@ -83,6 +83,18 @@ def tri_inputs(cs):
     return big, np.asarray(ipiv, np.int64) + off, lu, a
 
 
+#              m   n  nb  relative perturbation of the factors (0: FRESID is rounding only)
+FCHK_CASES = [(6, 6, 2, 1e-6), (13, 13, 4, 1e-6), (10, 14, 3, 1e-5), (15, 9, 4, 1e-6), (20, 20, 32, 1e-3), (13, 13, 4, 0.0), (10, 14, 3, 0.0)]
+
+
+def fchk_inputs(m, n, nb, pert):
+    a = O.pdmatgen(m, n, 100).copy(order="F")
+    lu = a.copy(order="F"); ipiv, info = O.getrf(lu, nb)
+    lu *= 1.0 + pert * np.cos(np.arange(m))[:, None] * np.sin(1.0 + np.arange(n))[None, :]
+    full_ip = np.arange(1, m + 1); full_ip[:min(m, n)] = ipiv[:min(m, n)]
+    return a, np.asfortranarray(lu), ipiv, full_ip
+
+
 if __name__ == "__main__":
     it = R.make(extra=R.SVX_UNITS + R.TRI_UNITS)
     store = {}
@@ -137,6 +149,10 @@ if __name__ == "__main__":
         info, lw, liw = R.pdgetri(it, big, ipiv, cs["nb"], ia=off + 1, ja=off + 1, n=cs["n"])
         store[f"tri{i}"] = np.array([info, lw, liw], np.int64)
         store[f"tri_inv{i}"] = big
+    itf = R.make(extra=R.CHK_UNITS, matgen=True)
+    for i, (m, n, nb, pert) in enumerate(FCHK_CASES):
+        a, lu, ipiv, full_ip = fchk_inputs(m, n, nb, pert)
+        store[f"fchk{i}"] = np.array(R.fresid(itf, lu, full_ip, nb, 100))          # (FRESID, ANORM)
     # argument errors and quick returns as the executed source reports them: (NORM, N, ANORM, LWORK) -> (INFO, RCOND)
     lu = O.pdmatgen(8, 8, 100).copy(order="F")
     a = lu.reshape(-1, order="F").copy()

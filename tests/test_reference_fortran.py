@@ -380,3 +380,21 @@ def test_solve_residual_against_the_executed_reference_fortran(O):
             assert ref < 10.0 and mine < 10.0                   # rounding level on both sides (the reference's threshold is 1 ... 3)
         else:
             assert mine == pytest.approx(ref, rel=1e-3), (n, nrhs, nb, nbr)
+
+
+def test_factorisation_residual_against_the_executed_reference_fortran(O):
+    """FRESID -- the parity tests' and the bench pre-flight's measure of a factorisation -- is the LU driver's: PDGETRRV rebuilds P L U
+    from the factors, PDLAFCHK subtracts the regenerated A and divides ||.||_inf by max(M, N) eps ||A||_inf (pdludriver.f:540-556).  The
+    oracle's orc_fresid against TESTING/traditional/LIN/pdgetrrv.f + pdlafchk.f + SRC/pdlange.f + the generator, executed."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_refine_golden as G
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refine_reference.npz"))
+    for i, (m, n, nb, pert) in enumerate(G.FCHK_CASES):
+        a, lu, ipiv, _ = G.fchk_inputs(m, n, nb, pert)
+        ref, anorm = [float(v) for v in g[f"fchk{i}"]]
+        assert anorm == np.abs(a).sum(axis=1).max()
+        mine = O.fresid(lu, ipiv, a)
+        if pert == 0.0:
+            assert ref < 1.0 and mine < 1.0                     # rounding only: the order of the products differs, the level does not
+        else:
+            assert mine == pytest.approx(ref, rel=1e-3), (m, n, nb)
