@@ -174,7 +174,7 @@ import bench_next as BN
 print("ROWS" + json.dumps(BN.run_row(sys.argv[1], n=70, nb=16, device="cpu")))
 ''' % dict(root=ROOT)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    for k, row in enumerate(["potrf", "gemr2d", "refine", "getrs_l3"] if world == 4 else ["getri", "pblas", "refine"]):
+    for k, row in enumerate(["potrf", "refine"] if world == 4 else ["getri", "pblas", "gemr2d", "getrs_l3"]):
         procs = []
         for r in range(world):
             env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port + 50 * k),
