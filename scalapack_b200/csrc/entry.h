@@ -52,10 +52,19 @@ inline void gather_global_ipiv(Grid *g, int n, int nb, int rsrc, const int *ipiv
     std::vector<int> mine((size_t)n, 0);
     for (int gi = 0; gi < n; ++gi)
         if (indxg2p(gi + 1, nb, rsrc, P) == g->myrow) mine[gi] = ipiv_local[indxg2l(gi + 1, nb, P) - 1] - row0;
-    if (P == 1) { ipg = mine; return; }
-    std::vector<int> all((size_t)n * P);
-    grid_allgather(g, 'C', mine.data(), all.data(), (size_t)n * sizeof(int));
-    for (int p = 0; p < P; ++p) for (int gi = 0; gi < n; ++gi) if (all[(size_t)p * n + gi] > ipg[gi]) ipg[gi] = all[(size_t)p * n + gi];
+    if (P == 1) ipg = mine;
+    else {
+        std::vector<int> all((size_t)n * P);
+        grid_allgather(g, 'C', mine.data(), all.data(), (size_t)n * sizeof(int));
+        for (int p = 0; p < P; ++p) for (int gi = 0; gi < n; ++gi) if (all[(size_t)p * n + gi] > ipg[gi]) ipg[gi] = all[(size_t)p * n + gi];
+    }
+    // what PDGETRF writes is a pivot sequence: row i is exchanged with a row at or below it, inside sub(A).  Anything else (an IPIV
+    // of another sub-matrix, an uninitialised array) would index outside the permutation below -- silently in the reference's PDLAPIV;
+    // here it stops the run with a message.
+    for (int gi = 0; gi < n; ++gi)
+        if (ipg[gi] < gi + 1 || ipg[gi] > n)
+            fatal("IPIV: the entry for row %d of sub(A) is %d (expected %d .. %d): not the pivots PDGETRF returned for this sub-matrix", gi + 1,
+                  ipg[gi], gi + 1, n);
 }
 
 // the right-hand sides sub(B) = B(IB:IB+N-1, JB:JB+NRHS-1): rows aligned with sub(A) (checked), columns anywhere in B

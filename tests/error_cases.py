@@ -94,7 +94,12 @@ def product_info(S, ctx, routine, a, ctx_other=None):
     VALID 1 x 1 context (the executed source sees a valid grid behind every handle; an invalid handle is a different error, on RSRC)"""
     A, B = matrices()
     d = {k: [(ctx_other if v == 1 else ctx) if i == 1 else v for i, v in enumerate(a[k])] for k in ("desca", "descaf", "descb", "descx")}
-    ip = np.concatenate([np.arange(1, MG + 1), np.zeros(NB)]).astype(np.int32)
+    # "no interchange" pivots: the entry of every local row is that row's own global index (the layout PDGETRF leaves, pdgetrf.f:118-121)
+    P, _, myrow, _ = S.blacs_gridinfo(ctx)
+    mb, rs = (a["desca"][4] if a["desca"][4] > 0 else 1), (a["desca"][6] if 0 <= a["desca"][6] < P else 0)
+    nloc = S.numroc(MG, mb, myrow, rs, P)
+    ip = np.zeros(MG + NB + 4, np.int32)
+    ip[:nloc] = [S.indxl2g(l + 1, mb, myrow, rs, P) for l in range(nloc)]
     if routine == "PDGETRF":
         return S.pdgetrf(a["m"], a["n"], A, a["ia"], a["ja"], d["desca"], ip)
     if routine == "PDGETRS":

@@ -263,3 +263,72 @@ print("ALL" + json.dumps(out))
         assert o["summary"]["rows_failed"] == [] and o["summary"]["grid"] == "1x2", o
         assert o["summary"]["entries"] == o["summary"]["ok"] == 8, o["summary"]
         assert o["potrf"]["_grid"] == "1x2"
+
+
+def test_info_codes_on_a_process_grid_are_collective(emul_lib):
+    """The same 894 argument combinations on a 2 x 2 grid (four processes over the TCP control plane): every call comes back on every
+    rank -- nobody returns early and leaves the others in a collective -- with the SAME INFO on all four, as PCHK1MAT / PCHK2MAT guarantee
+    in the reference; the grid-independent majority equals the executed reference's value."""
+    code = r'''
+import sys, json
+sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(root)s/tests")
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import scalapack_b200 as S
+import error_cases as E
+ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 2, 2)
+ctx2 = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 2, 2)
+g = json.load(open("%(root)s/tests/golden/errors_reference.json"))
+out = []
+for c in g["cases"]:
+    ch = {k: ([tuple(x) for x in v] if v and isinstance(v[0], list) else tuple(v)) if isinstance(v, list) else v for k, v in c["changes"].items()}
+    print("AT", c["routine"], c["label"], flush=True)
+    out.append(E.product_info(S, ctx, c["routine"], E.apply(c["routine"], ch), ctx2))
+print("INFOS" + json.dumps(out))
+''' % dict(root=ROOT)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(4):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="4", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SLB200_PORT_OFFSET="0",
+                   OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=300)
+            last = [ln for ln in o.splitlines() if ln.startswith("AT")][-1:]
+            assert p.returncode == 0, (last, e[-1500:])
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("INFOS")][0][5:]))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "errors_reference.json")))["cases"]
+    differ = [(c["routine"], c["label"], [o[i] for o in outs]) for i, c in enumerate(ref) if len({o[i] for o in outs}) != 1]
+    assert len(outs[0]) == len(ref) >= 890 and not differ, differ[:5]
+    assert sum(1 for i, c in enumerate(ref) if outs[0][i] == c["info"]) >= 0.8 * len(ref)
+
+
+def test_invalid_pivots_stop_the_run_with_a_message(emul_lib):
+    """An IPIV that is not the pivot sequence of PDGETRF for this sub-matrix (here: the pivots of sub-matrix (1, 1) passed with IA = 5)
+    indexes outside the row permutation -- silently in the reference; the product stops with a message instead of corrupting memory."""
+    code = r'''
+import sys
+sys.path.insert(0, "%(root)s")
+import numpy as np
+import scalapack_b200.api as api
+api._SO = "%(root)s/tests/emul/libslb_emul.so"
+import scalapack_b200 as S
+ctx = S.blacs_gridinit(S.blacs_get(-1, 0), "Row-major", 1, 1)
+a = np.asfortranarray(np.eye(12) * 3.0); b = np.asfortranarray(np.ones((12, 2)))
+da, _ = S.descinit(12, 12, 4, 4, 0, 0, ctx, 12); db, _ = S.descinit(12, 2, 4, 2, 0, 0, ctx, 12)
+ipiv = np.arange(1, 17, dtype=np.int32)
+assert S.pdgetrs("N", 8, 2, a, 1, 1, da, ipiv, b, 1, 1, db) == 0          # pivots of sub-matrix (1, 1): fine
+ipiv[4:12] = np.arange(1, 9)                                                 # rows 5 .. 12 "exchanged" with rows 1 .. 8: not PDGETRF's output for IA = 5
+S.pdgetrs("N", 8, 2, a, 5, 5, da, ipiv, b, 5, 1, db)
+print("NOT REACHED")
+''' % dict(root=ROOT)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+    assert run.returncode != 0 and "NOT REACHED" not in run.stdout
+    assert "IPIV: the entry for row 1 of sub(A) is -3" in run.stderr, run.stderr[-800:]
