@@ -169,6 +169,12 @@ def ipiv_local(m, mn, mb, nprow, myrow, ipiv_g, nloc, rsrc=0, fill=-1):
 
 
 # ---------------------------------------------------------------- LU / solve / residuals
+def tie_grid(nprow=1, rsrc=0):
+    """Exact ties in the pivot search are broken as the reference's PDAMAX breaks them on a grid with `nprow` process rows (the lowest
+    absolute process row wins, pdamax_.c:436-458); nprow = 1 (default): the first global index."""
+    lib().orc_set_tie_grid(int(nprow), int(rsrc))
+
+
 def getrf(a, nb, phase_times=False):
     """In-place restated PDGETRF on the global matrix.  Returns (ipiv[1-based], info)."""
     assert a.flags.f_contiguous

@@ -441,14 +441,28 @@ static int idamax0(int n, const double *x)
     return p;
 }
 
-/* Unblocked panel: SRC/pdgetf2.f:207-237 on the m x jb panel at a (lda).
+/* EXACT TIES.  With equal maxima the reference's answer depends on the process grid: PDAMAX combines the local candidates up a binary
+ * tree towards process row 0 and the receiver keeps its own on a tie (strict <, pdamax_.c:436-458), so the candidate of the LOWEST
+ * ABSOLUTE PROCESS ROW wins, and inside a process row the first local index (idamax).  On one process row that is the first global index
+ * (the default here).  orc_set_tie_grid(nprow, rsrc) makes the serial restatement answer as an nprow-row grid whose process row rsrc owns
+ * the first block row of sub(A) would: equilibrated matrices (PDGESVX, FACT = 'E') are full of entries that are exactly 1. */
+static int g_tie_nprow = 1, g_tie_rsrc = 0;
+void orc_set_tie_grid(int nprow, int rsrc) { g_tie_nprow = nprow > 1 ? nprow : 1; g_tie_rsrc = rsrc; }
+static inline int tie_prow(int grow, int nb) { return (g_tie_rsrc + grow / nb) % g_tie_nprow; }
+
+/* Unblocked panel: SRC/pdgetf2.f:207-237 on the m x jb panel at a (lda); row 0 of the panel is global row row0 of sub(A).
  * ipiv (0-based local to the panel) out; returns first zero-pivot column+1 or 0. */
-static int getf2_ref(int m, int jb, double *a, int64_t lda_, int *ipiv)
+static int getf2_ref(int m, int jb, double *a, int64_t lda_, int *ipiv, int row0, int nb)
 {
     int info = 0, lda = (int)lda_, one = 1;
     int mn = imin(m, jb);
     for (int j = 0; j < mn; ++j) {
         int p = j + idamax0(m - j, a + j + (int64_t)j * lda);      /* PDAMAX  :212 */
+        if (g_tie_nprow > 1) {
+            const double v = fabs(a[p + (int64_t)j * lda]); int best = tie_prow(row0 + p, nb);
+            for (int i = p + 1; i < m; ++i)
+                if (fabs(a[i + (int64_t)j * lda]) == v && tie_prow(row0 + i, nb) < best) { best = tie_prow(row0 + i, nb); p = i; }
+        }
         ipiv[j] = p;
         double gmax = a[p + (int64_t)j * lda];
         if (gmax != 0.0) {                                           /* :214 */
@@ -516,7 +530,7 @@ int orc_dgetrf(int m, int n, double *a, int64_t lda, int nb, int *ipiv, double *
     for (int j0 = 0; j0 < mn; j0 += nb) {                              /* DO 10 :254 */
         int jb = imin(nb, mn - j0);
         t0 = orc_wtime();
-        int iinfo = getf2_ref(m - j0, jb, a + j0 + (int64_t)j0 * lda, lda, piv + j0);   /* PDGETF2 :261 */
+        int iinfo = getf2_ref(m - j0, jb, a + j0 + (int64_t)j0 * lda, lda, piv + j0, j0, nb);   /* PDGETF2 :261 */
         for (int j = j0; j < j0 + imin(jb, m - j0); ++j) { piv[j] += j0; ipiv[j] = piv[j] + 1; }
         if (info == 0 && iinfo > 0) info = iinfo + j0;                 /* :263-264 */
         tp += orc_wtime() - t0; t0 = orc_wtime();
@@ -549,7 +563,7 @@ int orc_dgetrf_steps(int m, int n, double *a, int64_t lda, int nb, int *ipiv, in
     int step = 0;
     for (int j0 = 0; j0 < mn && step < nsteps; j0 += nb, ++step) {
         int jb = imin(nb, mn - j0);
-        int iinfo = getf2_ref(m - j0, jb, a + j0 + (int64_t)j0 * lda, lda, piv + j0);
+        int iinfo = getf2_ref(m - j0, jb, a + j0 + (int64_t)j0 * lda, lda, piv + j0, j0, nb);
         for (int j = j0; j < j0 + jb; ++j) { piv[j] += j0; ipiv[j] = piv[j] + 1; }
         if (info == 0 && iinfo > 0) info = iinfo + j0;
         double mm = m - j0, nn = n - j0 - jb;
@@ -678,12 +692,17 @@ static inline zdouble zrecip(zdouble z)
     return r;
 }
 
-static int zgetf2_ref(int m, int jb, zdouble *a, int64_t lda, int *ipiv)
+static int zgetf2_ref(int m, int jb, zdouble *a, int64_t lda, int *ipiv, int row0, int nb)
 {
     int info = 0, mn = imin(m, jb);
     for (int j = 0; j < mn; ++j) {
         int p = j; double v = cabs1(a[j + j * lda]);
         for (int i = j + 1; i < m; ++i) { double w = cabs1(a[i + j * lda]); if (w > v) { v = w; p = i; } }
+        if (g_tie_nprow > 1) {
+            int best = tie_prow(row0 + p, nb);
+            for (int i = p + 1; i < m; ++i)
+                if (cabs1(a[i + j * lda]) == v && tie_prow(row0 + i, nb) < best) { best = tie_prow(row0 + i, nb); p = i; }
+        }
         ipiv[j] = p;
         zdouble g = a[p + j * lda];
         if (g.re != 0.0 || g.im != 0.0) {
@@ -703,7 +722,7 @@ int orc_zgetrf(int m, int n, zdouble *a, int64_t lda, int nb, int *ipiv)
     int *piv = (int*)malloc(sizeof(int) * (size_t)(mn > 0 ? mn : 1));
     for (int j0 = 0; j0 < mn; j0 += nb) {
         int jb = imin(nb, mn - j0);
-        int iinfo = zgetf2_ref(m - j0, jb, a + j0 + j0 * lda, lda, piv + j0);
+        int iinfo = zgetf2_ref(m - j0, jb, a + j0 + j0 * lda, lda, piv + j0, j0, nb);
         for (int j = j0; j < j0 + jb; ++j) { piv[j] += j0; ipiv[j] = piv[j] + 1; }
         if (info == 0 && iinfo > 0) info = iinfo + j0;
         for (int i = j0; i < j0 + jb; ++i) { int ip = piv[i]; if (ip != i) {

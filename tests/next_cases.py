@@ -667,12 +667,15 @@ def run(S, ctx, cases):
             # instead of what the reference's source returns (pdlacon.f:188-189, the default of both)
             keep = bool(cs.get("lapack_estimator"))
             S.set_option("lacon_keep_estimate", 1 if keep else 0); O.lacon_keep_est(keep)
+            # exact ties in the pivot search (equilibrated matrices are full of entries that are exactly 1) are broken the way the
+            # reference's PDAMAX breaks them on THIS grid: the serial oracle is told the grid's process rows and A's source row
+            O.tie_grid(G.P, cs.get("rsrc", 0) % G.P)
             try:
                 res["msgs"] = CASES[cs["kind"]](G, cs)
             except Exception as e:          # noqa: BLE001 - a rank must report, not vanish
                 import traceback
                 res["msgs"] = [f"exception {e!r}", traceback.format_exc()[-1500:]]
-            S.set_option("lacon_keep_estimate", 0); O.lacon_keep_est(False)
+            S.set_option("lacon_keep_estimate", 0); O.lacon_keep_est(False); O.tie_grid(1, 0)
             res["ok"] = not res["msgs"]
         out.append(res)
     return out
@@ -690,6 +693,7 @@ F1_CASES = [
     dict(kind="gesvx", n=40, nb=8, fact="E"), dict(kind="gesvx", n=24, nb=4, fact="N", singular=True),
     dict(kind="gesvx", n=1, nb=4, fact="N", nrhs=1), dict(kind="gesvx", n=2, nb=4, fact="E", nrhs=1), dict(kind="gerfs", n=1, nb=2, nrhs=2), dict(kind="gecon", n=1, nb=2),
     dict(kind="gerfs", n=3, nb=2, nrhs=1, trans="T"),
+    dict(kind="gesvx", n=40, nb=1, nrhs=1, fact="E", cond=2),          # equilibrated: exact ties in the pivot search, broken by process row (found by scripts/fuzz_next_rows.py on 3x2)
     dict(kind="gecon", n=64, nb=8, lapack_estimator=True), dict(kind="gecon", n=45, nb=4, cond=2, lapack_estimator=True),
     dict(kind="gerfs", n=45, nb=4, nrhs=2, trans="T", cond=2, lapack_estimator=True), dict(kind="gesvx", n=45, nb=4, fact="E", cond=5, lapack_estimator=True),
     dict(kind="gesvx", n=24, nb=4, fact="N", singular=True, lapack_estimator=True),

@@ -43,7 +43,7 @@ def spawn(P, Q, cases, timeout=150):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3)])
+@pytest.mark.parametrize("P,Q", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
 def test_refinement_family(emul_lib, P, Q):
     spawn(P, Q, "F1_CASES")
 

@@ -311,3 +311,26 @@ def test_oracle_getrs_trans_against_numpy(O, cplx, trans):
     x = b0.copy(order="F"); O.getrs(ref, ipiv, x, trans)
     aop = {"N": a0, "T": a0.T, "C": a0.conj().T}[trans]
     assert np.abs(x - np.linalg.solve(aop, b0)).max() < 1e-11
+
+
+def test_exact_ties_are_broken_like_pdamax_on_a_grid(O):
+    """PBLAS/SRC/pdamax_.c:436-458: the local candidates go up a binary tree towards process row 0 and the receiver keeps its own on a tie,
+    so among equal maxima the one on the lowest absolute process row wins (first local index inside a row).  NB = 1, three process rows:
+    rows 0, 3, 6 live on process row 0, rows 1, 4, 7 on row 1, rows 2, 5, 8 on row 2."""
+    a = np.asfortranarray(np.eye(9) * 0.5 + 0.01 * np.arange(81).reshape(9, 9) / 81.0)
+    a[:, 0] = 0.25
+    a[[4, 6, 8], 0] = 2.0                                       # equal maxima at global rows 4 (process row 1), 6 (row 0), 8 (row 2)
+    try:
+        lu = a.copy(order="F"); ip, _ = O.getrf(lu, 1)
+        assert ip[0] == 5                                      # one process row: the first global index
+        O.tie_grid(3, 0)
+        lu = a.copy(order="F"); ip, _ = O.getrf(lu, 1)
+        assert ip[0] == 7                                      # row 6 sits on process row 0
+        O.tie_grid(3, 1)                                       # the first block row on process row 1: rows 0, 3, 6 -> process row 1; 2, 5, 8 -> row 0
+        lu = a.copy(order="F"); ip, _ = O.getrf(lu, 1)
+        assert ip[0] == 9
+        O.tie_grid(2, 0)                                       # two process rows: 4, 6, 8 all on process row 0 -> the first of them
+        lu = a.copy(order="F"); ip, _ = O.getrf(lu, 1)
+        assert ip[0] == 5
+    finally:
+        O.tie_grid(1, 0)
