@@ -88,7 +88,10 @@ static int getrf_lookahead_1x1(int M, int N, T *A, int64_t lld, int nb, int *ipi
     const int gmax_opt = (int)opt("panel_gmax", 32), chunk_opt = (int)opt("gemm_chunk", 4);
     const double overlap_min_ms = (double)opt("lookahead_min_us", 4000) * 1e-3;
     const bool pipe = opt("la_pipeline", 1) != 0;
-    const int64_t split_min = opt("la_split_min", 6144);      // fewer trailing columns: the step is not split
+    // fewer trailing columns: the step is not split.  The near half must hold the next panel and the re-split test below works in
+    // quarters of the trailing width, so the option is taken no lower than 2 NB and 4 (found by scripts/fuzz_lu_path.py: with 1-3
+    // trailing columns split, the near half ran empty and the next panel was factored before its update)
+    const int64_t split_min = std::max<int64_t>(opt("la_split_min", 6144), std::max<int64_t>(2 * (int64_t)nb, 4));
     const bool trace = opt("la_trace", 0) != 0;               // per-step timeline on stderr
 
     auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
@@ -538,7 +541,7 @@ int getrf_device(Grid *g, int M, int N, T *A, int64_t lld, int nb, int rsrc, int
         // unpack -> U12 solve; near half under the update of the previous step's far half, far half (+ the already
         // factored left columns) under this step's near update.  sg carries the three update launches of a step.
         cudaStream_t sg = sm, sq = r.s_prep;
-        const int64_t split_min = opt("la_split_min", 6144);
+        const int64_t split_min = std::max<int64_t>(opt("la_split_min", 6144), std::max<int64_t>(2 * (int64_t)nb, 4));   // see the 1 x 1 pipeline
         auto mkev = [](std::vector<cudaEvent_t> &v, size_t n) { v.resize(n); for (auto &e : v) SLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
         std::vector<cudaEvent_t> pdp, pdn, pdf, gdn, gdf;
         mkev(pdp, (size_t)nsteps); mkev(pdn, (size_t)nsteps); mkev(pdf, (size_t)nsteps); mkev(gdn, (size_t)nsteps); mkev(gdf, (size_t)nsteps);

@@ -92,3 +92,13 @@ def test_gpu_interface_tests_against_the_emulation(emul_lib):
     tail = run.stdout[-1500:]
     assert run.returncode == 0, tail + run.stderr[-1500:]
     assert " passed" in tail and "failed" not in tail, tail
+
+
+@pytest.mark.parametrize("P,Q", [(1, 1), (2, 2), (3, 2)])
+def test_degenerate_split_settings_are_clamped(emul_lib, P, Q):
+    """`la_split_min` below 2 NB (or below 4 columns) used to split steps whose near half could not hold the next panel: with 1-3 trailing
+    columns the near half ran empty and the next panel was factored before its update (wrong factors, silently; found by
+    scripts/fuzz_lu_path.py).  The option is now taken no lower than max(2 NB, 4); these are the reduced failing configurations."""
+    spawn(P * Q, [dict(P=P, Q=Q, m=6, n=6, nb=1, nrhs=1, split=3), dict(P=P, Q=Q, m=11, n=11, nb=1, nrhs=2, split=1, hoststream=True),
+                  dict(P=P, Q=Q, m=24, n=24, nb=3, nrhs=1, split=3), dict(P=P, Q=Q, m=63, n=53, nb=2, nrhs=1, split=2, hoststream=True),
+                  dict(P=P, Q=Q, m=47, n=44, nb=3, nrhs=1, z=True, split=3), dict(P=P, Q=Q, m=117, n=117, nb=1, nrhs=2, split=1, hoststream=True)])
