@@ -48,4 +48,24 @@ if __name__ == "__main__":
         except AssertionError as ex:
             total += 1
             print(f"{grid}: FAILED", str(ex)[:2500], flush=True)
+    # host-resident callers on one process: the column slabs of A arrive late by a varying number of polls, with and without the budget
+    # that keeps factored panels for the replay (tests/test_emul_lu.py::test_host_streaming_with_late_slabs, random shapes here)
+    for delay in (0, 1, 3, 7):
+        for save_mb in (16384, 0):
+            rng = random.Random(args.seed * 1000 + delay * 10 + (save_mb > 0))
+            cases = []
+            for _ in range(args.count // 4):
+                nb = rng.choice([4, 8, 16, 32])
+                m = rng.randint(1, 300)
+                n = m if rng.random() < 0.5 else rng.randint(1, 300)
+                cs = dict(P=1, Q=1, m=m, n=n, nb=nb, nrhs=rng.randint(0, 2), z=rng.random() < 0.25, hoststream=True)
+                if rng.random() < 0.6:
+                    cs["split"] = nb * rng.randint(2, 4)
+                cases.append(cs)
+            try:
+                T.spawn(1, cases, timeout=1500, extra_env={"SLB200_EMUL_SLAB_DELAY": str(delay), "SLB200_E2E_SAVE_MB": str(save_mb), "SLB200_E2E_SLAB_MB": "0"})
+                print(f"late slabs delay={delay} save_mb={save_mb}: {len(cases)} cases ok", flush=True)
+            except AssertionError as ex:
+                total += 1
+                print(f"late slabs delay={delay} save_mb={save_mb}: FAILED", str(ex)[:2000], flush=True)
     sys.exit(1 if total else 0)
