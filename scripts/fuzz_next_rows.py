@@ -35,7 +35,9 @@ def gen(kind, rng):
         ia, ja, ib, jb = (rng.randint(1, 9) for _ in range(4))
         return dict(kind=kind, m=m, n=n2, ia=ia, ja=ja, ib=ib, jb=jb, shape_a=(m + ia + rng.randint(0, 5), n2 + ja + rng.randint(0, 5)),
                     shape_b=(m + ib + rng.randint(0, 5), n2 + jb + rng.randint(0, 5)), blk_a=(rng.randint(1, 9), rng.randint(1, 9)), blk_b=(rng.randint(1, 20), rng.randint(1, 20)),
-                    src_a=(rng.randint(0, 3), rng.randint(0, 3)), src_b=(rng.randint(0, 3), rng.randint(0, 3)), z=rng.random() < 0.2)
+                    src_a=(rng.randint(0, 3), rng.randint(0, 3)), src_b=(rng.randint(0, 3), rng.randint(0, 3)), z=rng.random() < 0.2,
+                    **({"ga": rng.choice([(1, 1), (1, 2), (2, 1), (2, 2), (1, 3), (3, 1)])} if rng.random() < 0.3 else {}),
+                    **({"gb": rng.choice([(1, 1), (1, 2), (2, 1), (2, 2), (1, 3), (3, 1)])} if rng.random() < 0.3 else {}))
     if kind == "potrf":
         return dict(kind=kind, n=n, nb=nb, uplo=rng.choice("LU"), nrhs=rng.choice([1, 2, 5, 70]), off=rng.randint(0, 2), rsrc=rng.randint(0, 3), csrc=rng.randint(0, 3),
                     notpd=(rng.randint(0, n - 1) if rng.random() < 0.15 else None))
