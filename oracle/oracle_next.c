@@ -9,8 +9,11 @@
  * from any distributed run, so parity is to a stated tolerance, and the discrete decisions (sign vectors,
  * arg-max of PDLACON, the refinement stopping rule) are the same on tie-free data.
  *
- * Pinning: every routine here has a LAPACK twin (dlange, dgeequ, dlaqge, dlacon, dgecon, dgerfs, dgesvx,
- * dpotrf, dpotrs, dtrtri, dgetri); tests/test_oracle_next.py checks each against scipy's LAPACK.
+ * Pinning: (1) the reference's OWN source, executed by tests/fortran77_mini.py: pdgecon.f, pdlacon.f, pdgerfs.f, pdgesvx.f, pdgeequ.f,
+ * pdlaqge.f, pdlange.f, pdpotrf.f, pdpotf2.f, pdpotrs.f, pdgetri.f, pdtrtri.f, pdtrti2.f -- golden vectors in tests/golden/refine_reference.npz
+ * and chol_reference.npz, checked by tests/test_reference_fortran.py (that is how PDLACON's behaviour below was found); (2) every routine
+ * here also has a LAPACK twin (dlange, dgeequ, dlaqge, dlacon, dgecon, dgerfs, dgesvx, dpotrf, dpotrs, dtrtri, dgetri) and
+ * tests/test_oracle_next.py checks each against scipy's LAPACK (the estimator in LAPACK's mode).
  */
 #include <float.h>
 #include <math.h>
