@@ -68,7 +68,7 @@ def pair_mutations(routine, count=40, seed=7):
 
 def apply(routine, changes):
     """the argument set of one call, or None when the mutation does not concern this routine"""
-    names = ROUTINES[routine]
+    names = ROUTINES[routine.replace("PZ", "PD")]
     if any(k not in names for k in changes):
         return None
     a = base()
@@ -100,6 +100,13 @@ def product_info(S, ctx, routine, a, ctx_other=None):
     nloc = S.numroc(MG, mb, myrow, rs, P)
     ip = np.zeros(MG + NB + 4, np.int32)
     ip[:nloc] = [S.indxl2g(l + 1, mb, myrow, rs, P) for l in range(nloc)]
+    if routine in ("PZGETRF", "PZGETRS", "PZGESV"):                   # the complex entry points: the same checks (their source is the real one, type-swapped)
+        Az, Bz = (A + 0.5j * A.T).copy(order="F"), (B * (1 + 0.25j)).copy(order="F")
+        if routine == "PZGETRF":
+            return S.pzgetrf(a["m"], a["n"], Az, a["ia"], a["ja"], d["desca"], ip)
+        if routine == "PZGETRS":
+            return S.pzgetrs(a["trans"], a["n"], a["nrhs"], Az, a["ia"], a["ja"], d["desca"], ip, Bz, a["ib"], a["jb"], d["descb"])
+        return S.pzgesv(a["n"], a["nrhs"], Az, a["ia"], a["ja"], d["desca"], ip, Bz, a["ib"], a["jb"], d["descb"])
     if routine == "PDGETRF":
         return S.pdgetrf(a["m"], a["n"], A, a["ia"], a["ja"], d["desca"], ip)
     if routine == "PDGETRS":
